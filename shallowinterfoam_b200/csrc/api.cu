@@ -1,0 +1,375 @@
+// api.cu -- the extern "C" boundary declared in include/b200foam.h.  Host pointers in, host pointers out; no C++
+// exception leaves this file.
+#include <map>
+#include <memory>
+#include "comm.cuh"
+#include "device_mesh.cuh"
+#include "pcg.cuh"
+
+using namespace b200;
+
+static thread_local std::string g_lastError;
+static std::map<const void*, DeviceMesh*> g_registry;
+
+#define API_BEGIN try {
+#define API_END                                                      \
+    return B200_OK;                                                  \
+    }                                                                \
+    catch (const b200::Error& e) { g_lastError = e.what(); return e.code; } \
+    catch (const std::exception& e) { g_lastError = e.what(); return B200_ERR_STATE; }
+
+struct b200_polymesh { PolyMesh pm; };
+
+namespace b200 {
+__global__ void k_sumA(MeshView mv, const double* __restrict__ diag, const double* __restrict__ upS,
+                       const double* __restrict__ loS, const double* __restrict__ bou, double* __restrict__ out) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x, s = row >> 5, lane = row & 31;
+    if (row >= mv.N) return;
+    double sA = diag[row];
+    int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5;
+    for (int j = 0; j < nbw; j++) {
+        int pk = mv.loPk[nb0 + (j << 5) + lane];
+        if (pk >= 0) { int l; int pos = facePosOf(mv, pk, l); sA = sA + loS[pos]; }
+    }
+    int so0 = mv.sliceOff[s], ow = (mv.sliceOff[s + 1] - so0) >> 5;
+    for (int k = 0; k < ow; k++) { int pos = so0 + (k << 5) + lane; if (mv.upIdx[pos] >= 0) sA = sA + upS[pos]; }
+    if (bou && ((mv.bMask[s] >> lane) & 1u)) {
+        int i = mv.bBase[s] + __popc(mv.bMask[s] & ((1u << lane) - 1u));
+        for (int q = mv.bRowStart[i]; q < mv.bRowStart[i + 1]; q++) { int bf = mv.bRowFaces[q]; if (mv.bCoupled[bf]) sA = sA - bou[bf]; }
+    }
+    out[row] = sA;
+}
+}  // namespace b200
+
+static DeviceMesh* asMesh(b200_ldu_t* l) { return reinterpret_cast<DeviceMesh*>(l); }
+static DeviceMesh* asMesh(b200_mesh_t* l) { return reinterpret_cast<DeviceMesh*>(l); }
+static const DeviceMesh* asMesh(const b200_ldu_t* l) { return reinterpret_cast<const DeviceMesh*>(l); }
+
+static void requireSymmetric(const double* upper, const double* lower) {
+    B200_REQUIRE(lower == nullptr || lower == upper, B200_ERR_UNSUPPORTED,
+                 "b200PCG: asymmetric matrix (PCG is registered in the symMatrix table only)");
+}
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_lastError.c_str(); }
+
+int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int b200_init(int device, int rank, int nRanks, const void* ncclId, size_t ncclIdBytes) {
+    API_BEGIN
+    Runtime& r = rt();
+    B200_REQUIRE(!r.initialised || (r.device == device && r.rank == rank && r.nRanks == nRanks), B200_ERR_STATE,
+                 "b200_init called twice with different arguments");
+    if (!r.initialised) {
+        r.device = device; r.rank = rank; r.nRanks = nRanks;
+        requireDevice();
+        commInit(rank, nRanks, ncclId, ncclIdBytes);
+    }
+    API_END
+}
+int b200_nccl_unique_id(void* out128) {
+    API_BEGIN
+    commUniqueId(out128);
+    API_END
+}
+int b200_finalize(void) {
+    API_BEGIN
+    for (auto& kv : g_registry) delete kv.second;
+    g_registry.clear();
+    commFinalize();
+    API_END
+}
+long long b200_kernel_launch_count(void) { return rt().launches; }
+int b200_timers_reset(void) {
+    API_BEGIN
+    Timers& t = timers();
+    t.collect();
+    t.enabled = true;
+    for (int i = 0; i < T_COUNT; i++) { t.ms[i] = 0; t.calls[i] = 0; }
+    API_END
+}
+int b200_timers_get(double* outMs, long long* outCalls, int cap) {
+    API_BEGIN
+    Timers& t = timers();
+    t.collect();
+    for (int i = 0; i < T_COUNT && i < cap; i++) { outMs[i] = t.ms[i]; if (outCalls) outCalls[i] = t.calls[i]; }
+    API_END
+}
+const char* b200_timer_name(int i) { return timerName(i); }
+
+// ---------------------------------------------------------------------------------------------- ldu cache
+int b200_ldu_get_or_create(const void* key, int32_t nCells, int32_t nFaces, const int32_t* lower, const int32_t* upper,
+                           int32_t nPatches, const b200_patch_desc* patches, b200_ldu_t** out) {
+    API_BEGIN
+    requireDevice();
+    B200_REQUIRE(out && nCells >= 0 && nFaces >= 0 && (nFaces == 0 || (lower && upper)), B200_ERR_ARG, "b200_ldu_get_or_create: bad arguments");
+    if (key) {
+        auto it = g_registry.find(key);
+        if (it != g_registry.end()) {
+            B200_REQUIRE(it->second->N == nCells && it->second->F == nFaces, B200_ERR_STATE, "lduAddressing key reused with different sizes");
+            *out = reinterpret_cast<b200_ldu_t*>(it->second);
+            return B200_OK;
+        }
+    }
+    std::vector<Patch> pt; std::vector<int32_t> fc;
+    int32_t start = nFaces;
+    for (int p = 0; p < nPatches; p++) {
+        B200_REQUIRE(patches[p].nFaces == 0 || patches[p].faceCells, B200_ERR_ARG, "patch without faceCells");
+        Patch q; q.name = "patch" + std::to_string(p); q.start = start; q.size = patches[p].nFaces; q.neighbRank = patches[p].neighbRank;
+        fc.insert(fc.end(), patches[p].faceCells, patches[p].faceCells + patches[p].nFaces);
+        start += q.size; pt.push_back(q);
+    }
+    std::unique_ptr<DeviceMesh> m(new DeviceMesh());
+    m->build(nCells, nFaces, lower, upper, pt, fc);
+    m->key = key;
+    DeviceMesh* raw = m.release();
+    if (key) g_registry[key] = raw;
+    *out = reinterpret_cast<b200_ldu_t*>(raw);
+    API_END
+}
+int b200_ldu_release(b200_ldu_t* ldu) {
+    API_BEGIN
+    DeviceMesh* m = asMesh(ldu);
+    if (m) { if (m->key) g_registry.erase(m->key); delete m; }
+    API_END
+}
+int b200_ldu_get_renumbering(const b200_ldu_t* ldu, int32_t* rowCell, int32_t* cellLevel, int32_t* nLevels) {
+    API_BEGIN
+    const DeviceMesh* m = asMesh(ldu);
+    if (rowCell) memcpy(rowCell, m->rowCell.data(), 4 * (size_t)m->N);
+    if (cellLevel) memcpy(cellLevel, m->level.data(), 4 * (size_t)m->N);
+    if (nLevels) *nLevels = m->nLevels;
+    API_END
+}
+int b200_ldu_get_addressing(const b200_ldu_t* ldu, int32_t* ownerStart, int32_t* losort, int32_t* losortStart) {
+    API_BEGIN
+    const DeviceMesh* m = asMesh(ldu);
+    if (ownerStart) memcpy(ownerStart, m->ownerStart.data(), 4 * (size_t)(m->N + 1));
+    if (losort) memcpy(losort, m->losort.data(), 4 * (size_t)m->F);
+    if (losortStart) memcpy(losortStart, m->losortStart.data(), 4 * (size_t)(m->N + 1));
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------- a1..a4
+static void stageMatrix(DeviceMesh& m, PcgWorkspace& w, const double* diag, const double* upper, const double* bou) {
+    w.diag.ensure(m.N); w.upS.ensure(m.Fs + 1);
+    m.uploadCells(diag, w.diag);
+    m.uploadFaces(upper, w.upS, false);
+    if (bou && m.B) { w.bou.ensure(m.B); m.uploadBoundary(bou, w.bou); }
+}
+
+int b200_amul(b200_ldu_t* ldu, const double* diag, const double* upper, const double* lower, const double* psi,
+              double* Apsi, const double* bouCoeffs, const double* psiNbr) {
+    API_BEGIN
+    requireDevice();
+    DeviceMesh& m = *asMesh(ldu);
+    PcgWorkspace& w = pcgWorkspace(m);
+    stageMatrix(m, w, diag, upper, bouCoeffs);
+    DevBuf<double> loS;
+    const double* lo = w.upS;
+    if (lower && lower != upper) { loS.alloc(m.Fs + 1); m.uploadFaces(lower, loS, false); lo = loS; }
+    w.x.ensure(m.N); w.b.ensure(m.N);
+    m.uploadCells(psi, w.x);
+    if (bouCoeffs && psiNbr && m.B) {  // caller-supplied neighbour values (single process, explicit halo)
+        { ScopedTimer t(T_AMUL);
+          if (m.N) B200_LAUNCH(k_amul<0>, gridFor(m.N), BLOCK, rt().stream, m.view(), (const double*)w.diag.p, (const double*)w.upS.p, lo,
+                               (const double*)w.x.p, w.b.p, (PcgScalars*)nullptr, (double*)nullptr, (unsigned*)nullptr); }
+        m.uploadBoundary(psiNbr, w.recvBuf);
+        B200_LAUNCH(k_interface_update, gridFor(m.nBRows), BLOCK, rt().stream, m.view(), (const double*)w.bou.p, (const double*)w.recvBuf.p, w.b.p,
+                    m.nBRows, (const int*)w.bRowOfSlot.p);
+    } else {
+        amulDevice(m, w.diag, w.upS, lo, w.x, w.b, bouCoeffs ? w.bou.p : nullptr);
+    }
+    m.downloadCells(w.b, Apsi);
+    API_END
+}
+
+int b200_sumA(b200_ldu_t* ldu, const double* diag, const double* upper, const double* lower, double* sumA,
+              const double* bouCoeffs) {
+    API_BEGIN
+    requireDevice();
+    DeviceMesh& m = *asMesh(ldu);
+    PcgWorkspace& w = pcgWorkspace(m);
+    stageMatrix(m, w, diag, upper, bouCoeffs);
+    DevBuf<double> loS;
+    const double* lo = w.upS;
+    if (lower && lower != upper) { loS.alloc(m.Fs + 1); m.uploadFaces(lower, loS, false); lo = loS; }
+    w.b.ensure(m.N);
+    if (m.N) B200_LAUNCH(k_sumA, gridFor(m.N), BLOCK, rt().stream, m.view(), (const double*)w.diag.p, (const double*)w.upS.p, lo,
+                         bouCoeffs ? (const double*)w.bou.p : (const double*)nullptr, w.b.p);
+    m.downloadCells(w.b, sumA);
+    API_END
+}
+
+int b200_dic_calc_reciprocal_d(b200_ldu_t* ldu, const double* diag, const double* upper, double* rD) {
+    API_BEGIN
+    requireDevice();
+    DeviceMesh& m = *asMesh(ldu);
+    PcgWorkspace& w = pcgWorkspace(m);
+    stageMatrix(m, w, diag, upper, nullptr);
+    dicCalcReciprocalD(m, w.diag, w.upS, w.rD);
+    m.downloadCells(w.rD, rD);
+    API_END
+}
+
+int b200_dic_precondition(b200_ldu_t* ldu, const double* rD, const double* upper, const double* rA, double* wA) {
+    API_BEGIN
+    requireDevice();
+    DeviceMesh& m = *asMesh(ldu);
+    PcgWorkspace& w = pcgWorkspace(m);
+    w.upS.ensure(m.Fs + 1);
+    m.uploadFaces(upper, w.upS, false);
+    m.uploadCells(rD, w.rD);
+    m.uploadCells(rA, w.rA);
+    dicPrecondition(m, w.rD, w.upS, w.rA, w.wA);
+    m.downloadCells(w.wA, wA);
+    API_END
+}
+
+int b200_pcg_solve(b200_ldu_t* ldu, const double* diag, const double* upper, const double* lower,
+                   const double* bouCoeffs, double* x, const double* b, const b200_solver_controls* ctl,
+                   b200_solver_perf* perf, double* resHist, int32_t histCap) {
+    API_BEGIN
+    requireDevice();
+    requireSymmetric(upper, lower);
+    B200_REQUIRE(ctl && perf && x && b, B200_ERR_ARG, "b200_pcg_solve: null argument");
+    DeviceMesh& m = *asMesh(ldu);
+    PcgWorkspace& w = pcgWorkspace(m);
+    stageMatrix(m, w, diag, upper, bouCoeffs);
+    w.x.ensure(m.N); w.b.ensure(m.N);
+    m.uploadCells(x, w.x);
+    m.uploadCells(b, w.b);
+    std::vector<double> hist;
+    *perf = pcgSolveDevice(m, w.diag, w.upS, bouCoeffs ? w.bou.p : nullptr, w.x, w.b, *ctl, resHist ? &hist : nullptr);
+    m.downloadCells(w.x, x);
+    if (resHist) for (int i = 0; i < histCap && i < (int)hist.size(); i++) resHist[i] = hist[i];
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------- mesh
+int b200_mesh_create(const b200_mesh_desc* d, b200_mesh_t** out) {
+    API_BEGIN
+    requireDevice();
+    B200_REQUIRE(d && out, B200_ERR_ARG, "b200_mesh_create: null argument");
+    std::vector<Patch> pt; std::vector<int32_t> fc(d->owner + d->nInternalFaces, d->owner + d->nInternalFaces + d->nBoundaryFaces);
+    for (int p = 0; p < d->nPatches; p++) {
+        Patch q; q.name = "patch" + std::to_string(p); q.start = d->patchStart[p]; q.size = d->patchSize[p];
+        q.neighbRank = d->patchNeighbRank ? d->patchNeighbRank[p] : -1;
+        pt.push_back(q);
+    }
+    std::unique_ptr<DeviceMesh> m(new DeviceMesh());
+    m->build(d->nCells, d->nInternalFaces, d->owner, d->neighbour, pt, fc);
+    m->setGeometry(d->Sf, d->magSf, d->Cf, d->C, d->V, d->weights, d->deltaCoeffs);
+    *out = reinterpret_cast<b200_mesh_t*>(m.release());
+    API_END
+}
+int b200_mesh_release(b200_mesh_t* mesh) {
+    API_BEGIN
+    delete asMesh(mesh);
+    API_END
+}
+b200_ldu_t* b200_mesh_ldu(b200_mesh_t* mesh) { return reinterpret_cast<b200_ldu_t*>(mesh); }
+
+// ---------------------------------------------------------------------------------------------- host mesh tools
+int b200_polymesh_box(int32_t nx, int32_t ny, int32_t nz, double lx, double ly, double lz, b200_polymesh_t** out) {
+    API_BEGIN
+    B200_REQUIRE(nx > 0 && ny > 0 && nz > 0 && out, B200_ERR_ARG, "b200_polymesh_box: bad arguments");
+    *out = new b200_polymesh{makeBox(nx, ny, nz, lx, ly, lz)};
+    API_END
+}
+int b200_polymesh_box_weir(int32_t nx, int32_t ny, int32_t nz, double lx, double ly, double lz, double x0, double x1,
+                           double zfrac, b200_polymesh_t** out) {
+    API_BEGIN
+    B200_REQUIRE(nx > 0 && ny > 0 && nz > 0 && out, B200_ERR_ARG, "b200_polymesh_box_weir: bad arguments");
+    PolyMesh box = makeBox(nx, ny, nz, lx, ly, lz);
+    *out = new b200_polymesh{subsetMesh(box, weirKeepMask(nx, ny, nz, x0, x1, zfrac), "weir")};
+    API_END
+}
+int b200_polymesh_release(b200_polymesh_t* pm) { delete pm; return B200_OK; }
+int b200_polymesh_sizes(const b200_polymesh_t* pm, int32_t* nCells, int32_t* nIF, int32_t* nBF, int32_t* nPatches, int32_t* nPoints) {
+    API_BEGIN
+    if (nCells) *nCells = pm->pm.nCells;
+    if (nIF) *nIF = pm->pm.nInternalFaces();
+    if (nBF) *nBF = pm->pm.nBoundaryFaces();
+    if (nPatches) *nPatches = (int32_t)pm->pm.patches.size();
+    if (nPoints) *nPoints = (int32_t)(pm->pm.points.size() / 3);
+    API_END
+}
+int b200_polymesh_get(const b200_polymesh_t* pm, double* points, int32_t* faces4, int32_t* owner, int32_t* neighbour,
+                      int32_t* patchStart, int32_t* patchSize, int32_t* patchNeighbRank) {
+    API_BEGIN
+    const PolyMesh& m = pm->pm;
+    if (points) memcpy(points, m.points.data(), 8 * m.points.size());
+    if (faces4) memcpy(faces4, m.faces.data(), 16 * m.faces.size());
+    if (owner) memcpy(owner, m.owner.data(), 4 * m.owner.size());
+    if (neighbour) memcpy(neighbour, m.neighbour.data(), 4 * m.neighbour.size());
+    for (size_t p = 0; p < m.patches.size(); p++) {
+        if (patchStart) patchStart[p] = m.patches[p].start;
+        if (patchSize) patchSize[p] = m.patches[p].size;
+        if (patchNeighbRank) patchNeighbRank[p] = m.patches[p].neighbRank;
+    }
+    API_END
+}
+const char* b200_polymesh_patch_name(const b200_polymesh_t* pm, int32_t patch) {
+    if (!pm || patch < 0 || patch >= (int)pm->pm.patches.size()) return "";
+    return pm->pm.patches[patch].name.c_str();
+}
+int b200_polymesh_geometry(const b200_polymesh_t* pm, double* Sf, double* magSf, double* Cf, double* C, double* V,
+                           double* weights, double* deltaCoeffs) {
+    API_BEGIN
+    Geometry g = computeGeometry(pm->pm);
+    if (Sf) memcpy(Sf, g.Sf.data(), 8 * g.Sf.size());
+    if (magSf) memcpy(magSf, g.magSf.data(), 8 * g.magSf.size());
+    if (Cf) memcpy(Cf, g.Cf.data(), 8 * g.Cf.size());
+    if (C) memcpy(C, g.C.data(), 8 * g.C.size());
+    if (V) memcpy(V, g.V.data(), 8 * g.V.size());
+    if (weights) memcpy(weights, g.weights.data(), 8 * g.weights.size());
+    if (deltaCoeffs) memcpy(deltaCoeffs, g.deltaCoeffs.data(), 8 * g.deltaCoeffs.size());
+    API_END
+}
+int b200_decompose_simple(const b200_polymesh_t* pm, int32_t npx, int32_t npy, int32_t npz, int32_t* procOfCell) {
+    API_BEGIN
+    B200_REQUIRE(npx > 0 && npy > 0 && npz > 0 && procOfCell, B200_ERR_ARG, "b200_decompose_simple: bad arguments");
+    Geometry g = computeGeometry(pm->pm);
+    std::vector<int32_t> proc = decomposeSimple(g.C, pm->pm.nCells, npx, npy, npz);
+    memcpy(procOfCell, proc.data(), 4 * proc.size());
+    API_END
+}
+int b200_polymesh_submesh(const b200_polymesh_t* pm, const int32_t* procOfCell, int32_t nRanks, int32_t rank,
+                          b200_polymesh_t** out) {
+    API_BEGIN
+    std::vector<int32_t> proc(procOfCell, procOfCell + pm->pm.nCells);
+    *out = new b200_polymesh{subMesh(pm->pm, proc, nRanks, rank)};
+    API_END
+}
+int b200_polymesh_submesh_maps(const b200_polymesh_t* sub, int32_t* cellMap, int32_t* faceMap, int32_t* faceFlip) {
+    API_BEGIN
+    const PolyMesh& m = sub->pm;
+    if (cellMap) memcpy(cellMap, m.cellMap.data(), 4 * m.cellMap.size());
+    if (faceMap) memcpy(faceMap, m.faceMap.data(), 4 * m.faceMap.size());
+    if (faceFlip) for (size_t i = 0; i < m.faceFlip.size(); i++) faceFlip[i] = m.faceFlip[i];
+    API_END
+}
+int b200_mesh_create_from_polymesh(const b200_polymesh_t* pm, b200_mesh_t** out) {
+    API_BEGIN
+    requireDevice();
+    const PolyMesh& m = pm->pm;
+    Geometry g = computeGeometry(m);
+    std::vector<int32_t> ps, pz, pr;
+    for (const Patch& p : m.patches) { ps.push_back(p.start); pz.push_back(p.size); pr.push_back(p.neighbRank); }
+    b200_mesh_desc d;
+    d.nCells = m.nCells; d.nInternalFaces = m.nInternalFaces(); d.nBoundaryFaces = m.nBoundaryFaces(); d.nPatches = (int32_t)m.patches.size();
+    d.owner = m.owner.data(); d.neighbour = m.neighbour.data(); d.patchStart = ps.data(); d.patchSize = pz.data(); d.patchNeighbRank = pr.data();
+    d.Sf = g.Sf.data(); d.magSf = g.magSf.data(); d.Cf = g.Cf.data(); d.C = g.C.data(); d.V = g.V.data();
+    d.weights = g.weights.data(); d.deltaCoeffs = g.deltaCoeffs.data();
+    int rc = b200_mesh_create(&d, out);
+    if (rc != B200_OK) return rc;
+    API_END
+}
+
+}  // extern "C"

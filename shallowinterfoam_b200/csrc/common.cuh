@@ -1,0 +1,117 @@
+// common.cuh -- shared plumbing of libb200foam: error handling, device buffers, launch macro, timers.
+#pragma once
+#ifdef B200_EMU
+#include "simt_emu.h"   // tests/simt_emu: test-only SIMT emulator (never part of the product build)
+#else
+#include <cuda_runtime.h>
+#endif
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "b200foam.h"
+
+namespace b200 {
+
+// ---- errors: no C++ exception crosses the C-ABI (api.cu catches and stores the message) ------------------
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+#define B200_CHECK_CUDA(expr)                                                                            \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            throw b200::Error(B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " + \
+                                                 __FILE__ + ":" + std::to_string(__LINE__));             \
+    } while (0)
+#define B200_REQUIRE(cond, code, msg)                                   \
+    do {                                                                \
+        if (!(cond)) throw b200::Error(code, std::string(msg));        \
+    } while (0)
+
+// ---- runtime singleton -----------------------------------------------------------------------------------
+struct Runtime {
+    bool initialised = false;
+    int device = 0, rank = 0, nRanks = 1;
+    cudaStream_t stream = nullptr;
+    int numSMs = 148;
+    long long launches = 0;
+    void* nccl = nullptr;  // ncclComm_t (comm.cu)
+};
+Runtime& rt();
+void requireDevice();  // throws B200_ERR_NO_DEVICE when no CUDA device is usable
+
+// ---- kernel-class timers (CUDA events on the launching stream) -------------------------------------------
+enum TimerId { T_AMUL = 0, T_DIC_FWD, T_DIC_BWD, T_DIC_RD, T_PCG_VEC, T_PCG_SOLVE, T_MULES, T_FLUX, T_ASSEMBLY, T_UEQN, T_MISC, T_STEP, T_COUNT };
+const char* timerName(int i);
+struct Timers {
+    bool enabled = false;
+    double ms[T_COUNT] = {0};
+    long long calls[T_COUNT] = {0};
+    struct Pending { int id; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get();
+    void collect();
+};
+Timers& timers();
+struct ScopedTimer {  // records events around a launch sequence when timers are enabled
+    int id; cudaEvent_t a = nullptr, b = nullptr;
+    explicit ScopedTimer(int id_);
+    ~ScopedTimer();
+};
+
+// ---- launch macro: the ONLY way kernels are launched (counts launches; works under the emulator) ----------
+#ifdef B200_EMU
+#define B200_LAUNCH(kernel, grid, block, stream, ...)                         \
+    do {                                                                      \
+        b200::rt().launches++;                                                \
+        emu::launch(dim3(grid), dim3(block), [&]() { kernel(__VA_ARGS__); }); \
+    } while (0)
+#else
+#define B200_LAUNCH(kernel, grid, block, stream, ...)          \
+    do {                                                       \
+        b200::rt().launches++;                                 \
+        kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); \
+        B200_CHECK_CUDA(cudaGetLastError());                   \
+    } while (0)
+#endif
+
+// ---- device buffer ---------------------------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t n_) { alloc(n_); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t n_) {
+        release();
+        n = n_;
+        B200_CHECK_CUDA(cudaMalloc((void**)&p, sizeof(T) * (n ? n : 1)));
+    }
+    void ensure(size_t n_) { if (n < n_) alloc(n_); }
+    void zero() { B200_CHECK_CUDA(cudaMemsetAsync(p, 0, sizeof(T) * n, rt().stream)); }
+    void upload(const T* h, size_t cnt) { B200_CHECK_CUDA(cudaMemcpyAsync(p, h, sizeof(T) * cnt, cudaMemcpyHostToDevice, rt().stream)); }
+    void upload(const std::vector<T>& h) { alloc(h.size()); if (!h.empty()) upload(h.data(), h.size()); }
+    void download(T* h, size_t cnt) const { B200_CHECK_CUDA(cudaMemcpyAsync(h, p, sizeof(T) * cnt, cudaMemcpyDeviceToHost, rt().stream)); }
+    operator T*() const { return p; }
+};
+inline void syncStream() { B200_CHECK_CUDA(cudaStreamSynchronize(rt().stream)); }
+
+constexpr int BLOCK = 256;  // rows per CTA for the row/face kernels (8 slices)
+inline int gridFor(long long n, int block = BLOCK) { return (int)((n + block - 1) / block); }
+
+// "not ready" marker of the data-flow DIC sweeps: a quiet NaN whose 32-bit halves are equal, so one
+// 32-bit memset pattern fills it.  Arithmetic never produces this payload.
+constexpr unsigned long long SENTINEL_BITS = 0x7FF8B2007FF8B200ull;
+
+}  // namespace b200

@@ -1,0 +1,199 @@
+// device_mesh.cu -- build the renumbered owner-slot SELL-32 layout on the host, upload it, and convert fields
+// between foam-extend's host layout and the device layout.
+#include "device_mesh.cuh"
+#include <algorithm>
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------ kernels
+__global__ void k_fill_bits(unsigned long long* p, size_t n, unsigned long long bits) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = bits;
+}
+__global__ void k_gather(const double* __restrict__ src, const int* __restrict__ idx, double* __restrict__ dst, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { int j = idx[i]; dst[i] = j >= 0 ? src[j] : 0.0; }
+}
+__global__ void k_gather_vec(const double* __restrict__ srcXYZ, const int* __restrict__ idx, double* __restrict__ dx,
+                             double* __restrict__ dy, double* __restrict__ dz, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        int j = idx[i];
+        dx[i] = j >= 0 ? srcXYZ[3 * (size_t)j] : 0.0;
+        dy[i] = j >= 0 ? srcXYZ[3 * (size_t)j + 1] : 0.0;
+        dz[i] = j >= 0 ? srcXYZ[3 * (size_t)j + 2] : 0.0;
+    }
+}
+__global__ void k_scatter_vec_to_aos(const double* __restrict__ dx, const double* __restrict__ dy,
+                                     const double* __restrict__ dz, const int* __restrict__ idx,
+                                     double* __restrict__ dstXYZ, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;  // i = original cell; idx[i] = row
+    if (i < n) { int r = idx[i]; dstXYZ[3 * (size_t)i] = dx[r]; dstXYZ[3 * (size_t)i + 1] = dy[r]; dstXYZ[3 * (size_t)i + 2] = dz[r]; }
+}
+__global__ void k_copy_vec_b(const double* __restrict__ srcXYZ, double* __restrict__ dx, double* __restrict__ dy,
+                             double* __restrict__ dz, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { dx[i] = srcXYZ[3 * (size_t)i]; dy[i] = srcXYZ[3 * (size_t)i + 1]; dz[i] = srcXYZ[3 * (size_t)i + 2]; }
+}
+
+void fillSentinel(double* p, size_t n) {
+    if (n) B200_LAUNCH(k_fill_bits, gridFor((long long)n), BLOCK, rt().stream, (unsigned long long*)p, n, SENTINEL_BITS);
+}
+void fillValue(double* p, size_t n, double v) {
+    unsigned long long bits; memcpy(&bits, &v, 8);
+    if (n) B200_LAUNCH(k_fill_bits, gridFor((long long)n), BLOCK, rt().stream, (unsigned long long*)p, n, bits);
+}
+
+// -------------------------------------------------------------------------------------------------- build
+void DeviceMesh::build(int32_t nCells, int32_t nFaces, const int32_t* lo, const int32_t* up,
+                       const std::vector<Patch>& pt, const std::vector<int32_t>& fc) {
+    N = nCells; F = nFaces; patches = pt; faceCells = fc; B = (int)fc.size();
+    lower.assign(lo, lo + F); upper.assign(up, up + F);
+    for (int f = 0; f < F; f++)
+        B200_REQUIRE(lower[f] >= 0 && upper[f] < N, B200_ERR_ARG, "lduAddressing label out of range");
+    for (int b = 0; b < B; b++) B200_REQUIRE(fc[b] >= 0 && fc[b] < N, B200_ERR_ARG, "faceCells label out of range");
+    try {
+        levelRenumbering(N, lower.data(), upper.data(), F, level, rowCell, cellRow, nLevels);
+    } catch (const std::exception& e) { throw Error(B200_ERR_ARG, e.what()); }
+    lduDerived(N, lower, upper, ownerStart, losort, losortStart);
+    levelStart.assign(nLevels + 1, 0);
+    for (int c = 0; c < N; c++) levelStart[level[c] + 1]++;
+    for (int l = 0; l < nLevels; l++) levelStart[l + 1] += levelStart[l];
+
+    nSlices = (N + 31) / 32;
+    std::vector<int> sliceOff(nSlices + 1, 0), nbrOff(nSlices + 1, 0);
+    int maxOw = 1;
+    for (int s = 0; s < nSlices; s++) {
+        int wo = 0, wn = 0;
+        for (int r = s * 32; r < std::min(N, s * 32 + 32); r++) {
+            int c = rowCell[r];
+            wo = std::max(wo, ownerStart[c + 1] - ownerStart[c]);
+            wn = std::max(wn, losortStart[c + 1] - losortStart[c]);
+        }
+        maxOw = std::max(maxOw, wo);
+        sliceOff[s + 1] = sliceOff[s] + 32 * wo;
+        nbrOff[s + 1] = nbrOff[s] + 32 * wn;
+    }
+    Fs = sliceOff[nSlices]; Ls = nbrOff[nSlices];
+    KB = 1;
+    while ((1 << KB) < maxOw) KB++;
+    B200_REQUIRE(((long long)N << KB) < (1ll << 31), B200_ERR_UNSUPPORTED, "mesh too large for packed 32-bit face references");
+    std::vector<int> upIdx(Fs, -1), slotFace(Fs, -1), loPk(Ls, -1);
+    facePosHost.assign(F, -1);
+    for (int r = 0; r < N; r++) {
+        int c = rowCell[r], s = r >> 5, lane = r & 31;
+        for (int f = ownerStart[c]; f < ownerStart[c + 1]; f++) {
+            int k = f - ownerStart[c], pos = sliceOff[s] + k * 32 + lane;
+            upIdx[pos] = cellRow[upper[f]]; slotFace[pos] = f; facePosHost[f] = pos;
+        }
+        for (int j = losortStart[c]; j < losortStart[c + 1]; j++) {
+            int f = losort[j], l = lower[f];
+            int q = nbrOff[s] + (j - losortStart[c]) * 32 + lane;
+            loPk[q] = (cellRow[l] << KB) | (f - ownerStart[l]);
+        }
+    }
+    // boundary CSR by row
+    std::vector<int> cnt(N, 0);
+    for (int b = 0; b < B; b++) cnt[cellRow[fc[b]]]++;
+    std::vector<unsigned> bMask(nSlices, 0u);
+    std::vector<int> bBase(nSlices, 0), bRowStart(1, 0), bRowFaces(B), rowSlot(N, -1);
+    nBRows = 0;
+    for (int s = 0; s < nSlices; s++) {
+        bBase[s] = nBRows;
+        for (int r = s * 32; r < std::min(N, s * 32 + 32); r++)
+            if (cnt[r] > 0) { bMask[s] |= (1u << (r & 31)); rowSlot[r] = nBRows++; bRowStart.push_back(bRowStart.back() + cnt[r]); }
+    }
+    std::vector<int> cur(bRowStart.begin(), bRowStart.end() - 1), bFaceRow(B), bPatch(B, 0), bCoupled(B, 0);
+    for (int b = 0; b < B; b++) { int r = cellRow[fc[b]]; bFaceRow[b] = r; bRowFaces[cur[rowSlot[r]]++] = b; }
+    for (size_t p = 0; p < patches.size(); p++)
+        for (int f = patches[p].start; f < patches[p].start + patches[p].size; f++) {
+            B200_REQUIRE(f - F >= 0 && f - F < B, B200_ERR_ARG, "patch range outside the boundary faces");
+            bPatch[f - F] = (int)p; bCoupled[f - F] = patches[p].neighbRank >= 0 ? 1 : 0;
+        }
+    dSliceOff.upload(sliceOff); dNbrOff.upload(nbrOff); dUpIdx.upload(upIdx); dLoPk.upload(loPk);
+    dSlotFace.upload(slotFace); dFacePos.upload(facePosHost); dRowCell.upload(rowCell); dCellRow.upload(cellRow);
+    dBMask.upload(bMask); dBBase.upload(bBase); dBRowStart.upload(bRowStart); dBRowFaces.upload(bRowFaces);
+    dBFaceRow.upload(bFaceRow); dBPatch.upload(bPatch); dBCoupled.upload(bCoupled);
+    syncStream();
+}
+
+void DeviceMesh::setGeometry(const double* Sf, const double* magSf, const double* Cf, const double* C,
+                             const double* V, const double* w, const double* dc) {
+    size_t nf = nFaceField();
+    dV.alloc(N); dCx.alloc(N); dCy.alloc(N); dCz.alloc(N);
+    dSfx.alloc(nf); dSfy.alloc(nf); dSfz.alloc(nf); dCfx.alloc(nf); dCfy.alloc(nf); dCfz.alloc(nf);
+    dMagSf.alloc(nf); dW.alloc(nf); dDc.alloc(nf);
+    uploadCells(V, dV); uploadCellVec(C, dCx, dCy, dCz);
+    uploadFaceVec(Sf, dSfx, dSfy, dSfz); uploadFaceVec(Cf, dCfx, dCfy, dCfz);
+    uploadFaces(magSf, dMagSf, true); uploadFaces(w, dW, true); uploadFaces(dc, dDc, true);
+    syncStream();
+    hasGeometry = true;
+}
+
+MeshView DeviceMesh::view() const {
+    MeshView v;
+    v.N = N; v.F = F; v.B = B; v.nSlices = nSlices; v.KB = KB; v.Fs = Fs;
+    v.sliceOff = dSliceOff; v.nbrOff = dNbrOff; v.upIdx = dUpIdx; v.loPk = dLoPk;
+    v.bMask = dBMask; v.bBase = dBBase; v.bRowStart = dBRowStart; v.bRowFaces = dBRowFaces;
+    v.bFaceRow = dBFaceRow; v.bPatch = dBPatch; v.bCoupled = dBCoupled;
+    v.V = dV; v.Cx = dCx; v.Cy = dCy; v.Cz = dCz; v.Sfx = dSfx; v.Sfy = dSfy; v.Sfz = dSfz;
+    v.magSf = dMagSf; v.w = dW; v.dc = dDc;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------ layout conversion
+void DeviceMesh::uploadCells(const double* host, double* dev) {
+    double* st = stage(stageA, N);
+    B200_CHECK_CUDA(cudaMemcpyAsync(st, host, 8 * (size_t)N, cudaMemcpyHostToDevice, rt().stream));
+    if (N) B200_LAUNCH(k_gather, gridFor(N), BLOCK, rt().stream, st, dRowCell.p, dev, N);
+}
+void DeviceMesh::downloadCells(const double* dev, double* host) {
+    double* st = stage(stageA, N);
+    if (N) B200_LAUNCH(k_gather, gridFor(N), BLOCK, rt().stream, dev, dCellRow.p, st, N);
+    B200_CHECK_CUDA(cudaMemcpyAsync(host, st, 8 * (size_t)N, cudaMemcpyDeviceToHost, rt().stream));
+    syncStream();
+}
+void DeviceMesh::uploadCellVec(const double* hostXYZ, double* dx, double* dy, double* dz) {
+    double* st = stage(stageA, 3 * (size_t)N);
+    B200_CHECK_CUDA(cudaMemcpyAsync(st, hostXYZ, 24 * (size_t)N, cudaMemcpyHostToDevice, rt().stream));
+    if (N) B200_LAUNCH(k_gather_vec, gridFor(N), BLOCK, rt().stream, st, dRowCell.p, dx, dy, dz, N);
+}
+void DeviceMesh::downloadCellVec(const double* dx, const double* dy, const double* dz, double* hostXYZ) {
+    double* st = stage(stageA, 3 * (size_t)N);
+    if (N) B200_LAUNCH(k_scatter_vec_to_aos, gridFor(N), BLOCK, rt().stream, dx, dy, dz, dCellRow.p, st, N);
+    B200_CHECK_CUDA(cudaMemcpyAsync(hostXYZ, st, 24 * (size_t)N, cudaMemcpyDeviceToHost, rt().stream));
+    syncStream();
+}
+void DeviceMesh::uploadFaces(const double* host, double* dev, bool withBoundary) {
+    size_t n = (size_t)F + (withBoundary ? B : 0);
+    double* st = stage(stageA, n);
+    B200_CHECK_CUDA(cudaMemcpyAsync(st, host, 8 * n, cudaMemcpyHostToDevice, rt().stream));
+    if (Fs) B200_LAUNCH(k_gather, gridFor(Fs), BLOCK, rt().stream, st, dSlotFace.p, dev, Fs);
+    if (withBoundary && B)
+        B200_CHECK_CUDA(cudaMemcpyAsync(dev + Fs, st + F, 8 * (size_t)B, cudaMemcpyDeviceToDevice, rt().stream));
+}
+void DeviceMesh::downloadFaces(const double* dev, double* host, bool withBoundary) {
+    size_t n = (size_t)F + (withBoundary ? B : 0);
+    double* st = stage(stageA, n);
+    if (F) B200_LAUNCH(k_gather, gridFor(F), BLOCK, rt().stream, dev, dFacePos.p, st, F);
+    if (withBoundary && B)
+        B200_CHECK_CUDA(cudaMemcpyAsync(st + F, dev + Fs, 8 * (size_t)B, cudaMemcpyDeviceToDevice, rt().stream));
+    B200_CHECK_CUDA(cudaMemcpyAsync(host, st, 8 * n, cudaMemcpyDeviceToHost, rt().stream));
+    syncStream();
+}
+void DeviceMesh::uploadFaceVec(const double* hostXYZ, double* dx, double* dy, double* dz) {
+    size_t n = (size_t)F + B;
+    double* st = stage(stageA, 3 * n);
+    B200_CHECK_CUDA(cudaMemcpyAsync(st, hostXYZ, 24 * n, cudaMemcpyHostToDevice, rt().stream));
+    if (Fs) B200_LAUNCH(k_gather_vec, gridFor(Fs), BLOCK, rt().stream, st, dSlotFace.p, dx, dy, dz, Fs);
+    if (B) B200_LAUNCH(k_copy_vec_b, gridFor(B), BLOCK, rt().stream, st + 3 * (size_t)F, dx + Fs, dy + Fs, dz + Fs, B);
+}
+void DeviceMesh::uploadBoundary(const double* host, double* dev, int nc) {
+    if (B) B200_CHECK_CUDA(cudaMemcpyAsync(dev, host, 8 * (size_t)B * nc, cudaMemcpyHostToDevice, rt().stream));
+}
+void DeviceMesh::downloadBoundary(const double* dev, double* host, int nc) {
+    if (B) B200_CHECK_CUDA(cudaMemcpyAsync(host, dev, 8 * (size_t)B * nc, cudaMemcpyDeviceToHost, rt().stream));
+    syncStream();
+}
+
+}  // namespace b200

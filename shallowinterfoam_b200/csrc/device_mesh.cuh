@@ -1,0 +1,93 @@
+// device_mesh.cuh -- the device-resident mesh: renumbered rows + "owner-slot SELL-32" face layout.
+//
+// Layout:
+//  * rows   : cells renumbered by forward DIC level (level-major, original index within a level).  All cell
+//             fields live in row order; vectors are SoA (x[N], y[N], z[N]).
+//  * slices : 32 consecutive rows = one warp.
+//  * faces  : every internal face is stored ONCE, with its ORIGINAL owner's row, in a sliced-ELL slot:
+//             pos = sliceOff[s] + k*32 + lane   (k = index of the face among the owner's faces, ascending
+//             original face id).  Face fields (upper, phi, weights, Sf ...) are [Fs + B]: slots, then the B
+//             boundary faces in original order.  upIdx[pos] = row of the face's neighbour cell (-1 = padding).
+//  * nbr side: each row also lists the faces where it is the original NEIGHBOUR, ascending original face id,
+//             as packed entries (ownerRow << KB | k) in a second sliced-ELL (nbrOff); -1 = padding.
+//             => a row gathers  [nbr-side faces asc] + [owner faces asc] + [boundary faces asc], which is
+//             exactly the per-cell summation order of upstream's sequential face loops, with no atomics.
+//  * boundary: per-slice bit mask of rows owning boundary faces + CSR of their boundary faces.
+#pragma once
+#include "common.cuh"
+#include "host_mesh.h"
+
+namespace b200 {
+
+struct MeshView {  // POD handed to kernels by value
+    int N, F, B, nSlices, KB, Fs;
+    const int* sliceOff;   // [nSlices+1]
+    const int* nbrOff;     // [nSlices+1]
+    const int* upIdx;      // [Fs]
+    const int* loPk;       // [Ls]
+    const unsigned* bMask; // [nSlices]
+    const int* bBase;      // [nSlices]
+    const int* bRowStart;  // [nBRows+1]
+    const int* bRowFaces;  // [B]
+    const int* bFaceRow;   // [B] row of the face cell
+    const int* bPatch;     // [B] patch index
+    const int* bCoupled;   // [B] 1 = processor face
+    // geometry (null when created through b200_ldu_get_or_create)
+    const double* V;                 // [N]
+    const double *Cx, *Cy, *Cz;      // [N]
+    const double *Sfx, *Sfy, *Sfz;   // [Fs+B]
+    const double *magSf, *w, *dc;    // [Fs+B]
+};
+
+__device__ __forceinline__ int facePosOf(const MeshView& mv, int pk, int& l) {
+    l = pk >> mv.KB;
+    int k = pk & ((1 << mv.KB) - 1);
+    return mv.sliceOff[l >> 5] + (k << 5) + (l & 31);
+}
+
+struct PcgWorkspace;  // pcg.cu
+
+struct DeviceMesh {
+    int N = 0, F = 0, B = 0, nSlices = 0, KB = 0, Fs = 0, Ls = 0, nLevels = 0, nBRows = 0;
+    bool hasGeometry = false;
+    std::vector<Patch> patches;            // start = boundary-face offset + F (absolute), as given
+    std::vector<int32_t> lower, upper;     // original LDU addressing (host)
+    std::vector<int32_t> faceCells;        // [B]
+    std::vector<int32_t> level, rowCell, cellRow;
+    std::vector<int32_t> ownerStart, losort, losortStart;
+    std::vector<int32_t> facePosHost;      // [F] slot of original face
+    std::vector<int32_t> levelStart;       // [nLevels+1] first row of each level
+    DevBuf<int> dSliceOff, dNbrOff, dUpIdx, dLoPk, dBBase, dBRowStart, dBRowFaces, dBFaceRow, dBPatch, dBCoupled;
+    DevBuf<unsigned> dBMask;
+    DevBuf<int> dSlotFace, dFacePos, dRowCell, dCellRow;
+    DevBuf<double> dV, dCx, dCy, dCz, dSfx, dSfy, dSfz, dMagSf, dW, dDc, dCfx, dCfy, dCfz;
+    // staging buffers for the host-pointer API
+    DevBuf<double> stageA, stageB;
+    PcgWorkspace* pcg = nullptr;
+    const void* key = nullptr;
+
+    ~DeviceMesh();
+    void build(int32_t nCells, int32_t nFaces, const int32_t* lower, const int32_t* upper,
+               const std::vector<Patch>& patches, const std::vector<int32_t>& faceCells);
+    void setGeometry(const double* Sf, const double* magSf, const double* Cf, const double* C, const double* V,
+                     const double* w, const double* dc);
+    MeshView view() const;
+    size_t nFaceField() const { return (size_t)Fs + B; }
+
+    // ---- host <-> device layout conversion (all on rt().stream) -------------------------------------------
+    void uploadCells(const double* host, double* dev);                 // scalar [N] original order -> rows
+    void downloadCells(const double* dev, double* host);
+    void uploadCellVec(const double* hostXYZ, double* dx, double* dy, double* dz);  // AoS [3N] -> SoA rows
+    void downloadCellVec(const double* dx, const double* dy, const double* dz, double* hostXYZ);
+    void uploadFaces(const double* host, double* dev, bool withBoundary);  // [F(+B)] -> [Fs(+B)]
+    void downloadFaces(const double* dev, double* host, bool withBoundary);
+    void uploadFaceVec(const double* hostXYZ, double* dx, double* dy, double* dz);  // [3(F+B)] AoS -> SoA slots+B
+    void uploadBoundary(const double* host, double* dev, int nc = 1);  // [nc*B] plain copy
+    void downloadBoundary(const double* dev, double* host, int nc = 1);
+    double* stage(DevBuf<double>& buf, size_t n) { buf.ensure(n); return buf.p; }
+};
+
+void fillSentinel(double* p, size_t n);
+void fillValue(double* p, size_t n, double v);
+
+}  // namespace b200

@@ -1,0 +1,395 @@
+// ldu_kernels.cuh -- sm_100a kernels of the lduMatrix solve: Amul / sumA (row gather on the owner-slot SELL
+// layout), data-flow level-scheduled DIC sweeps, fused PCG vector updates and deterministic reductions.
+// FP64, HBM-bound, no tensor cores.  Compiled with --fmad=false: every expression is evaluated in upstream's
+// operation order with IEEE mul/add (foam-extend's x86-64 build has no FMA contraction), so Amul and DIC are
+// bitwise equal to the sequential loops of lduMatrixATmul.C / DICPreconditioner.C.
+#pragma once
+#include "device_mesh.cuh"
+
+namespace b200 {
+
+// ----------------------------------------------------------------------------- deterministic reductions
+// block tree (shuffle + smem) -> partials[slot] ; the last block to finish sums all partials in a fixed order.
+struct OpSum { __device__ static double id() { return 0.0; } __device__ static double op(double a, double b) { return a + b; } };
+struct OpMax { __device__ static double id() { return -1.0e300; } __device__ static double op(double a, double b) { return a > b ? a : b; } };
+struct OpMin { __device__ static double id() { return 1.0e300; } __device__ static double op(double a, double b) { return a < b ? a : b; } };
+
+template <class Op>
+__device__ __forceinline__ double warpReduce(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = Op::op(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+// result valid in thread 0
+template <class Op>
+__device__ __forceinline__ double blockReduce(double v, double* sh /*[32]*/) {
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warpReduce<Op>(v);
+    __syncthreads();  // protect sh reuse
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    v = (threadIdx.x < (unsigned)nw) ? sh[threadIdx.x] : Op::id();
+    if (warp == 0) v = warpReduce<Op>(v);
+    return v;
+}
+// NV values per block -> partials[slot*NV+i]; last block writes out[i] = reduce over nSlots slots (fixed order)
+template <int NV, class Op0, class Op1 = Op0, class Op2 = Op0>
+__device__ __forceinline__ void gridReduce(double (&v)[NV], int slot, int nSlots, double* partials, unsigned* counter,
+                                           double* out0, double* out1 = nullptr, double* out2 = nullptr) {
+    __shared__ double sh[32];
+    __shared__ int isLast;
+    double r0 = blockReduce<Op0>(v[0], sh), r1 = 0, r2 = 0;
+    if (NV > 1) r1 = blockReduce<Op1>(v[1 % NV], sh);
+    if (NV > 2) r2 = blockReduce<Op2>(v[2 % NV], sh);
+    if (threadIdx.x == 0) {
+        partials[(size_t)slot * NV] = r0;
+        if (NV > 1) partials[(size_t)slot * NV + 1] = r1;
+        if (NV > 2) partials[(size_t)slot * NV + 2] = r2;
+    }
+    (void)nSlots;
+}
+// called once per block after its last gridReduce slot was written
+template <int NV, class Op0, class Op1 = Op0, class Op2 = Op0>
+__device__ __forceinline__ void gridFinalize(int nSlots, const double* partials, unsigned* counter, double* out0,
+                                             double* out1 = nullptr, double* out2 = nullptr) {
+    __shared__ double sh[32];
+    __shared__ int isLast;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned t = atomicInc(counter, gridDim.x - 1);  // wraps back to 0 for the next launch
+        isLast = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    const volatile double* vp = partials;
+    double a0 = Op0::id(), a1 = Op1::id(), a2 = Op2::id();
+    for (int j = threadIdx.x; j < nSlots; j += blockDim.x) {
+        a0 = Op0::op(a0, vp[(size_t)j * NV]);
+        if (NV > 1) a1 = Op1::op(a1, vp[(size_t)j * NV + 1]);
+        if (NV > 2) a2 = Op2::op(a2, vp[(size_t)j * NV + 2]);
+    }
+    a0 = blockReduce<Op0>(a0, sh);
+    if (NV > 1) a1 = blockReduce<Op1>(a1, sh);
+    if (NV > 2) a2 = blockReduce<Op2>(a2, sh);
+    if (threadIdx.x == 0) {
+        *out0 = a0;
+        if (NV > 1 && out1) *out1 = a1;
+        if (NV > 2 && out2) *out2 = a2;
+    }
+}
+
+// ----------------------------------------------------------------------------- PCG device scalars
+struct PcgScalars {
+    double sumX, sumMagR, nfSum, wArA, wArAold, wApA, normFactor, initialResidual, finalResidual, tol, relTol, nGlobal;
+    int nIter, minIter, maxIter, stop, singular, converged, histCap, pad;
+};
+
+__device__ __forceinline__ bool isSentinel(double v) { return (unsigned long long)__double_as_longlong(v) == SENTINEL_BITS; }
+__device__ __forceinline__ double sentinel() { return __longlong_as_double((long long)SENTINEL_BITS); }
+__device__ __forceinline__ double ldPoll(const double* p) { return *(const volatile double*)p; }
+__device__ __forceinline__ void stPublish(double* p, double v) { *(volatile double*)p = v; }
+
+// ----------------------------------------------------------------------------- a1: Amul (row gather)
+// Apsi[row] = diag*psi + sum_{nbr-side faces asc} lower_f*psi[l] + sum_{owner faces asc} upper_f*psi[u]
+// MODE 0: plain; MODE 1: also accumulates sum(Apsi*psi) into sc->wApA (PCG); skips everything when sc->stop.
+template <int MODE>
+static __global__ void __launch_bounds__(BLOCK) k_amul(MeshView mv, const double* __restrict__ diag,
+                                                 const double* __restrict__ upS, const double* __restrict__ loS,
+                                                 const double* __restrict__ psi, double* __restrict__ Apsi,
+                                                 PcgScalars* sc, double* partials, unsigned* counter) {
+    if (MODE == 1 && sc->stop) return;
+    int row = blockIdx.x * blockDim.x + threadIdx.x, s = row >> 5, lane = row & 31;
+    double acc = 0.0, p = 0.0;
+    if (row < mv.N) {
+        p = psi[row];
+        acc = diag[row] * p;
+        int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5;
+        for (int j = 0; j < nbw; j++) {
+            int pk = mv.loPk[nb0 + (j << 5) + lane];
+            if (pk >= 0) { int l; int pos = facePosOf(mv, pk, l); acc = acc + loS[pos] * psi[l]; }
+        }
+        int so0 = mv.sliceOff[s], ow = (mv.sliceOff[s + 1] - so0) >> 5;
+        for (int k = 0; k < ow; k++) {
+            int pos = so0 + (k << 5) + lane;
+            int u = mv.upIdx[pos];
+            if (u >= 0) acc = acc + upS[pos] * psi[u];
+        }
+        Apsi[row] = acc;
+    }
+    if (MODE == 1) {
+        double v[1] = {row < mv.N ? acc * p : 0.0};
+        gridReduce<1, OpSum>(v, blockIdx.x, gridDim.x, partials, counter, nullptr);
+        gridFinalize<1, OpSum>(gridDim.x, partials, counter, &sc->wApA);
+    }
+}
+
+// processor-interface update  Apsi[faceCells] -= bouCoeffs*psiNbr, per boundary row in patch order
+static __global__ void k_interface_update(MeshView mv, const double* __restrict__ bou, const double* __restrict__ psiNbr,
+                                   double* __restrict__ Apsi, int nBRows, const int* __restrict__ bRowOfSlot) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nBRows) return;
+    int row = bRowOfSlot[i];
+    double acc = Apsi[row];
+    bool any = false;
+    for (int q = mv.bRowStart[i]; q < mv.bRowStart[i + 1]; q++) {
+        int b = mv.bRowFaces[q];
+        if (mv.bCoupled[b]) { acc = acc - bou[b] * psiNbr[b]; any = true; }
+    }
+    if (any) Apsi[row] = acc;
+}
+
+// ----------------------------------------------------------------------------- PCG start-up
+// wA = A x ; rA = b - wA ; sumA -> pA (scratch, as upstream normFactor) ; partial sum(x), sum|rA|
+static __global__ void __launch_bounds__(BLOCK) k_pcg_init1(MeshView mv, const double* __restrict__ diag,
+                                                      const double* __restrict__ upS, const double* __restrict__ x,
+                                                      const double* __restrict__ b, const double* __restrict__ bou,
+                                                      double* __restrict__ wA, double* __restrict__ rA,
+                                                      double* __restrict__ pA, PcgScalars* sc, double* partials,
+                                                      unsigned* counter) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x, s = row >> 5, lane = row & 31;
+    double v[2] = {0.0, 0.0};
+    if (row < mv.N) {
+        double xr = x[row], d = diag[row];
+        double acc = d * xr, sA = d;
+        int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5;
+        for (int j = 0; j < nbw; j++) {
+            int pk = mv.loPk[nb0 + (j << 5) + lane];
+            if (pk >= 0) { int l; int pos = facePosOf(mv, pk, l); double c = upS[pos]; acc = acc + c * x[l]; sA = sA + c; }
+        }
+        int so0 = mv.sliceOff[s], ow = (mv.sliceOff[s + 1] - so0) >> 5;
+        for (int k = 0; k < ow; k++) {
+            int pos = so0 + (k << 5) + lane;
+            int u = mv.upIdx[pos];
+            if (u >= 0) { double c = upS[pos]; acc = acc + c * x[u]; sA = sA + c; }
+        }
+        if (bou && ((mv.bMask[s] >> lane) & 1u)) {  // sumA: coupled patches subtract bouCoeffs
+            int i = mv.bBase[s] + __popc(mv.bMask[s] & ((1u << lane) - 1u));
+            for (int q = mv.bRowStart[i]; q < mv.bRowStart[i + 1]; q++) { int bf = mv.bRowFaces[q]; if (mv.bCoupled[bf]) sA = sA - bou[bf]; }
+        }
+        wA[row] = acc; pA[row] = sA;
+        double r = b[row] - acc;
+        rA[row] = r;
+        v[0] = xr; v[1] = fabs(r);
+    }
+    gridReduce<2, OpSum>(v, blockIdx.x, gridDim.x, partials, counter, nullptr);
+    gridFinalize<2, OpSum>(gridDim.x, partials, counter, &sc->sumX, &sc->sumMagR);
+}
+// after the interface update of wA (multi-rank) rA must be recomputed; single-rank path skips this
+static __global__ void k_pcg_resid(int N, const double* __restrict__ b, const double* __restrict__ wA, double* __restrict__ rA,
+                            PcgScalars* sc, double* partials, unsigned* counter) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[1] = {0.0};
+    if (row < N) { double r = b[row] - wA[row]; rA[row] = r; v[0] = fabs(r); }
+    gridReduce<1, OpSum>(v, blockIdx.x, gridDim.x, partials, counter, nullptr);
+    gridFinalize<1, OpSum>(gridDim.x, partials, counter, &sc->sumMagR);
+}
+// nfSum = sum(|wA - xRef*sumA| + |b - xRef*sumA|)
+static __global__ void __launch_bounds__(BLOCK) k_pcg_init2(int N, const double* __restrict__ wA, const double* __restrict__ b,
+                                                      const double* __restrict__ sumA, PcgScalars* sc, double* partials,
+                                                      unsigned* counter) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    double xRef = sc->sumX / sc->nGlobal;
+    double v[1] = {0.0};
+    if (row < N) { double t = sumA[row] * xRef; v[0] = fabs(wA[row] - t) + fabs(b[row] - t); }
+    gridReduce<1, OpSum>(v, blockIdx.x, gridDim.x, partials, counter, nullptr);
+    gridFinalize<1, OpSum>(gridDim.x, partials, counter, &sc->nfSum);
+}
+__device__ __forceinline__ bool pcgConverged(const PcgScalars* sc) {
+    return sc->finalResidual < sc->tol || (sc->relTol > 0 && sc->finalResidual < sc->relTol * sc->initialResidual);
+}
+static __global__ void k_pcg_check0(PcgScalars* sc, double* hist) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    sc->normFactor = sc->nfSum + 1.0e-20;
+    sc->initialResidual = sc->finalResidual = sc->sumMagR / sc->normFactor;
+    sc->nIter = 0; sc->singular = 0;
+    sc->converged = pcgConverged(sc) ? 1 : 0;
+    sc->stop = (0 >= sc->minIter) && (0 >= sc->maxIter || sc->converged);
+    sc->wArA = 1.0e20; sc->wArAold = 1.0e20;
+    if (hist && sc->histCap > 0) hist[0] = sc->initialResidual;
+}
+// end of an iteration: residual, convergence, iteration count
+static __global__ void k_pcg_check(PcgScalars* sc, double* hist) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (sc->stop) return;
+    if (fabs(sc->wApA) / sc->normFactor <= 1.0e-300) { sc->singular = 1; sc->stop = 1; return; }
+    sc->finalResidual = sc->sumMagR / sc->normFactor;
+    sc->nIter = sc->nIter + 1;
+    sc->wArAold = sc->wArA;
+    if (hist && sc->nIter < sc->histCap) hist[sc->nIter] = sc->finalResidual;
+    sc->converged = pcgConverged(sc) ? 1 : 0;
+    sc->stop = (sc->nIter >= sc->minIter) && (sc->nIter >= sc->maxIter || sc->converged);
+}
+
+// pA = z + beta*pA (first iteration: pA = z);  z <- sentinel (re-armed for the next sweep)
+static __global__ void __launch_bounds__(BLOCK) k_pcg_p_update(int N, double* __restrict__ z, double* __restrict__ pA,
+                                                         const PcgScalars* sc) {
+    if (sc->stop) return;
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= N) return;
+    double zv = z[row];
+    if (sc->nIter == 0) pA[row] = zv;
+    else { double beta = sc->wArA / sc->wArAold; pA[row] = zv + beta * pA[row]; }
+    z[row] = sentinel();
+}
+// x += alpha*pA ; rA -= alpha*wA ; partial sum|rA|
+static __global__ void __launch_bounds__(BLOCK) k_pcg_xr_update(int N, double* __restrict__ x, double* __restrict__ rA,
+                                                          const double* __restrict__ pA, const double* __restrict__ wA,
+                                                          PcgScalars* sc, double* partials, unsigned* counter) {
+    if (sc->stop) return;
+    bool singular = fabs(sc->wApA) / sc->normFactor <= 1.0e-300;
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[1] = {0.0};
+    if (row < N) {
+        double r = rA[row];
+        if (!singular) {
+            double alpha = sc->wArA / sc->wApA;
+            x[row] = x[row] + alpha * pA[row];
+            r = r - alpha * wA[row];
+            rA[row] = r;
+        }
+        v[0] = fabs(r);
+    }
+    gridReduce<1, OpSum>(v, blockIdx.x, gridDim.x, partials, counter, nullptr);
+    gridFinalize<1, OpSum>(gridDim.x, partials, counter, &sc->sumMagR);
+}
+
+// ----------------------------------------------------------------------------- a2/a3: data-flow DIC sweeps
+// Rows are stored level-major, so every dependency of a row has a SMALLER row index (forward sweep) or a
+// LARGER one (backward sweep).  Chunks of blockDim rows are handed out in that order by an atomic ticket, so a
+// running warp only ever waits on rows owned by warps that are already running: no grid barrier, no
+// co-residency requirement.  Readiness is carried by the data itself: outputs are pre-filled with a NaN
+// sentinel and published with one 64-bit store; consumers poll L2 until the value is not the sentinel.
+// Within a row the updates are applied in upstream's face order => bitwise the sequential result.
+struct SweepCtl { unsigned* ticket; unsigned* done; };
+
+__device__ __forceinline__ int nextChunk(SweepCtl c) {
+    __shared__ int sChunk;
+    __syncthreads();
+    if (threadIdx.x == 0) sChunk = (int)atomicAdd(c.ticket, 1u);
+    __syncthreads();
+    return sChunk;
+}
+__device__ __forceinline__ void sweepExit(SweepCtl c) {
+    if (threadIdx.x == 0) {
+        unsigned d = atomicInc(c.done, gridDim.x - 1);
+        if (d == gridDim.x - 1) { *c.ticket = 0u; __threadfence(); }
+    }
+}
+
+// calcReciprocalD: Dt[row] = diag - sum_{nbr-side faces asc} upper_f^2 / Dt[l] ; rD = 1/Dt
+static __global__ void __launch_bounds__(BLOCK) k_dic_calc_rd(MeshView mv, const double* __restrict__ diag,
+                                                        const double* __restrict__ upS, double* Dt, double* __restrict__ rD,
+                                                        SweepCtl ctl, int nChunks) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, spc = blockDim.x >> 5;
+    for (;;) {
+        int chunk = nextChunk(ctl);
+        if (chunk >= nChunks) break;
+        int s = chunk * spc + warp;
+        if (s >= mv.nSlices) continue;
+        int row = (s << 5) + lane;
+        bool done = row >= mv.N;
+        double d = done ? 0.0 : diag[row];
+        int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5, j = 0;
+        for (;;) {
+            if (!done) {
+                while (j < nbw) {
+                    int pk = mv.loPk[nb0 + (j << 5) + lane];
+                    if (pk < 0) { j = nbw; break; }
+                    int l; int pos = facePosOf(mv, pk, l);
+                    double v = ldPoll(Dt + l);
+                    if (isSentinel(v)) break;
+                    double u = upS[pos];
+                    d = d - u * u / v;
+                    j++;
+                }
+                if (j >= nbw) { stPublish(Dt + row, d); rD[row] = 1.0 / d; done = true; }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+    }
+    sweepExit(ctl);
+}
+
+// forward: y[row] = rD*rA - sum_{nbr-side faces asc} (rD[row]*upper_f)*y[l]
+static __global__ void __launch_bounds__(BLOCK) k_dic_fwd(MeshView mv, const double* __restrict__ rD,
+                                                    const double* __restrict__ upS, const double* __restrict__ rA,
+                                                    double* y, SweepCtl ctl, int nChunks, const PcgScalars* sc) {
+    if (sc && sc->stop) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, spc = blockDim.x >> 5;
+    for (;;) {
+        int chunk = nextChunk(ctl);
+        if (chunk >= nChunks) break;
+        int s = chunk * spc + warp;
+        if (s >= mv.nSlices) continue;
+        int row = (s << 5) + lane;
+        bool done = row >= mv.N;
+        double rd = done ? 0.0 : rD[row];
+        double w = done ? 0.0 : rd * rA[row];
+        int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5, j = 0;
+        for (;;) {
+            if (!done) {
+                while (j < nbw) {
+                    int pk = mv.loPk[nb0 + (j << 5) + lane];
+                    if (pk < 0) { j = nbw; break; }
+                    int l; int pos = facePosOf(mv, pk, l);
+                    double v = ldPoll(y + l);
+                    if (isSentinel(v)) break;
+                    w = w - rd * upS[pos] * v;
+                    j++;
+                }
+                if (j >= nbw) { stPublish(y + row, w); done = true; }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+    }
+    sweepExit(ctl);
+}
+
+// backward: z[row] = y[row] - sum_{owner faces DESC} (rD[row]*upper_f)*z[u] ; y[row] <- sentinel ;
+// per-chunk partial of sum(z*rA) (fixed rows per partial => deterministic) -> sc->wArA
+static __global__ void __launch_bounds__(BLOCK) k_dic_bwd(MeshView mv, const double* __restrict__ rD,
+                                                    const double* __restrict__ upS, const double* __restrict__ rA,
+                                                    double* y, double* z, SweepCtl ctl, int nChunks, PcgScalars* sc,
+                                                    double* partials, unsigned* counter) {
+    if (sc && sc->stop) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, spc = blockDim.x >> 5;
+    for (;;) {
+        int chunk = nextChunk(ctl);
+        if (chunk >= nChunks) break;
+        int s = (nChunks - 1 - chunk) * spc + warp;
+        double dotv = 0.0;
+        if (s < mv.nSlices) {
+            int row = (s << 5) + lane;
+            bool done = row >= mv.N;
+            double rd = done ? 0.0 : rD[row];
+            double w = done ? 0.0 : y[row];
+            int so0 = mv.sliceOff[s], k = ((mv.sliceOff[s + 1] - so0) >> 5) - 1;
+            for (;;) {
+                if (!done) {
+                    while (k >= 0) {
+                        int pos = so0 + (k << 5) + lane;
+                        int u = mv.upIdx[pos];
+                        if (u >= 0) {
+                            double v = ldPoll(z + u);
+                            if (isSentinel(v)) break;
+                            w = w - rd * upS[pos] * v;
+                        }
+                        k--;
+                    }
+                    if (k < 0) { stPublish(z + row, w); y[row] = sentinel(); dotv = w * rA[row]; done = true; }
+                }
+                if (__all_sync(0xffffffffu, done)) break;
+            }
+        }
+        if (partials) {
+            double v[1] = {dotv};
+            gridReduce<1, OpSum>(v, nChunks - 1 - chunk, nChunks, partials, counter, nullptr);
+        }
+    }
+    if (partials) gridFinalize<1, OpSum>(nChunks, partials, counter, &sc->wArA);
+    sweepExit(ctl);
+}
+
+}  // namespace b200

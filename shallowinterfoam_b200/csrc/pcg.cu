@@ -1,0 +1,185 @@
+// pcg.cu -- b200PCG driver: PCG::solve [UPSTREAM PCG.C] with the DIC preconditioner, every vector resident in HBM.
+// The iteration is 5 kernels + a 1-thread convergence kernel; all scalars (alpha, beta, residuals, iteration count,
+// stop flag) stay on the device.  The host enqueues iterations in batches and only polls the stop flag through a
+// pinned mirror, so launch latency overlaps execution; iterations enqueued past convergence are no-ops.
+#include "pcg.cuh"
+#include "comm.cuh"
+
+namespace b200 {
+
+PcgWorkspace::~PcgWorkspace() {
+    if (hsc) cudaFreeHost(hsc);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+}
+DeviceMesh::~DeviceMesh() { delete pcg; }
+
+__global__ void k_brow_of_slot(MeshView mv, int* out) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= mv.N) return;
+    int s = row >> 5, lane = row & 31;
+    if ((mv.bMask[s] >> lane) & 1u) out[mv.bBase[s] + __popc(mv.bMask[s] & ((1u << lane) - 1u))] = row;
+}
+__global__ void k_dot(int N, const double* __restrict__ a, const double* __restrict__ b, double* out, double* partials,
+                      unsigned* counter, const PcgScalars* sc) {
+    if (sc && sc->stop) return;
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[1] = {row < N ? a[row] * b[row] : 0.0};
+    gridReduce<1, OpSum>(v, blockIdx.x, gridDim.x, partials, counter, nullptr);
+    gridFinalize<1, OpSum>(gridDim.x, partials, counter, out);
+}
+
+PcgWorkspace& pcgWorkspace(DeviceMesh& m) {
+    if (m.pcg) return *m.pcg;
+    PcgWorkspace* w = new PcgWorkspace();
+    m.pcg = w;
+    size_t N = m.N;
+    w->pA.alloc(N); w->wA.alloc(N); w->rA.alloc(N); w->y.alloc(N); w->z.alloc(N); w->rD.alloc(N); w->Dt.alloc(N);
+    int nBlocks = gridFor(m.N) + 1;
+    w->partials.alloc(3 * (size_t)nBlocks + 8);
+    w->sc.alloc(1); w->counters.alloc(4); w->counters.zero();
+    B200_CHECK_CUDA(cudaMallocHost((void**)&w->hsc, 2 * sizeof(PcgScalars)));
+    for (auto& e : w->ev) B200_CHECK_CUDA(cudaEventCreate(&e));
+    fillSentinel(w->y, N); fillSentinel(w->z, N);
+    w->bRowOfSlot.alloc(m.nBRows + 1);
+    if (m.N) B200_LAUNCH(k_brow_of_slot, gridFor(m.N), BLOCK, rt().stream, m.view(), w->bRowOfSlot.p);
+    if (m.B) { w->sendBuf.alloc(m.B); w->recvBuf.alloc(m.B); }
+    // persistent sweep grid: a few CTAs per SM; chunks are handed out by ticket so any size is deadlock-free
+    w->sweepGrid = std::max(1, std::min(gridFor(m.N), rt().numSMs * 4));
+    syncStream();
+    return *w;
+}
+
+static SweepCtl sweepCtl(PcgWorkspace& w) { return SweepCtl{w.counters.p + 1, w.counters.p + 2}; }
+
+void amulDevice(DeviceMesh& m, const double* diag, const double* upS, const double* loS, const double* psi, double* Apsi,
+                const double* bou) {
+    PcgWorkspace& w = pcgWorkspace(m);
+    ScopedTimer t(T_AMUL);
+    bool halo = bou && rt().nRanks > 1 && meshHasProcessorPatches(m);
+    if (halo) haloPack(m, psi, w.sendBuf);
+    if (m.N) B200_LAUNCH(k_amul<0>, gridFor(m.N), BLOCK, rt().stream, m.view(), diag, upS, loS, psi, Apsi, (PcgScalars*)nullptr,
+                         (double*)nullptr, (unsigned*)nullptr);
+    if (halo) {
+        haloExchange(m, w.sendBuf, w.recvBuf);
+        B200_LAUNCH(k_interface_update, gridFor(m.nBRows), BLOCK, rt().stream, m.view(), bou, w.recvBuf.p, Apsi, m.nBRows, w.bRowOfSlot.p);
+    }
+}
+
+void dicCalcReciprocalD(DeviceMesh& m, const double* diag, const double* upS, double* rD) {
+    PcgWorkspace& w = pcgWorkspace(m);
+    ScopedTimer t(T_DIC_RD);
+    if (!m.N) return;
+    fillSentinel(w.Dt, m.N);
+    int nChunks = gridFor(m.N);
+    B200_LAUNCH(k_dic_calc_rd, w.sweepGrid, BLOCK, rt().stream, m.view(), diag, upS, w.Dt.p, rD, sweepCtl(w), nChunks);
+}
+
+void dicPrecondition(DeviceMesh& m, const double* rD, const double* upS, const double* rA, double* wA) {
+    PcgWorkspace& w = pcgWorkspace(m);
+    if (!m.N) return;
+    int nChunks = gridFor(m.N);
+    { ScopedTimer t(T_DIC_FWD);
+      B200_LAUNCH(k_dic_fwd, w.sweepGrid, BLOCK, rt().stream, m.view(), rD, upS, rA, w.y.p, sweepCtl(w), nChunks, (const PcgScalars*)nullptr); }
+    { ScopedTimer t(T_DIC_BWD);
+      B200_LAUNCH(k_dic_bwd, w.sweepGrid, BLOCK, rt().stream, m.view(), rD, upS, rA, w.y.p, w.z.p, sweepCtl(w), nChunks,
+                  (PcgScalars*)nullptr, (double*)nullptr, (unsigned*)nullptr); }
+    B200_CHECK_CUDA(cudaMemcpyAsync(wA, w.z.p, 8 * (size_t)m.N, cudaMemcpyDeviceToDevice, rt().stream));
+    fillSentinel(w.z, m.N);
+}
+
+b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double* upS, const double* bou, double* x,
+                                const double* b, const b200_solver_controls& ctl, std::vector<double>* resHist) {
+    PcgWorkspace& w = pcgWorkspace(m);
+    ScopedTimer tt(T_PCG_SOLVE);
+    cudaStream_t st = rt().stream;
+    const int N = m.N, grid = std::max(1, gridFor(N)), nChunks = gridFor(N);
+    const bool multi = rt().nRanks > 1;
+    const bool halo = multi && bou && meshHasProcessorPatches(m);
+    MeshView mv = m.view();
+    int histCap = resHist ? ctl.maxIter + 2 : 0;
+    if (histCap > 0) w.hist.ensure(histCap);
+    PcgScalars h; memset(&h, 0, sizeof(h));
+    h.tol = ctl.tolerance; h.relTol = ctl.relTol; h.minIter = ctl.minIter; h.maxIter = ctl.maxIter; h.histCap = histCap;
+    double nGlobal = (double)N;
+    h.nGlobal = nGlobal;
+    w.hsc[0] = h;
+    B200_CHECK_CUDA(cudaMemcpyAsync(w.sc.p, &w.hsc[0], sizeof(PcgScalars), cudaMemcpyHostToDevice, st));
+    PcgScalars* sc = w.sc.p;
+    double* part = w.partials.p; unsigned* cnt = w.counters.p;
+    double* hist = histCap > 0 ? w.hist.p : nullptr;
+    if (multi) allReduce(&sc->nGlobal, 1, RED_SUM);
+    // --- start-up: wA = A x, rA = b - wA, normFactor, initial residual
+    const double* bouOrNull = halo ? bou : nullptr;
+    if (halo) haloPack(m, x, w.sendBuf);
+    B200_LAUNCH(k_pcg_init1, grid, BLOCK, st, mv, diag, upS, (const double*)x, b, bouOrNull, w.wA.p, w.rA.p, w.pA.p, sc, part, cnt);
+    if (halo) {
+        haloExchange(m, w.sendBuf, w.recvBuf);
+        B200_LAUNCH(k_interface_update, gridFor(m.nBRows), BLOCK, st, mv, bou, w.recvBuf.p, w.wA.p, m.nBRows, w.bRowOfSlot.p);
+        B200_LAUNCH(k_pcg_resid, grid, BLOCK, st, N, b, w.wA.p, w.rA.p, sc, part, cnt);
+    }
+    if (multi) { allReduce(&sc->sumX, 1, RED_SUM); allReduce(&sc->sumMagR, 1, RED_SUM); }
+    B200_LAUNCH(k_pcg_init2, grid, BLOCK, st, N, w.wA.p, b, w.pA.p, sc, part, cnt);
+    if (multi) allReduce(&sc->nfSum, 1, RED_SUM);
+    B200_LAUNCH(k_pcg_check0, 1, 32, st, sc, hist);
+    B200_CHECK_CUDA(cudaMemcpyAsync(&w.hsc[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
+    B200_CHECK_CUDA(cudaEventRecord(w.ev[0], st));
+    // calcReciprocalD is enqueued before the host learns whether it is needed (one sweep; keeps the GPU busy)
+    if (N) { fillSentinel(w.Dt, N); B200_LAUNCH(k_dic_calc_rd, w.sweepGrid, BLOCK, st, mv, diag, upS, w.Dt.p, w.rD.p, sweepCtl(w), nChunks); }
+    B200_CHECK_CUDA(cudaEventSynchronize(w.ev[0]));
+    bool stopped = w.hsc[0].stop != 0;
+    const int BATCH = 8;
+    int slot = 0, enq = 0;
+    auto enqueueIteration = [&]() {
+        if (N) {
+            B200_LAUNCH(k_dic_fwd, w.sweepGrid, BLOCK, st, mv, (const double*)w.rD.p, upS, (const double*)w.rA.p, w.y.p, sweepCtl(w), nChunks, (const PcgScalars*)sc);
+            B200_LAUNCH(k_dic_bwd, w.sweepGrid, BLOCK, st, mv, (const double*)w.rD.p, upS, (const double*)w.rA.p, w.y.p, w.z.p, sweepCtl(w), nChunks, sc, part, cnt);
+        }
+        if (multi) allReduce(&sc->wArA, 1, RED_SUM);
+        B200_LAUNCH(k_pcg_p_update, grid, BLOCK, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc);
+        if (halo) {
+            haloPack(m, w.pA, w.sendBuf);
+            B200_LAUNCH(k_amul<0>, grid, BLOCK, st, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt);
+            haloExchange(m, w.sendBuf, w.recvBuf);
+            B200_LAUNCH(k_interface_update, gridFor(m.nBRows), BLOCK, st, mv, bou, w.recvBuf.p, w.wA.p, m.nBRows, w.bRowOfSlot.p);
+            B200_LAUNCH(k_dot, grid, BLOCK, st, N, (const double*)w.wA.p, (const double*)w.pA.p, &sc->wApA, part, cnt, (const PcgScalars*)sc);
+        } else {
+            B200_LAUNCH(k_amul<1>, grid, BLOCK, st, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt);
+        }
+        if (multi) allReduce(&sc->wApA, 1, RED_SUM);
+        B200_LAUNCH(k_pcg_xr_update, grid, BLOCK, st, N, x, w.rA.p, (const double*)w.pA.p, (const double*)w.wA.p, sc, part, cnt);
+        if (multi) allReduce(&sc->sumMagR, 1, RED_SUM);
+        B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist);
+    };
+    // two batches in flight: while the host waits for batch i's flag, batch i+1 is already queued
+    int pendingSlots = 0;
+    while (!stopped) {
+        while (pendingSlots < 2 && enq < ctl.maxIter + BATCH) {
+            for (int i = 0; i < BATCH; i++) enqueueIteration();
+            enq += BATCH;
+            int sl = (slot + pendingSlots) & 1;
+            B200_CHECK_CUDA(cudaMemcpyAsync(&w.hsc[sl], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
+            B200_CHECK_CUDA(cudaEventRecord(w.ev[sl], st));
+            pendingSlots++;
+        }
+        if (pendingSlots == 0) break;
+        B200_CHECK_CUDA(cudaEventSynchronize(w.ev[slot]));
+        stopped = w.hsc[slot].stop != 0;
+        h = w.hsc[slot];
+        slot ^= 1; pendingSlots--;
+    }
+    // drain anything still queued (no-op iterations) and read the final scalars
+    B200_CHECK_CUDA(cudaMemcpyAsync(&w.hsc[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
+    syncStream();
+    h = w.hsc[0];
+    b200_solver_perf perf;
+    perf.initialResidual = h.initialResidual; perf.finalResidual = h.finalResidual; perf.nIterations = h.nIter;
+    perf.converged = h.converged; perf.singular = h.singular;
+    if (resHist) {
+        resHist->resize(h.nIter + 1);
+        B200_CHECK_CUDA(cudaMemcpyAsync(resHist->data(), w.hist.p, 8 * (size_t)(h.nIter + 1), cudaMemcpyDeviceToHost, st));
+        syncStream();
+    }
+    return perf;
+}
+
+}  // namespace b200

@@ -1,0 +1,35 @@
+// pcg.cuh -- b200PCG: device-resident DIC-preconditioned CG on the cached lduAddressing.
+#pragma once
+#include "device_mesh.cuh"
+#include "ldu_kernels.cuh"
+
+namespace b200 {
+
+struct Halo;  // comm.cuh
+
+struct PcgWorkspace {
+    DevBuf<double> pA, wA, rA, y, z, rD, Dt, partials, hist;
+    DevBuf<double> diag, upS, x, b, bou;       // staging for the host-pointer API
+    DevBuf<double> sendBuf, recvBuf;           // processor-patch halo
+    DevBuf<PcgScalars> sc;
+    DevBuf<unsigned> counters;                 // [0] reduce counter, [1] sweep ticket, [2] sweep done
+    DevBuf<int> bRowOfSlot;
+    PcgScalars* hsc = nullptr;                 // pinned mirror (2 slots)
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int histCap = 0;
+    int sweepGrid = 0;
+    ~PcgWorkspace();
+};
+
+PcgWorkspace& pcgWorkspace(DeviceMesh& m);
+
+// device-pointer forms (row order / slot order); used by the region3d step and by the host API wrappers
+void amulDevice(DeviceMesh& m, const double* diag, const double* upS, const double* loS, const double* psi, double* Apsi,
+                const double* bou /*[B] or null*/);
+void dicCalcReciprocalD(DeviceMesh& m, const double* diag, const double* upS, double* rD);
+void dicPrecondition(DeviceMesh& m, const double* rD, const double* upS, const double* rA, double* wA);
+// x in/out (rows); bou = interface coefficients of processor patches ([B], may be null)
+b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double* upS, const double* bou, double* x,
+                                const double* b, const b200_solver_controls& ctl, std::vector<double>* resHist);
+
+}  // namespace b200
