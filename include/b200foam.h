@@ -87,6 +87,8 @@ int b200_nccl_unique_id(void* out128);
 int b200_finalize(void);
 const char* b200_last_error(void);
 int b200_device_count(void);
+/* tuning knobs (defaults are the measured best): "sweep_grid" = CTAs of the data-flow DIC sweeps (0 = auto) */
+int b200_set_option(const char* name, double value);
 /* number of kernels this library launched since process start (bench.py's gpu_launches) */
 long long b200_kernel_launch_count(void);
 /* CUDA-event timing of kernel classes since the last reset: out[0..n) milliseconds, names via b200_timer_name */

@@ -19,7 +19,7 @@ SCHEME_VANLEER, SCHEME_INTERFACE_COMPRESSION, SCHEME_UPWIND, SCHEME_LINEAR = 0, 
 
 EXPORTS = [
     "b200_init", "b200_nccl_unique_id", "b200_finalize", "b200_last_error", "b200_device_count",
-    "b200_kernel_launch_count", "b200_timers_reset", "b200_timers_get", "b200_timer_name",
+    "b200_kernel_launch_count", "b200_set_option", "b200_timers_reset", "b200_timers_get", "b200_timer_name",
     "b200_ldu_get_or_create", "b200_ldu_release", "b200_ldu_get_renumbering", "b200_ldu_get_addressing",
     "b200_amul", "b200_sumA", "b200_dic_calc_reciprocal_d", "b200_dic_precondition", "b200_pcg_solve",
     "b200_mesh_create", "b200_mesh_release", "b200_mesh_ldu",
@@ -147,6 +147,9 @@ class B200Lib:
         buf = (C.c_char * 128)()
         self.check(self.c.b200_nccl_unique_id(buf))
         return bytes(buf)
+
+    def set_option(self, name, value):
+        self.check(self.c.b200_set_option(name.encode(), C.c_double(value)))
 
     def launches(self):
         return int(self.c.b200_kernel_launch_count())

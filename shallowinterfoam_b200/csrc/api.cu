@@ -5,6 +5,7 @@
 #include "comm.cuh"
 #include "device_mesh.cuh"
 #include "pcg.cuh"
+#include "region3d.cuh"
 
 using namespace b200;
 
@@ -85,6 +86,12 @@ int b200_finalize(void) {
     API_END
 }
 long long b200_kernel_launch_count(void) { return rt().launches; }
+int b200_set_option(const char* name, double value) {
+    API_BEGIN
+    B200_REQUIRE(name, B200_ERR_ARG, "b200_set_option: null name");
+    rt().opts[name] = value;
+    API_END
+}
 int b200_timers_reset(void) {
     API_BEGIN
     Timers& t = timers();
@@ -369,6 +376,316 @@ int b200_mesh_create_from_polymesh(const b200_polymesh_t* pm, b200_mesh_t** out)
     d.weights = g.weights.data(); d.deltaCoeffs = g.deltaCoeffs.data();
     int rc = b200_mesh_create(&d, out);
     if (rc != B200_OK) return rc;
+    API_END
+}
+
+
+// ---------------------------------------------------------------------------------------------- fv building blocks
+namespace {
+struct Stage {   // host-pointer API staging on the mesh's cached buffers
+    DeviceMesh& m; FvWorkspace& w; int next = 0;
+    explicit Stage(DeviceMesh& m_) : m(m_), w(fvWorkspace(m_)) {}
+    double* buf(size_t n) { B200_REQUIRE(next < 16, B200_ERR_STATE, "staging exhausted"); DevBuf<double>& b = w.stg[next++]; b.ensure(n ? n : 1); return b.p; }
+    double* cells(const double* h) { double* d = buf(m.N); m.uploadCells(h, d); return d; }
+    double* faces(const double* h) { double* d = buf(m.nFaceField()); m.uploadFaces(h, d, true); return d; }
+    double* facesInt(const double* h) { double* d = buf(m.Fs + 1); m.uploadFaces(h, d, false); return d; }
+    double* bnd(const double* h, int nc = 1) { double* d = buf((size_t)nc * m.B); m.uploadBoundary(h, d, nc); return d; }
+};
+DeviceMesh& geoMesh(b200_mesh_t* mesh) {
+    requireDevice();
+    B200_REQUIRE(mesh, B200_ERR_ARG, "null mesh");
+    DeviceMesh& m = *asMesh(mesh);
+    B200_REQUIRE(m.hasGeometry, B200_ERR_ARG, "mesh has no geometry");
+    return m;
+}
+int nmaxOf(const DeviceMesh& m) { return std::max(std::max(m.N, m.B), 1); }
+}  // namespace
+
+int b200_interpolate(b200_mesh_t* mesh, const double* vf, const double* vfBoundary, int32_t nCmpt, double* out) {
+    API_BEGIN
+    DeviceMesh& m = geoMesh(mesh);
+    B200_REQUIRE(nCmpt == 1 || nCmpt == 3, B200_ERR_ARG, "b200_interpolate: nCmpt must be 1 or 3");
+    size_t nF = (size_t)m.F + m.B;
+    std::vector<double> hc(m.N), hb(m.B), ho(nF);
+    for (int k = 0; k < nCmpt; k++) {
+        Stage s(m);
+        for (int i = 0; i < m.N; i++) hc[i] = vf[(size_t)nCmpt * i + k];
+        for (int i = 0; i < m.B; i++) hb[i] = vfBoundary[(size_t)nCmpt * i + k];
+        double* d = s.cells(hc.data()); double* db = s.bnd(hb.data()); double* o = s.buf(m.nFaceField());
+        B200_LAUNCH(k_interpolate, gridFor(nmaxOf(m)), BLOCK, rt().stream, m.view(), (const double*)d, (const double*)db, o);
+        m.downloadFaces(o, ho.data(), true);
+        for (size_t i = 0; i < nF; i++) out[(size_t)nCmpt * i + k] = ho[i];
+    }
+    API_END
+}
+int b200_sngrad(b200_mesh_t* mesh, const b200_bc* bc, const double* vf, const double* vfBoundary, double* out) {
+    API_BEGIN
+    DeviceMesh& m = geoMesh(mesh);
+    DevBC dbc; dbc.upload(m, bc, 1);
+    Stage s(m);
+    double* d = s.cells(vf); double* db = s.bnd(vfBoundary); double* o = s.buf(m.nFaceField());
+    B200_LAUNCH(k_sngrad, gridFor(nmaxOf(m)), BLOCK, rt().stream, m.view(), dbc.view(), (const double*)d, (const double*)db, o);
+    m.downloadFaces(o, out, true);
+    API_END
+}
+int b200_surface_integrate(b200_mesh_t* mesh, const double* ssf, double* out) {
+    API_BEGIN
+    DeviceMesh& m = geoMesh(mesh);
+    Stage s(m);
+    double* f = s.faces(ssf); double* o = s.buf(m.N);
+    if (m.N) B200_LAUNCH(k_surface_integrate, gridFor(m.N), BLOCK, rt().stream, m.view(), (const double*)f, o, 1.0);
+    m.downloadCells(o, out);
+    API_END
+}
+int b200_grad_gauss(b200_mesh_t* mesh, const b200_bc* bc, const double* vf, const double* vfBoundary, double* grad, double* gradBoundary) {
+    API_BEGIN
+    DeviceMesh& m = geoMesh(mesh);
+    DevBC dbc; dbc.upload(m, bc, 1);
+    Stage s(m);
+    FvWorkspace& w = s.w;
+    double* d = s.cells(vf); double* db = s.bnd(vfBoundary);
+    if (m.N) B200_LAUNCH(k_grad_scalar, gridFor(m.N), BLOCK, rt().stream, m.view(), (const double*)d, (const double*)db, w.gx.p, w.gy.p, w.gz.p);
+    m.downloadCellVec(w.gx, w.gy, w.gz, grad);
+    if (gradBoundary && m.B) {
+        B200_LAUNCH(k_grad_boundary, gridFor(m.B), BLOCK, rt().stream, m.view(), dbc.view(), (const double*)d, (const double*)db, (const double*)w.gx.p,
+                    (const double*)w.gy.p, (const double*)w.gz.p, w.gb.p);
+        double* aos = s.buf(3 * (size_t)m.B);
+        B200_LAUNCH(k_soa_to_aos, gridFor(m.B), BLOCK, rt().stream, (const double*)w.gb.p, aos, m.B, 3);
+        m.downloadBoundary(aos, gradBoundary, 3);
+    }
+    API_END
+}
+int b200_reconstruct(b200_mesh_t* mesh, const double* ssf, double* out) {
+    API_BEGIN
+    DeviceMesh& m = geoMesh(mesh);
+    Stage s(m);
+    double* f = s.faces(ssf); double* ox = s.buf(m.N); double* oy = s.buf(m.N); double* oz = s.buf(m.N);
+    if (m.N) B200_LAUNCH(k_reconstruct<0>, gridFor(m.N), BLOCK, rt().stream, m.view(), reconTensor(m), (const double*)f, (const double*)nullptr,
+                         (const double*)nullptr, (const double*)nullptr, ox, oy, oz);
+    m.downloadCellVec(ox, oy, oz, out);
+    API_END
+}
+int b200_flux_limited(b200_mesh_t* mesh, int32_t scheme, const b200_bc* bc, const double* faceFlux, const double* vf,
+                      const double* vfBoundary, double* out) {
+    API_BEGIN
+    DeviceMesh& m = geoMesh(mesh);
+    B200_REQUIRE(scheme >= 0 && scheme <= 3, B200_ERR_ARG, "b200_flux_limited: unknown scheme");
+    (void)bc;
+    Stage s(m);
+    FvWorkspace& w = s.w;
+    double* ff = s.faces(faceFlux); double* d = s.cells(vf); double* db = s.bnd(vfBoundary); double* o = s.buf(m.nFaceField());
+    ScopedTimer t(T_FLUX);
+    if (scheme == B200_SCHEME_VANLEER && m.N)
+        B200_LAUNCH(k_grad_scalar, gridFor(m.N), BLOCK, rt().stream, m.view(), (const double*)d, (const double*)db, w.gx.p, w.gy.p, w.gz.p);
+    B200_LAUNCH(k_flux_limited, gridFor(nmaxOf(m)), BLOCK, rt().stream, m.view(), (int)scheme, (const double*)ff, (const double*)d, (const double*)db,
+                (const double*)w.gx.p, (const double*)w.gy.p, (const double*)w.gz.p, o);
+    m.downloadFaces(o, out, true);
+    API_END
+}
+int b200_mules_explicit_solve(b200_mesh_t* mesh, const b200_bc* bc, double* psi, const double* psiBoundary, const double* psi0,
+                              const double* phi, double* phiPsi, double deltaT, double psiMax, double psiMin, double* lambdaOut) {
+    API_BEGIN
+    DeviceMesh& m = geoMesh(mesh);
+    DevBC dbc; dbc.upload(m, bc, 1);
+    Stage s(m);
+    double* dpsi = s.cells(psi); double* dpsib = s.bnd(psiBoundary); double* dpsi0 = s.cells(psi0);
+    double* dphi = s.faces(phi); double* dphiPsi = s.faces(phiPsi);
+    double* dlam = lambdaOut ? s.buf(m.nFaceField()) : nullptr;
+    mulesExplicitDevice(m, dbc.view(), dpsi, dpsib, dpsi0, dphi, dphiPsi, deltaT, psiMax, psiMin, (int)rt().opt("mules_include_own", 0), 3, dlam);
+    m.downloadCells(dpsi, psi);
+    m.downloadFaces(dphiPsi, phiPsi, true);
+    if (lambdaOut) m.downloadFaces(dlam, lambdaOut, true);
+    API_END
+}
+int b200_mules_limiter(b200_mesh_t* mesh, const b200_bc* bc, const double* psi, const double* psiBoundary, const double* psi0,
+                       const double* phiBD, const double* phiCorr, double deltaT, double psiMax, double psiMin,
+                       int32_t nLimiterIter, double* lambda) {
+    API_BEGIN
+    DeviceMesh& m = geoMesh(mesh);
+    B200_REQUIRE(nLimiterIter >= 0 && lambda, B200_ERR_ARG, "b200_mules_limiter: bad arguments");
+    DevBC dbc; dbc.upload(m, bc, 1);
+    Stage s(m);
+    double* dpsi = s.cells(psi); double* dpsib = s.bnd(psiBoundary); double* dpsi0 = s.cells(psi0);
+    double* dbd = s.faces(phiBD); double* dcorr = s.faces(phiCorr); double* dlam = s.buf(m.nFaceField());
+    mulesLimiterDevice(m, dbc.view(), dpsi, dpsib, dpsi0, dbd, dcorr, deltaT, psiMax, psiMin, (int)rt().opt("mules_include_own", 0), nLimiterIter, dlam);
+    m.downloadFaces(dlam, lambda, true);
+    API_END
+}
+int b200_laplacian_assemble(b200_mesh_t* mesh, const b200_bc* bc, const double* gammaf, const double* psiBoundary, const double* phi,
+                            double* diag, double* upper, double* source, double* internalCoeffs, double* boundaryCoeffs) {
+    API_BEGIN
+    DeviceMesh& m = geoMesh(mesh);
+    DevBC dbc; dbc.upload(m, bc, 1);
+    Stage s(m);
+    double* g = s.faces(gammaf); double* pb = s.bnd(psiBoundary); double* dphi = phi ? s.faces(phi) : nullptr;
+    double* dd = s.buf(m.N); double* du = s.buf(m.nFaceField()); double* ds = s.buf(m.N); double* dic = s.buf(m.B); double* dbc2 = s.buf(m.B);
+    ScopedTimer t(T_ASSEMBLY);
+    if (m.N) B200_LAUNCH(k_lap_row, gridFor(m.N), BLOCK, rt().stream, m.view(), (const double*)g, (const double*)dphi, dd, du, ds);
+    if (m.B) B200_LAUNCH(k_lap_boundary, gridFor(m.B), BLOCK, rt().stream, m.view(), dbc.view(), (const double*)g, (const double*)pb, dic, dbc2);
+    m.downloadCells(dd, diag); m.downloadFaces(du, upper, false); m.downloadCells(ds, source);
+    m.downloadBoundary(dic, internalCoeffs); m.downloadBoundary(dbc2, boundaryCoeffs);
+    API_END
+}
+int b200_matrix_flux(b200_mesh_t* mesh, const double* upper, const double* lower, const double* internalCoeffs,
+                     const double* boundaryCoeffs, const double* psi, double* flux) {
+    API_BEGIN
+    DeviceMesh& m = geoMesh(mesh);
+    Stage s(m);
+    double* du = s.facesInt(upper); double* dl = (lower && lower != upper) ? s.facesInt(lower) : du;
+    double* dic = s.bnd(internalCoeffs); double* dbc2 = s.bnd(boundaryCoeffs); double* dpsi = s.cells(psi); double* o = s.buf(m.nFaceField());
+    B200_LAUNCH(k_matrix_flux<false>, gridFor(nmaxOf(m)), BLOCK, rt().stream, m.view(), (const double*)du, (const double*)dl, (const double*)dic,
+                (const double*)dbc2, (const double*)dpsi, o);
+    m.downloadFaces(o, flux, true);
+    API_END
+}
+int b200_alpha_stats(b200_mesh_t* mesh, const double* alpha, const double* alphaBoundary, double* out3) {
+    API_BEGIN
+    DeviceMesh& m = geoMesh(mesh);
+    Stage s(m);
+    FvWorkspace& w = s.w;
+    double* a = s.cells(alpha); double* ab = s.bnd(alphaBoundary);
+    B200_LAUNCH(k_alpha_stats, gridFor(nmaxOf(m)), BLOCK, rt().stream, m.view(), (const double*)a, (const double*)ab, w.scal.p, w.partials.p, w.counter.p);
+    if (rt().nRanks > 1) { allReduce(w.scal.p, 2, RED_SUM); allReduce(w.scal.p + 2, 1, RED_MIN); allReduce(w.scal.p + 3, 1, RED_MAX); }
+    double h[4];
+    w.scal.download(h, 4); syncStream();
+    out3[0] = h[0] / h[1]; out3[1] = h[2]; out3[2] = h[3];
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------- region3d
+static Region3D* asRegion(b200_region3d_t* r) { return reinterpret_cast<Region3D*>(r); }
+
+int b200_region3d_create(b200_mesh_t* mesh, const b200_region3d_controls* ctl, const b200_bc* bcAlpha, const b200_bc* bcU,
+                         const b200_bc* bcPd, const double* alpha1, const double* U, const double* pd, b200_region3d_t** out) {
+    API_BEGIN
+    DeviceMesh& m = geoMesh(mesh);
+    B200_REQUIRE(ctl && bcAlpha && bcU && bcPd && alpha1 && U && pd && out, B200_ERR_ARG, "b200_region3d_create: null argument");
+    std::unique_ptr<Region3D> r(new Region3D());
+    r->create(&m, *ctl, bcAlpha, bcU, bcPd, alpha1, U, pd);
+    *out = reinterpret_cast<b200_region3d_t*>(r.release());
+    API_END
+}
+int b200_region3d_release(b200_region3d_t* r) {
+    API_BEGIN
+    delete asRegion(r);
+    API_END
+}
+int b200_region3d_correct_phi(b200_region3d_t* r) {
+    API_BEGIN
+    asRegion(r)->correctPhi();
+    API_END
+}
+int b200_region3d_step(b200_region3d_t* r, int32_t nSteps) {
+    API_BEGIN
+    for (int i = 0; i < nSteps; i++) asRegion(r)->step();
+    API_END
+}
+int b200_region3d_set_fields(b200_region3d_t* rr, const double* alpha1, const double* U, const double* pd, const double* phi) {
+    API_BEGIN
+    Region3D& r = *asRegion(rr);
+    DeviceMesh& m = *r.m;
+    if (alpha1) { m.uploadCells(alpha1, r.alpha); r.evalAlphaBC(); }
+    if (U) { m.uploadCellVec(U, r.Ux, r.Uy, r.Uz); r.evalUBC(); }
+    if (pd) {
+        m.uploadCells(pd, r.pd);
+        if (m.B) B200_LAUNCH(k_bc_evaluate, gridFor(m.B), BLOCK, rt().stream, m.view(), r.bcPd.view(), 1, (const double*)r.pd.p, (const double*)nullptr,
+                             (const double*)nullptr, r.pdb.p);
+    }
+    if (phi) m.uploadFaces(phi, r.phi, true);
+    syncStream();
+    API_END
+}
+int b200_region3d_get_fields(b200_region3d_t* rr, double* alpha1, double* U, double* pd, double* phi, double* p, double* rho) {
+    API_BEGIN
+    Region3D& r = *asRegion(rr);
+    DeviceMesh& m = *r.m;
+    if (alpha1) m.downloadCells(r.alpha, alpha1);
+    if (U) m.downloadCellVec(r.Ux, r.Uy, r.Uz, U);
+    if (pd) m.downloadCells(r.pd, pd);
+    if (phi) m.downloadFaces(r.phi, phi, true);
+    if (p) m.downloadCells(r.p, p);
+    if (rho) m.downloadCells(r.rho, rho);
+    API_END
+}
+int b200_region3d_step_host(b200_region3d_t* rr, double* alpha1, double* U, double* pd, double* phi, double* p) {
+    API_BEGIN
+    B200_REQUIRE(alpha1 && U && pd && phi && p, B200_ERR_ARG, "b200_region3d_step_host: null argument");
+    int rc = b200_region3d_set_fields(rr, alpha1, U, pd, phi);
+    if (rc != B200_OK) return rc;
+    asRegion(rr)->step();
+    rc = b200_region3d_get_fields(rr, alpha1, U, pd, phi, p, nullptr);
+    if (rc != B200_OK) return rc;
+    API_END
+}
+int b200_region3d_set_patch_mixed(b200_region3d_t* rr, int32_t field, int32_t patch, const double* refValue, const double* refGrad,
+                                  const double* valueFraction) {
+    API_BEGIN
+    Region3D& r = *asRegion(rr);
+    DeviceMesh& m = *r.m;
+    B200_REQUIRE(field >= 0 && field <= 2 && patch >= 0 && patch < (int)m.patches.size(), B200_ERR_ARG, "b200_region3d_set_patch_mixed: bad field/patch");
+    DevBC& bc = field == 0 ? r.bcAlpha : field == 1 ? r.bcU : r.bcPd;
+    B200_REQUIRE(bc.types[patch] == B200_BC_MIXED, B200_ERR_ARG, "patch is not a mixed patch");
+    int off = m.patches[patch].start - m.F, n = m.patches[patch].size, nc = bc.nc;
+    std::vector<double> tmp(n);
+    for (int k = 0; k < nc; k++) {
+        for (int i = 0; i < n; i++) tmp[i] = refValue[(size_t)nc * i + k];
+        B200_CHECK_CUDA(cudaMemcpyAsync(bc.rv.p + (size_t)k * m.B + off, tmp.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, rt().stream));
+        syncStream();
+        for (int i = 0; i < n; i++) tmp[i] = refGrad[(size_t)nc * i + k];
+        B200_CHECK_CUDA(cudaMemcpyAsync(bc.rg.p + (size_t)k * m.B + off, tmp.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, rt().stream));
+        syncStream();
+    }
+    B200_CHECK_CUDA(cudaMemcpyAsync(bc.vf.p + off, valueFraction, 8 * (size_t)n, cudaMemcpyHostToDevice, rt().stream));
+    syncStream();
+    API_END
+}
+int b200_region3d_get_patch_internal(b200_region3d_t* rr, int32_t field, int32_t patch, double* out) {
+    API_BEGIN
+    Region3D& r = *asRegion(rr);
+    DeviceMesh& m = *r.m;
+    B200_REQUIRE(field >= 0 && field <= 2 && patch >= 0 && patch < (int)m.patches.size() && out, B200_ERR_ARG, "b200_region3d_get_patch_internal: bad arguments");
+    int off = m.patches[patch].start - m.F, n = m.patches[patch].size;
+    if (n == 0) return B200_OK;
+    Stage s(m);
+    const double* src[3] = {field == 0 ? r.alpha.p : field == 1 ? r.Ux.p : r.pd.p, r.Uy.p, r.Uz.p};
+    int nc = field == 1 ? 3 : 1;
+    std::vector<double> tmp(n);
+    double* d = s.buf(n);
+    for (int k = 0; k < nc; k++) {
+        B200_LAUNCH(k_gather_patch, gridFor(n), BLOCK, rt().stream, (const int*)(m.dBFaceRow.p + off), n, src[k], d);
+        B200_CHECK_CUDA(cudaMemcpyAsync(tmp.data(), d, 8 * (size_t)n, cudaMemcpyDeviceToHost, rt().stream));
+        syncStream();
+        for (int i = 0; i < n; i++) out[(size_t)nc * i + k] = tmp[i];
+    }
+    API_END
+}
+int b200_region3d_num_solves(b200_region3d_t* r) { return (int)asRegion(r)->perfs.size(); }
+int b200_region3d_get_perfs(b200_region3d_t* r, b200_solver_perf* out, int32_t cap) {
+    API_BEGIN
+    auto& v = asRegion(r)->perfs;
+    for (int i = 0; i < cap && i < (int)v.size(); i++) out[i] = v[i];
+    API_END
+}
+int b200_region3d_get_res_hist(b200_region3d_t* r, double* out, int32_t cap) {
+    auto& v = asRegion(r)->resHist;
+    for (int i = 0; out && i < cap && i < (int)v.size(); i++) out[i] = v[i];
+    return (int)v.size();
+}
+int b200_region3d_get_alpha_stats(b200_region3d_t* r, double* out, int32_t cap) {
+    auto& v = asRegion(r)->alphaStats;
+    for (int i = 0; out && i < cap && i < (int)v.size(); i++) out[i] = v[i];
+    return (int)v.size();
+}
+int b200_region3d_get_cont_errs(b200_region3d_t* rr, double* out3) {
+    API_BEGIN
+    Region3D& r = *asRegion(rr);
+    out3[0] = r.sumLocalContErr; out3[1] = r.globalContErr; out3[2] = r.cumulativeContErr;
+    API_END
+}
+int b200_region3d_clear_log(b200_region3d_t* rr) {
+    API_BEGIN
+    Region3D& r = *asRegion(rr);
+    r.perfs.clear(); r.resHist.clear(); r.alphaStats.clear(); r.pendingStats.clear();
     API_END
 }
 

@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -40,6 +41,8 @@ struct Runtime {
     int numSMs = 148;
     long long launches = 0;
     void* nccl = nullptr;  // ncclComm_t (comm.cu)
+    std::map<std::string, double> opts;  // tuning knobs (b200_set_option)
+    double opt(const char* k, double dflt) const { auto it = opts.find(k); return it == opts.end() ? dflt : it->second; }
 };
 Runtime& rt();
 void requireDevice();  // throws B200_ERR_NO_DEVICE when no CUDA device is usable

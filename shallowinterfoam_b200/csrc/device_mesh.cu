@@ -120,6 +120,7 @@ void DeviceMesh::build(int32_t nCells, int32_t nFaces, const int32_t* lo, const 
 void DeviceMesh::setGeometry(const double* Sf, const double* magSf, const double* Cf, const double* C,
                              const double* V, const double* w, const double* dc) {
     size_t nf = nFaceField();
+    hostV.assign(V, V + N);
     dV.alloc(N); dCx.alloc(N); dCy.alloc(N); dCz.alloc(N);
     dSfx.alloc(nf); dSfy.alloc(nf); dSfz.alloc(nf); dCfx.alloc(nf); dCfy.alloc(nf); dCfz.alloc(nf);
     dMagSf.alloc(nf); dW.alloc(nf); dDc.alloc(nf);

@@ -14,6 +14,7 @@
 //             exactly the per-cell summation order of upstream's sequential face loops, with no atomics.
 //  * boundary: per-slice bit mask of rows owning boundary faces + CSR of their boundary faces.
 #pragma once
+#include <memory>
 #include "common.cuh"
 #include "host_mesh.h"
 
@@ -64,6 +65,8 @@ struct DeviceMesh {
     // staging buffers for the host-pointer API
     DevBuf<double> stageA, stageB;
     PcgWorkspace* pcg = nullptr;
+    std::shared_ptr<void> fvHolder;        // FvWorkspace (region3d.cu)
+    std::vector<double> hostV;             // cell volumes, original order (deltaN of interfaceProperties)
     const void* key = nullptr;
 
     ~DeviceMesh();

@@ -88,8 +88,20 @@ struct PcgScalars {
 
 __device__ __forceinline__ bool isSentinel(double v) { return (unsigned long long)__double_as_longlong(v) == SENTINEL_BITS; }
 __device__ __forceinline__ double sentinel() { return __longlong_as_double((long long)SENTINEL_BITS); }
+// gpu-scope relaxed accesses: served by L2 (never a stale L1 line), single-copy atomic for the aligned 8 bytes
+#ifdef B200_EMU
 __device__ __forceinline__ double ldPoll(const double* p) { return *(const volatile double*)p; }
 __device__ __forceinline__ void stPublish(double* p, double v) { *(volatile double*)p = v; }
+#else
+__device__ __forceinline__ double ldPoll(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stPublish(double* p, double v) {
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+#endif
 
 // ----------------------------------------------------------------------------- a1: Amul (row gather)
 // Apsi[row] = diag*psi + sum_{nbr-side faces asc} lower_f*psi[l] + sum_{owner faces asc} upper_f*psi[u]
@@ -278,6 +290,29 @@ __device__ __forceinline__ void sweepExit(SweepCtl c) {
     }
 }
 
+// The sweeps first load everything that does not depend on other rows (dependency indices, coefficients) into
+// registers, then poll ALL outstanding dependencies with independent loads (one L2 round trip per poll) and apply the
+// updates in upstream's order once they have all arrived.  Rows with more than SWEEP_MAXD dependencies (polyhedral
+// cells) take the generic one-at-a-time path.
+#define SWEEP_MAXD 8
+
+// returns when every lane of the warp has published; `apply` is called once per lane with the gathered values
+#define SWEEP_POLL_AND_PUBLISH(src, APPLY_AND_PUBLISH)                                        \
+    {                                                                                         \
+        unsigned pend = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);                         \
+        for (;;) {                                                                            \
+            if (!done) {                                                                      \
+                _Pragma("unroll") for (int j = 0; j < SWEEP_MAXD; j++)                        \
+                    if ((pend >> j) & 1u) {                                                   \
+                        double t = ldPoll((src) + dl[j]);                                     \
+                        if (!isSentinel(t)) { dv[j] = t; pend &= ~(1u << j); }                \
+                    }                                                                         \
+                if (!pend) { APPLY_AND_PUBLISH; done = true; }                                \
+            }                                                                                 \
+            if (__all_sync(0xffffffffu, done)) break;                                         \
+        }                                                                                     \
+    }
+
 // calcReciprocalD: Dt[row] = diag - sum_{nbr-side faces asc} upper_f^2 / Dt[l] ; rD = 1/Dt
 static __global__ void __launch_bounds__(BLOCK) k_dic_calc_rd(MeshView mv, const double* __restrict__ diag,
                                                         const double* __restrict__ upS, double* Dt, double* __restrict__ rD,
@@ -291,22 +326,38 @@ static __global__ void __launch_bounds__(BLOCK) k_dic_calc_rd(MeshView mv, const
         int row = (s << 5) + lane;
         bool done = row >= mv.N;
         double d = done ? 0.0 : diag[row];
-        int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5, j = 0;
-        for (;;) {
-            if (!done) {
-                while (j < nbw) {
+        int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5;
+        if (nbw <= SWEEP_MAXD) {
+            int dl[SWEEP_MAXD]; double dc[SWEEP_MAXD], dv[SWEEP_MAXD]; int cnt = 0;
+#pragma unroll
+            for (int j = 0; j < SWEEP_MAXD; j++) {
+                dl[j] = 0; dc[j] = 0.0; dv[j] = 0.0;
+                if (j < nbw && !done) {
                     int pk = mv.loPk[nb0 + (j << 5) + lane];
-                    if (pk < 0) { j = nbw; break; }
-                    int l; int pos = facePosOf(mv, pk, l);
-                    double v = ldPoll(Dt + l);
-                    if (isSentinel(v)) break;
-                    double u = upS[pos];
-                    d = d - u * u / v;
-                    j++;
+                    if (pk >= 0) { int l; int pos = facePosOf(mv, pk, l); dl[j] = l; dc[j] = upS[pos]; cnt = j + 1; }
                 }
-                if (j >= nbw) { stPublish(Dt + row, d); rD[row] = 1.0 / d; done = true; }
             }
-            if (__all_sync(0xffffffffu, done)) break;
+            SWEEP_POLL_AND_PUBLISH(Dt, {
+                _Pragma("unroll") for (int j = 0; j < SWEEP_MAXD; j++) if (j < cnt) d = d - dc[j] * dc[j] / dv[j];
+                stPublish(Dt + row, d); rD[row] = 1.0 / d; })
+        } else {
+            int j = 0;
+            for (;;) {
+                if (!done) {
+                    while (j < nbw) {
+                        int pk = mv.loPk[nb0 + (j << 5) + lane];
+                        if (pk < 0) { j = nbw; break; }
+                        int l; int pos = facePosOf(mv, pk, l);
+                        double v = ldPoll(Dt + l);
+                        if (isSentinel(v)) break;
+                        double u = upS[pos];
+                        d = d - u * u / v;
+                        j++;
+                    }
+                    if (j >= nbw) { stPublish(Dt + row, d); rD[row] = 1.0 / d; done = true; }
+                }
+                if (__all_sync(0xffffffffu, done)) break;
+            }
         }
     }
     sweepExit(ctl);
@@ -327,21 +378,37 @@ static __global__ void __launch_bounds__(BLOCK) k_dic_fwd(MeshView mv, const dou
         bool done = row >= mv.N;
         double rd = done ? 0.0 : rD[row];
         double w = done ? 0.0 : rd * rA[row];
-        int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5, j = 0;
-        for (;;) {
-            if (!done) {
-                while (j < nbw) {
+        int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5;
+        if (nbw <= SWEEP_MAXD) {
+            int dl[SWEEP_MAXD]; double dc[SWEEP_MAXD], dv[SWEEP_MAXD]; int cnt = 0;
+#pragma unroll
+            for (int j = 0; j < SWEEP_MAXD; j++) {
+                dl[j] = 0; dc[j] = 0.0; dv[j] = 0.0;
+                if (j < nbw && !done) {
                     int pk = mv.loPk[nb0 + (j << 5) + lane];
-                    if (pk < 0) { j = nbw; break; }
-                    int l; int pos = facePosOf(mv, pk, l);
-                    double v = ldPoll(y + l);
-                    if (isSentinel(v)) break;
-                    w = w - rd * upS[pos] * v;
-                    j++;
+                    if (pk >= 0) { int l; int pos = facePosOf(mv, pk, l); dl[j] = l; dc[j] = rd * upS[pos]; cnt = j + 1; }
                 }
-                if (j >= nbw) { stPublish(y + row, w); done = true; }
             }
-            if (__all_sync(0xffffffffu, done)) break;
+            SWEEP_POLL_AND_PUBLISH(y, {
+                _Pragma("unroll") for (int j = 0; j < SWEEP_MAXD; j++) if (j < cnt) w = w - dc[j] * dv[j];
+                stPublish(y + row, w); })
+        } else {
+            int j = 0;
+            for (;;) {
+                if (!done) {
+                    while (j < nbw) {
+                        int pk = mv.loPk[nb0 + (j << 5) + lane];
+                        if (pk < 0) { j = nbw; break; }
+                        int l; int pos = facePosOf(mv, pk, l);
+                        double v = ldPoll(y + l);
+                        if (isSentinel(v)) break;
+                        w = w - rd * upS[pos] * v;
+                        j++;
+                    }
+                    if (j >= nbw) { stPublish(y + row, w); done = true; }
+                }
+                if (__all_sync(0xffffffffu, done)) break;
+            }
         }
     }
     sweepExit(ctl);
@@ -365,22 +432,45 @@ static __global__ void __launch_bounds__(BLOCK) k_dic_bwd(MeshView mv, const dou
             bool done = row >= mv.N;
             double rd = done ? 0.0 : rD[row];
             double w = done ? 0.0 : y[row];
-            int so0 = mv.sliceOff[s], k = ((mv.sliceOff[s + 1] - so0) >> 5) - 1;
-            for (;;) {
-                if (!done) {
-                    while (k >= 0) {
-                        int pos = so0 + (k << 5) + lane;
-                        int u = mv.upIdx[pos];
-                        if (u >= 0) {
-                            double v = ldPoll(z + u);
-                            if (isSentinel(v)) break;
-                            w = w - rd * upS[pos] * v;
-                        }
-                        k--;
+            double ra = done ? 0.0 : rA[row];
+            int so0 = mv.sliceOff[s], ow = (mv.sliceOff[s + 1] - so0) >> 5;
+            if (ow <= SWEEP_MAXD) {
+                int dl[SWEEP_MAXD]; double dc[SWEEP_MAXD], dv[SWEEP_MAXD]; int cnt = 0;
+#pragma unroll
+                for (int j = 0; j < SWEEP_MAXD; j++) { dl[j] = 0; dc[j] = 0.0; dv[j] = 0.0; }
+                // application order = descending face index: walk k downwards, pack the real entries
+                for (int k = ow - 1; k >= 0; k--) {
+                    if (done) break;
+                    int pos = so0 + (k << 5) + lane;
+                    int u = mv.upIdx[pos];
+                    if (u >= 0) {
+                        double c = rd * upS[pos];
+#pragma unroll
+                        for (int j = 0; j < SWEEP_MAXD; j++) if (j == cnt) { dl[j] = u; dc[j] = c; }
+                        cnt++;
                     }
-                    if (k < 0) { stPublish(z + row, w); y[row] = sentinel(); dotv = w * rA[row]; done = true; }
                 }
-                if (__all_sync(0xffffffffu, done)) break;
+                SWEEP_POLL_AND_PUBLISH(z, {
+                    _Pragma("unroll") for (int j = 0; j < SWEEP_MAXD; j++) if (j < cnt) w = w - dc[j] * dv[j];
+                    stPublish(z + row, w); y[row] = sentinel(); dotv = w * ra; })
+            } else {
+                int k = ow - 1;
+                for (;;) {
+                    if (!done) {
+                        while (k >= 0) {
+                            int pos = so0 + (k << 5) + lane;
+                            int u = mv.upIdx[pos];
+                            if (u >= 0) {
+                                double v = ldPoll(z + u);
+                                if (isSentinel(v)) break;
+                                w = w - rd * upS[pos] * v;
+                            }
+                            k--;
+                        }
+                        if (k < 0) { stPublish(z + row, w); y[row] = sentinel(); dotv = w * ra; done = true; }
+                    }
+                    if (__all_sync(0xffffffffu, done)) break;
+                }
             }
         }
         if (partials) {

@@ -45,11 +45,21 @@ PcgWorkspace& pcgWorkspace(DeviceMesh& m) {
     if (m.B) { w->sendBuf.alloc(m.B); w->recvBuf.alloc(m.B); }
     // persistent sweep grid: a few CTAs per SM; chunks are handed out by ticket so any size is deadlock-free
     w->sweepGrid = std::max(1, std::min(gridFor(m.N), rt().numSMs * 4));
+    w->rowsPerLevel = m.nLevels > 0 ? (double)m.N / m.nLevels : 1.0;
     syncStream();
     return *w;
 }
 
 static SweepCtl sweepCtl(PcgWorkspace& w) { return SweepCtl{w.counters.p + 1, w.counters.p + 2}; }
+// CTAs of a data-flow sweep: enough to keep `sweep_window` levels in flight (the rest would only poll L2)
+static int sweepGridOf(const DeviceMesh& m, const PcgWorkspace& w) {
+    int forced = (int)rt().opt("sweep_grid", 0);
+    if (forced > 0) return std::min(forced, std::max(1, gridFor(m.N)));
+    double window = rt().opt("sweep_window", 4.0);
+    int want = (int)(window * w.rowsPerLevel / BLOCK) + 1;
+    want = std::max(want, (int)rt().opt("sweep_min_grid", 32));
+    return std::max(1, std::min(std::min(want, gridFor(m.N)), rt().numSMs * 4));
+}
 
 void amulDevice(DeviceMesh& m, const double* diag, const double* upS, const double* loS, const double* psi, double* Apsi,
                 const double* bou) {
@@ -71,7 +81,7 @@ void dicCalcReciprocalD(DeviceMesh& m, const double* diag, const double* upS, do
     if (!m.N) return;
     fillSentinel(w.Dt, m.N);
     int nChunks = gridFor(m.N);
-    B200_LAUNCH(k_dic_calc_rd, w.sweepGrid, BLOCK, rt().stream, m.view(), diag, upS, w.Dt.p, rD, sweepCtl(w), nChunks);
+    B200_LAUNCH(k_dic_calc_rd, sweepGridOf(m, w), BLOCK, rt().stream, m.view(), diag, upS, w.Dt.p, rD, sweepCtl(w), nChunks);
 }
 
 void dicPrecondition(DeviceMesh& m, const double* rD, const double* upS, const double* rA, double* wA) {
@@ -79,9 +89,9 @@ void dicPrecondition(DeviceMesh& m, const double* rD, const double* upS, const d
     if (!m.N) return;
     int nChunks = gridFor(m.N);
     { ScopedTimer t(T_DIC_FWD);
-      B200_LAUNCH(k_dic_fwd, w.sweepGrid, BLOCK, rt().stream, m.view(), rD, upS, rA, w.y.p, sweepCtl(w), nChunks, (const PcgScalars*)nullptr); }
+      B200_LAUNCH(k_dic_fwd, sweepGridOf(m, w), BLOCK, rt().stream, m.view(), rD, upS, rA, w.y.p, sweepCtl(w), nChunks, (const PcgScalars*)nullptr); }
     { ScopedTimer t(T_DIC_BWD);
-      B200_LAUNCH(k_dic_bwd, w.sweepGrid, BLOCK, rt().stream, m.view(), rD, upS, rA, w.y.p, w.z.p, sweepCtl(w), nChunks,
+      B200_LAUNCH(k_dic_bwd, sweepGridOf(m, w), BLOCK, rt().stream, m.view(), rD, upS, rA, w.y.p, w.z.p, sweepCtl(w), nChunks,
                   (PcgScalars*)nullptr, (double*)nullptr, (unsigned*)nullptr); }
     B200_CHECK_CUDA(cudaMemcpyAsync(wA, w.z.p, 8 * (size_t)m.N, cudaMemcpyDeviceToDevice, rt().stream));
     fillSentinel(w.z, m.N);
@@ -124,15 +134,15 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
     B200_CHECK_CUDA(cudaMemcpyAsync(&w.hsc[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
     B200_CHECK_CUDA(cudaEventRecord(w.ev[0], st));
     // calcReciprocalD is enqueued before the host learns whether it is needed (one sweep; keeps the GPU busy)
-    if (N) { fillSentinel(w.Dt, N); B200_LAUNCH(k_dic_calc_rd, w.sweepGrid, BLOCK, st, mv, diag, upS, w.Dt.p, w.rD.p, sweepCtl(w), nChunks); }
+    if (N) { fillSentinel(w.Dt, N); B200_LAUNCH(k_dic_calc_rd, sweepGridOf(m, w), BLOCK, st, mv, diag, upS, w.Dt.p, w.rD.p, sweepCtl(w), nChunks); }
     B200_CHECK_CUDA(cudaEventSynchronize(w.ev[0]));
     bool stopped = w.hsc[0].stop != 0;
     const int BATCH = 8;
     int slot = 0, enq = 0;
     auto enqueueIteration = [&]() {
         if (N) {
-            B200_LAUNCH(k_dic_fwd, w.sweepGrid, BLOCK, st, mv, (const double*)w.rD.p, upS, (const double*)w.rA.p, w.y.p, sweepCtl(w), nChunks, (const PcgScalars*)sc);
-            B200_LAUNCH(k_dic_bwd, w.sweepGrid, BLOCK, st, mv, (const double*)w.rD.p, upS, (const double*)w.rA.p, w.y.p, w.z.p, sweepCtl(w), nChunks, sc, part, cnt);
+            B200_LAUNCH(k_dic_fwd, sweepGridOf(m, w), BLOCK, st, mv, (const double*)w.rD.p, upS, (const double*)w.rA.p, w.y.p, sweepCtl(w), nChunks, (const PcgScalars*)sc);
+            B200_LAUNCH(k_dic_bwd, sweepGridOf(m, w), BLOCK, st, mv, (const double*)w.rD.p, upS, (const double*)w.rA.p, w.y.p, w.z.p, sweepCtl(w), nChunks, sc, part, cnt);
         }
         if (multi) allReduce(&sc->wArA, 1, RED_SUM);
         B200_LAUNCH(k_pcg_p_update, grid, BLOCK, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc);

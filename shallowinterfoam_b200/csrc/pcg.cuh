@@ -18,6 +18,7 @@ struct PcgWorkspace {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     int histCap = 0;
     int sweepGrid = 0;
+    double rowsPerLevel = 1.0;
     ~PcgWorkspace();
 };
 
