@@ -460,7 +460,8 @@ int b200_reconstruct(b200_mesh_t* mesh, const double* ssf, double* out) {
     DeviceMesh& m = geoMesh(mesh);
     Stage s(m);
     double* f = s.faces(ssf); double* ox = s.buf(m.N); double* oy = s.buf(m.N); double* oz = s.buf(m.N);
-    if (m.N) B200_LAUNCH(k_reconstruct<0>, gridFor(m.N), BLOCK, rt().stream, m.view(), reconTensor(m), (const double*)f, (const double*)nullptr,
+    const double* invT = reconTensor(m);
+    if (m.N) B200_LAUNCH(k_reconstruct<0>, gridFor(m.N), BLOCK, rt().stream, m.view(), invT, (const double*)f, (const double*)nullptr,
                          (const double*)nullptr, (const double*)nullptr, ox, oy, oz);
     m.downloadCellVec(ox, oy, oz, out);
     API_END

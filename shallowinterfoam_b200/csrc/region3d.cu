@@ -627,7 +627,8 @@ void Region3D::pEqn(int corr) {
                           nonOrth == ctl.nNonOrthCorr);
     }
     { ScopedTimer t(T_ASSEMBLY);
-      B200_LAUNCH(k_reconstruct<1>, gridFor(N), BLOCK, st, mv, reconTensor(*m), (const double*)phi.p, (const double*)phiU.p, (const double*)rUAf.p,
+      const double* invT = reconTensor(*m);
+      B200_LAUNCH(k_reconstruct<1>, gridFor(N), BLOCK, st, mv, invT, (const double*)phi.p, (const double*)phiU.p, (const double*)rUAf.p,
                   (const double*)rUA.p, Ux.p, Uy.p, Uz.p);
       evalUBC(); }
 }
