@@ -3,6 +3,7 @@
 // stop flag) stay on the device.  The host enqueues iterations in batches and only polls the stop flag through a
 // pinned mirror, so launch latency overlaps execution; iterations enqueued past convergence are no-ops.
 #include "pcg.cuh"
+#include <memory>
 #include "comm.cuh"
 
 namespace b200 {
@@ -139,27 +140,36 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
     bool stopped = w.hsc[0].stop != 0;
     const int BATCH = 8;
     int slot = 0, enq = 0;
+    const bool kt = timers().enabled && rt().opt("pcg_kernel_timers", 0) > 0;   // per-kernel-class events (roofline pass)
+#define KT(id) std::unique_ptr<ScopedTimer> _kt(kt ? new ScopedTimer(id) : nullptr)
     auto enqueueIteration = [&]() {
         if (N) {
-            B200_LAUNCH(k_dic_fwd, sweepGridOf(m, w), BLOCK, st, mv, (const double*)w.rD.p, upS, (const double*)w.rA.p, w.y.p, sweepCtl(w), nChunks, (const PcgScalars*)sc);
-            B200_LAUNCH(k_dic_bwd, sweepGridOf(m, w), BLOCK, st, mv, (const double*)w.rD.p, upS, (const double*)w.rA.p, w.y.p, w.z.p, sweepCtl(w), nChunks, sc, part, cnt);
+            { KT(T_DIC_FWD);
+              B200_LAUNCH(k_dic_fwd, sweepGridOf(m, w), BLOCK, st, mv, (const double*)w.rD.p, upS, (const double*)w.rA.p, w.y.p, sweepCtl(w), nChunks, (const PcgScalars*)sc); }
+            { KT(T_DIC_BWD);
+              B200_LAUNCH(k_dic_bwd, sweepGridOf(m, w), BLOCK, st, mv, (const double*)w.rD.p, upS, (const double*)w.rA.p, w.y.p, w.z.p, sweepCtl(w), nChunks, sc, part, cnt); }
         }
         if (multi) allReduce(&sc->wArA, 1, RED_SUM);
-        B200_LAUNCH(k_pcg_p_update, grid, BLOCK, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc);
+        { KT(T_PCG_VEC);
+          B200_LAUNCH(k_pcg_p_update, grid, BLOCK, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc); }
         if (halo) {
             haloPack(m, w.pA, w.sendBuf);
-            B200_LAUNCH(k_amul<0>, grid, BLOCK, st, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt);
+            { KT(T_AMUL);
+              B200_LAUNCH(k_amul<0>, grid, BLOCK, st, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt); }
             haloExchange(m, w.sendBuf, w.recvBuf);
             B200_LAUNCH(k_interface_update, gridFor(m.nBRows), BLOCK, st, mv, bou, w.recvBuf.p, w.wA.p, m.nBRows, w.bRowOfSlot.p);
             B200_LAUNCH(k_dot, grid, BLOCK, st, N, (const double*)w.wA.p, (const double*)w.pA.p, &sc->wApA, part, cnt, (const PcgScalars*)sc);
         } else {
+            KT(T_AMUL);
             B200_LAUNCH(k_amul<1>, grid, BLOCK, st, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt);
         }
         if (multi) allReduce(&sc->wApA, 1, RED_SUM);
-        B200_LAUNCH(k_pcg_xr_update, grid, BLOCK, st, N, x, w.rA.p, (const double*)w.pA.p, (const double*)w.wA.p, sc, part, cnt);
+        { KT(T_PCG_VEC);
+          B200_LAUNCH(k_pcg_xr_update, grid, BLOCK, st, N, x, w.rA.p, (const double*)w.pA.p, (const double*)w.wA.p, sc, part, cnt); }
         if (multi) allReduce(&sc->sumMagR, 1, RED_SUM);
         B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist);
     };
+#undef KT
     // two batches in flight: while the host waits for batch i's flag, batch i+1 is already queued
     int pendingSlots = 0;
     while (!stopped) {
