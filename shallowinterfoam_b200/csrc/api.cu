@@ -272,6 +272,7 @@ int b200_mesh_create(const b200_mesh_desc* d, b200_mesh_t** out) {
     std::unique_ptr<DeviceMesh> m(new DeviceMesh());
     m->build(d->nCells, d->nInternalFaces, d->owner, d->neighbour, pt, fc);
     m->setGeometry(d->Sf, d->magSf, d->Cf, d->C, d->V, d->weights, d->deltaCoeffs);
+    m->coupleGeometry();   // collective when the mesh has processor patches
     *out = reinterpret_cast<b200_mesh_t*>(m.release());
     API_END
 }
@@ -479,7 +480,7 @@ int b200_flux_limited(b200_mesh_t* mesh, int32_t scheme, const b200_bc* bc, cons
     if (scheme == B200_SCHEME_VANLEER && m.N)
         B200_LAUNCH(k_grad_scalar, gridFor(m.N), BLOCK, rt().stream, m.view(), (const double*)d, (const double*)db, w.gx.p, w.gy.p, w.gz.p);
     B200_LAUNCH(k_flux_limited, gridFor(nmaxOf(m)), BLOCK, rt().stream, m.view(), (int)scheme, (const double*)ff, (const double*)d, (const double*)db,
-                (const double*)w.gx.p, (const double*)w.gy.p, (const double*)w.gz.p, o);
+                (const double*)w.gx.p, (const double*)w.gy.p, (const double*)w.gz.p, (const double*)w.gb.p, o);
     m.downloadFaces(o, out, true);
     API_END
 }
@@ -535,7 +536,7 @@ int b200_matrix_flux(b200_mesh_t* mesh, const double* upper, const double* lower
     double* du = s.facesInt(upper); double* dl = (lower && lower != upper) ? s.facesInt(lower) : du;
     double* dic = s.bnd(internalCoeffs); double* dbc2 = s.bnd(boundaryCoeffs); double* dpsi = s.cells(psi); double* o = s.buf(m.nFaceField());
     B200_LAUNCH(k_matrix_flux<false>, gridFor(nmaxOf(m)), BLOCK, rt().stream, m.view(), (const double*)du, (const double*)dl, (const double*)dic,
-                (const double*)dbc2, (const double*)dpsi, o);
+                (const double*)dbc2, (const double*)dpsi, (const double*)nullptr, o);
     m.downloadFaces(o, flux, true);
     API_END
 }
@@ -589,8 +590,7 @@ int b200_region3d_set_fields(b200_region3d_t* rr, const double* alpha1, const do
     if (U) { m.uploadCellVec(U, r.Ux, r.Uy, r.Uz); r.evalUBC(); }
     if (pd) {
         m.uploadCells(pd, r.pd);
-        if (m.B) B200_LAUNCH(k_bc_evaluate, gridFor(m.B), BLOCK, rt().stream, m.view(), r.bcPd.view(), 1, (const double*)r.pd.p, (const double*)nullptr,
-                             (const double*)nullptr, r.pdb.p);
+        r.evalPdBC(r.bcPd, r.pd, r.pdb);
     }
     if (phi) m.uploadFaces(phi, r.phi, true);
     syncStream();

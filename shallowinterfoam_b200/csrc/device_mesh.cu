@@ -124,6 +124,7 @@ void DeviceMesh::setGeometry(const double* Sf, const double* magSf, const double
     dV.alloc(N); dCx.alloc(N); dCy.alloc(N); dCz.alloc(N);
     dSfx.alloc(nf); dSfy.alloc(nf); dSfz.alloc(nf); dCfx.alloc(nf); dCfy.alloc(nf); dCfz.alloc(nf);
     dMagSf.alloc(nf); dW.alloc(nf); dDc.alloc(nf);
+    dCnx.alloc(B); dCny.alloc(B); dCnz.alloc(B); dCnx.zero(); dCny.zero(); dCnz.zero();
     uploadCells(V, dV); uploadCellVec(C, dCx, dCy, dCz);
     uploadFaceVec(Sf, dSfx, dSfy, dSfz); uploadFaceVec(Cf, dCfx, dCfy, dCfz);
     uploadFaces(magSf, dMagSf, true); uploadFaces(w, dW, true); uploadFaces(dc, dDc, true);
@@ -138,7 +139,7 @@ MeshView DeviceMesh::view() const {
     v.bMask = dBMask; v.bBase = dBBase; v.bRowStart = dBRowStart; v.bRowFaces = dBRowFaces;
     v.bFaceRow = dBFaceRow; v.bPatch = dBPatch; v.bCoupled = dBCoupled;
     v.V = dV; v.Cx = dCx; v.Cy = dCy; v.Cz = dCz; v.Sfx = dSfx; v.Sfy = dSfy; v.Sfz = dSfz;
-    v.magSf = dMagSf; v.w = dW; v.dc = dDc;
+    v.magSf = dMagSf; v.w = dW; v.dc = dDc; v.Cnx = dCnx; v.Cny = dCny; v.Cnz = dCnz;
     return v;
 }
 

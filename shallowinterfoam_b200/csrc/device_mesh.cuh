@@ -37,7 +37,8 @@ struct MeshView {  // POD handed to kernels by value
     const double* V;                 // [N]
     const double *Cx, *Cy, *Cz;      // [N]
     const double *Sfx, *Sfy, *Sfz;   // [Fs+B]
-    const double *magSf, *w, *dc;    // [Fs+B]
+    const double *magSf, *w, *dc;    // [Fs+B]  (processor faces: internal-face weights / deltaCoeffs, see coupleGeometry)
+    const double *Cnx, *Cny, *Cnz;   // [B] neighbour cell centre of processor faces
 };
 
 __device__ __forceinline__ int facePosOf(const MeshView& mv, int pk, int& l) {
@@ -61,6 +62,7 @@ struct DeviceMesh {
     DevBuf<int> dSliceOff, dNbrOff, dUpIdx, dLoPk, dBBase, dBRowStart, dBRowFaces, dBFaceRow, dBPatch, dBCoupled;
     DevBuf<unsigned> dBMask;
     DevBuf<int> dSlotFace, dFacePos, dRowCell, dCellRow;
+    DevBuf<double> dCnx, dCny, dCnz;
     DevBuf<double> dV, dCx, dCy, dCz, dSfx, dSfy, dSfz, dMagSf, dW, dDc, dCfx, dCfy, dCfz;
     // staging buffers for the host-pointer API
     DevBuf<double> stageA, stageB;
@@ -75,6 +77,7 @@ struct DeviceMesh {
     void setGeometry(const double* Sf, const double* magSf, const double* Cf, const double* C, const double* V,
                      const double* w, const double* dc);
     MeshView view() const;
+    void coupleGeometry();   // collective: processor-face weights/deltaCoeffs/neighbour centres from a halo swap of C
     size_t nFaceField() const { return (size_t)Fs + B; }
 
     // ---- host <-> device layout conversion (all on rt().stream) -------------------------------------------

@@ -69,6 +69,12 @@ __device__ __forceinline__ double bcGradBouCoeff(const BCView& bc, int t, int b,
     return 0.0;
 }
 
+// face value on a boundary face: the patch value, or -- processor patch -- the linear interpolate with the neighbour cell
+// (vfb holds patchNeighbourField there) [UPSTREAM surfaceInterpolationScheme::interpolate coupled branch]
+__device__ __forceinline__ double bndFaceValue(const MeshView& mv, int b, double own, double bv) {
+    return mv.bCoupled[b] ? mv.w[mv.Fs + b] * (own - bv) + bv : bv;
+}
+
 // evaluate(): nc components, SoA boundary arrays (component k at bval + k*B); internal SoA pointers i0,i1,i2
 static __global__ void k_bc_evaluate(MeshView mv, BCView bc, int nc, const double* __restrict__ i0,
                                      const double* __restrict__ i1, const double* __restrict__ i2, double* bval) {
@@ -96,7 +102,7 @@ static __global__ void k_interpolate(MeshView mv, const double* __restrict__ vf,
         double a = vf[row];
         FOR_OWN_FACES(mv, s, lane, pos, u) double n = vf[u]; out[pos] = mv.w[pos] * (a - n) + n; END_FACES
     }
-    if (row < mv.B) out[mv.Fs + row] = vfb[row];
+    if (row < mv.B) out[mv.Fs + row] = bndFaceValue(mv, row, vf[mv.bFaceRow[row]], vfb[row]);
 }
 static __global__ void k_sngrad(MeshView mv, BCView bc, const double* __restrict__ vf, const double* __restrict__ vfb,
                                 double* __restrict__ out) {
@@ -139,7 +145,7 @@ static __global__ void k_grad_scalar(MeshView mv, const double* __restrict__ vf,
         x = x + mv.Sfx[pos] * sf; y = y + mv.Sfy[pos] * sf; z = z + mv.Sfz[pos] * sf;
     END_FACES
     FOR_BND_FACES(mv, s, lane, b)
-        double v = vfb[b]; int p = mv.Fs + b;
+        double v = bndFaceValue(mv, b, a, vfb[b]); int p = mv.Fs + b;
         x = x + mv.Sfx[p] * v; y = y + mv.Sfy[p] * v; z = z + mv.Sfz[p] * v;
     END_BND
     double V = mv.V[row];
@@ -154,8 +160,9 @@ static __global__ void k_grad_boundary(MeshView mv, BCView bc, const double* __r
     int c = mv.bFaceRow[b], p = mv.Fs + b, t = bc.type[mv.bPatch[b]];
     double ms = mv.magSf[p];
     double n0 = mv.Sfx[p] / ms, n1 = mv.Sfy[p] / ms, n2 = mv.Sfz[p] / ms;
+    if (t == B200_BC_PROCESSOR) return;   // filled by the halo swap of the neighbour's cell gradient
     double g0 = gx[c], g1 = gy[c], g2 = gz[c];
-    if (t != B200_BC_PROCESSOR) {
+    {
         double sn = bcSnGrad(bc, t, b, b, mv.dc[p], vf[c], vfb[b]);
         double nd = n0 * g0 + n1 * g1 + n2 * g2;
         g0 += n0 * (sn - nd); g1 += n1 * (sn - nd); g2 += n2 * (sn - nd);
@@ -191,7 +198,8 @@ __device__ __forceinline__ double limitedFaceFlux(double lim, double w, double f
 static __global__ void k_flux_limited(MeshView mv, int scheme, const double* __restrict__ faceFlux,
                                       const double* __restrict__ vf, const double* __restrict__ vfb,
                                       const double* __restrict__ gx, const double* __restrict__ gy,
-                                      const double* __restrict__ gz, double* __restrict__ out) {
+                                      const double* __restrict__ gz, const double* __restrict__ gbn /*[3B] neighbour gradient on processor faces*/,
+                                      double* __restrict__ out) {
     ROW_PROLOGUE(mv)
     if (row < mv.N) {
         double a = vf[row];
@@ -206,7 +214,22 @@ static __global__ void k_flux_limited(MeshView mv, int scheme, const double* __r
             out[pos] = limitedFaceFlux(lim, mv.w[pos], ff, a, n);
         END_FACES
     }
-    if (row < mv.B) out[mv.Fs + row] = faceFlux[mv.Fs + row] * vfb[row];
+    if (row < mv.B) {
+        int b = row, p = mv.Fs + b;
+        double ff = faceFlux[p], n = vfb[b];
+        if (!mv.bCoupled[b]) out[p] = ff * n;
+        else {   // processor face: same formula as an internal face, own cell = P, neighbour-rank cell = N
+            int c = mv.bFaceRow[b];
+            double a = vf[c], lim;
+            if (scheme == B200_SCHEME_VANLEER)
+                lim = vanLeerLimiter(a, n, gx[c], gy[c], gz[c], gbn[b], gbn[mv.B + b], gbn[2 * mv.B + b], mv.Cnx[b] - mv.Cx[c],
+                                     mv.Cny[b] - mv.Cy[c], mv.Cnz[b] - mv.Cz[c], ff);
+            else if (scheme == B200_SCHEME_INTERFACE_COMPRESSION) lim = compressionLimiter(a, n);
+            else if (scheme == B200_SCHEME_UPWIND) lim = 0.0;
+            else lim = 1.0;
+            out[p] = limitedFaceFlux(lim, mv.w[p], ff, a, n);
+        }
+    }
 }
 
 // max(|phi/magSf|) over internal + boundary faces [REF region3d/alphaEqn.H:6-8]
@@ -224,8 +247,8 @@ static __global__ void k_phic_max(MeshView mv, const double* __restrict__ phi, d
 static __global__ void __launch_bounds__(BLOCK) k_alpha_flux(MeshView mv, const double* __restrict__ phi,
                                                               const double* __restrict__ alpha, const double* __restrict__ alphab,
                                                               const double* __restrict__ gx, const double* __restrict__ gy,
-                                                              const double* __restrict__ gz, const double* __restrict__ nHatf,
-                                                              double cAlpha, const double* __restrict__ maxPhic,
+                                                              const double* __restrict__ gz, const double* __restrict__ gbn,
+                                                              const double* __restrict__ nHatf, double cAlpha, const double* __restrict__ maxPhic,
                                                               double* __restrict__ phiAlpha) {
     ROW_PROLOGUE(mv)
     double mx = *maxPhic;
@@ -250,10 +273,22 @@ static __global__ void __launch_bounds__(BLOCK) k_alpha_flux(MeshView mv, const 
         double ff = phi[p], ab = alphab[row];
         double phic = fmin(cAlpha * fabs(ff / mv.magSf[p]), mx);
         double phir = phic * nHatf[p];
-        double f1 = ff * ab;
-        double t1 = (-phir) * (1.0 - ab);
-        t1 = -t1;
-        phiAlpha[p] = f1 + t1 * ab;
+        if (!mv.bCoupled[row]) {
+            double f1 = ff * ab;
+            double t1 = (-phir) * (1.0 - ab);
+            t1 = -t1;
+            phiAlpha[p] = f1 + t1 * ab;
+        } else {
+            int b = row, c = mv.bFaceRow[b];
+            double a = alpha[c], n = ab, w = mv.w[p];
+            double lim = vanLeerLimiter(a, n, gx[c], gy[c], gz[c], gbn[b], gbn[mv.B + b], gbn[2 * mv.B + b], mv.Cnx[b] - mv.Cx[c],
+                                        mv.Cny[b] - mv.Cy[c], mv.Cnz[b] - mv.Cz[c], ff);
+            double f1 = limitedFaceFlux(lim, w, ff, a, n);
+            double oa = 1.0 - a, on = 1.0 - n, mphir = -phir;
+            double t1 = limitedFaceFlux(compressionLimiter(oa, on), w, mphir, oa, on);
+            t1 = -t1;
+            phiAlpha[p] = f1 + limitedFaceFlux(compressionLimiter(a, n), w, t1, a, n);
+        }
     }
 }
 
@@ -270,7 +305,12 @@ static __global__ void k_mules_bd_corr(MeshView mv, const double* __restrict__ p
             phiBD[pos] = bd; phiPsi[pos] = phiPsi[pos] - bd;
         END_FACES
     }
-    if (row < mv.B) { int p = mv.Fs + row; double bd = phi[p] * psib[row]; phiBD[p] = bd; phiPsi[p] = phiPsi[p] - bd; }
+    if (row < mv.B) {
+        int p = mv.Fs + row;
+        double ff = phi[p];
+        double bd = ff * ((mv.bCoupled[row] && ff >= 0) ? psi[mv.bFaceRow[row]] : psib[row]);
+        phiBD[p] = bd; phiPsi[p] = phiPsi[p] - bd;
+    }
 }
 // local extrema and admissible in/out-flows
 static __global__ void __launch_bounds__(BLOCK) k_mules_bounds(MeshView mv, BCView bc, const double* __restrict__ psi,
@@ -434,8 +474,12 @@ static __global__ void k_lap_boundary(MeshView mv, BCView bc, const double* __re
     if (b >= mv.B) return;
     int p = mv.Fs + b, t = bc.type[mv.bPatch[b]];
     double pg = gammaf[p] * mv.magSf[p], dc = mv.dc[p];
-    ic[b] = pg * bcGradIntCoeff(bc, t, b, dc);
-    bcv[b] = -pg * bcGradBouCoeff(bc, t, b, b, dc, pb[b]);
+    if (t == B200_BC_PROCESSOR) {   // coupledFvPatchField: gradientInternalCoeffs = -deltaCoeffs, gradientBoundaryCoeffs = +deltaCoeffs
+        ic[b] = pg * (-1.0 * dc); bcv[b] = -pg * dc;
+    } else {
+        ic[b] = pg * bcGradIntCoeff(bc, t, b, dc);
+        bcv[b] = -pg * bcGradBouCoeff(bc, t, b, b, dc, pb[b]);
+    }
 }
 // fvScalarMatrix::solve prologue: diag[faceCells] += internalCoeffs ; source[faceCells] += boundaryCoeffs (non-coupled)
 static __global__ void k_add_boundary(MeshView mv, const double* __restrict__ ic, const double* __restrict__ bcv,
@@ -455,6 +499,7 @@ static __global__ void k_add_boundary(MeshView mv, const double* __restrict__ ic
 template <bool SUB>
 static __global__ void k_matrix_flux(MeshView mv, const double* __restrict__ upper, const double* __restrict__ lower,
                                      const double* __restrict__ ic, const double* __restrict__ bcv, const double* __restrict__ psi,
+                                     const double* __restrict__ psib /*patchNeighbourField on processor faces (may be null without them)*/,
                                      double* __restrict__ out) {
     ROW_PROLOGUE(mv)
     if (row < mv.N) {
@@ -466,7 +511,7 @@ static __global__ void k_matrix_flux(MeshView mv, const double* __restrict__ upp
     }
     if (row < mv.B) {
         int b = row, p = mv.Fs + b;
-        double fl = ic[b] * psi[mv.bFaceRow[b]] - bcv[b];
+        double fl = ic[b] * psi[mv.bFaceRow[b]] - (mv.bCoupled[b] ? bcv[b] * psib[b] : bcv[b]);
         if (SUB) out[p] = out[p] - fl; else out[p] = fl;
     }
 }

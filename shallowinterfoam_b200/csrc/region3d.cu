@@ -49,7 +49,8 @@ FvWorkspace& fvWorkspace(DeviceMesh& m) {
         w->phiBD.alloc(nf); w->lamA.alloc(nf); w->lamB.alloc(nf); w->flux.alloc(nf); w->flux.zero();
         w->psiMaxn.alloc(N); w->psiMinn.alloc(N); w->sumPhip.alloc(N); w->mSumPhim.alloc(N);
         w->lamP0.alloc(N); w->lamM0.alloc(N); w->lamP1.alloc(N); w->lamM1.alloc(N);
-        w->gx.alloc(N); w->gy.alloc(N); w->gz.alloc(N); w->gb.alloc(3 * (size_t)m.B);
+        w->gx.alloc(N); w->gy.alloc(N); w->gz.alloc(N); w->gb.alloc(3 * (size_t)m.B); w->gb.zero();
+        w->lamPn.alloc(m.B); w->lamMn.alloc(m.B); w->haloSend.alloc(m.B);
         w->partials.alloc(8 * (size_t)(gridFor(std::max<long long>(m.N, m.B)) + 2));
         w->scal.alloc(16); w->counter.alloc(2); w->counter.zero();
         syncStream();
@@ -76,6 +77,8 @@ static void mulesCore(DeviceMesh& m, const BCView& bc, const double* psi, const 
     int grid = gridFor(m.N);
     if (!m.N) return;
     const double* nul = nullptr;
+    const bool halo = rt().nRanks > 1 && meshHasProcessorPatches(m);
+    const double* lpn = halo ? w.lamPn.p : nul; const double* lmn = halo ? w.lamMn.p : nul;
     B200_LAUNCH(k_mules_bounds, grid, BLOCK, st, mv, bc, psi, psib, nul, psi0, phiBD, phiCorr, deltaT, psiMax, psiMin, includeOwn,
                 w.psiMaxn.p, w.psiMinn.p, w.sumPhip.p, w.mSumPhim.p);
     // iteration it (1-based) consumes cell lambdas of it-1 and face lambdas of it-2, writes face lambdas of it-1
@@ -87,10 +90,14 @@ static void mulesCore(DeviceMesh& m, const BCView& bc, const double* psi, const 
                         (const double*)w.psiMaxn.p, (const double*)w.psiMinn.p, (const double*)w.sumPhip.p, (const double*)w.mSumPhim.p, lpNew, lmNew);
         else {
             B200_LAUNCH(k_mules_iter<false>, grid, BLOCK, st, mv, phiCorr, (const double*)facePrev, faceOut, (const double*)lpPrev,
-                        (const double*)lmPrev, nul, nul, mv.bCoupled, (const double*)w.psiMaxn.p, (const double*)w.psiMinn.p,
+                        (const double*)lmPrev, lpn, lmn, mv.bCoupled, (const double*)w.psiMaxn.p, (const double*)w.psiMinn.p,
                         (const double*)w.sumPhip.p, (const double*)w.mSumPhim.p, lpNew, lmNew);
             facePrev = faceOut;
             faceOut = (faceOut == w.lamA.p) ? w.lamB.p : w.lamA.p;
+        }
+        if (halo) {   // the other side of a processor face limits with its own cell: swap lambdap/lambdam (syncFaceList(minEqOp))
+            haloPack(m, lpNew, w.haloSend); haloExchange(m, w.haloSend, w.lamPn);
+            haloPack(m, lmNew, w.haloSend); haloExchange(m, w.haloSend, w.lamMn);
         }
         lpPrev = lpNew; lmPrev = lmNew;
         lpNew = (lpNew == w.lamP0.p) ? w.lamP1.p : w.lamP0.p;
@@ -99,9 +106,10 @@ static void mulesCore(DeviceMesh& m, const BCView& bc, const double* psi, const 
     if (nIter == 0) {  // lambda = 1 everywhere: cell lambdas of "iteration 0" are 1
         fillValue(w.lamP0, m.N, 1.0); fillValue(w.lamM0, m.N, 1.0);
         lpPrev = w.lamP0.p; lmPrev = w.lamM0.p;
+        if (halo) { fillValue(w.lamPn, m.B, 1.0); fillValue(w.lamMn, m.B, 1.0); }
     }
     B200_LAUNCH(k_mules_update, grid, BLOCK, st, mv, phiBD, (double*)nullptr, phiCorr, (const double*)facePrev, (const double*)lpPrev,
-                (const double*)lmPrev, nul, nul, mv.bCoupled, psi0, deltaT, psiOut, lambdaOut, fluxOut);
+                (const double*)lmPrev, lpn, lmn, mv.bCoupled, psi0, deltaT, psiOut, lambdaOut, fluxOut);
 }
 
 void mulesExplicitDevice(DeviceMesh& m, const BCView& bc, double* psi, const double* psib, const double* psi0,
@@ -138,7 +146,11 @@ static __global__ void k_init_phi(MeshView mv, const double* __restrict__ Ux, co
             phi[pos] = fx * mv.Sfx[pos] + fy * mv.Sfy[pos] + fz * mv.Sfz[pos];
         END_FACES
     }
-    if (row < mv.B) { int p = mv.Fs + row, B = mv.B; phi[p] = Ub[row] * mv.Sfx[p] + Ub[B + row] * mv.Sfy[p] + Ub[2 * B + row] * mv.Sfz[p]; }
+    if (row < mv.B) {
+        int p = mv.Fs + row, B = mv.B, c = mv.bFaceRow[row];
+        double fx = bndFaceValue(mv, row, Ux[c], Ub[row]), fy = bndFaceValue(mv, row, Uy[c], Ub[B + row]), fz = bndFaceValue(mv, row, Uz[c], Ub[2 * B + row]);
+        phi[p] = fx * mv.Sfx[p] + fy * mv.Sfy[p] + fz * mv.Sfz[p];
+    }
 }
 // rho = alpha*rho1 + (1-alpha)*rho2 (cells and boundary) [REF region3d/alphaEqnSubCycle.H:35]
 static __global__ void k_rho(int N, int B, const double* __restrict__ a, const double* __restrict__ ab, double rho1, double rho2,
@@ -180,7 +192,8 @@ static __global__ void k_nhatf(MeshView mv, const double* __restrict__ gx, const
     }
     if (row < mv.B) {
         int p = mv.Fs + row, B = mv.B;
-        double fx = gb[row], fy = gb[B + row], fz = gb[2 * B + row];
+        int c = mv.bFaceRow[row];
+        double fx = bndFaceValue(mv, row, gx[c], gb[row]), fy = bndFaceValue(mv, row, gy[c], gb[B + row]), fz = bndFaceValue(mv, row, gz[c], gb[2 * B + row]);
         double den = sqrt(fx * fx + fy * fy + fz * fz) + deltaN;
         nHatf[p] = (fx / den) * mv.Sfx[p] + (fy / den) * mv.Sfy[p] + (fz / den) * mv.Sfz[p];
     }
@@ -197,7 +210,7 @@ static __global__ void k_muf(MeshView mv, const double* __restrict__ alpha, cons
             muf[pos] = af * rho1 * nu1 + (1.0 - af) * rho2 * nu2;
         END_FACES
     }
-    if (row < mv.B) { double af = fmin(fmax(alphab[row], 0.0), 1.0); muf[mv.Fs + row] = af * rho1 * nu1 + (1.0 - af) * rho2 * nu2; }
+    if (row < mv.B) { double af = fmin(fmax(bndFaceValue(mv, row, alpha[mv.bFaceRow[row]], alphab[row]), 0.0), 1.0); muf[mv.Fs + row] = af * rho1 * nu1 + (1.0 - af) * rho2 * nu2; }
 }
 // UEqn = ddt(rho,U) + div(rhoPhi,U) - laplacian(muEff,U) - (grad(U) & grad(muEff))  [REF region3d/UEqn.H:8-15]
 // one row pass: diag, final lower/upper of the owner faces, source (incl. the explicit gradient term)
@@ -246,7 +259,7 @@ static __global__ void __launch_bounds__(BLOCK) k_ueqn_row(MeshView mv, int upwi
     FOR_BND_FACES(mv, s, lane, b)
         int p = mv.Fs + b, B = mv.B;
         double S[3] = {mv.Sfx[p], mv.Sfy[p], mv.Sfz[p]};
-        double ub[3] = {Ub[b], Ub[B + b], Ub[2 * B + b]};
+        double ub[3] = {bndFaceValue(mv, b, ux, Ub[b]), bndFaceValue(mv, b, uy, Ub[B + b]), bndFaceValue(mv, b, uz, Ub[2 * B + b])};
 #pragma unroll
         for (int i = 0; i < 3; i++) {
 #pragma unroll
@@ -273,6 +286,16 @@ static __global__ void k_ueqn_boundary(MeshView mv, BCView bc, const double* __r
     if (b >= mv.B) return;
     int p = mv.Fs + b, t = bc.type[mv.bPatch[b]], B = mv.B;
     double pf = rhoPhi[p], pg = muf[p] * mv.magSf[p], dc = mv.dc[p];
+    if (t == B200_BC_PROCESSOR) {   // coupledFvPatchField: value coeffs (w, 1-w), gradient coeffs (-dc, +dc)
+        double w = mv.w[p];
+        for (int k = 0; k < 3; k++) {
+            int idx = k * B + b;
+            double dIC = pf * (1.0 * w), dBC = -pf * (1.0 * (1.0 - w));
+            double lIC = pg * (-1.0 * dc), lBC = -pg * dc;
+            uIC[idx] = dIC - lIC; uBC[idx] = dBC - lBC;
+        }
+        return;
+    }
     for (int k = 0; k < 3; k++) {
         int idx = k * B + b;
         double dIC = pf * bcValueIntCoeff(bc, t, b);
@@ -286,8 +309,8 @@ static __global__ void k_ueqn_boundary(MeshView mv, BCView bc, const double* __r
 // rUA = 1/UEqn.A() ; Unew = rUA*UEqn.H()  [REF region3d/pEqn.H:2,5] [UPSTREAM fvMatrix::A(), H(); lduMatrix::H]
 static __global__ void __launch_bounds__(BLOCK) k_ua_h(MeshView mv, const double* __restrict__ uDiag, const double* __restrict__ uLower,
         const double* __restrict__ uUpper, const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ sz,
-        const double* __restrict__ uIC, const double* __restrict__ uBC, const double* __restrict__ Ux, const double* __restrict__ Uy,
-        const double* __restrict__ Uz, double* __restrict__ rUA, double* __restrict__ Hx, double* __restrict__ Hy, double* __restrict__ Hz) {
+        const double* __restrict__ uIC, const double* __restrict__ uBC, const double* __restrict__ Ub, const double* __restrict__ Ux,
+        const double* __restrict__ Uy, const double* __restrict__ Uz, double* __restrict__ rUA, double* __restrict__ Hx, double* __restrict__ Hy, double* __restrict__ Hz) {
     ROW_PROLOGUE(mv)
     if (row >= mv.N) return;
     int B = mv.B;
@@ -320,6 +343,7 @@ static __global__ void __launch_bounds__(BLOCK) k_ua_h(MeshView mv, const double
     h0 = h0 + (l0 + sx[row]); h1 = h1 + (l1 + sy[row]); h2 = h2 + (l2 + sz[row]);
     FOR_BND_FACES(mv, s, lane, b)
         if (!mv.bCoupled[b]) { h0 = h0 + uBC[b]; h1 = h1 + uBC[B + b]; h2 = h2 + uBC[2 * B + b]; }
+        else { h0 = h0 + uBC[b] * Ub[b]; h1 = h1 + uBC[B + b] * Ub[B + b]; h2 = h2 + uBC[2 * B + b] * Ub[2 * B + b]; }   // boundaryCoeffs*patchNeighbourField
     END_BND
     h0 = h0 / V; h1 = h1 / V; h2 = h2 / V;
     rUA[row] = ra;
@@ -330,7 +354,8 @@ static __global__ void k_ub_assign(MeshView mv, BCView bc, const double* __restr
                                    const double* __restrict__ Uz, double* __restrict__ Ub) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= mv.B) return;
-    if (bc.type[mv.bPatch[b]] == B200_BC_FIXED_VALUE) return;
+    int t = bc.type[mv.bPatch[b]];
+    if (t == B200_BC_FIXED_VALUE || t == B200_BC_PROCESSOR) return;   // processor faces: halo swap of the new U
     int c = mv.bFaceRow[b], B = mv.B;
     Ub[b] = Ux[c]; Ub[B + b] = Uy[c]; Ub[2 * B + b] = Uz[c];
 }
@@ -338,7 +363,7 @@ static __global__ void k_ub_assign(MeshView mv, BCView bc, const double* __restr
 static __global__ void __launch_bounds__(BLOCK) k_phiU(MeshView mv, BCView bcU, double rDeltaT, const double* __restrict__ rUA,
         const double* __restrict__ Ux, const double* __restrict__ Uy, const double* __restrict__ Uz, const double* __restrict__ Ub,
         const double* __restrict__ U0x, const double* __restrict__ U0y, const double* __restrict__ U0z, const double* __restrict__ U0b,
-        const double* __restrict__ rho0, const double* __restrict__ rho0b, const double* __restrict__ phi0,
+        const double* __restrict__ rho0, const double* __restrict__ rho0b, const double* __restrict__ phi0, const double* __restrict__ rUAb,
         double* __restrict__ phiU, double* __restrict__ rUAf) {
     ROW_PROLOGUE(mv)
     if (row < mv.N) {
@@ -364,6 +389,22 @@ static __global__ void __launch_bounds__(BLOCK) k_phiU(MeshView mv, BCView bcU, 
     if (row < mv.B) {
         int b = row, p = mv.Fs + b, c = mv.bFaceRow[b], B = mv.B;
         double S0 = mv.Sfx[p], S1 = mv.Sfy[p], S2 = mv.Sfz[p];
+        if (mv.bCoupled[b]) {   // processor face: the internal-face formula with the neighbour rank's cell as N
+            double w = mv.w[p], rl = rUA[c], ru = rUAb[b], rArl = rl * rho0[c], rAru = ru * rho0b[b];
+            rUAf[p] = w * (rl - ru) + ru;
+            double fx = w * (Ux[c] - Ub[b]) + Ub[b], fy = w * (Uy[c] - Ub[B + b]) + Ub[B + b], fz = w * (Uz[c] - Ub[2 * B + b]) + Ub[2 * B + b];
+            double rArf = w * (rArl - rAru) + rAru;
+            double lx = rArl * U0x[c], ly = rArl * U0y[c], lz = rArl * U0z[c];
+            double qx = rAru * U0b[b], qy = rAru * U0b[B + b], qz = rAru * U0b[2 * B + b];
+            double gx = w * (lx - qx) + qx, gy = w * (ly - qy) + qy, gz = w * (lz - qz) + qz;
+            double px = w * (U0x[c] - U0b[b]) + U0b[b], py = w * (U0y[c] - U0b[B + b]) + U0b[B + b], pz = w * (U0z[c] - U0b[2 * B + b]) + U0b[2 * B + b];
+            double p0 = phi0[p];
+            double phiCorr = p0 - (px * S0 + py * S1 + pz * S2);
+            double coeff = 1.0 - fmin(fabs(phiCorr) / (fabs(p0) + FV_SMALL), 1.0);
+            double ddt = coeff * rDeltaT * (rArf * p0 - (gx * S0 + gy * S1 + gz * S2));
+            phiU[p] = (fx * S0 + fy * S1 + fz * S2) + ddt;
+            return;
+        }
         double rb = rUA[c];
         rUAf[p] = rb;
         double rArb = rb * rho0b[b];
@@ -407,7 +448,7 @@ static __global__ void k_adjust_scale(MeshView mv, BCView bcU, const double* __r
     if (f > 0.0) phiU[mv.Fs + b] = f * massCorr;
 }
 // phi = phiU + (interpolate(sigmaK)*snGrad(alpha1) - ghf*snGrad(rho))*rUAf*magSf  [REF region3d/pEqn.H:16-20]
-static __global__ void __launch_bounds__(BLOCK) k_phi(MeshView mv, BCView bcA, double sigma, const double* __restrict__ K,
+static __global__ void __launch_bounds__(BLOCK) k_phi(MeshView mv, BCView bcA, double sigma, const double* __restrict__ K, const double* __restrict__ Kb,
         const double* __restrict__ alpha, const double* __restrict__ alphab, const double* __restrict__ rho, const double* __restrict__ rhob,
         const double* __restrict__ ghf, const double* __restrict__ rUAf, const double* __restrict__ phiU, double* __restrict__ phi) {
     ROW_PROLOGUE(mv)
@@ -424,6 +465,7 @@ static __global__ void __launch_bounds__(BLOCK) k_phi(MeshView mv, BCView bcA, d
         int b = row, p = mv.Fs + b, c = mv.bFaceRow[b], t = bcA.type[mv.bPatch[b]];
         double dc = mv.dc[p];
         double sKf = sigma * K[c];
+        if (mv.bCoupled[b]) { double sKn = sigma * Kb[b]; sKf = mv.w[p] * (sKf - sKn) + sKn; }
         double sga = bcSnGrad(bcA, t, b, b, dc, alpha[c], alphab[b]);
         double sgr = bcSnGrad(bcA, t, b, b, dc, rho[c], rhob[b]);
         phi[p] = phiU[p] + (sKf * sga - ghf[p] * sgr) * rUAf[p] * mv.magSf[p];
@@ -453,13 +495,25 @@ static __global__ void k_p(int N, const double* __restrict__ pd, const double* _
 // ================================================================================================ Region3D
 Region3D::~Region3D() { if (hscal) cudaFreeHost(hscal); }
 
+bool Region3D::coupled() const { return rt().nRanks > 1 && meshHasProcessorPatches(*m); }
+void Region3D::haloScalar(const double* cellField, double* bdst) {
+    if (!coupled()) return;
+    haloPack(*m, cellField, haloSend.p);
+    haloExchange(*m, haloSend.p, bdst);
+}
+void Region3D::evalPdBC(const DevBC& bc, const double* psi, double* psib) {
+    if (m->B) B200_LAUNCH(k_bc_evaluate, gridFor(m->B), BLOCK, rt().stream, m->view(), bc.view(), 1, psi, (const double*)nullptr, (const double*)nullptr, psib);
+    haloScalar(psi, psib);
+}
 void Region3D::evalAlphaBC() {
     if (m->B) B200_LAUNCH(k_bc_evaluate, gridFor(m->B), BLOCK, rt().stream, m->view(), bcAlpha.view(), 1, (const double*)alpha.p,
                           (const double*)nullptr, (const double*)nullptr, alphab.p);
+    haloScalar(alpha, alphab);
 }
 void Region3D::evalUBC() {
     if (m->B) B200_LAUNCH(k_bc_evaluate, gridFor(m->B), BLOCK, rt().stream, m->view(), bcU.view(), 3, (const double*)Ux.p, (const double*)Uy.p,
                           (const double*)Uz.p, Ub.p);
+    haloScalar(Ux, Ub.p); haloScalar(Uy, Ub.p + m->B); haloScalar(Uz, Ub.p + 2 * (size_t)m->B);
 }
 
 void Region3D::create(DeviceMesh* mesh, const b200_region3d_controls& c, const b200_bc* a, const b200_bc* u, const b200_bc* pbc,
@@ -475,7 +529,7 @@ void Region3D::create(DeviceMesh* mesh, const b200_region3d_controls& c, const b
     bcPcorr.setTypes(*m, tp, 1);
     for (DevBuf<double>* b : {&alpha, &alpha0, &alphaStart, &pd, &rho, &rho0, &K, &rUA, &p, &gh, &uDiag, &pdDiag, &pdSource, &pcorr,
                               &Ux, &Uy, &Uz, &U0x, &U0y, &U0z, &Hx, &Hy, &Hz, &uSx, &uSy, &uSz}) { b->alloc(N); b->zero(); }
-    for (DevBuf<double>* b : {&alphab, &pdb, &rhob, &rho0b, &ic, &bcv, &pcorrb}) { b->alloc(B); b->zero(); }
+    for (DevBuf<double>* b : {&alphab, &pdb, &rhob, &rho0b, &ic, &bcv, &pcorrb, &Kb, &rUAb, &haloSend}) { b->alloc(B); b->zero(); }
     for (DevBuf<double>* b : {&Ub, &U0b, &uIC, &uBC}) { b->alloc(3 * B); b->zero(); }
     for (DevBuf<double>* b : {&phi, &phi0, &rhoPhi, &rhoPhiSum, &nHatf, &ghf, &phiAlpha, &phiU, &rUAf, &muf, &uLower, &uUpper, &pdUpper, &oneF}) { b->alloc(nf); b->zero(); }
     scal.alloc(64); scal.zero();
@@ -485,7 +539,7 @@ void Region3D::create(DeviceMesh* mesh, const b200_region3d_controls& c, const b
     cudaStream_t st = rt().stream;
     m->uploadCells(alpha1, alpha); m->uploadCellVec(U, Ux, Uy, Uz); m->uploadCells(pdHost, pd);
     evalAlphaBC(); evalUBC();
-    if (B) B200_LAUNCH(k_bc_evaluate, gridFor(B), BLOCK, st, mv, bcPd.view(), 1, (const double*)pd.p, (const double*)nullptr, (const double*)nullptr, pdb.p);
+    evalPdBC(bcPd, pd, pdb);
     int nmax = (int)std::max<size_t>(std::max(N, B), 1);
     B200_LAUNCH(k_init_phi, gridFor(nmax), BLOCK, st, mv, (const double*)Ux.p, (const double*)Uy.p, (const double*)Uz.p, (const double*)Ub.p, phi.p);
     B200_LAUNCH(k_rho, gridFor(nmax), BLOCK, st, (int)N, (int)B, (const double*)alpha.p, (const double*)alphab.p, c.rho1, c.rho2, rho.p, rhob.p);
@@ -495,7 +549,16 @@ void Region3D::create(DeviceMesh* mesh, const b200_region3d_controls& c, const b
     reconTensor(*m);
     double sV = 0;
     for (size_t i = 0; i < N; i++) sV += m->hostV[i];
-    deltaN = 1e-8 / std::pow(sV / (double)N, 1.0 / 3.0);
+    double nGlobal = (double)N;
+    if (rt().nRanks > 1) {   // average(mesh.V()) is a global average (gAverage)
+        double h2[2] = {sV, nGlobal};
+        B200_CHECK_CUDA(cudaMemcpyAsync(scal.p + 40, h2, 16, cudaMemcpyHostToDevice, st));
+        allReduce(scal.p + 40, 2, RED_SUM);
+        B200_CHECK_CUDA(cudaMemcpyAsync(h2, scal.p + 40, 16, cudaMemcpyDeviceToHost, st));
+        syncStream();
+        sV = h2[0]; nGlobal = h2[1];
+    }
+    deltaN = 1e-8 / std::pow(sV / nGlobal, 1.0 / 3.0);
     calculateK();   // interfaceProperties constructor [REF region3d/create3dFields.H:254-263]
     syncStream();
 }
@@ -509,8 +572,10 @@ void Region3D::calculateK() {
     B200_LAUNCH(k_grad_scalar, gridFor(N), BLOCK, st, mv, (const double*)alpha.p, (const double*)alphab.p, w.gx.p, w.gy.p, w.gz.p);
     if (B) B200_LAUNCH(k_grad_boundary, gridFor(B), BLOCK, st, mv, bcAlpha.view(), (const double*)alpha.p, (const double*)alphab.p,
                        (const double*)w.gx.p, (const double*)w.gy.p, (const double*)w.gz.p, w.gb.p);
+    haloScalar(w.gx, w.gb.p); haloScalar(w.gy, w.gb.p + B); haloScalar(w.gz, w.gb.p + 2 * (size_t)B);
     B200_LAUNCH(k_nhatf, gridFor(nmax), BLOCK, st, mv, (const double*)w.gx.p, (const double*)w.gy.p, (const double*)w.gz.p, (const double*)w.gb.p, deltaN, nHatf.p);
     B200_LAUNCH(k_surface_integrate, gridFor(N), BLOCK, st, mv, (const double*)nHatf.p, K.p, -1.0);
+    haloScalar(K, Kb);
 }
 
 // [REF region3d/alphaEqn.H:1-41]
@@ -526,8 +591,9 @@ void Region3D::alphaEqn(double dt) {
     for (int aCorr = 0; aCorr < ctl.nAlphaCorr; aCorr++) {
         { ScopedTimer t(T_FLUX);
           B200_LAUNCH(k_grad_scalar, gridFor(N), BLOCK, st, mv, (const double*)alpha.p, (const double*)alphab.p, w.gx.p, w.gy.p, w.gz.p);
+          haloScalar(w.gx, w.gb.p); haloScalar(w.gy, w.gb.p + B); haloScalar(w.gz, w.gb.p + 2 * (size_t)B);
           B200_LAUNCH(k_alpha_flux, gridFor(nmax), BLOCK, st, mv, (const double*)phi.p, (const double*)alpha.p, (const double*)alphab.p,
-                      (const double*)w.gx.p, (const double*)w.gy.p, (const double*)w.gz.p, (const double*)nHatf.p, ctl.cAlpha, (const double*)scal.p, phiAlpha.p); }
+                      (const double*)w.gx.p, (const double*)w.gy.p, (const double*)w.gz.p, (const double*)w.gb.p, (const double*)nHatf.p, ctl.cAlpha, (const double*)scal.p, phiAlpha.p); }
         evalAlphaBC();
         mulesExplicitDevice(*m, bcAlpha.view(), alpha, alphab, alpha0, phi, phiAlpha, dt, 1.0, 0.0, ctl.mulesIncludeOwn, 3, nullptr);
         evalAlphaBC();
@@ -536,6 +602,7 @@ void Region3D::alphaEqn(double dt) {
     // Info: weightedAverage / min / max [REF region3d/alphaEqn.H:36-40]
     int slot = 16 + 4 * (int)(alphaStats.size() / 3 % 8);
     B200_LAUNCH(k_alpha_stats, gridFor(nmax), BLOCK, st, mv, (const double*)alpha.p, (const double*)alphab.p, scal.p + slot, w.partials.p, w.counter.p);
+    if (rt().nRanks > 1) { allReduce(scal.p + slot, 2, RED_SUM); allReduce(scal.p + slot + 2, 1, RED_MIN); allReduce(scal.p + slot + 3, 1, RED_MAX); }
     B200_CHECK_CUDA(cudaMemcpyAsync(hscal + slot, scal.p + slot, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     alphaStats.push_back((double)slot); alphaStats.push_back(0); alphaStats.push_back(0);  // resolved after the next sync
     pendingStats.push_back(alphaStats.size() - 3);
@@ -578,14 +645,14 @@ void Region3D::solvePressureLike(const DevBC& bc, const double* gammaf, double* 
       } }
     b200_solver_controls sc{tol, relTol, ctl.minIter, ctl.maxIter};
     std::vector<double> hist;
-    b200_solver_perf perf = pcgSolveDevice(*m, pdDiag, pdUpper, nullptr, psi, pdSource, sc, keepHist ? &hist : nullptr);
+    b200_solver_perf perf = pcgSolveDevice(*m, pdDiag, pdUpper, coupled() ? bcv.p : nullptr, psi, pdSource, sc, keepHist ? &hist : nullptr);
     perfs.push_back(perf);
     if (keepHist) resHist.insert(resHist.end(), hist.begin(), hist.end());
     { ScopedTimer t(T_ASSEMBLY);
-      if (B) B200_LAUNCH(k_bc_evaluate, gridFor(B), BLOCK, st, mv, bc.view(), 1, (const double*)psi, (const double*)nullptr, (const double*)nullptr, psib);
+      evalPdBC(bc, psi, psib);
       if (subtractFlux)
           B200_LAUNCH(k_matrix_flux<true>, gridFor(nmax), BLOCK, st, mv, (const double*)pdUpper.p, (const double*)pdUpper.p, (const double*)ic.p,
-                      (const double*)bcv.p, (const double*)psi, phi.p); }
+                      (const double*)bcv.p, (const double*)psi, (const double*)psib, phi.p); }
 }
 
 // [REF region3d/correctPhi.H]
@@ -605,21 +672,22 @@ void Region3D::pEqn(int corr) {
     double rDeltaT = 1.0 / ctl.deltaT;
     { ScopedTimer t(T_UEQN);
       B200_LAUNCH(k_ua_h, gridFor(N), BLOCK, st, mv, (const double*)uDiag.p, (const double*)uLower.p, (const double*)uUpper.p, (const double*)uSx.p,
-                  (const double*)uSy.p, (const double*)uSz.p, (const double*)uIC.p, (const double*)uBC.p, (const double*)Ux.p, (const double*)Uy.p,
-                  (const double*)Uz.p, rUA.p, Hx.p, Hy.p, Hz.p);
+                  (const double*)uSy.p, (const double*)uSz.p, (const double*)uIC.p, (const double*)uBC.p, (const double*)Ub.p, (const double*)Ux.p,
+                  (const double*)Uy.p, (const double*)Uz.p, rUA.p, Hx.p, Hy.p, Hz.p);
       std::swap(Ux, Hx); std::swap(Uy, Hy); std::swap(Uz, Hz);   // U = rUA*UEqn.H()
-      if (B) B200_LAUNCH(k_ub_assign, gridFor(B), BLOCK, st, mv, bcU.view(), (const double*)Ux.p, (const double*)Uy.p, (const double*)Uz.p, Ub.p); }
+      if (B) B200_LAUNCH(k_ub_assign, gridFor(B), BLOCK, st, mv, bcU.view(), (const double*)Ux.p, (const double*)Uy.p, (const double*)Uz.p, Ub.p);
+      haloScalar(Ux, Ub.p); haloScalar(Uy, Ub.p + B); haloScalar(Uz, Ub.p + 2 * (size_t)B); haloScalar(rUA, rUAb); }
     { ScopedTimer t(T_ASSEMBLY);
       B200_LAUNCH(k_phiU, gridFor(nmax), BLOCK, st, mv, bcU.view(), rDeltaT, (const double*)rUA.p, (const double*)Ux.p, (const double*)Uy.p,
                   (const double*)Uz.p, (const double*)Ub.p, (const double*)U0x.p, (const double*)U0y.p, (const double*)U0z.p, (const double*)U0b.p,
-                  (const double*)rho0.p, (const double*)rho0b.p, (const double*)phi0.p, phiU.p, rUAf.p);
+                  (const double*)rho0.p, (const double*)rho0b.p, (const double*)phi0.p, (const double*)rUAb.p, phiU.p, rUAf.p);
       if (ctl.adjustPhi) {   // adjustPhi(phiU, U, p) [REF region3d/pEqn.H:14]
           B200_LAUNCH(k_adjust_bsums, gridFor(std::max(B, 1)), BLOCK, st, mv, bcU.view(), (const double*)phiU.p, scal.p + 1, w.partials.p, w.counter.p);
           B200_LAUNCH(k_abs_sum_faces, gridFor(std::max(N, 1)), BLOCK, st, mv, (const double*)phiU.p, scal.p + 4, w.partials.p, w.counter.p);
           if (rt().nRanks > 1) allReduce(scal.p + 1, 4, RED_SUM);
           if (B) B200_LAUNCH(k_adjust_scale, gridFor(B), BLOCK, st, mv, bcU.view(), (const double*)(scal.p + 1), phiU.p);
       }
-      B200_LAUNCH(k_phi, gridFor(nmax), BLOCK, st, mv, bcAlpha.view(), ctl.sigma, (const double*)K.p, (const double*)alpha.p, (const double*)alphab.p,
+      B200_LAUNCH(k_phi, gridFor(nmax), BLOCK, st, mv, bcAlpha.view(), ctl.sigma, (const double*)K.p, (const double*)Kb.p, (const double*)alpha.p, (const double*)alphab.p,
                   (const double*)rho.p, (const double*)rhob.p, (const double*)ghf.p, (const double*)rUAf.p, (const double*)phiU.p, phi.p); }
     for (int nonOrth = 0; nonOrth <= ctl.nNonOrthCorr; nonOrth++) {
         bool fin = (corr == ctl.nCorr - 1 && nonOrth == ctl.nNonOrthCorr);

@@ -22,7 +22,7 @@ struct DevBC {
 // scratch of the finite-volume operators, cached per mesh
 struct FvWorkspace {
     DevBuf<double> phiBD, lamA, lamB, flux, psiMaxn, psiMinn, sumPhip, mSumPhim, lamP0, lamM0, lamP1, lamM1;
-    DevBuf<double> gx, gy, gz, gb, partials, scal;
+    DevBuf<double> gx, gy, gz, gb, partials, scal, lamPn, lamMn, haloSend;
     DevBuf<double> stg[16];  // staging for the host-pointer API
     DevBuf<unsigned> counter;
     DevBuf<double> invT;
@@ -48,7 +48,7 @@ struct Region3D {
     DevBuf<double> alpha, alpha0, alphaStart, pd, rho, rho0, K, rUA, p, gh, uDiag, pdDiag, pdSource, pcorr;
     DevBuf<double> Ux, Uy, Uz, U0x, U0y, U0z, Hx, Hy, Hz, uSx, uSy, uSz;
     // boundary fields
-    DevBuf<double> alphab, pdb, rhob, rho0b, Ub, U0b, uIC, uBC, ic, bcv, pcorrb;
+    DevBuf<double> alphab, pdb, rhob, rho0b, Ub, U0b, uIC, uBC, ic, bcv, pcorrb, Kb, rUAb, haloSend;
     // face fields
     DevBuf<double> phi, phi0, rhoPhi, rhoPhiSum, nHatf, ghf, phiAlpha, phiU, rUAf, muf, uLower, uUpper, pdUpper, oneF;
     DevBuf<double> scal;  // device scalars: [0] maxPhic, [1..4] adjustPhi sums, [5..8] alpha stats, [9..11] contErr sums
@@ -72,6 +72,9 @@ struct Region3D {
     void correctPhi();
     void step();
     void resolveStats();
+    bool coupled() const;                                   // nRanks > 1 and the mesh has processor patches
+    void haloScalar(const double* cellField, double* bdst);  // patchNeighbourField of processor faces -> bdst[b]
+    void evalPdBC(const DevBC& bc, const double* psi, double* psib);
     void evalAlphaBC();
     void evalUBC();
 };
