@@ -167,6 +167,10 @@ def pinned(n):
 
 
 def run_ours(args):
+    try:
+        import torch  # noqa: F401  (first, so libb200foam.so binds to the NCCL torch bundles; pinned host buffers; torch.distributed plumbing)
+    except Exception:
+        pass
     from shallowinterfoam_b200 import capi
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     lib = capi.load()

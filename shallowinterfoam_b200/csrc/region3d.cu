@@ -280,14 +280,14 @@ static __global__ void __launch_bounds__(BLOCK) k_ueqn_row(MeshView mv, int upwi
     sx[row] = s0; sy[row] = s1; sz[row] = s2;
 }
 // boundary coefficients of UEqn: internalCoeffs = div - lap, boundaryCoeffs = div - lap  (per component, SoA [3B])
-static __global__ void k_ueqn_boundary(MeshView mv, BCView bc, const double* __restrict__ rhoPhi, const double* __restrict__ muf,
+static __global__ void k_ueqn_boundary(MeshView mv, BCView bc, int upwind, const double* __restrict__ rhoPhi, const double* __restrict__ muf,
                                        const double* __restrict__ Ub, double* __restrict__ uIC, double* __restrict__ uBC) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= mv.B) return;
     int p = mv.Fs + b, t = bc.type[mv.bPatch[b]], B = mv.B;
     double pf = rhoPhi[p], pg = muf[p] * mv.magSf[p], dc = mv.dc[p];
     if (t == B200_BC_PROCESSOR) {   // coupledFvPatchField: value coeffs (w, 1-w), gradient coeffs (-dc, +dc)
-        double w = mv.w[p];
+        double w = upwind ? (pf >= 0 ? 1.0 : 0.0) : mv.w[p];   // the convection scheme's own weights on the coupled patch
         for (int k = 0; k < 3; k++) {
             int idx = k * B + b;
             double dIC = pf * (1.0 * w), dBC = -pf * (1.0 * (1.0 - w));
@@ -627,7 +627,7 @@ void Region3D::assembleUEqn() {
     B200_LAUNCH(k_ueqn_row, gridFor(N), BLOCK, st, mv, ctl.divUScheme == B200_SCHEME_UPWIND ? 1 : 0, rDeltaT, (const double*)rho.p, (const double*)rho0.p,
                 (const double*)Ux.p, (const double*)Uy.p, (const double*)Uz.p, (const double*)Ub.p, (const double*)U0x.p, (const double*)U0y.p,
                 (const double*)U0z.p, (const double*)rhoPhi.p, (const double*)muf.p, uDiag.p, uLower.p, uUpper.p, uSx.p, uSy.p, uSz.p);
-    if (B) B200_LAUNCH(k_ueqn_boundary, gridFor(B), BLOCK, st, mv, bcU.view(), (const double*)rhoPhi.p, (const double*)muf.p, (const double*)Ub.p, uIC.p, uBC.p);
+    if (B) B200_LAUNCH(k_ueqn_boundary, gridFor(B), BLOCK, st, mv, bcU.view(), ctl.divUScheme == B200_SCHEME_UPWIND ? 1 : 0, (const double*)rhoPhi.p, (const double*)muf.p, (const double*)Ub.p, uIC.p, uBC.p);
 }
 
 void Region3D::solvePressureLike(const DevBC& bc, const double* gammaf, double* psi, double* psib, double tol, double relTol,

@@ -1,0 +1,126 @@
+"""Worker of tests/test_multirank.py: one process per rank (gloo, CPU).  Loads the SIMT-emulated test build of the library,
+routes its all-reduces / halo swaps through torch.distributed, and checks the decomposed path against the oracle."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from cases import channel_case, default_controls, oracle_mesh_of, random_spd  # noqa: E402
+from oracle import foam_oracle as fo, multirank_oracle as mro  # noqa: E402
+from shallowinterfoam_b200 import capi  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = capi.B200Lib(os.path.join(ROOT, "tests", "simt_emu", "libb200foam_emu.so"))
+    dp = C.POINTER(C.c_double)
+
+    @C.CFUNCTYPE(None, dp, C.c_int, C.c_int)
+    def allreduce(p, count, op):
+        a = np.ctypeslib.as_array(p, shape=(count,))
+        t = torch.from_numpy(a)
+        dist.all_reduce(t, op=[dist.ReduceOp.SUM, dist.ReduceOp.MAX, dist.ReduceOp.MIN][op])
+
+    @C.CFUNCTYPE(None, dp, dp, C.c_int, C.c_int)
+    def sendrecv(send, recv, count, peer):
+        s = torch.from_numpy(np.ctypeslib.as_array(send, shape=(count,)).copy())
+        r = torch.from_numpy(np.ctypeslib.as_array(recv, shape=(count,)))
+        req = dist.isend(s, peer)
+        dist.recv(r, peer)
+        req.wait()
+
+    lib.c.b200_emu_set_comm(allreduce, sendrecv)
+    lib.init(0, rank, world)
+
+    dims = (16, 4, 8); L = (5.0, 1.0, 2.0)
+    gpm = lib.polymesh_box(*dims, *L, weir=(0.45, 0.6, 0.3))
+    n = (world, 1, 1) if world != 4 else (2, 1, 2)
+    proc = gpm.decompose_simple(n)
+    subs = [gpm.submesh(proc, world, r) for r in range(world)]
+    pm = subs[rank]
+    gm = oracle_mesh_of(gpm)
+
+    # ---------------- a1/a4: decomposed Amul and PCG (block-Jacobi DIC) vs the N-rank oracle
+    diag, upper = random_spd(gm, seed=4, shift=(1e-3, 1e-2))
+    rng = np.random.default_rng(5)
+    psi = rng.uniform(0, 1, gm.N); b = rng.uniform(-1, 1, gm.N)
+    osubs = []
+    for s in subs:
+        om = oracle_mesh_of(s)
+        osubs.append(dict(mesh=om, patches=[(s.patchNames[p], int(s.patchStart[p]), int(s.patchSize[p]), int(s.patchNeighbRank[p])) for p in range(s.nPatches)]))
+    def restrict(s):
+        F = s.nInternalFaces
+        d = diag[s.cellMap]; u = upper[s.faceMap[:F]]
+        bou = np.zeros(s.nBoundaryFaces)
+        for p in range(s.nPatches):
+            if s.patchNeighbRank[p] >= 0:
+                sl = slice(s.patchStart[p] - F, s.patchStart[p] - F + s.patchSize[p])
+                bou[sl] = -upper[s.faceMap[s.patchStart[p]:s.patchStart[p] + s.patchSize[p]]]
+        return d, u, bou
+    mats = [restrict(s) for s in subs]
+    ldu = pm.ldu()
+    d, u, bou = mats[rank]
+    A_loc = ldu.amul(d, u, psi[pm.cellMap], bou=bou)                      # halo over the (emulated) comm layer
+    A_ref = mro.amul_multi(osubs, [m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], [psi[s.cellMap] for s in subs])[rank]
+    assert np.array_equal(A_loc, A_ref), "decomposed Amul differs from the N-rank oracle"
+    A_ser = fo.amul(gm, diag, upper, upper, psi)[pm.cellMap]
+    assert np.allclose(A_loc, A_ser, rtol=1e-13, atol=1e-13), "decomposed Amul differs from the serial Amul"
+    xg, pg, hg = ldu.pcg_solve(d, u, np.zeros(pm.nCells), b[pm.cellMap], tol=1e-9, maxIter=300, bou=bou)
+    xo, po, ho = mro.pcg_solve_multi(osubs, [m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats],
+                                     [np.zeros(s.nCells) for s in subs], [b[s.cellMap] for s in subs], tol=1e-9, maxIter=300)
+    assert pg.nIterations == po["nIterations"], (pg.nIterations, po["nIterations"])
+    assert np.allclose(hg, ho, rtol=1e-8, atol=1e-13 * ho[0])
+    assert np.abs(xg - xo[rank]).max() <= 1e-10 * np.abs(xo[rank]).max()
+    xs, ps, hs = fo.pcg_solve(gm, diag, upper, np.zeros(gm.N), b, tol=1e-9, maxIter=300)
+    assert np.abs(xg - xs[pm.cellMap]).max() <= 1e-6 * np.abs(xs).max()      # same solution, different (rank-local) preconditioner
+
+    # ---------------- the decomposed region step vs the serial oracle step (tight solver tolerances)
+    cs = channel_case(gpm, *L)
+    def tight(c):
+        c.pdTol = 1e-13; c.pdRelTol = 0.0; c.pdFinalTol = 1e-13; c.pcorrTol = 1e-13; c.maxIter = 2000
+        return c
+    ro = fo.Region(gm, tight(default_controls(fo.OrcControls)), fo.BC(gm, cs["tA"], 1, cs["rvA"]), fo.BC(gm, cs["tU"], 3, cs["rvU"]),
+                   fo.BC(gm, cs["tP"], 1), cs["alpha"], cs["U"], cs["pd"])
+    F = pm.nInternalFaces
+    bmap = pm.faceMap[F:]                                   # global face of every local boundary face
+    PR = 3
+    def types(t):
+        return [PR if pm.patchNeighbRank[p] >= 0 else t[gpm.patchNames.index(pm.patchNames[p])] for p in range(pm.nPatches)]
+    phys = np.array([pm.patchNeighbRank[p] < 0 for p in range(pm.nPatches) for _ in range(pm.patchSize[p])])
+    rvA = np.zeros(pm.nBoundaryFaces); rvU = np.zeros((pm.nBoundaryFaces, 3))
+    gB0 = gpm.nInternalFaces
+    rvA[phys] = cs["rvA"][bmap[phys] - gB0]; rvU[phys] = cs["rvU"][bmap[phys] - gB0]
+    dm = pm.device_mesh()                                    # collective: halo swap of cell centres
+    rg = dm.region3d(tight(default_controls(capi.Region3dControls)), dm.bc(types(cs["tA"]), 1, rvA), dm.bc(types(cs["tU"]), 3, rvU),
+                     dm.bc(types(cs["tP"]), 1), cs["alpha"][pm.cellMap], cs["U"][pm.cellMap], cs["pd"][pm.cellMap])
+    def check(tag, tol):
+        fo_, fg = ro.fields(), rg.fields()
+        for k in ("alpha1", "U", "pd", "p", "rho"):
+            ref = fo_[k][pm.cellMap]
+            scale = max(np.abs(fo_[k]).max(), 1e-300)
+            err = np.abs(ref - fg[k]).max() / scale
+            assert err <= tol, (tag, k, err)
+        sign = np.where(pm.faceFlip != 0, -1.0, 1.0)
+        err = np.abs(fo_["phi"][pm.faceMap] * sign - fg["phi"]).max() / np.abs(fo_["phi"]).max()
+        assert err <= tol, (tag, "phi", err)
+    check("init", 1e-13)
+    ro.correct_phi(); rg.correct_phi()
+    check("correctPhi", 1e-9)
+    for s in range(2):
+        ro.step(); rg.step()
+        check("step%d" % s, 1e-7)
+    so, sg = ro.alpha_stats()[-1], rg.alpha_stats()[-1]
+    assert np.allclose(so, sg, rtol=1e-8, atol=1e-12)
+    dist.barrier()
+    if rank == 0:
+        print("MULTIRANK_OK world=%d" % world)
+
+
+if __name__ == "__main__":
+    main()
