@@ -104,6 +104,9 @@ int b200_ldu_get_or_create(const void* key, int32_t nCells, int32_t nFaces, cons
 int b200_ldu_release(b200_ldu_t* ldu);
 /* renumbering used on the device: rowCell[row] = original cell of device row `row`; level[cell] = forward DIC level */
 int b200_ldu_get_renumbering(const b200_ldu_t* ldu, int32_t* rowCell, int32_t* cellLevel, int32_t* nLevels);
+/* DIC tiles of the device row order: rows are ordered (tile, level, original cell); tileStart[nTiles+1].
+ * Pass tileStart = NULL to query the sizes only. */
+int b200_ldu_get_tiling(const b200_ldu_t* ldu, int32_t* bandLevels, int32_t* tileRows, int32_t* nTiles, int32_t* tileStart);
 /* derived addressing, for bit-exact parity with lduAddressing::ownerStartAddr/losortAddr/losortStartAddr */
 int b200_ldu_get_addressing(const b200_ldu_t* ldu, int32_t* ownerStart, int32_t* losort, int32_t* losortStart);
 

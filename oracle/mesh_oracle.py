@@ -323,6 +323,26 @@ def level_renumbering(lower, upper, N):
     return lev, perm, inv
 
 
+def tile_renumbering(lower, upper, N, band_levels=16, tile_rows=1024):
+    """DIC tiling of the device rows (this repo's own design, DESIGN.md section 4): band = level // band_levels; inside a band
+    the cells in ascending original index are cut into chunks of tile_rows; tile = (band, chunk) numbered band-major;
+    device row order = (tile, level, original index).  Returns level, rowCell, cellRow, tileStart."""
+    lev = forward_levels(lower, upper, N)
+    band = lev // band_levels
+    idx = np.arange(N)
+    by_band = np.lexsort((idx, band))                       # band-major, ascending index inside
+    rank_in_band = np.empty(N, dtype=np.int64)
+    bstart = np.searchsorted(band[by_band], np.arange(band.max() + 2 if N else 1))
+    rank_in_band[by_band] = np.arange(N) - np.repeat(bstart[:-1], np.diff(bstart))
+    chunk = rank_in_band // tile_rows
+    row_order = np.lexsort((idx, lev, chunk, band)).astype(np.int32)   # (band, chunk, level, index)
+    cell_row = np.empty(N, dtype=np.int32)
+    cell_row[row_order] = np.arange(N, dtype=np.int32)
+    key = band[row_order].astype(np.int64) * (chunk.max() + 1 if N else 1) + chunk[row_order]
+    tile_start = np.concatenate([[0], np.nonzero(np.diff(key))[0] + 1, [N]]).astype(np.int32) if N else np.zeros(1, np.int32)
+    return lev, row_order, cell_row, tile_start
+
+
 # ----------------------------------------------------------------------------
 # decomposePar-style sub-mesh construction for `simple` decomposition
 # [UPSTREAM applications/utilities/parallelProcessing/decomposePar/domainDecomposition*.C]

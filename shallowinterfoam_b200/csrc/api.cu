@@ -153,6 +153,15 @@ int b200_ldu_get_renumbering(const b200_ldu_t* ldu, int32_t* rowCell, int32_t* c
     if (nLevels) *nLevels = m->nLevels;
     API_END
 }
+int b200_ldu_get_tiling(const b200_ldu_t* ldu, int32_t* bandLevels, int32_t* tileRows, int32_t* nTiles, int32_t* tileStart) {
+    API_BEGIN
+    const DeviceMesh* m = asMesh(ldu);
+    if (bandLevels) *bandLevels = m->bandLevels;
+    if (tileRows) *tileRows = m->tileRows;
+    if (nTiles) *nTiles = m->nTiles;
+    if (tileStart) memcpy(tileStart, m->tileStart.data(), 4 * m->tileStart.size());
+    API_END
+}
 int b200_ldu_get_addressing(const b200_ldu_t* ldu, int32_t* ownerStart, int32_t* losort, int32_t* losortStart) {
     API_BEGIN
     const DeviceMesh* m = asMesh(ldu);

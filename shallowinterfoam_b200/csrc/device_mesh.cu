@@ -52,9 +52,15 @@ void DeviceMesh::build(int32_t nCells, int32_t nFaces, const int32_t* lo, const 
     for (int f = 0; f < F; f++)
         B200_REQUIRE(lower[f] >= 0 && upper[f] < N, B200_ERR_ARG, "lduAddressing label out of range");
     for (int b = 0; b < B; b++) B200_REQUIRE(fc[b] >= 0 && fc[b] < N, B200_ERR_ARG, "faceCells label out of range");
+    bandLevels = std::max(1, (int)rt().opt("sweep_band_levels", 16));
+    tileRows = std::max(32, (int)rt().opt("sweep_tile_rows", 1024));
     try {
-        levelRenumbering(N, lower.data(), upper.data(), F, level, rowCell, cellRow, nLevels);
+        tileRenumbering(N, lower.data(), upper.data(), F, bandLevels, tileRows, SWEEP_BLOCK, level, rowCell, cellRow, nLevels,
+                        tileStart, tileSegStart, segRow);
     } catch (const std::exception& e) { throw Error(B200_ERR_ARG, e.what()); }
+    nTiles = (int)tileStart.size() - 1;
+    B200_REQUIRE(tileRows <= SWEEP_TILE_MAX, B200_ERR_ARG, "sweep_tile_rows too large");
+    dTileStart.upload(tileStart); dTileSegStart.upload(tileSegStart); dSegRow.upload(segRow);
     lduDerived(N, lower, upper, ownerStart, losort, losortStart);
     levelStart.assign(nLevels + 1, 0);
     for (int c = 0; c < N; c++) levelStart[level[c] + 1]++;

@@ -47,6 +47,16 @@ __device__ __forceinline__ int facePosOf(const MeshView& mv, int pk, int& l) {
     return mv.sliceOff[l >> 5] + (k << 5) + (l & 31);
 }
 
+constexpr int SWEEP_BLOCK = 128;      // threads per DIC tile CTA = longest level segment handled in one step
+constexpr int SWEEP_TILE_MAX = 2048;  // rows per tile held in shared memory
+
+struct TileView {  // DIC tiles handed to the sweep kernels
+    int nTiles;
+    const int* tileStart;     // [nTiles+1] first row of each tile
+    const int* tileSegStart;  // [nTiles+1] CSR into segRow
+    const int* segRow;        // [nSegs+1] first row of each level segment (segments never exceed SWEEP_BLOCK rows)
+};
+
 struct PcgWorkspace;  // pcg.cu
 
 struct DeviceMesh {
@@ -58,7 +68,11 @@ struct DeviceMesh {
     std::vector<int32_t> level, rowCell, cellRow;
     std::vector<int32_t> ownerStart, losort, losortStart;
     std::vector<int32_t> facePosHost;      // [F] slot of original face
-    std::vector<int32_t> levelStart;       // [nLevels+1] first row of each level
+    std::vector<int32_t> levelStart;       // [nLevels+1] number of cells below each level (diagnostic)
+    // DIC tiles (host_mesh.h tileRenumbering): rows are ordered (tile, level, original index)
+    int bandLevels = 16, tileRows = 1024, nTiles = 0;
+    std::vector<int32_t> tileStart, tileSegStart, segRow;
+    DevBuf<int> dTileStart, dTileSegStart, dSegRow;
     DevBuf<int> dSliceOff, dNbrOff, dUpIdx, dLoPk, dBBase, dBRowStart, dBRowFaces, dBFaceRow, dBPatch, dBCoupled;
     DevBuf<unsigned> dBMask;
     DevBuf<int> dSlotFace, dFacePos, dRowCell, dCellRow;
@@ -77,6 +91,7 @@ struct DeviceMesh {
     void setGeometry(const double* Sf, const double* magSf, const double* Cf, const double* C, const double* V,
                      const double* w, const double* dc);
     MeshView view() const;
+    TileView tiles() const { return TileView{nTiles, dTileStart.p, dTileSegStart.p, dSegRow.p}; }
     void coupleGeometry();   // collective: processor-face weights/deltaCoeffs/neighbour centres from a halo swap of C
     size_t nFaceField() const { return (size_t)Fs + B; }
 

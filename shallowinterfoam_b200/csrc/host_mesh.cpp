@@ -294,4 +294,38 @@ void levelRenumbering(int32_t N, const int32_t* lower, const int32_t* upper, int
     for (int32_t c = 0; c < N; c++) { int32_t r = start[level[c]]++; rowCell[r] = c; cellRow[c] = r; }
 }
 
+void tileRenumbering(int32_t N, const int32_t* lower, const int32_t* upper, int32_t F, int bandLevels, int tileRows, int maxSeg,
+                     std::vector<int32_t>& level, std::vector<int32_t>& rowCell, std::vector<int32_t>& cellRow, int32_t& nLevels,
+                     std::vector<int32_t>& tileStart, std::vector<int32_t>& tileSegStart, std::vector<int32_t>& segRow) {
+    std::vector<int32_t> lvRow, lvCell;
+    levelRenumbering(N, lower, upper, F, level, lvRow, lvCell, nLevels);   // level[] + validity checks
+    int nBands = (nLevels + bandLevels - 1) / bandLevels;
+    // cells of each band in ascending original index (counting sort by band keeps index order)
+    std::vector<int32_t> bandStart(nBands + 1, 0);
+    for (int32_t c = 0; c < N; c++) bandStart[level[c] / bandLevels + 1]++;
+    for (int b = 0; b < nBands; b++) bandStart[b + 1] += bandStart[b];
+    std::vector<int32_t> byBand(N), cur(bandStart.begin(), bandStart.end() - 1);
+    for (int32_t c = 0; c < N; c++) byBand[cur[level[c] / bandLevels]++] = c;
+    rowCell.resize(N); cellRow.resize(N);
+    tileStart.assign(1, 0); tileSegStart.assign(1, 0); segRow.clear();
+    int32_t row = 0;
+    std::vector<int32_t> cnt(bandLevels + 1);
+    for (int b = 0; b < nBands; b++)
+        for (int32_t c0 = bandStart[b]; c0 < bandStart[b + 1]; c0 += tileRows) {
+            int32_t c1 = std::min<int32_t>(c0 + tileRows, bandStart[b + 1]);
+            // inside the tile: stable counting sort by level (keeps ascending index inside a level)
+            std::fill(cnt.begin(), cnt.end(), 0);
+            for (int32_t i = c0; i < c1; i++) cnt[level[byBand[i]] - b * bandLevels + 1]++;
+            for (int t = 0; t < bandLevels; t++) cnt[t + 1] += cnt[t];
+            std::vector<int32_t> pos(cnt.begin(), cnt.end() - 1);
+            for (int32_t i = c0; i < c1; i++) { int32_t c = byBand[i]; int32_t r = row + pos[level[c] - b * bandLevels]++; rowCell[r] = c; cellRow[c] = r; }
+            for (int t = 0; t < bandLevels; t++)
+                for (int32_t s0 = cnt[t]; s0 < cnt[t + 1]; s0 += maxSeg) segRow.push_back(row + s0);
+            row += c1 - c0;
+            tileStart.push_back(row);
+            tileSegStart.push_back((int32_t)segRow.size());
+        }
+    segRow.push_back(N);
+}
+
 }  // namespace b200

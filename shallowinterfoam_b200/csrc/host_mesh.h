@@ -58,4 +58,14 @@ void levelRenumbering(int32_t nCells, const int32_t* lower, const int32_t* upper
                       std::vector<int32_t>& level, std::vector<int32_t>& rowCell, std::vector<int32_t>& cellRow,
                       int32_t& nLevels);
 
+// DIC tiling: cells are grouped into bands of `bandLevels` consecutive forward levels; inside a band the
+// cells, in ascending original index, are cut into chunks of `tileRows`; tile = (band, chunk), numbered band-major.  Every
+// dependency l -> u (l < u, level(l) < level(u)) goes to the same or a LATER tile, so tiles processed in order never deadlock.
+// Device row order = (tile, level, original index).  tileSegStart/segRow: CSR of the per-tile level segments (segments longer
+// than `maxSeg` rows are split); segRow has one extra entry (= nCells).
+void tileRenumbering(int32_t nCells, const int32_t* lower, const int32_t* upper, int32_t nFaces, int bandLevels, int tileRows,
+                     int maxSeg, std::vector<int32_t>& level, std::vector<int32_t>& rowCell, std::vector<int32_t>& cellRow,
+                     int32_t& nLevels, std::vector<int32_t>& tileStart, std::vector<int32_t>& tileSegStart,
+                     std::vector<int32_t>& segRow);
+
 }  // namespace b200

@@ -267,219 +267,6 @@ static __global__ void __launch_bounds__(BLOCK) k_pcg_xr_update(int N, double* _
     gridFinalize<1, OpSum>(gridDim.x, partials, counter, &sc->sumMagR);
 }
 
-// ----------------------------------------------------------------------------- a2/a3: data-flow DIC sweeps
-// Rows are stored level-major, so every dependency of a row has a SMALLER row index (forward sweep) or a
-// LARGER one (backward sweep).  Chunks of blockDim rows are handed out in that order by an atomic ticket, so a
-// running warp only ever waits on rows owned by warps that are already running: no grid barrier, no
-// co-residency requirement.  Readiness is carried by the data itself: outputs are pre-filled with a NaN
-// sentinel and published with one 64-bit store; consumers poll L2 until the value is not the sentinel.
-// Within a row the updates are applied in upstream's face order => bitwise the sequential result.
-struct SweepCtl { unsigned* ticket; unsigned* done; };
-
-__device__ __forceinline__ int nextChunk(SweepCtl c) {
-    __shared__ int sChunk;
-    __syncthreads();
-    if (threadIdx.x == 0) sChunk = (int)atomicAdd(c.ticket, 1u);
-    __syncthreads();
-    return sChunk;
-}
-__device__ __forceinline__ void sweepExit(SweepCtl c) {
-    if (threadIdx.x == 0) {
-        unsigned d = atomicInc(c.done, gridDim.x - 1);
-        if (d == gridDim.x - 1) { *c.ticket = 0u; __threadfence(); }
-    }
-}
-
-// The sweeps first load everything that does not depend on other rows (dependency indices, coefficients) into
-// registers, then poll ALL outstanding dependencies with independent loads (one L2 round trip per poll) and apply the
-// updates in upstream's order once they have all arrived.  Rows with more than SWEEP_MAXD dependencies (polyhedral
-// cells) take the generic one-at-a-time path.
-#define SWEEP_MAXD 8
-
-// returns when every lane of the warp has published; `apply` is called once per lane with the gathered values
-#define SWEEP_POLL_AND_PUBLISH(src, APPLY_AND_PUBLISH)                                        \
-    {                                                                                         \
-        unsigned pend = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);                         \
-        for (;;) {                                                                            \
-            if (!done) {                                                                      \
-                _Pragma("unroll") for (int j = 0; j < SWEEP_MAXD; j++)                        \
-                    if ((pend >> j) & 1u) {                                                   \
-                        double t = ldPoll((src) + dl[j]);                                     \
-                        if (!isSentinel(t)) { dv[j] = t; pend &= ~(1u << j); }                \
-                    }                                                                         \
-                if (!pend) { APPLY_AND_PUBLISH; done = true; }                                \
-            }                                                                                 \
-            if (__all_sync(0xffffffffu, done)) break;                                         \
-        }                                                                                     \
-    }
-
-// calcReciprocalD: Dt[row] = diag - sum_{nbr-side faces asc} upper_f^2 / Dt[l] ; rD = 1/Dt
-static __global__ void __launch_bounds__(BLOCK) k_dic_calc_rd(MeshView mv, const double* __restrict__ diag,
-                                                        const double* __restrict__ upS, double* Dt, double* __restrict__ rD,
-                                                        SweepCtl ctl, int nChunks) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, spc = blockDim.x >> 5;
-    for (;;) {
-        int chunk = nextChunk(ctl);
-        if (chunk >= nChunks) break;
-        int s = chunk * spc + warp;
-        if (s >= mv.nSlices) continue;
-        int row = (s << 5) + lane;
-        bool done = row >= mv.N;
-        double d = done ? 0.0 : diag[row];
-        int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5;
-        if (nbw <= SWEEP_MAXD) {
-            int dl[SWEEP_MAXD]; double dc[SWEEP_MAXD], dv[SWEEP_MAXD]; int cnt = 0;
-#pragma unroll
-            for (int j = 0; j < SWEEP_MAXD; j++) {
-                dl[j] = 0; dc[j] = 0.0; dv[j] = 0.0;
-                if (j < nbw && !done) {
-                    int pk = mv.loPk[nb0 + (j << 5) + lane];
-                    if (pk >= 0) { int l; int pos = facePosOf(mv, pk, l); dl[j] = l; dc[j] = upS[pos]; cnt = j + 1; }
-                }
-            }
-            SWEEP_POLL_AND_PUBLISH(Dt, {
-                _Pragma("unroll") for (int j = 0; j < SWEEP_MAXD; j++) if (j < cnt) d = d - dc[j] * dc[j] / dv[j];
-                stPublish(Dt + row, d); rD[row] = 1.0 / d; })
-        } else {
-            int j = 0;
-            for (;;) {
-                if (!done) {
-                    while (j < nbw) {
-                        int pk = mv.loPk[nb0 + (j << 5) + lane];
-                        if (pk < 0) { j = nbw; break; }
-                        int l; int pos = facePosOf(mv, pk, l);
-                        double v = ldPoll(Dt + l);
-                        if (isSentinel(v)) break;
-                        double u = upS[pos];
-                        d = d - u * u / v;
-                        j++;
-                    }
-                    if (j >= nbw) { stPublish(Dt + row, d); rD[row] = 1.0 / d; done = true; }
-                }
-                if (__all_sync(0xffffffffu, done)) break;
-            }
-        }
-    }
-    sweepExit(ctl);
-}
-
-// forward: y[row] = rD*rA - sum_{nbr-side faces asc} (rD[row]*upper_f)*y[l]
-static __global__ void __launch_bounds__(BLOCK) k_dic_fwd(MeshView mv, const double* __restrict__ rD,
-                                                    const double* __restrict__ upS, const double* __restrict__ rA,
-                                                    double* y, SweepCtl ctl, int nChunks, const PcgScalars* sc) {
-    if (sc && sc->stop) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, spc = blockDim.x >> 5;
-    for (;;) {
-        int chunk = nextChunk(ctl);
-        if (chunk >= nChunks) break;
-        int s = chunk * spc + warp;
-        if (s >= mv.nSlices) continue;
-        int row = (s << 5) + lane;
-        bool done = row >= mv.N;
-        double rd = done ? 0.0 : rD[row];
-        double w = done ? 0.0 : rd * rA[row];
-        int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5;
-        if (nbw <= SWEEP_MAXD) {
-            int dl[SWEEP_MAXD]; double dc[SWEEP_MAXD], dv[SWEEP_MAXD]; int cnt = 0;
-#pragma unroll
-            for (int j = 0; j < SWEEP_MAXD; j++) {
-                dl[j] = 0; dc[j] = 0.0; dv[j] = 0.0;
-                if (j < nbw && !done) {
-                    int pk = mv.loPk[nb0 + (j << 5) + lane];
-                    if (pk >= 0) { int l; int pos = facePosOf(mv, pk, l); dl[j] = l; dc[j] = rd * upS[pos]; cnt = j + 1; }
-                }
-            }
-            SWEEP_POLL_AND_PUBLISH(y, {
-                _Pragma("unroll") for (int j = 0; j < SWEEP_MAXD; j++) if (j < cnt) w = w - dc[j] * dv[j];
-                stPublish(y + row, w); })
-        } else {
-            int j = 0;
-            for (;;) {
-                if (!done) {
-                    while (j < nbw) {
-                        int pk = mv.loPk[nb0 + (j << 5) + lane];
-                        if (pk < 0) { j = nbw; break; }
-                        int l; int pos = facePosOf(mv, pk, l);
-                        double v = ldPoll(y + l);
-                        if (isSentinel(v)) break;
-                        w = w - rd * upS[pos] * v;
-                        j++;
-                    }
-                    if (j >= nbw) { stPublish(y + row, w); done = true; }
-                }
-                if (__all_sync(0xffffffffu, done)) break;
-            }
-        }
-    }
-    sweepExit(ctl);
-}
-
-// backward: z[row] = y[row] - sum_{owner faces DESC} (rD[row]*upper_f)*z[u] ; y[row] <- sentinel ;
-// per-chunk partial of sum(z*rA) (fixed rows per partial => deterministic) -> sc->wArA
-static __global__ void __launch_bounds__(BLOCK) k_dic_bwd(MeshView mv, const double* __restrict__ rD,
-                                                    const double* __restrict__ upS, const double* __restrict__ rA,
-                                                    double* y, double* z, SweepCtl ctl, int nChunks, PcgScalars* sc,
-                                                    double* partials, unsigned* counter) {
-    if (sc && sc->stop) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, spc = blockDim.x >> 5;
-    for (;;) {
-        int chunk = nextChunk(ctl);
-        if (chunk >= nChunks) break;
-        int s = (nChunks - 1 - chunk) * spc + warp;
-        double dotv = 0.0;
-        if (s < mv.nSlices) {
-            int row = (s << 5) + lane;
-            bool done = row >= mv.N;
-            double rd = done ? 0.0 : rD[row];
-            double w = done ? 0.0 : y[row];
-            double ra = done ? 0.0 : rA[row];
-            int so0 = mv.sliceOff[s], ow = (mv.sliceOff[s + 1] - so0) >> 5;
-            if (ow <= SWEEP_MAXD) {
-                int dl[SWEEP_MAXD]; double dc[SWEEP_MAXD], dv[SWEEP_MAXD]; int cnt = 0;
-#pragma unroll
-                for (int j = 0; j < SWEEP_MAXD; j++) { dl[j] = 0; dc[j] = 0.0; dv[j] = 0.0; }
-                // application order = descending face index: walk k downwards, pack the real entries
-                for (int k = ow - 1; k >= 0; k--) {
-                    if (done) break;
-                    int pos = so0 + (k << 5) + lane;
-                    int u = mv.upIdx[pos];
-                    if (u >= 0) {
-                        double c = rd * upS[pos];
-#pragma unroll
-                        for (int j = 0; j < SWEEP_MAXD; j++) if (j == cnt) { dl[j] = u; dc[j] = c; }
-                        cnt++;
-                    }
-                }
-                SWEEP_POLL_AND_PUBLISH(z, {
-                    _Pragma("unroll") for (int j = 0; j < SWEEP_MAXD; j++) if (j < cnt) w = w - dc[j] * dv[j];
-                    stPublish(z + row, w); y[row] = sentinel(); dotv = w * ra; })
-            } else {
-                int k = ow - 1;
-                for (;;) {
-                    if (!done) {
-                        while (k >= 0) {
-                            int pos = so0 + (k << 5) + lane;
-                            int u = mv.upIdx[pos];
-                            if (u >= 0) {
-                                double v = ldPoll(z + u);
-                                if (isSentinel(v)) break;
-                                w = w - rd * upS[pos] * v;
-                            }
-                            k--;
-                        }
-                        if (k < 0) { stPublish(z + row, w); y[row] = sentinel(); dotv = w * ra; done = true; }
-                    }
-                    if (__all_sync(0xffffffffu, done)) break;
-                }
-            }
-        }
-        if (partials) {
-            double v[1] = {dotv};
-            gridReduce<1, OpSum>(v, nChunks - 1 - chunk, nChunks, partials, counter, nullptr);
-        }
-    }
-    if (partials) gridFinalize<1, OpSum>(nChunks, partials, counter, &sc->wArA);
-    sweepExit(ctl);
-}
-
 }  // namespace b200
+
+#include "dic_kernels.cuh"

@@ -36,7 +36,7 @@ PcgWorkspace& pcgWorkspace(DeviceMesh& m) {
     size_t N = m.N;
     w->pA.alloc(N); w->wA.alloc(N); w->rA.alloc(N); w->y.alloc(N); w->z.alloc(N); w->rD.alloc(N); w->Dt.alloc(N);
     int nBlocks = gridFor(m.N) + 1;
-    w->partials.alloc(3 * (size_t)nBlocks + 8);
+    w->partials.alloc(3 * (size_t)std::max(nBlocks, m.nTiles) + 8);
     w->sc.alloc(1); w->counters.alloc(4); w->counters.zero();
     B200_CHECK_CUDA(cudaMallocHost((void**)&w->hsc, 2 * sizeof(PcgScalars)));
     for (auto& e : w->ev) B200_CHECK_CUDA(cudaEventCreate(&e));
@@ -52,14 +52,11 @@ PcgWorkspace& pcgWorkspace(DeviceMesh& m) {
 }
 
 static SweepCtl sweepCtl(PcgWorkspace& w) { return SweepCtl{w.counters.p + 1, w.counters.p + 2}; }
-// CTAs of a data-flow sweep: enough to keep `sweep_window` levels in flight (the rest would only poll L2)
-static int sweepGridOf(const DeviceMesh& m, const PcgWorkspace& w) {
+// CTAs of a tiled sweep: one CTA per tile in flight; tiles are handed out in order by ticket, so any grid size is deadlock-free
+static int sweepGridOf(const DeviceMesh& m, const PcgWorkspace&) {
     int forced = (int)rt().opt("sweep_grid", 0);
-    if (forced > 0) return std::min(forced, std::max(1, gridFor(m.N)));
-    double window = rt().opt("sweep_window", 4.0);
-    int want = (int)(window * w.rowsPerLevel / BLOCK) + 1;
-    want = std::max(want, (int)rt().opt("sweep_min_grid", 32));
-    return std::max(1, std::min(std::min(want, gridFor(m.N)), rt().numSMs * 4));
+    int g = forced > 0 ? forced : rt().numSMs * (int)rt().opt("sweep_ctas_per_sm", 8);
+    return std::max(1, std::min(g, std::max(1, m.nTiles)));
 }
 
 void amulDevice(DeviceMesh& m, const double* diag, const double* upS, const double* loS, const double* psi, double* Apsi,
@@ -82,7 +79,8 @@ void dicCalcReciprocalD(DeviceMesh& m, const double* diag, const double* upS, do
     if (!m.N) return;
     fillSentinel(w.Dt, m.N);
     int nChunks = gridFor(m.N);
-    B200_LAUNCH(k_dic_calc_rd, sweepGridOf(m, w), BLOCK, rt().stream, m.view(), diag, upS, w.Dt.p, rD, sweepCtl(w), nChunks);
+    B200_LAUNCH(k_dic_fwd_tiled<1>, sweepGridOf(m, w), SWEEP_BLOCK, rt().stream, m.view(), m.tiles(), diag, (const double*)nullptr, upS, w.Dt.p, rD,
+                sweepCtl(w), (const PcgScalars*)nullptr);
 }
 
 void dicPrecondition(DeviceMesh& m, const double* rD, const double* upS, const double* rA, double* wA) {
@@ -90,9 +88,10 @@ void dicPrecondition(DeviceMesh& m, const double* rD, const double* upS, const d
     if (!m.N) return;
     int nChunks = gridFor(m.N);
     { ScopedTimer t(T_DIC_FWD);
-      B200_LAUNCH(k_dic_fwd, sweepGridOf(m, w), BLOCK, rt().stream, m.view(), rD, upS, rA, w.y.p, sweepCtl(w), nChunks, (const PcgScalars*)nullptr); }
+      B200_LAUNCH(k_dic_fwd_tiled<0>, sweepGridOf(m, w), SWEEP_BLOCK, rt().stream, m.view(), m.tiles(), rD, rA, upS, w.y.p, (double*)nullptr, sweepCtl(w),
+                  (const PcgScalars*)nullptr); }
     { ScopedTimer t(T_DIC_BWD);
-      B200_LAUNCH(k_dic_bwd, sweepGridOf(m, w), BLOCK, rt().stream, m.view(), rD, upS, rA, w.y.p, w.z.p, sweepCtl(w), nChunks,
+      B200_LAUNCH(k_dic_bwd_tiled, sweepGridOf(m, w), SWEEP_BLOCK, rt().stream, m.view(), m.tiles(), rD, upS, rA, w.y.p, w.z.p, sweepCtl(w),
                   (PcgScalars*)nullptr, (double*)nullptr, (unsigned*)nullptr); }
     B200_CHECK_CUDA(cudaMemcpyAsync(wA, w.z.p, 8 * (size_t)m.N, cudaMemcpyDeviceToDevice, rt().stream));
     fillSentinel(w.z, m.N);
@@ -135,7 +134,7 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
     B200_CHECK_CUDA(cudaMemcpyAsync(&w.hsc[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
     B200_CHECK_CUDA(cudaEventRecord(w.ev[0], st));
     // calcReciprocalD is enqueued before the host learns whether it is needed (one sweep; keeps the GPU busy)
-    if (N) { fillSentinel(w.Dt, N); B200_LAUNCH(k_dic_calc_rd, sweepGridOf(m, w), BLOCK, st, mv, diag, upS, w.Dt.p, w.rD.p, sweepCtl(w), nChunks); }
+    if (N) { fillSentinel(w.Dt, N); B200_LAUNCH(k_dic_fwd_tiled<1>, sweepGridOf(m, w), SWEEP_BLOCK, st, mv, m.tiles(), diag, (const double*)nullptr, upS, w.Dt.p, w.rD.p, sweepCtl(w), (const PcgScalars*)nullptr); }
     B200_CHECK_CUDA(cudaEventSynchronize(w.ev[0]));
     bool stopped = w.hsc[0].stop != 0;
     const int BATCH = 8;
@@ -145,9 +144,9 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
     auto enqueueIteration = [&]() {
         if (N) {
             { KT(T_DIC_FWD);
-              B200_LAUNCH(k_dic_fwd, sweepGridOf(m, w), BLOCK, st, mv, (const double*)w.rD.p, upS, (const double*)w.rA.p, w.y.p, sweepCtl(w), nChunks, (const PcgScalars*)sc); }
+              B200_LAUNCH(k_dic_fwd_tiled<0>, sweepGridOf(m, w), SWEEP_BLOCK, st, mv, m.tiles(), (const double*)w.rD.p, (const double*)w.rA.p, upS, w.y.p, (double*)nullptr, sweepCtl(w), (const PcgScalars*)sc); }
             { KT(T_DIC_BWD);
-              B200_LAUNCH(k_dic_bwd, sweepGridOf(m, w), BLOCK, st, mv, (const double*)w.rD.p, upS, (const double*)w.rA.p, w.y.p, w.z.p, sweepCtl(w), nChunks, sc, part, cnt); }
+              B200_LAUNCH(k_dic_bwd_tiled, sweepGridOf(m, w), SWEEP_BLOCK, st, mv, m.tiles(), (const double*)w.rD.p, upS, (const double*)w.rA.p, w.y.p, w.z.p, sweepCtl(w), sc, part, cnt); }
         }
         if (multi) allReduce(&sc->wArA, 1, RED_SUM);
         { KT(T_PCG_VEC);

@@ -20,8 +20,13 @@ def test_renumbering_and_addressing_bit_exact(lib, oracle, dims, weir):
     pm, ldu = make(lib, dims, weir)
     F = pm.nInternalFaces
     rowCell, level, nLevels = ldu.renumbering()
-    lev, perm, inv = mo.level_renumbering(pm.owner[:F], pm.neighbour, pm.nCells)
-    assert np.array_equal(level, lev) and np.array_equal(rowCell, perm)
+    band_levels, tile_rows, tile_start = ldu.tiling()
+    lev, perm, inv, ts = mo.tile_renumbering(pm.owner[:F], pm.neighbour, pm.nCells, band_levels, tile_rows)
+    assert np.array_equal(level, lev) and np.array_equal(rowCell, perm) and np.array_equal(tile_start, ts)
+    # tile order is a topological order of the tile graph: every dependency goes to the same or a later tile
+    tile_of_row = np.searchsorted(tile_start, np.arange(pm.nCells), side="right") - 1
+    if F:
+        assert np.all(tile_of_row[inv[pm.owner[:F]]] <= tile_of_row[inv[pm.neighbour]])
     assert sorted(rowCell.tolist()) == list(range(pm.nCells))          # a permutation
     assert nLevels == (lev.max() + 1 if pm.nCells else 0)
     if weir is None:
@@ -122,3 +127,34 @@ def test_bad_addressing_is_rejected(lib):
         lib.ldu_create(3, [1, 0], [2, 1])      # not sorted by lower
     with pytest.raises(B200Error):
         lib.ldu_create(3, [0, 2], [1, 1])      # lower >= upper
+
+
+@pytest.mark.parametrize("band,rows", [(1, 32), (3, 64), (5, 96), (64, 2048)])
+def test_dic_tiling_variants_bitwise(lib, oracle, band, rows):
+    """small tiles force cross-tile (polled) dependencies at every level; huge tiles keep everything in one CTA"""
+    from oracle import mesh_oracle as mo
+    lib.set_option("sweep_band_levels", band); lib.set_option("sweep_tile_rows", rows)
+    try:
+        pm, ldu = make(lib, (14, 9, 11), (0.45, 0.6, 0.3))
+        m = oracle_mesh_of(pm)
+        F = pm.nInternalFaces
+        bl, tr, ts = ldu.tiling()
+        assert (bl, tr) == (band, rows)
+        lev, perm, inv, ts_ref = mo.tile_renumbering(pm.owner[:F], pm.neighbour, pm.nCells, band, rows)
+        rowCell, level, _ = ldu.renumbering()
+        assert np.array_equal(rowCell, perm) and np.array_equal(ts, ts_ref)
+        diag, upper = random_spd(m, seed=21)
+        rng = np.random.default_rng(22)
+        rA = rng.uniform(-1, 1, m.N)
+        rD = oracle.dic_calc_rd(m, diag, upper)
+        assert np.array_equal(rD, ldu.dic_calc_rd(diag, upper))
+        w = oracle.dic_precondition(m, rD, upper, rA)
+        for _ in range(2):
+            assert np.array_equal(w, ldu.dic_precondition(rD, upper, rA))
+        b = rng.uniform(-1, 1, m.N)
+        xo, po, ho = oracle.pcg_solve(m, diag, upper, np.zeros(m.N), b, tol=1e-9, maxIter=300)
+        xg, pg, hg = ldu.pcg_solve(diag, upper, np.zeros(m.N), b, tol=1e-9, maxIter=300)
+        assert pg.nIterations == po.nIterations and np.allclose(hg, ho, rtol=1e-8, atol=1e-13 * ho[0])
+        ldu.release()
+    finally:
+        lib.set_option("sweep_band_levels", 16); lib.set_option("sweep_tile_rows", 1024)

@@ -16,7 +16,7 @@ def test_library_exports_every_declared_symbol(hostlib):
     # every function declared in include/b200foam.h is in EXPORTS
     import os, re
     hdr = open(os.path.join(os.path.dirname(capi.__file__), "..", "include", "b200foam.h")).read()
-    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(b200_[A-Za-z0-9_]+)\s*\(", hdr))
     assert declared == set(capi.EXPORTS)
 
 
