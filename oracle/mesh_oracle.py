@@ -323,24 +323,122 @@ def level_renumbering(lower, upper, N):
     return lev, perm, inv
 
 
-def tile_renumbering(lower, upper, N, band_levels=16, tile_rows=1024):
-    """DIC tiling of the device rows (this repo's own design, DESIGN.md section 4): band = level // band_levels; inside a band
-    the cells in ascending original index are cut into chunks of tile_rows; tile = (band, chunk) numbered band-major;
-    device row order = (tile, level, original index).  Returns level, rowCell, cellRow, tileStart."""
-    lev = forward_levels(lower, upper, N)
-    band = lev // band_levels
-    idx = np.arange(N)
-    by_band = np.lexsort((idx, band))                       # band-major, ascending index inside
-    rank_in_band = np.empty(N, dtype=np.int64)
-    bstart = np.searchsorted(band[by_band], np.arange(band.max() + 2 if N else 1))
-    rank_in_band[by_band] = np.arange(N) - np.repeat(bstart[:-1], np.diff(bstart))
-    chunk = rank_in_band // tile_rows
-    row_order = np.lexsort((idx, lev, chunk, band)).astype(np.int32)   # (band, chunk, level, index)
-    cell_row = np.empty(N, dtype=np.int32)
-    cell_row[row_order] = np.arange(N, dtype=np.int32)
-    key = band[row_order].astype(np.int64) * (chunk.max() + 1 if N else 1) + chunk[row_order]
-    tile_start = np.concatenate([[0], np.nonzero(np.diff(key))[0] + 1, [N]]).astype(np.int32) if N else np.zeros(1, np.int32)
-    return lev, row_order, cell_row, tile_start
+def sweep_smem_bytes(n_rows, n_slots, n_halo, d):
+    return 8 * ((n_rows + n_halo + 4) // 2 * 2) + 8 * n_slots * (d + (d + 3) // 4) + 64
+
+
+def sweep_plan(lower, upper, N, band_levels=16, max_rows=2048, smem_budget=110 * 1024, lanes=128):
+    """DIC sweep plan of the device rows (this repo's own design; restates csrc/host_mesh.cpp buildSweepPlan).
+    Three potentials that never decrease along a dependency l -> u: level, potJ / potK = most faces of stride class 1 / 2 on any
+    path (stride classes = the three dominant magnitudes of upper - lower).  Tile class = (level // band, potK // binK, potJ // binJ);
+    oversized classes are cut into consecutive pieces of their (level, index) order; tiles are ordered by their longest-path level
+    in the tile graph; device row order = (tile, level, original index)."""
+    lower = np.asarray(lower, dtype=np.int64); upper = np.asarray(upper, dtype=np.int64)
+    F = lower.size
+    band_levels = max(1, band_levels); max_rows = max(8, min(max_rows, 32768)); lanes = max(32, min(lanes, 1024)) // 32 * 32
+    lev = forward_levels(lower.astype(np.int32), upper.astype(np.int32), N).astype(np.int64)
+    out = dict(level=lev.astype(np.int32), bandLevels=band_levels, maxRows=max_rows)
+    if N == 0:
+        out.update(rowCell=np.zeros(0, np.int32), cellRow=np.zeros(0, np.int32), tileStart=np.zeros(1, np.int32),
+                   tileLevel=np.zeros(0, np.int32), potJ=np.zeros(0, np.int32), potK=np.zeros(0, np.int32), binJ=1, binK=1)
+        return out
+    n_levels = int(lev.max()) + 1
+    # 1. stride classes
+    d = upper - lower
+    vals, cnts = np.unique(d, return_counts=True)
+    removed = np.zeros(vals.size, dtype=bool)
+    cen = []
+    for _ in range(3):
+        if removed.all():
+            break
+        c_ = np.where(removed, -1, cnts)
+        best = int(np.argmax(c_))                      # ties: smallest value first
+        c = int(vals[best]); cen.append(c)
+        removed |= (2 * vals > c) & (vals < 2 * c)
+    cen.sort()
+    cls = np.zeros(F, dtype=np.int64)
+    if len(cen) > 1:
+        cls[d * d >= cen[0] * cen[1]] = 1
+    if len(cen) > 2:
+        cls[d * d >= cen[1] * cen[2]] = 2
+    # 2. potentials (sequential ascending face pass)
+    pj = [0] * N; pk = [0] * N
+    lo = lower.tolist(); up = upper.tolist(); cl = cls.tolist()
+    for f in range(F):
+        l, u, c = lo[f], up[f], cl[f]
+        a = pj[l] + (1 if c == 1 else 0); b = pk[l] + (1 if c == 2 else 0)
+        if a > pj[u]: pj[u] = a
+        if b > pk[u]: pk[u] = b
+    potJ = np.asarray(pj, dtype=np.int64); potK = np.asarray(pk, dtype=np.int64)
+    extJ, extK = int(potJ.max()) + 1, int(potK.max()) + 1
+    # 3. bins
+    n_triples = np.unique((lev * extJ + potJ) * extK + potK).size
+    A = max(1, max_rows * n_triples // (band_levels * N))
+    best = None
+    for bj in range(1, min(extJ, A) + 1):
+        bk = min(extK, max(1, A // bj))
+        cost = -(-extJ // bj) + -(-extK // bk); prod = bj * bk
+        if best is None or cost < best[0] or (cost == best[0] and prod > best[1]):
+            best = (cost, prod, bj, bk)
+    binJ, binK = best[2], best[3]
+    nJb, nKb = -(-extJ // binJ), -(-extK // binK)
+    # 4. sort + pieces
+    cls_key = ((lev // band_levels) * nKb + potK // binK) * nJb + potJ // binJ
+    order = np.lexsort((np.arange(N), lev, cls_key))
+    ck = cls_key[order]
+    bounds = np.concatenate([[0], np.nonzero(np.diff(ck))[0] + 1, [N]])
+    pieces = []
+    for b0, e0 in zip(bounds[:-1], bounds[1:]):
+        n = int(e0 - b0); npc = -(-n // max_rows); base, rem = divmod(n, npc); at = int(b0)
+        for q in range(npc):
+            sz = base + (1 if q < rem else 0); pieces.append((at, at + sz)); at += sz
+    owner_start, losort, losort_start = ldu_addressing(lower.astype(np.int32), upper.astype(np.int32), N)
+    # 5. budget
+    while True:
+        piece_of = np.empty(N, dtype=np.int64)
+        for p, (b, e) in enumerate(pieces):
+            piece_of[order[b:e]] = p
+        nxt = []; changed = False
+        for p, (b, e) in enumerate(pieces):
+            cells = order[b:e]; n = e - b
+            dF = int((losort_start[cells + 1] - losort_start[cells]).max()); dB = int((owner_start[cells + 1] - owner_start[cells]).max())
+            lows = np.concatenate([lower[losort[losort_start[c]:losort_start[c + 1]]] for c in cells]) if dF else np.zeros(0, np.int64)
+            ups = np.concatenate([upper[owner_start[c]:owner_start[c + 1]] for c in cells]) if dB else np.zeros(0, np.int64)
+            hF = np.unique(lows[piece_of[lows] != p]).size; hB = np.unique(ups[piece_of[ups] != p]).size
+            runs = np.diff(np.concatenate([[0], np.nonzero(np.diff(lev[cells]))[0] + 1, [n]]))   # rows per level of the piece
+            n_steps = int((-(-runs // lanes)).sum()); S = n_steps * lanes                        # steps of <= lanes rows
+            need = max(sweep_smem_bytes(n, S, hF, dF), sweep_smem_bytes(n, S, hB, dB))
+            if (need > smem_budget or n + max(hF, hB) + 2 > 8191 or n_steps > 256) and n > 1:
+                mid = b + n // 2; nxt += [(b, mid), (mid, e)]; changed = True
+            else:
+                nxt.append((b, e))
+        pieces = nxt
+        if not changed:
+            break
+    nT = len(pieces)
+    # 6. tile graph levels (longest path) -- Kahn in piece order
+    a, b = piece_of[lower], piece_of[upper]
+    m = a != b
+    edges = np.unique(np.stack([a[m], b[m]], axis=1), axis=0) if m.any() else np.zeros((0, 2), np.int64)
+    tl = [0] * nT; indeg = [0] * nT; adj = [[] for _ in range(nT)]
+    for x, y in edges.tolist():
+        adj[x].append(y); indeg[y] += 1
+    queue = [t for t in range(nT) if indeg[t] == 0]
+    h = 0
+    while h < len(queue):
+        t = queue[h]; h += 1
+        for v in adj[t]:
+            tl[v] = max(tl[v], tl[t] + 1); indeg[v] -= 1
+            if indeg[v] == 0:
+                queue.append(v)
+    assert len(queue) == nT, "tile graph is cyclic"
+    ticket = np.argsort(np.asarray(tl), kind="stable")
+    row_cell = np.concatenate([order[pieces[t][0]:pieces[t][1]] for t in ticket]).astype(np.int32)
+    cell_row = np.empty(N, dtype=np.int32); cell_row[row_cell] = np.arange(N, dtype=np.int32)
+    tile_start = np.concatenate([[0], np.cumsum([pieces[t][1] - pieces[t][0] for t in ticket])]).astype(np.int32)
+    out.update(rowCell=row_cell, cellRow=cell_row, tileStart=tile_start, tileLevel=np.asarray(tl, np.int32)[ticket],
+               potJ=potJ.astype(np.int32), potK=potK.astype(np.int32), binJ=binJ, binK=binK)
+    return out
 
 
 # ----------------------------------------------------------------------------

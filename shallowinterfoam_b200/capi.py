@@ -20,7 +20,7 @@ SCHEME_VANLEER, SCHEME_INTERFACE_COMPRESSION, SCHEME_UPWIND, SCHEME_LINEAR = 0, 
 EXPORTS = [
     "b200_init", "b200_nccl_unique_id", "b200_finalize", "b200_last_error", "b200_device_count",
     "b200_kernel_launch_count", "b200_set_option", "b200_timers_reset", "b200_timers_get", "b200_timer_name",
-    "b200_ldu_get_or_create", "b200_ldu_release", "b200_ldu_get_renumbering", "b200_ldu_get_tiling", "b200_ldu_get_addressing",
+    "b200_ldu_get_or_create", "b200_ldu_release", "b200_ldu_get_renumbering", "b200_ldu_get_tiling", "b200_ldu_get_addressing", "b200_debug_get_sweep_trace",
     "b200_amul", "b200_sumA", "b200_dic_calc_reciprocal_d", "b200_dic_precondition", "b200_pcg_solve",
     "b200_mesh_create", "b200_mesh_release", "b200_mesh_ldu",
     "b200_interpolate", "b200_sngrad", "b200_surface_integrate", "b200_grad_gauss", "b200_reconstruct",
@@ -214,6 +214,13 @@ class Ldu:
         ts = np.empty(nt.value + 1, dtype=np.int32)
         self.lib.check(self.lib.c.b200_ldu_get_tiling(self.h, None, None, None, _i(ts)))
         return bl.value, tr.value, ts
+
+    def sweep_trace(self):
+        _, _, ts = self.tiling()
+        nt = ts.size - 1
+        out = np.zeros(8 * nt, dtype=np.uint64); tl = np.zeros(nt, dtype=np.int32)
+        self.lib.check(self.lib.c.b200_debug_get_sweep_trace(self.h, out.ctypes.data_as(C.POINTER(C.c_ulonglong)), C.c_int32(out.size), _i(tl)))
+        return out.reshape(nt, 8), tl, ts
 
     def addressing(self):
         os_ = np.empty(self.N + 1, dtype=np.int32); lo = np.empty(self.F, dtype=np.int32); ls = np.empty(self.N + 1, dtype=np.int32)

@@ -156,10 +156,19 @@ int b200_ldu_get_renumbering(const b200_ldu_t* ldu, int32_t* rowCell, int32_t* c
 int b200_ldu_get_tiling(const b200_ldu_t* ldu, int32_t* bandLevels, int32_t* tileRows, int32_t* nTiles, int32_t* tileStart) {
     API_BEGIN
     const DeviceMesh* m = asMesh(ldu);
-    if (bandLevels) *bandLevels = m->bandLevels;
-    if (tileRows) *tileRows = m->tileRows;
+    if (bandLevels) *bandLevels = m->plan.bandLevels;
+    if (tileRows) *tileRows = m->plan.maxRows;
     if (nTiles) *nTiles = m->nTiles;
-    if (tileStart) memcpy(tileStart, m->tileStart.data(), 4 * m->tileStart.size());
+    if (tileStart) memcpy(tileStart, m->plan.tileStart.data(), 4 * m->plan.tileStart.size());
+    API_END
+}
+int b200_debug_get_sweep_trace(const b200_ldu_t* ldu, unsigned long long* out, int32_t cap, int32_t* tileLevel) {
+    API_BEGIN
+    const DeviceMesh* m = asMesh(ldu);
+    size_t n = std::min<size_t>((size_t)cap, 8 * (size_t)m->nTiles);
+    syncStream();
+    B200_CHECK_CUDA(cudaMemcpy(out, m->dTrace.p, 8 * n, cudaMemcpyDeviceToHost));
+    if (tileLevel) memcpy(tileLevel, m->plan.tileLevel.data(), 4 * (size_t)m->nTiles);
     API_END
 }
 int b200_ldu_get_addressing(const b200_ldu_t* ldu, int32_t* ownerStart, int32_t* losort, int32_t* losortStart) {

@@ -74,7 +74,20 @@ struct ScopedTimer {  // records events around a launch sequence when timers are
         b200::rt().launches++;                                                \
         emu::launch(dim3(grid), dim3(block), [&]() { kernel(__VA_ARGS__); }); \
     } while (0)
+#define B200_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...)                        \
+    do {                                                                                \
+        b200::rt().launches++;                                                          \
+        emu::launch(dim3(grid), dim3(block), [&]() { kernel(__VA_ARGS__); }, (smem));   \
+    } while (0)
 #else
+// dynamic shared memory above 48 KB needs the opt-in attribute (set on every launch: a cheap host-side call)
+#define B200_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...)                                                         \
+    do {                                                                                                                 \
+        b200::rt().launches++;                                                                                           \
+        B200_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)));        \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                                      \
+        B200_CHECK_CUDA(cudaGetLastError());                                                                             \
+    } while (0)
 #define B200_LAUNCH(kernel, grid, block, stream, ...)          \
     do {                                                       \
         b200::rt().launches++;                                 \

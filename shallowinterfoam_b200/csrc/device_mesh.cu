@@ -52,15 +52,16 @@ void DeviceMesh::build(int32_t nCells, int32_t nFaces, const int32_t* lo, const 
     for (int f = 0; f < F; f++)
         B200_REQUIRE(lower[f] >= 0 && upper[f] < N, B200_ERR_ARG, "lduAddressing label out of range");
     for (int b = 0; b < B; b++) B200_REQUIRE(fc[b] >= 0 && fc[b] < N, B200_ERR_ARG, "faceCells label out of range");
-    bandLevels = std::max(1, (int)rt().opt("sweep_band_levels", 16));
-    tileRows = std::max(32, (int)rt().opt("sweep_tile_rows", 1024));
+    int bandLevels = std::min(SWEEP_MAX_STEPS, std::max(1, (int)rt().opt("sweep_band_levels", 16)));
+    int lanes = std::max(32, std::min(SWEEP_THREADS, (int)rt().opt("sweep_threads", 128))) / 32 * 32;
+    int tileRows = std::max(8, (int)rt().opt("sweep_tile_rows", 2048));
+    int smemBudget = std::min(227 * 1024, std::max(4096, (int)rt().opt("sweep_smem_bytes", 110 * 1024)));
     try {
-        tileRenumbering(N, lower.data(), upper.data(), F, bandLevels, tileRows, SWEEP_BLOCK, level, rowCell, cellRow, nLevels,
-                        tileStart, tileSegStart, segRow);
+        buildSweepPlan(N, lower.data(), upper.data(), F, bandLevels, tileRows, smemBudget, lanes, plan);
     } catch (const std::exception& e) { throw Error(B200_ERR_ARG, e.what()); }
-    nTiles = (int)tileStart.size() - 1;
-    B200_REQUIRE(tileRows <= SWEEP_TILE_MAX, B200_ERR_ARG, "sweep_tile_rows too large");
-    dTileStart.upload(tileStart); dTileSegStart.upload(tileSegStart); dSegRow.upload(segRow);
+    level = plan.level; rowCell = plan.rowCell; cellRow = plan.cellRow; nLevels = plan.nLevels;
+    nTiles = plan.nTiles;
+    sweepSmem = std::max(plan.smemFwd, plan.smemBwd);
     lduDerived(N, lower, upper, ownerStart, losort, losortStart);
     levelStart.assign(nLevels + 1, 0);
     for (int c = 0; c < N; c++) levelStart[level[c] + 1]++;
@@ -97,6 +98,61 @@ void DeviceMesh::build(int32_t nCells, int32_t nFaces, const int32_t* lo, const 
             int q = nbrOff[s] + (j - losortStart[c]) * 32 + lane;
             loPk[q] = (cellRow[l] << KB) | (f - ownerStart[l]);
         }
+    }
+    {   // sweep-plan upload: descriptors, level segments, operand-block templates (source offsets) and face slots, halo rows
+        std::vector<SweepTile> tf(nTiles), tb(nTiles);
+        size_t blkF = 0, blkB = 0;
+        for (int t = 0; t < nTiles; t++) {
+            SweepTile d; memset(&d, 0, sizeof(d));
+            d.row0 = plan.tileStart[t]; d.nRows = plan.tileStart[t + 1] - d.row0;
+            d.step0 = plan.tileStepStart[t]; d.nSteps = plan.tileStepStart[t + 1] - d.step0;
+            const size_t S = (size_t)d.nSteps * plan.lanes;
+            tf[t] = d; tb[t] = d;
+            tf[t].d = plan.fwdD[t]; tf[t].halo = plan.fwdHalo[t]; tf[t].nHalo = plan.fwdHalo[t + 1] - plan.fwdHalo[t];
+            tb[t].d = plan.bwdD[t]; tb[t].halo = plan.bwdHalo[t]; tb[t].nHalo = plan.bwdHalo[t + 1] - plan.bwdHalo[t];
+            tf[t].blk = (int)blkF; tb[t].blk = (int)blkB;
+            blkF += (size_t)(tf[t].d + (tf[t].d + 3) / 4) * S; blkB += (size_t)(tb[t].d + (tb[t].d + 3) / 4) * S;
+            B200_REQUIRE(blkF < ((size_t)1 << 31) && blkB < ((size_t)1 << 31), B200_ERR_UNSUPPORTED, "mesh too large for 32-bit sweep block offsets");
+        }
+        fwdBlkSize = blkF; bwdBlkSize = blkB;
+        for (int dir = 0; dir < 2; dir++) {
+            const std::vector<SweepTile>& tl = dir == 0 ? tf : tb;
+            const std::vector<uint16_t>& idx = dir == 0 ? plan.fwdIdx : plan.bwdIdx;
+            const std::vector<int32_t>& face = dir == 0 ? plan.fwdFace : plan.bwdFace;
+            const std::vector<int32_t>& ell = dir == 0 ? plan.fwdEll : plan.bwdEll;
+            size_t total = dir == 0 ? blkF : blkB;
+            std::vector<double> blk0(total, 0.0);
+            std::vector<int> pos(total, -1);
+            for (int t = 0; t < nTiles; t++) {
+                const SweepTile& d = tl[t];
+                const size_t S = (size_t)d.nSteps * plan.lanes;
+                uint16_t* offs = reinterpret_cast<uint16_t*>(blk0.data() + d.blk + (size_t)d.d * S);
+                const int nq = (d.d + 3) / 4;
+                const uint16_t padOff = (uint16_t)(8 * (d.nRows + d.nHalo)), trashOff = (uint16_t)(8 * (d.nRows + d.nHalo + 1));
+                for (size_t e = 0; e < (size_t)nq * S * 4; e++) offs[e] = padOff;
+                for (int j = 0; j < d.d; j++)
+                    for (size_t sl = 0; sl < S; sl++) {
+                        size_t e = (size_t)ell[t] + (size_t)j * S + sl;
+                        offs[((size_t)(j / 4) * S + sl) * 4 + (j % 4)] = (uint16_t)(8 * idx[e]);
+                        pos[d.blk + (size_t)j * S + sl] = face[e] >= 0 ? facePosHost[face[e]] : -1;
+                    }
+                if (d.d >= 1 && d.d <= 3)   // lane 3 of the offset word: where the slot's own row lives in the value array
+                    for (int k = 0; k < d.nSteps; k++)
+                        for (int i = 0; i < plan.lanes; i++) {
+                            int len = plan.stepLen[d.step0 + k], rl = plan.stepRow[d.step0 + k] - d.row0 + i;
+                            offs[((size_t)k * plan.lanes + i) * 4 + 3] = i < len ? (uint16_t)(8 * rl) : trashOff;
+                        }
+            }
+            (dir == 0 ? dFwdBlk0 : dBwdBlk0).upload(blk0);
+            (dir == 0 ? dFwdPos : dBwdPos).upload(pos);
+            syncStream();
+        }
+        dTilesF.upload(tf); dTilesB.upload(tb); dStepRow.upload(plan.stepRow); dStepLen.upload(plan.stepLen);
+        dFwdHaloRow.upload(plan.fwdHaloRow); dBwdHaloRow.upload(plan.bwdHaloRow);
+        dTrace.alloc(8 * (size_t)nTiles + 8); dTrace.zero();
+        syncStream();   // the host vectors above go out of scope
+        plan.fwdFace.clear(); plan.fwdFace.shrink_to_fit(); plan.bwdFace.clear(); plan.bwdFace.shrink_to_fit();
+        plan.fwdIdx.clear(); plan.fwdIdx.shrink_to_fit(); plan.bwdIdx.clear(); plan.bwdIdx.shrink_to_fit();
     }
     // boundary CSR by row
     std::vector<int> cnt(N, 0);

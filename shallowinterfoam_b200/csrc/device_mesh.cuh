@@ -47,14 +47,26 @@ __device__ __forceinline__ int facePosOf(const MeshView& mv, int pk, int& l) {
     return mv.sliceOff[l >> 5] + (k << 5) + (l & 31);
 }
 
-constexpr int SWEEP_BLOCK = 128;      // threads per DIC tile CTA = longest level segment handled in one step
-constexpr int SWEEP_TILE_MAX = 2048;  // rows per tile held in shared memory
-
-struct TileView {  // DIC tiles handed to the sweep kernels
+constexpr int SWEEP_THREADS = 256;    // most threads (= lanes) of a sweep CTA
+// DIC sweep tiles (host_mesh.h SweepPlan, uploaded).  One descriptor per tile and sweep direction.
+struct SweepTile {
+    int row0, nRows;       // device rows [row0, row0+nRows)
+    int step0, nSteps;     // steps: stepRow/stepLen[step0 .. step0+nSteps); S = nSteps*lanes value slots
+    int blk, d;            // operand block offset (doubles) and ELL width; block = d coefficient columns [S] followed by
+                           // ceil(d/4) columns of packed 16-bit BYTE offsets of the sources in the tile's value array
+    int halo, nHalo;       // halo list offset and length
+    int pad[4];
+};
+struct SweepView {
     int nTiles;
-    const int* tileStart;     // [nTiles+1] first row of each tile
-    const int* tileSegStart;  // [nTiles+1] CSR into segRow
-    const int* segRow;        // [nSegs+1] first row of each level segment (segments never exceed SWEEP_BLOCK rows)
+    const SweepTile *fwd, *bwd;              // [nTiles] in ticket order
+    const int *stepRow, *stepLen;            // first device row / rows of each step
+    int lanes;                               // rows per step = threads of a sweep CTA
+    const int *fwdPos, *bwdPos;              // face slot of each coefficient entry of the operand blocks (-1 = padding)
+    const int *fwdHaloRow, *bwdHaloRow;      // device rows a tile polls
+    int pollNs;                              // back-off between polls of a not-yet-published halo value
+    int weakPublish;                         // experiment: publish with plain stores
+    unsigned long long* trace;               // debug: [8*nTiles] globaltimer stamps per tile (ticket, staged, halo ready, steps done, published) or null
 };
 
 struct PcgWorkspace;  // pcg.cu
@@ -69,10 +81,15 @@ struct DeviceMesh {
     std::vector<int32_t> ownerStart, losort, losortStart;
     std::vector<int32_t> facePosHost;      // [F] slot of original face
     std::vector<int32_t> levelStart;       // [nLevels+1] number of cells below each level (diagnostic)
-    // DIC tiles (host_mesh.h tileRenumbering): rows are ordered (tile, level, original index)
-    int bandLevels = 16, tileRows = 1024, nTiles = 0;
-    std::vector<int32_t> tileStart, tileSegStart, segRow;
-    DevBuf<int> dTileStart, dTileSegStart, dSegRow;
+    // DIC sweep plan (host_mesh.h buildSweepPlan): rows are ordered (tile in ticket order, level, original index)
+    SweepPlan plan;
+    int nTiles = 0;
+    size_t sweepSmem = 0;                  // dynamic shared memory of the sweep kernels (bytes)
+    DevBuf<SweepTile> dTilesF, dTilesB;
+    DevBuf<int> dStepRow, dStepLen, dFwdPos, dBwdPos, dFwdHaloRow, dBwdHaloRow;
+    DevBuf<double> dFwdBlk0, dBwdBlk0;     // operand-block templates: coefficient columns 0, source-offset columns filled
+    size_t fwdBlkSize = 0, bwdBlkSize = 0; // doubles
+    DevBuf<unsigned long long> dTrace;     // debug trace of the last sweep (option sweep_trace)
     DevBuf<int> dSliceOff, dNbrOff, dUpIdx, dLoPk, dBBase, dBRowStart, dBRowFaces, dBFaceRow, dBPatch, dBCoupled;
     DevBuf<unsigned> dBMask;
     DevBuf<int> dSlotFace, dFacePos, dRowCell, dCellRow;
@@ -91,7 +108,10 @@ struct DeviceMesh {
     void setGeometry(const double* Sf, const double* magSf, const double* Cf, const double* C, const double* V,
                      const double* w, const double* dc);
     MeshView view() const;
-    TileView tiles() const { return TileView{nTiles, dTileStart.p, dTileSegStart.p, dSegRow.p}; }
+    SweepView sweep() const {
+        return SweepView{nTiles, dTilesF.p, dTilesB.p, dStepRow.p, dStepLen.p, plan.lanes, dFwdPos.p, dBwdPos.p, dFwdHaloRow.p, dBwdHaloRow.p, (int)rt().opt("sweep_poll_ns", 0), (int)rt().opt("sweep_weak_publish", 0),
+                         rt().opt("sweep_trace", 0) > 0 ? dTrace.p : nullptr};
+    }
     void coupleGeometry();   // collective: processor-face weights/deltaCoeffs/neighbour centres from a halo swap of C
     size_t nFaceField() const { return (size_t)Fs + B; }
 

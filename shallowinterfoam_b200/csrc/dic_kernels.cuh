@@ -1,18 +1,20 @@
-// dic_kernels.cuh -- a2/a3: DICPreconditioner as SM-local tiled data-flow sweeps.
+// dic_kernels.cuh -- a2/a3: DICPreconditioner as CLOSED-TILE data-flow sweeps on a tile DAG.
 //
 // [UPSTREAM DICPreconditioner.C]  calcReciprocalD: rD[u] -= upper^2/rD[l] (faces ascending), rD = 1/rD
 //                                 precondition   : wA = rD*rA; forward faces asc wA[u] -= rD[u]*upper*wA[l];
 //                                                  backward faces desc wA[l] -= rD[l]*upper*wA[u]
 // A row needs its lower (forward) / upper (backward) neighbours: a sparse triangular solve whose critical path is the number
-// of levels (348 at 1 M cells).  Going through L2 for every level costs ~1 us per level, so rows are grouped into TILES
-// (host_mesh.h tileRenumbering: band of 16 levels x chunk of 1024 cells in original index order).  One CTA owns a tile and walks
-// its level segments with __syncthreads between them; values produced inside the tile are exchanged through shared memory
-// (~0.1 us per level), values from other tiles are polled from L2 (the output array is pre-filled with a NaN sentinel and every
-// row is published with one relaxed 64-bit store).  Tiles are handed out in order by an atomic ticket and every dependency
-// points to the same or an earlier (forward) / later (backward) tile, so a running CTA only waits on CTAs that are already
-// running: no grid barrier, no co-residency requirement.  Operands that do not depend on other rows (indices, coefficients)
-// are prefetched one level ahead into registers.  Inside a row the updates keep upstream's face order => bitwise the
-// sequential result.
+// of levels (348 at 1 M cells).  One L2 round trip per level (~1 us) is what bounds a row-level schedule, so the rows are grouped
+// into tiles by host_mesh.h buildSweepPlan: tile = (band of levels) x (bin of the two stride-class potentials).  All three tile
+// coordinates are monotone along every dependency, so the tile graph is acyclic and a tile's external inputs ("halo") all
+// come from tiles with an earlier ticket.  One CTA owns a tile:
+//   1. stage everything that does not depend on other rows (coefficients, tile-local source indices, rD*rA) in shared memory,
+//   2. poll the halo values from L2 ONCE (outputs are pre-filled with a NaN sentinel; every row is published with a relaxed
+//      64-bit store, so the data is its own ready flag: one L2 round trip per tile hop instead of one per level),
+//   3. walk the tile's level segments out of shared memory with __syncthreads between them (~50 ns per level).
+// Tiles are handed out in ticket order (sorted by longest-path level in the tile graph), so a running CTA only waits on CTAs
+// that are already running: no grid barrier, no co-residency requirement, deadlock-free for any grid size.  Inside a row the
+// updates keep upstream's face order and (rD*upper)*w association => bitwise the sequential result.
 #pragma once
 #include "ldu_kernels.cuh"
 
@@ -34,165 +36,319 @@ __device__ __forceinline__ void sweepExit(SweepCtl c) {
     }
 }
 
-#define TILE_MAXD 6
-
-struct RowWork {          // what a row needs that does not depend on other rows
-    int row, cnt, more;   // row < 0: idle thread; more: dependencies beyond TILE_MAXD (generic tail)
-    int dl[TILE_MAXD];
-    double dc[TILE_MAXD];
-    double w0, rd;
-};
-
-__device__ __forceinline__ double pollValue(const double* p) {
-    double v = ldPoll(p);
-    while (isSentinel(v)) {
 #ifdef B200_EMU
-        emu::yield();
+#define B200_DYN_SMEM(name) unsigned char* name = emu::dynSmem()
+#else
+#define B200_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
-        v = ldPoll(p);
-    }
-    return v;
-}
 
-// MODE 0: forward precondition sweep (w0 = rD*rA, c = rD*upper) ; MODE 1: calcReciprocalD (w0 = diag, c = upper)
-template <int MODE>
-__device__ __forceinline__ void loadFwd(RowWork& r, int row, bool valid, const MeshView& mv, const double* __restrict__ a0,
-                                        const double* __restrict__ a1, const double* __restrict__ upS) {
-    r.row = valid ? row : -1; r.cnt = 0; r.more = 0; r.w0 = 0.0; r.rd = 0.0;
+// ---- TMA bulk copies (cp.async.bulk, 1-D) + mbarrier: one elected thread streams a tile's operand block into shared memory
+// while the other threads compute rD*rA and poll the halo.
+#ifdef B200_EMU
+struct TileBar { int dummy; };
+__device__ __forceinline__ void barInit(TileBar*) {}
+__device__ __forceinline__ void barExpect(TileBar*, unsigned) {}
+__device__ __forceinline__ void bulkLoad(void* dst, const void* src, unsigned bytes, TileBar*) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void barWait(TileBar*, unsigned) {}
+__device__ __forceinline__ void fenceAsyncProxy() {}
+__device__ __forceinline__ void bulkStore(void* dst, const void* src, unsigned bytes) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void bulkStoreCommit() {}
+__device__ __forceinline__ void bulkStoreWaitRead() {}
+#else
+struct TileBar { unsigned long long word; };
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void barInit(TileBar* b) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(b)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void barExpect(TileBar* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkLoad(void* dst, const void* src, unsigned bytes, TileBar* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smemAddr(dst)), "l"(src), "r"(bytes), "r"(smemAddr(b)) : "memory");
+}
+__device__ __forceinline__ void barWait(TileBar* b, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smemAddr(b)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// generic-proxy accesses of the previous tile (ordered by the CTA barrier) before the async proxy touches the buffer
+__device__ __forceinline__ void fenceAsyncProxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// TMA store shared -> global (lands in L2, where the polling loads of the dependent tiles look)
+__device__ __forceinline__ void bulkStore(void* dst, const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smemAddr(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkStoreCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulkStoreWaitRead() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+#endif
+constexpr unsigned BULK_MAX = 32768;   // bytes per cp.async.bulk (multiple of 16)
+__device__ __forceinline__ void bulkLoadChunks(void* dst, const void* src, size_t bytes, TileBar* b) {
+    for (size_t o = 0; o < bytes; o += BULK_MAX)
+        bulkLoad((char*)dst + o, (const char*)src + o, (unsigned)(bytes - o < BULK_MAX ? bytes - o : BULK_MAX), b);
+}
+#ifdef B200_EMU
+__device__ __forceinline__ unsigned long long globalTimerNs() { return 0; }
+#else
+__device__ __forceinline__ unsigned long long globalTimerNs() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#endif
+#define SWEEP_TRACE(slot) do { if (sv.trace && threadIdx.x == 0) sv.trace[8 * ti + (slot)] = globalTimerNs(); } while (0)
+
+struct TileSmem {
+    double* vals;          // [nRows + nHalo + 2] rows of the tile (start values, overwritten in place by the results), halo values,
+                           // padding slot (1.0), trash slot (0.0).  &vals[r] is 16-byte aligned iff device row row0+r is even.
+    double* blk;           // [(d + ceil(d/4)) * S] coefficient columns, then packed 16-bit byte offsets into vals (slot layout)
+    int S;
+};
+__device__ __forceinline__ TileSmem carveTile(unsigned char* smem, const SweepTile& t, int lanes) {
+    TileSmem s;
+    s.S = t.nSteps * lanes;
+    s.vals = (double*)smem + (t.row0 & 1);
+    s.blk = (double*)smem + ((t.nRows + t.nHalo + 4) & ~1);
+    return s;
+}
+__device__ __forceinline__ double ldsAt(const double* vals, unsigned byteOff) { return *(const double*)((const char*)vals + byteOff); }
+__device__ __forceinline__ void stsAt(double* vals, unsigned byteOff, double v) { *(double*)((char*)vals + byteOff) = v; }
+
+// poll the tile's halo rows out of `src` (sentinel = not yet published) into vals[nRows ..); loads of one pass are independent
+__device__ __forceinline__ void pollHalo(const SweepTile& t, const TileSmem& s, const int* __restrict__ haloRow, const double* src, int pollNs) {
+    constexpr int U = 4;
+    for (int h0 = threadIdx.x; h0 < t.nHalo; h0 += U * blockDim.x) {
+        const double* p[U]; double v[U]; bool need[U];
 #pragma unroll
-    for (int j = 0; j < TILE_MAXD; j++) { r.dl[j] = 0; r.dc[j] = 0.0; }
-    if (!valid) return;
-    int s = row >> 5, lane = row & 31;
-    if (MODE == 0) { r.rd = a0[row]; r.w0 = r.rd * a1[row]; } else { r.w0 = a0[row]; r.rd = 1.0; }
-    int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5;
-#pragma unroll
-    for (int j = 0; j < TILE_MAXD; j++)
-        if (j < nbw) {
-            int pk = mv.loPk[nb0 + (j << 5) + lane];
-            if (pk >= 0) { int l; int pos = facePosOf(mv, pk, l); r.dl[j] = l; r.dc[j] = (MODE == 0) ? r.rd * upS[pos] : upS[pos]; r.cnt = j + 1; }
+        for (int q = 0; q < U; q++) {
+            int h = h0 + q * blockDim.x;
+            need[q] = h < t.nHalo;
+            p[q] = src + (need[q] ? haloRow[t.halo + h] : 0);
         }
-    if (nbw > TILE_MAXD && mv.loPk[nb0 + (TILE_MAXD << 5) + lane] >= 0) r.more = 1;
-}
-
-template <int MODE>
-static __global__ void __launch_bounds__(SWEEP_BLOCK) k_dic_fwd_tiled(MeshView mv, TileView tv, const double* __restrict__ a0,
-        const double* __restrict__ a1, const double* __restrict__ upS, double* y, double* __restrict__ rDout, SweepCtl ctl,
-        const PcgScalars* sc) {
-    __shared__ double ys[SWEEP_TILE_MAX];
-    if (sc && sc->stop) return;
-    for (;;) {
-        int tile = nextTicket(ctl);
-        if (tile >= tv.nTiles) break;
-        const int tile0 = tv.tileStart[tile];
-        const int seg0 = tv.tileSegStart[tile], seg1 = tv.tileSegStart[tile + 1];
-        RowWork cur, nxt;
-        { int b = tv.segRow[seg0], e = tv.segRow[seg0 + 1], row = b + (int)threadIdx.x; loadFwd<MODE>(cur, row, seg0 < seg1 && row < e, mv, a0, a1, upS); }
-        for (int sg = seg0; sg < seg1; sg++) {
-            if (sg + 1 < seg1) { int b = tv.segRow[sg + 1], e = tv.segRow[sg + 2], row = b + (int)threadIdx.x; loadFwd<MODE>(nxt, row, row < e, mv, a0, a1, upS); }
-            if (cur.row >= 0) {
-                double w = cur.w0;
+        bool pending;
+        do {
+            pending = false;
 #pragma unroll
-                for (int j = 0; j < TILE_MAXD; j++)
-                    if (j < cur.cnt) {
-                        int l = cur.dl[j];
-                        double v = (l >= tile0) ? ys[l - tile0] : pollValue(y + l);
-                        if (MODE == 0) w = w - cur.dc[j] * v; else w = w - cur.dc[j] * cur.dc[j] / v;
-                    }
-                if (cur.more) {   // polyhedral rows with more than TILE_MAXD lower neighbours
-                    int s = cur.row >> 5, lane = cur.row & 31, nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5;
-                    for (int j = TILE_MAXD; j < nbw; j++) {
-                        int pk = mv.loPk[nb0 + (j << 5) + lane];
-                        if (pk < 0) break;
-                        int l; int pos = facePosOf(mv, pk, l);
-                        double v = (l >= tile0) ? ys[l - tile0] : pollValue(y + l);
-                        double u = upS[pos];
-                        if (MODE == 0) w = w - cur.rd * u * v; else w = w - u * u / v;
-                    }
+            for (int q = 0; q < U; q++) if (need[q]) v[q] = ldPoll(p[q]);
+#pragma unroll
+            for (int q = 0; q < U; q++)
+                if (need[q]) {
+                    if (isSentinel(v[q])) pending = true;
+                    else { s.vals[t.nRows + h0 + q * blockDim.x] = v[q]; need[q] = false; }
                 }
-                ys[cur.row - tile0] = w;
-                stPublish(y + cur.row, w);
-                if (MODE == 1) rDout[cur.row] = 1.0 / w;
+#ifdef B200_EMU
+            if (pending) emu::yield();
+#else
+            if (pending && pollNs > 0) __nanosleep(pollNs);
+#endif
+        } while (pending);
+    }
+}
+
+// The steps of one tile.  Step k = up to `lanes` rows of one level, one row per thread; its operands live in the slots
+// [k*lanes, (k+1)*lanes) of the operand block (unused lanes carry zero coefficients and point at the trash slot).  A GPU thread
+// retires ~1 dependent instruction per 4-6 cycles, so what bounds a step is the instruction count between two barriers: the
+// slot layout makes every operand address a fixed increment (no segment look-ups, no validity tests), the next step's operands
+// (D coefficients, one 64-bit word of packed offsets: D sources + the row's own place, start value) are fetched while the
+// current gathers are in flight, and the critical path is
+//   BAR -> D x LDS.64 (sources) -> D x DMUL -> D x DADD -> STS -> BAR.
+// No global access inside the loop: bar.sync would wait for the L2 acknowledge of a gpu-scope store (~400 cycles per step).
+// OP 0: w -= c*v ; OP 1: w -= c*c/v (calcReciprocalD).  DIR +1: steps upwards (forward sweep), -1: downwards (backward).
+template <int OP, int DIR, int D>
+__device__ __forceinline__ void sweepStepsD(const TileSmem& s, const SweepTile& t) {
+    const int W = blockDim.x, S = s.S;
+    int slot = (DIR > 0 ? 0 : (t.nSteps - 1) * W) + (int)threadIdx.x;
+    const double* C = s.blk;
+    const uint2* PK = (const uint2*)(s.blk + D * S);
+    double c0 = C[slot], c1 = D > 1 ? C[S + slot] : 0.0, c2 = D > 2 ? C[2 * S + slot] : 0.0;
+    uint2 pk = PK[slot];
+    double w = ldsAt(s.vals, pk.y >> 16);
+    for (int it = 0; it < t.nSteps; it++) {
+        const double v0 = ldsAt(s.vals, pk.x & 0xffffu);
+        const double v1 = D > 1 ? ldsAt(s.vals, pk.x >> 16) : 0.0;
+        const double v2 = D > 2 ? ldsAt(s.vals, pk.y & 0xffffu) : 0.0;
+        const int nslot = it + 1 < t.nSteps ? slot + DIR * W : slot;
+        const double n0 = C[nslot], n1 = D > 1 ? C[S + nslot] : 0.0, n2 = D > 2 ? C[2 * S + nslot] : 0.0;
+        const uint2 npk = PK[nslot];
+        const double nw = ldsAt(s.vals, npk.y >> 16);   // the next step's own rows still hold their start values
+        if (OP == 0) { w = w - c0 * v0; if (D > 1) w = w - c1 * v1; if (D > 2) w = w - c2 * v2; }
+        else { w = w - c0 * c0 / v0; if (D > 1) w = w - c1 * c1 / v1; if (D > 2) w = w - c2 * c2 / v2; }
+        stsAt(s.vals, pk.y >> 16, w);
+        __syncthreads();
+        c0 = n0; c1 = n1; c2 = n2; w = nw; pk = npk; slot = nslot;
+    }
+}
+template <int OP, int DIR>
+__device__ __forceinline__ void sweepSteps(const TileSmem& s, const SweepTile& t, const int* sRow, const int* sLen) {
+    if (t.nSteps == 0) return;
+    if (t.d == 3) { sweepStepsD<OP, DIR, 3>(s, t); return; }
+    if (t.d == 2) { sweepStepsD<OP, DIR, 2>(s, t); return; }
+    if (t.d == 1) { sweepStepsD<OP, DIR, 1>(s, t); return; }
+    const int W = blockDim.x, S = s.S;
+    const unsigned short* OFF = (const unsigned short*)(s.blk + t.d * S);   // [ceil(d/4)][S][4]
+    for (int k = DIR > 0 ? 0 : t.nSteps - 1; k >= 0 && k < t.nSteps; k += DIR) {   // polyhedral rows (d > 3), isolated rows (d = 0)
+        if ((int)threadIdx.x < sLen[k]) {
+            const int slot = k * W + threadIdx.x, r = sRow[k] - t.row0 + threadIdx.x;
+            double w = s.vals[r];
+            for (int j = 0; j < t.d; j++) {
+                double c = s.blk[j * S + slot], v = ldsAt(s.vals, OFF[((j >> 2) * S + slot) * 4 + (j & 3)]);
+                if (OP == 0) w = w - c * v; else w = w - c * c / v;
             }
-            __syncthreads();
-            cur = nxt;
+            s.vals[r] = w;
         }
+        __syncthreads();
+    }
+}
+
+// stage the operand block of a tile: one elected thread issues the TMA bulk copies (the whole block is contiguous)
+__device__ __forceinline__ void stageBlock(const TileSmem& s, const SweepTile& t, const double* __restrict__ blocks, TileBar* bar) {
+    if (threadIdx.x == 0) {
+        const size_t bytes = (size_t)(t.d + ((t.d + 3) >> 2)) * s.S * 8;
+        fenceAsyncProxy();
+        barExpect(bar, (unsigned)bytes);
+        bulkLoadChunks(s.blk, blocks + t.blk, bytes, bar);
+    }
+}
+// step table of the tile -> shared memory (global first row, length)
+__device__ __forceinline__ void stageSteps(const SweepView& sv, const SweepTile& t, int* sRow, int* sLen) {
+    for (int k = threadIdx.x; k < t.nSteps; k += blockDim.x) { sRow[k] = sv.stepRow[t.step0 + k]; sLen[k] = sv.stepLen[t.step0 + k]; }
+}
+// publish the tile's rows: the results sit contiguously in vals[0..nRows) = device rows [row0, row0+nRows): one TMA bulk
+// store for the 16-byte aligned middle, scalar gpu-scope stores for an odd first / last row.  Called by one thread after the
+// CTA barrier that ends the last step.
+__device__ __forceinline__ void publishTile(const TileSmem& s, const SweepTile& t, double* out) {
+    const int a = t.row0 & 1, e = t.nRows - ((t.row0 + t.nRows) & 1);   // local range [a, e) is aligned
+    if (e > a) {
+        fenceAsyncProxy();
+        for (int o = a; o < e; o += (int)(BULK_MAX / 8)) bulkStore(out + t.row0 + o, s.vals + o, (unsigned)((e - o < (int)(BULK_MAX / 8) ? e - o : (int)(BULK_MAX / 8)) * 8));
+        bulkStoreCommit();
+    }
+    if (a && t.nRows > 0) stPublish(out + t.row0, s.vals[0]);
+    if (e < t.nRows && e >= a) stPublish(out + t.row0 + t.nRows - 1, s.vals[t.nRows - 1]);
+}
+
+// MODE 0: forward precondition sweep: y[row] = rD*rA - sum_j cf_j * y[src_j]              (cf = rD[row]*upper, per solve)
+// MODE 1: calcReciprocalD           : Dt[row] = diag - sum_j up_j*up_j / Dt[src_j] ; rD = 1/Dt (up gathered through fwdPos)
+template <int MODE>
+static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, const double* __restrict__ a0,
+        const double* __restrict__ a1, const double* __restrict__ coef, const double* __restrict__ blocks, double* y,
+        double* __restrict__ rDout, SweepCtl ctl, const PcgScalars* sc) {
+    B200_DYN_SMEM(smem);
+    __shared__ int sRow[SWEEP_MAX_STEPS], sLen[SWEEP_MAX_STEPS];
+    __shared__ TileBar sBar;
+    if (sc && sc->stop) return;
+    if (threadIdx.x == 0) barInit(&sBar);
+    unsigned phase = 0;
+    const int W = blockDim.x, tid = threadIdx.x;
+    for (;;) {
+        int ti = nextTicket(ctl);
+        if (ti >= sv.nTiles) break;
+        const SweepTile t = sv.fwd[ti];
+        SWEEP_TRACE(0);
+        TileSmem s = carveTile(smem, t, W);
+        const int n = t.nRows;
+        // 1. row-independent operands: the operand block by TMA bulk copy, start values by batched loads
+        stageBlock(s, t, blocks, &sBar);
+        for (int r0 = tid; r0 < n; r0 += 8 * W) {
+            double a[8], b[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) { int r = r0 + k * W; if (r < n) { a[k] = a0[t.row0 + r]; b[k] = (MODE == 0) ? a1[t.row0 + r] : 1.0; } }
+#pragma unroll
+            for (int k = 0; k < 8; k++) { int r = r0 + k * W; if (r < n) s.vals[r] = (MODE == 0) ? a[k] * b[k] : a[k]; }
+        }
+        stageSteps(sv, t, sRow, sLen);
+        if (tid == 0) { s.vals[n + t.nHalo] = 1.0; s.vals[n + t.nHalo + 1] = 0.0; }
+        // 2. external inputs
+        if (sv.trace) { __syncthreads(); SWEEP_TRACE(1); }
+        pollHalo(t, s, sv.fwdHaloRow, y, sv.pollNs);
+        barWait(&sBar, phase); phase ^= 1u;
+        if (MODE == 1) {   // the block's coefficient columns are not valid yet: gather upper through the face slots
+            __syncthreads();
+            const int tot = t.d * s.S;
+            for (int e0 = tid; e0 < tot; e0 += 4 * W) {
+                int pos[4]; double c[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { int e = e0 + k * W; if (e < tot) pos[k] = sv.fwdPos[t.blk + e]; }
+#pragma unroll
+                for (int k = 0; k < 4; k++) { int e = e0 + k * W; if (e < tot) c[k] = pos[k] >= 0 ? coef[pos[k]] : 0.0; }
+#pragma unroll
+                for (int k = 0; k < 4; k++) { int e = e0 + k * W; if (e < tot) s.blk[e] = c[k]; }
+            }
+        }
+        __syncthreads();
+        SWEEP_TRACE(2);
+        // 3. the steps, then publish
+        sweepSteps<MODE, 1>(s, t, sRow, sLen);
+        SWEEP_TRACE(3);
+        if (tid == 0) publishTile(s, t, y);
+        if (MODE == 1) for (int r = tid; r < n; r += W) rDout[t.row0 + r] = 1.0 / s.vals[r];
+        if (tid == 0) bulkStoreWaitRead();   // the value array is reused by the next tile
+        SWEEP_TRACE(4);
     }
     sweepExit(ctl);
 }
 
-// backward: z[row] = y[row] - sum_{owner faces DESC} (rD[row]*upper_f)*z[u] ; y[row] <- sentinel (re-armed) ;
-// per-tile partial of sum(z*rA) (fixed rows per partial => deterministic) -> sc->wArA
-__device__ __forceinline__ void loadBwd(RowWork& r, int row, bool valid, const MeshView& mv, const double* __restrict__ rD,
-                                        const double* y, const double* __restrict__ upS) {
-    r.row = valid ? row : -1; r.cnt = 0; r.more = 0; r.w0 = 0.0; r.rd = 0.0;
-#pragma unroll
-    for (int j = 0; j < TILE_MAXD; j++) { r.dl[j] = 0; r.dc[j] = 0.0; }
-    if (!valid) return;
-    int s = row >> 5, lane = row & 31;
-    r.rd = rD[row]; r.w0 = y[row];
-    int so0 = mv.sliceOff[s], ow = (mv.sliceOff[s + 1] - so0) >> 5;
-    // application order = descending face index: count the real entries, then fill from the last one down
-    int n = 0;
-    for (int k = 0; k < ow; k++) { if (mv.upIdx[so0 + (k << 5) + lane] < 0) break; n++; }
-    if (n > TILE_MAXD) { r.more = 1; return; }
-#pragma unroll
-    for (int j = 0; j < TILE_MAXD; j++)
-        if (j < n) { int pos = so0 + ((n - 1 - j) << 5) + lane; r.dl[j] = mv.upIdx[pos]; r.dc[j] = r.rd * upS[pos]; }
-    r.cnt = n;
-}
-
-static __global__ void __launch_bounds__(SWEEP_BLOCK) k_dic_bwd_tiled(MeshView mv, TileView tv, const double* __restrict__ rD,
-        const double* __restrict__ upS, const double* __restrict__ rA, double* y, double* z, SweepCtl ctl, PcgScalars* sc,
-        double* partials, unsigned* counter) {
-    __shared__ double zs[SWEEP_TILE_MAX];
+// backward: z[row] = y[row] - sum_{owner faces DESC} cb_j * z[u_j]   (cb = rD[row]*upper) ; y[row] <- sentinel (re-armed) ;
+// per-tile partial of sum(z*rA) (fixed rows per partial, fixed order => deterministic) -> sc->wArA
+static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, const double* __restrict__ blocks,
+        const double* __restrict__ rA, double* y, double* z, SweepCtl ctl, PcgScalars* sc, double* partials, unsigned* counter) {
+    B200_DYN_SMEM(smem);
+    __shared__ int sRow[SWEEP_MAX_STEPS], sLen[SWEEP_MAX_STEPS];
+    __shared__ TileBar sBar;
     if (sc && sc->stop) return;
+    if (threadIdx.x == 0) barInit(&sBar);
+    unsigned phase = 0;
+    const int W = blockDim.x, tid = threadIdx.x;
     for (;;) {
-        int t = nextTicket(ctl);
-        if (t >= tv.nTiles) break;
-        const int tile = tv.nTiles - 1 - t;
-        const int tile0 = tv.tileStart[tile], tileEnd = tv.tileStart[tile + 1];
-        const int seg0 = tv.tileSegStart[tile], seg1 = tv.tileSegStart[tile + 1];
-        RowWork cur, nxt;
-        double dotv = 0.0;
-        { int sg = seg1 - 1; bool any = seg0 < seg1; int b = any ? tv.segRow[sg] : 0, e = any ? tv.segRow[sg + 1] : 0, row = b + (int)threadIdx.x;
-          loadBwd(cur, row, any && row < e, mv, rD, y, upS); }
-        for (int sg = seg1 - 1; sg >= seg0; sg--) {
-            if (sg - 1 >= seg0) { int b = tv.segRow[sg - 1], e = tv.segRow[sg], row = b + (int)threadIdx.x; loadBwd(nxt, row, row < e, mv, rD, y, upS); }
-            if (cur.row >= 0) {
-                double w = cur.w0;
-                if (!cur.more) {
+        int tk = nextTicket(ctl);
+        if (tk >= sv.nTiles) break;
+        const int ti = sv.nTiles - 1 - tk;
+        const SweepTile t = sv.bwd[ti];
+        TileSmem s = carveTile(smem, t, W);
+        const int n = t.nRows;
+        stageBlock(s, t, blocks, &sBar);
+        for (int r0 = tid; r0 < n; r0 += 8 * W) {
+            double a[8];
 #pragma unroll
-                    for (int j = 0; j < TILE_MAXD; j++)
-                        if (j < cur.cnt) {
-                            int u = cur.dl[j];
-                            double v = (u < tileEnd) ? zs[u - tile0] : pollValue(z + u);
-                            w = w - cur.dc[j] * v;
-                        }
-                } else {
-                    int s = cur.row >> 5, lane = cur.row & 31, so0 = mv.sliceOff[s], ow = (mv.sliceOff[s + 1] - so0) >> 5;
-                    for (int k = ow - 1; k >= 0; k--) {
-                        int pos = so0 + (k << 5) + lane;
-                        int u = mv.upIdx[pos];
-                        if (u < 0) continue;
-                        double v = (u < tileEnd) ? zs[u - tile0] : pollValue(z + u);
-                        w = w - cur.rd * upS[pos] * v;
-                    }
-                }
-                zs[cur.row - tile0] = w;
-                stPublish(z + cur.row, w);
-                y[cur.row] = sentinel();
-                dotv = dotv + w * rA[cur.row];
-            }
-            __syncthreads();
-            cur = nxt;
+            for (int k = 0; k < 8; k++) { int r = r0 + k * W; if (r < n) a[k] = y[t.row0 + r]; }
+#pragma unroll
+            for (int k = 0; k < 8; k++) { int r = r0 + k * W; if (r < n) { s.vals[r] = a[k]; y[t.row0 + r] = sentinel(); } }
         }
+        stageSteps(sv, t, sRow, sLen);
+        if (tid == 0) { s.vals[n + t.nHalo] = 1.0; s.vals[n + t.nHalo + 1] = 0.0; }
+        pollHalo(t, s, sv.bwdHaloRow, z, sv.pollNs);
+        barWait(&sBar, phase); phase ^= 1u;
+        __syncthreads();
+        sweepSteps<0, -1>(s, t, sRow, sLen);
+        if (tid == 0) publishTile(s, t, z);
         if (partials) {
+            double dotv = 0.0;
+            for (int r = tid; r < n; r += W) dotv = dotv + s.vals[r] * rA[t.row0 + r];
             double v[1] = {dotv};
-            gridReduce<1, OpSum>(v, tile, tv.nTiles, partials, counter, nullptr);
+            gridReduce<1, OpSum>(v, ti, sv.nTiles, partials, counter, nullptr);
+        }
+        if (tid == 0) bulkStoreWaitRead();
+    }
+    if (partials) gridFinalize<1, OpSum>(sv.nTiles, partials, counter, &sc->wArA);
+    sweepExit(ctl);
+}
+
+// per solve: coefficient columns of the operand blocks: cf = rD[row]*upper (forward), cb = rD[row]*upper (backward).
+// grid = 2*nTiles (forward tiles, then backward tiles); block = lanes
+static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_coeffs(SweepView sv, const double* __restrict__ rD,
+        const double* __restrict__ upS, double* __restrict__ cf, double* __restrict__ cb) {
+    const bool bw = (int)blockIdx.x >= sv.nTiles;
+    const SweepTile t = bw ? sv.bwd[blockIdx.x - sv.nTiles] : sv.fwd[blockIdx.x];
+    const int* pos = bw ? sv.bwdPos : sv.fwdPos;
+    double* out = bw ? cb : cf;
+    const int W = blockDim.x, S = t.nSteps * W;
+    for (int k = 0; k < t.nSteps; k++) {
+        const bool valid = (int)threadIdx.x < sv.stepLen[t.step0 + k];
+        const double rd = valid ? rD[sv.stepRow[t.step0 + k] + threadIdx.x] : 0.0;
+        for (int j = 0; j < t.d; j++) {
+            const int e = t.blk + j * S + k * W + threadIdx.x;
+            const int p = valid ? pos[e] : -1;
+            out[e] = p >= 0 ? rd * upS[p] : 0.0;
         }
     }
-    if (partials) gridFinalize<1, OpSum>(tv.nTiles, partials, counter, &sc->wArA);
-    sweepExit(ctl);
 }
 
 }  // namespace b200

@@ -294,38 +294,222 @@ void levelRenumbering(int32_t N, const int32_t* lower, const int32_t* upper, int
     for (int32_t c = 0; c < N; c++) { int32_t r = start[level[c]]++; rowCell[r] = c; cellRow[c] = r; }
 }
 
-void tileRenumbering(int32_t N, const int32_t* lower, const int32_t* upper, int32_t F, int bandLevels, int tileRows, int maxSeg,
-                     std::vector<int32_t>& level, std::vector<int32_t>& rowCell, std::vector<int32_t>& cellRow, int32_t& nLevels,
-                     std::vector<int32_t>& tileStart, std::vector<int32_t>& tileSegStart, std::vector<int32_t>& segRow) {
+// --------------------------------------------------------------------------------------------- sweep plan
+namespace {
+struct Piece { int32_t b, e; };   // range in the (class, level, index)-sorted cell order
+}
+
+void buildSweepPlan(int32_t N, const int32_t* lower, const int32_t* upper, int32_t F, int bandLevels, int maxRows, int smemBudget,
+                    int lanes, SweepPlan& P) {
+    P = SweepPlan();
+    P.lanes = std::max(32, std::min(lanes, 1024)) / 32 * 32;
+    const int W = P.lanes;
+    P.bandLevels = std::max(1, bandLevels);
+    P.maxRows = std::max(8, std::min(maxRows, 32768));
+    P.smemBudget = smemBudget;
     std::vector<int32_t> lvRow, lvCell;
-    levelRenumbering(N, lower, upper, F, level, lvRow, lvCell, nLevels);   // level[] + validity checks
-    int nBands = (nLevels + bandLevels - 1) / bandLevels;
-    // cells of each band in ascending original index (counting sort by band keeps index order)
-    std::vector<int32_t> bandStart(nBands + 1, 0);
-    for (int32_t c = 0; c < N; c++) bandStart[level[c] / bandLevels + 1]++;
-    for (int b = 0; b < nBands; b++) bandStart[b + 1] += bandStart[b];
-    std::vector<int32_t> byBand(N), cur(bandStart.begin(), bandStart.end() - 1);
-    for (int32_t c = 0; c < N; c++) byBand[cur[level[c] / bandLevels]++] = c;
-    rowCell.resize(N); cellRow.resize(N);
-    tileStart.assign(1, 0); tileSegStart.assign(1, 0); segRow.clear();
-    int32_t row = 0;
-    std::vector<int32_t> cnt(bandLevels + 1);
-    for (int b = 0; b < nBands; b++)
-        for (int32_t c0 = bandStart[b]; c0 < bandStart[b + 1]; c0 += tileRows) {
-            int32_t c1 = std::min<int32_t>(c0 + tileRows, bandStart[b + 1]);
-            // inside the tile: stable counting sort by level (keeps ascending index inside a level)
-            std::fill(cnt.begin(), cnt.end(), 0);
-            for (int32_t i = c0; i < c1; i++) cnt[level[byBand[i]] - b * bandLevels + 1]++;
-            for (int t = 0; t < bandLevels; t++) cnt[t + 1] += cnt[t];
-            std::vector<int32_t> pos(cnt.begin(), cnt.end() - 1);
-            for (int32_t i = c0; i < c1; i++) { int32_t c = byBand[i]; int32_t r = row + pos[level[c] - b * bandLevels]++; rowCell[r] = c; cellRow[c] = r; }
-            for (int t = 0; t < bandLevels; t++)
-                for (int32_t s0 = cnt[t]; s0 < cnt[t + 1]; s0 += maxSeg) segRow.push_back(row + s0);
-            row += c1 - c0;
-            tileStart.push_back(row);
-            tileSegStart.push_back((int32_t)segRow.size());
+    levelRenumbering(N, lower, upper, F, P.level, lvRow, lvCell, P.nLevels);   // level[] + validity checks
+    P.tileStart.assign(1, 0); P.tileStepStart.assign(1, 0);
+    P.fwdEll.assign(1, 0); P.bwdEll.assign(1, 0); P.fwdHalo.assign(1, 0); P.bwdHalo.assign(1, 0);
+    P.potJ.assign(N, 0); P.potK.assign(N, 0); P.rowCell.resize(N); P.cellRow.resize(N);
+    if (N == 0) return;
+    const int B = P.bandLevels;
+
+    // ---- 1. stride classes of (upper - lower): up to three dominant magnitudes
+    int nc = 0; long long cen[3] = {0, 0, 0};
+    {
+        std::vector<int32_t> d(F);
+        for (int32_t f = 0; f < F; f++) d[f] = upper[f] - lower[f];
+        std::sort(d.begin(), d.end());
+        std::vector<std::pair<int32_t, int32_t>> hist;
+        for (int32_t f = 0; f < F; f++) { if (hist.empty() || hist.back().first != d[f]) hist.push_back({d[f], 0}); hist.back().second++; }
+        std::vector<char> removed(hist.size(), 0);
+        for (int it = 0; it < 3; it++) {
+            int best = -1;
+            for (size_t i = 0; i < hist.size(); i++)
+                if (!removed[i] && (best < 0 || hist[i].second > hist[best].second)) best = (int)i;
+            if (best < 0) break;
+            long long c = hist[best].first;
+            cen[nc++] = c;
+            for (size_t i = 0; i < hist.size(); i++) { long long v = hist[i].first; if (!removed[i] && 2 * v > c && v < 2 * c) removed[i] = 1; }
         }
-    segRow.push_back(N);
+        for (int a = 0; a < nc; a++) for (int b = a + 1; b < nc; b++) if (cen[b] < cen[a]) std::swap(cen[a], cen[b]);
+        for (int k = 0; k < nc; k++) P.stride[k] = (int)cen[k];
+    }
+    auto classOf = [&](long long d) { int c = 0; if (nc > 1 && d * d >= cen[0] * cen[1]) c = 1; if (nc > 2 && d * d >= cen[1] * cen[2]) c = 2; return c; };
+    // ---- 2. potentials: most class-1 / class-2 faces on any path (faces are sorted by lower => one ascending pass)
+    for (int32_t f = 0; f < F; f++) {
+        int32_t l = lower[f], u = upper[f];
+        int c = classOf((long long)u - l);
+        int32_t a = P.potJ[l] + (c == 1 ? 1 : 0), b = P.potK[l] + (c == 2 ? 1 : 0);
+        if (a > P.potJ[u]) P.potJ[u] = a;
+        if (b > P.potK[u]) P.potK[u] = b;
+    }
+    long long extJ = 0, extK = 0;
+    for (int32_t c = 0; c < N; c++) { extJ = std::max<long long>(extJ, P.potJ[c] + 1); extK = std::max<long long>(extK, P.potK[c] + 1); }
+    // ---- 3. bin sizes: A = target cells of one (potJ, potK) bin column per level; minimise the number of bins crossed
+    long long nTriples = 0;
+    {
+        std::vector<long long> key(N);
+        for (int32_t c = 0; c < N; c++) key[c] = ((long long)P.level[c] * extJ + P.potJ[c]) * extK + P.potK[c];
+        std::sort(key.begin(), key.end());
+        for (int32_t c = 0; c < N; c++) if (c == 0 || key[c] != key[c - 1]) nTriples++;
+    }
+    long long A = std::max<long long>(1, (long long)P.maxRows * nTriples / ((long long)B * N));
+    {
+        long long bestBj = 1, bestBk = 1, bestCost = -1, bestProd = 0;
+        for (long long bj = 1; bj <= std::min(extJ, A); bj++) {
+            long long bk = std::min(extK, std::max<long long>(1, A / bj));
+            long long cost = (extJ + bj - 1) / bj + (extK + bk - 1) / bk, prod = bj * bk;
+            if (bestCost < 0 || cost < bestCost || (cost == bestCost && prod > bestProd)) { bestCost = cost; bestProd = prod; bestBj = bj; bestBk = bk; }
+        }
+        P.binJ = (int)bestBj; P.binK = (int)bestBk;
+    }
+    const long long nJb = (extJ + P.binJ - 1) / P.binJ, nKb = (extK + P.binK - 1) / P.binK;
+    // ---- 4. cells sorted by (band, binK, binJ, level, index); classes -> pieces of at most maxRows cells
+    std::vector<long long> ckey(N);
+    for (int32_t c = 0; c < N; c++)
+        ckey[c] = ((((long long)(P.level[c] / B) * nKb + P.potK[c] / P.binK) * nJb + P.potJ[c] / P.binJ) * P.nLevels) + P.level[c];
+    std::vector<int32_t> order(N);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return ckey[a] < ckey[b]; });
+    std::vector<Piece> pieces;
+    for (int32_t b0 = 0; b0 < N;) {
+        long long cls = ckey[order[b0]] / P.nLevels;
+        int32_t e0 = b0;
+        while (e0 < N && ckey[order[e0]] / P.nLevels == cls) e0++;
+        int32_t n = e0 - b0, np = (n + P.maxRows - 1) / P.maxRows, base = n / np, rem = n % np, at = b0;
+        for (int q = 0; q < np; q++) { int32_t sz = base + (q < rem ? 1 : 0); pieces.push_back({at, at + sz}); at += sz; }
+        b0 = e0;
+    }
+    std::vector<int32_t> ownerStart, losort, losortStart;
+    {
+        std::vector<int32_t> lo(lower, lower + F), up(upper, upper + F);
+        lduDerived(N, lo, up, ownerStart, losort, losortStart);
+    }
+    // ---- 5. shared-memory / index-width budget: offending pieces are halved until they fit
+    std::vector<int32_t> pieceOf(N), stamp(N, -1), stampB(N, -1);
+    for (;;) {
+        for (size_t p = 0; p < pieces.size(); p++) for (int32_t i = pieces[p].b; i < pieces[p].e; i++) pieceOf[order[i]] = (int32_t)p;
+        std::fill(stamp.begin(), stamp.end(), -1); std::fill(stampB.begin(), stampB.end(), -1);
+        std::vector<Piece> next; next.reserve(pieces.size());
+        bool changed = false;
+        for (size_t p = 0; p < pieces.size(); p++) {
+            int n = pieces[p].e - pieces[p].b, dF = 0, dB = 0, hF = 0, hB = 0, nSteps = 0, run = 0;
+            for (int32_t i = pieces[p].b; i < pieces[p].e; i++) {
+                int32_t c = order[i];
+                if (i > pieces[p].b && P.level[c] != P.level[order[i - 1]]) { nSteps += (run + W - 1) / W; run = 0; }
+                run++;
+                dF = std::max(dF, losortStart[c + 1] - losortStart[c]);
+                dB = std::max(dB, ownerStart[c + 1] - ownerStart[c]);
+                for (int32_t q = losortStart[c]; q < losortStart[c + 1]; q++) { int32_t l = lower[losort[q]]; if (pieceOf[l] != (int32_t)p && stamp[l] != (int32_t)p) { stamp[l] = (int32_t)p; hF++; } }
+                for (int32_t f = ownerStart[c]; f < ownerStart[c + 1]; f++) { int32_t u = upper[f]; if (pieceOf[u] != (int32_t)p && stampB[u] != (int32_t)p) { stampB[u] = (int32_t)p; hB++; } }
+            }
+            nSteps += (run + W - 1) / W;
+            const int S = nSteps * W;
+            size_t need = std::max(sweepSmemBytes(n, S, hF, dF), sweepSmemBytes(n, S, hB, dB));
+            bool tooBig = need > (size_t)smemBudget || n + std::max(hF, hB) + 2 > SWEEP_MAX_SLOTS || nSteps > SWEEP_MAX_STEPS;
+            if (tooBig && n > 1) {
+                int32_t mid = pieces[p].b + n / 2;
+                next.push_back({pieces[p].b, mid}); next.push_back({mid, pieces[p].e});
+                changed = true;
+            } else {
+                if (tooBig) throw std::runtime_error("DIC sweep plan: a single row exceeds the shared-memory budget");
+                next.push_back(pieces[p]);
+            }
+        }
+        pieces.swap(next);
+        if (!changed) break;
+    }
+    const int nT = (int)pieces.size();
+    // ---- 6. tile graph, longest-path levels (Kahn), ticket order = (tile level, class order)
+    std::vector<long long> edges;
+    for (int32_t f = 0; f < F; f++) { int32_t a = pieceOf[lower[f]], b = pieceOf[upper[f]]; if (a != b) edges.push_back(((long long)a << 32) | (unsigned)b); }
+    std::sort(edges.begin(), edges.end());
+    edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+    std::vector<int32_t> adjStart(nT + 1, 0), indeg(nT, 0), tl(nT, 0);
+    for (long long e : edges) { adjStart[(e >> 32) + 1]++; indeg[(int32_t)(e & 0xffffffff)]++; }
+    for (int t = 0; t < nT; t++) adjStart[t + 1] += adjStart[t];
+    std::vector<int32_t> queue; queue.reserve(nT);
+    for (int t = 0; t < nT; t++) if (indeg[t] == 0) queue.push_back(t);
+    for (size_t h = 0; h < queue.size(); h++) {
+        int32_t t = queue[h];
+        for (int32_t q = adjStart[t]; q < adjStart[t + 1]; q++) {   // edges are sorted by source, so edges[q] belongs to t
+            int32_t v = (int32_t)(edges[q] & 0xffffffff);
+            tl[v] = std::max(tl[v], tl[t] + 1);
+            if (--indeg[v] == 0) queue.push_back(v);
+        }
+    }
+    if ((int)queue.size() != nT) throw std::runtime_error("DIC sweep plan: tile graph is cyclic (internal error)");
+    std::vector<int32_t> ticket(nT);
+    std::iota(ticket.begin(), ticket.end(), 0);
+    std::stable_sort(ticket.begin(), ticket.end(), [&](int32_t a, int32_t b) { return tl[a] < tl[b]; });
+    // ---- 7. rows and steps
+    P.nTiles = nT; P.tileLevel.resize(nT);
+    std::vector<int32_t> tileOfCell(N);
+    int32_t row = 0;
+    for (int t = 0; t < nT; t++) {
+        const Piece& pc = pieces[ticket[t]];
+        P.tileLevel[t] = tl[ticket[t]];
+        P.nTileLevels = std::max(P.nTileLevels, tl[ticket[t]] + 1);
+        for (int32_t i = pc.b; i < pc.e; i++) {
+            int32_t c = order[i];
+            bool newLevel = i == pc.b || P.level[c] != P.level[order[i - 1]];
+            if (newLevel || P.stepLen.back() == W) { P.stepRow.push_back(row); P.stepLen.push_back(0); }
+            P.stepLen.back()++;
+            P.rowCell[row] = c; P.cellRow[c] = row; tileOfCell[c] = t; row++;
+        }
+        P.tileStart.push_back(row);
+        P.tileStepStart.push_back((int32_t)P.stepRow.size());
+    }
+    // ---- 8. per-tile ELL (slot layout) + halo lists of the two sweeps
+    P.fwdD.resize(nT); P.bwdD.resize(nT);
+    std::vector<int32_t> slot(N, -1), slotOfRow(N);
+    for (int t = 0; t < nT; t++)
+        for (int32_t k = P.tileStepStart[t]; k < P.tileStepStart[t + 1]; k++)
+            for (int32_t i = 0; i < P.stepLen[k]; i++) slotOfRow[P.stepRow[k] + i] = (k - P.tileStepStart[t]) * W + i;
+    std::fill(stamp.begin(), stamp.end(), -1);
+    for (int t = 0; t < nT; t++) {
+        const int32_t r0 = P.tileStart[t], n = P.tileStart[t + 1] - r0;
+        const int S = (P.tileStepStart[t + 1] - P.tileStepStart[t]) * W;
+        for (int dir = 0; dir < 2; dir++) {
+            std::vector<uint16_t>& idx = dir == 0 ? P.fwdIdx : P.bwdIdx;
+            std::vector<int32_t>& face = dir == 0 ? P.fwdFace : P.bwdFace;
+            std::vector<int32_t>& haloRow = dir == 0 ? P.fwdHaloRow : P.bwdHaloRow;
+            std::vector<int32_t>& ell = dir == 0 ? P.fwdEll : P.bwdEll;
+            std::vector<int32_t>& halo = dir == 0 ? P.fwdHalo : P.bwdHalo;
+            int D = 0;
+            for (int32_t r = 0; r < n; r++) {
+                int32_t c = P.rowCell[r0 + r];
+                D = std::max(D, dir == 0 ? losortStart[c + 1] - losortStart[c] : ownerStart[c + 1] - ownerStart[c]);
+            }
+            (dir == 0 ? P.fwdD : P.bwdD)[t] = D;
+            size_t e0 = idx.size();
+            idx.resize(e0 + (size_t)D * S, 0xffff); face.resize(e0 + (size_t)D * S, -1);
+            int nHalo = 0;
+            int32_t st = 2 * t + dir;
+            for (int32_t r = 0; r < n; r++) {
+                int32_t c = P.rowCell[r0 + r], sl = slotOfRow[r0 + r];
+                int cnt = dir == 0 ? losortStart[c + 1] - losortStart[c] : ownerStart[c + 1] - ownerStart[c];
+                for (int j = 0; j < cnt; j++) {
+                    int32_t f = dir == 0 ? losort[losortStart[c] + j] : ownerStart[c + 1] - 1 - j;
+                    int32_t o = dir == 0 ? lower[f] : upper[f];
+                    int32_t id;
+                    if (tileOfCell[o] == t) id = P.cellRow[o] - r0;
+                    else {
+                        if (stamp[o] != st) { stamp[o] = st; slot[o] = nHalo++; haloRow.push_back(P.cellRow[o]); }
+                        id = n + slot[o];
+                    }
+                    idx[e0 + (size_t)j * S + sl] = (uint16_t)id; face[e0 + (size_t)j * S + sl] = f;
+                }
+            }
+            for (size_t e = e0; e < idx.size(); e++) if (face[e] < 0) idx[e] = (uint16_t)(n + nHalo);
+            ell.push_back((int32_t)idx.size()); halo.push_back((int32_t)haloRow.size());
+            size_t need = sweepSmemBytes(n, S, nHalo, D);
+            if (dir == 0) P.smemFwd = std::max(P.smemFwd, need); else P.smemBwd = std::max(P.smemBwd, need);
+        }
+    }
+    if (P.fwdIdx.size() >= (size_t)1 << 31 || P.bwdIdx.size() >= (size_t)1 << 31) throw std::runtime_error("DIC sweep plan: mesh too large for 32-bit ELL offsets");
 }
 
 }  // namespace b200

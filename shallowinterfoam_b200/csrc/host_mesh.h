@@ -58,14 +58,51 @@ void levelRenumbering(int32_t nCells, const int32_t* lower, const int32_t* upper
                       std::vector<int32_t>& level, std::vector<int32_t>& rowCell, std::vector<int32_t>& cellRow,
                       int32_t& nLevels);
 
-// DIC tiling: cells are grouped into bands of `bandLevels` consecutive forward levels; inside a band the
-// cells, in ascending original index, are cut into chunks of `tileRows`; tile = (band, chunk), numbered band-major.  Every
-// dependency l -> u (l < u, level(l) < level(u)) goes to the same or a LATER tile, so tiles processed in order never deadlock.
-// Device row order = (tile, level, original index).  tileSegStart/segRow: CSR of the per-tile level segments (segments longer
-// than `maxSeg` rows are split); segRow has one extra entry (= nCells).
-void tileRenumbering(int32_t nCells, const int32_t* lower, const int32_t* upper, int32_t nFaces, int bandLevels, int tileRows,
-                     int maxSeg, std::vector<int32_t>& level, std::vector<int32_t>& rowCell, std::vector<int32_t>& cellRow,
-                     int32_t& nLevels, std::vector<int32_t>& tileStart, std::vector<int32_t>& tileSegStart,
-                     std::vector<int32_t>& segRow);
+// DIC sweep plan: CLOSED tiles on a tile DAG.
+//  * three integer potentials per cell, each non-decreasing along every dependency l -> u (l < u):
+//      level  = longest path from a source (the classic wavefront number),
+//      potJ/K = largest number of "stride class 1 / class 2" faces on any path to the cell.  The stride classes come from
+//               the histogram of (upper - lower): its three dominant magnitudes (1, nx, nx*ny on a blockMesh-ordered hex block,
+//               also after subsetMesh) => potJ = j, potK = k on such meshes; on any other mesh they are still monotone.
+//  * tile class = (level / bandLevels, potJ / binJ, potK / binK).  Because every component is monotone, the tile graph is acyclic
+//    for ANY mesh; classes larger than the row / shared-memory budget are cut into consecutive pieces of their (level, index) order,
+//    which keeps it acyclic.  A tile's external dependencies all lie in tiles that precede it in the ticket order (tiles sorted by
+//    their longest-path level in the tile graph), so a CTA waits once, then sweeps its local levels out of shared memory.
+//  * device row order = (tile in ticket order, level, original index).
+struct SweepPlan {
+    // parameters used
+    int bandLevels = 16, binJ = 1, binK = 1, maxRows = 2048, smemBudget = 110 * 1024, lanes = 128;
+    int stride[3] = {0, 0, 0};                      // detected stride-class centres (0 = absent)
+    std::vector<int32_t> level, potJ, potK;         // per cell
+    int32_t nLevels = 0;
+    std::vector<int32_t> rowCell, cellRow;          // device row <-> original cell
+    int nTiles = 0, nTileLevels = 0;
+    std::vector<int32_t> tileStart;                 // [nTiles+1] first row
+    std::vector<int32_t> tileLevel;                 // [nTiles] longest-path level of the tile in the tile graph
+    // a tile is executed as STEPS of at most `lanes` rows of one level (one row per thread, a barrier after every step);
+    // step k of tile t owns the operand slots [k*lanes, (k+1)*lanes) of the tile's operand block (unused lanes are inert).
+    std::vector<int32_t> tileStepStart;             // [nTiles+1] CSR into stepRow / stepLen
+    std::vector<int32_t> stepRow, stepLen;          // first device row and number of rows of each step
+    // per-tile ELL of the two sweeps in SLOT layout: column j of tile t = entries [ell[t] + j*S, +S), S = nSteps*lanes.
+    // idx: source in the tile's value array (0..nRows-1 = row of this tile, nRows+h = halo entry h, nRows+nHalo = padding);
+    // face: ORIGINAL face index of the coefficient (-1 = padding).  Forward columns are in ascending face order, backward
+    // columns in descending face order = the order upstream's sequential loops apply them to the row.
+    std::vector<int32_t> fwdEll, fwdD, fwdHalo;     // [nTiles+1] offsets, [nTiles] widths, [nTiles+1] halo offsets
+    std::vector<int32_t> bwdEll, bwdD, bwdHalo;
+    std::vector<uint16_t> fwdIdx, bwdIdx;           // [fwdEll.back()], [bwdEll.back()]
+    std::vector<int32_t> fwdFace, bwdFace;
+    std::vector<int32_t> fwdHaloRow, bwdHaloRow;    // device rows polled by the tile
+    size_t smemFwd = 0, smemBwd = 0;                // largest per-tile shared-memory need (bytes)
+};
+// shared-memory bytes of one tile (the formula the kernels use): the value array (rows, start values overwritten in place by the
+// results; halo; padding; trash; +1 alignment shift) and the operand block: d coefficient columns and ceil(d/4) columns of
+// packed 16-bit offsets
+inline size_t sweepSmemBytes(int nRows, int nSlots, int nHalo, int d) {
+    return 8 * ((size_t)((nRows + nHalo + 3 + 1) / 2 * 2)) + 8 * (size_t)nSlots * (size_t)(d + (d + 3) / 4) + 64;
+}
+constexpr int SWEEP_MAX_SLOTS = 8191;   // nRows + nHalo + 2 (sources are stored as 16-bit BYTE offsets into the value array)
+constexpr int SWEEP_MAX_STEPS = 256;    // steps per tile (staged in shared memory)
+void buildSweepPlan(int32_t nCells, const int32_t* lower, const int32_t* upper, int32_t nFaces, int bandLevels, int maxRows,
+                    int smemBudget, int lanes, SweepPlan& plan);
 
 }  // namespace b200

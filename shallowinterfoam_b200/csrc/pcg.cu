@@ -37,6 +37,9 @@ PcgWorkspace& pcgWorkspace(DeviceMesh& m) {
     w->pA.alloc(N); w->wA.alloc(N); w->rA.alloc(N); w->y.alloc(N); w->z.alloc(N); w->rD.alloc(N); w->Dt.alloc(N);
     int nBlocks = gridFor(m.N) + 1;
     w->partials.alloc(3 * (size_t)std::max(nBlocks, m.nTiles) + 8);
+    w->cf.alloc(m.fwdBlkSize); w->cb.alloc(m.bwdBlkSize);   // operand blocks: templates carry the (static) source offsets
+    if (m.fwdBlkSize) B200_CHECK_CUDA(cudaMemcpyAsync(w->cf.p, m.dFwdBlk0.p, 8 * m.fwdBlkSize, cudaMemcpyDeviceToDevice, rt().stream));
+    if (m.bwdBlkSize) B200_CHECK_CUDA(cudaMemcpyAsync(w->cb.p, m.dBwdBlk0.p, 8 * m.bwdBlkSize, cudaMemcpyDeviceToDevice, rt().stream));
     w->sc.alloc(1); w->counters.alloc(4); w->counters.zero();
     B200_CHECK_CUDA(cudaMallocHost((void**)&w->hsc, 2 * sizeof(PcgScalars)));
     for (auto& e : w->ev) B200_CHECK_CUDA(cudaEventCreate(&e));
@@ -52,11 +55,31 @@ PcgWorkspace& pcgWorkspace(DeviceMesh& m) {
 }
 
 static SweepCtl sweepCtl(PcgWorkspace& w) { return SweepCtl{w.counters.p + 1, w.counters.p + 2}; }
-// CTAs of a tiled sweep: one CTA per tile in flight; tiles are handed out in order by ticket, so any grid size is deadlock-free
+// CTAs of a tiled sweep: as many as fit (shared memory bound); tiles are handed out in ticket order, so any grid size is deadlock-free
 static int sweepGridOf(const DeviceMesh& m, const PcgWorkspace&) {
     int forced = (int)rt().opt("sweep_grid", 0);
-    int g = forced > 0 ? forced : rt().numSMs * (int)rt().opt("sweep_ctas_per_sm", 8);
+    int perSM = std::max(1, std::min(8, (int)((size_t)(227 * 1024) / (m.sweepSmem + 2048))));
+    int cap = (int)rt().opt("sweep_ctas_per_sm", 0);
+    if (cap > 0) perSM = std::min(perSM, cap);
+    int g = forced > 0 ? forced : rt().numSMs * perSM;
     return std::max(1, std::min(g, std::max(1, m.nTiles)));
+}
+static int sweepThreads(const DeviceMesh& m) { return m.plan.lanes; }   // one row per thread per step
+static void launchCalcRD(DeviceMesh& m, PcgWorkspace& w, const double* diag, const double* upS, double* rD) {
+    fillSentinel(w.Dt, m.N);
+    B200_LAUNCH_SMEM(k_dic_fwd<1>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), diag, (const double*)nullptr, upS,
+                     (const double*)w.cf.p, w.Dt.p, rD, sweepCtl(w), (const PcgScalars*)nullptr);
+}
+static void launchCoeffs(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* upS) {
+    B200_LAUNCH(k_dic_coeffs, 2 * m.nTiles, sweepThreads(m), rt().stream, m.sweep(), rD, upS, w.cf.p, w.cb.p);
+}
+static void launchFwd(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* rA, const PcgScalars* sc) {
+    B200_LAUNCH_SMEM(k_dic_fwd<0>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), rD, rA, (const double*)nullptr,
+                     (const double*)w.cf.p, w.y.p, (double*)nullptr, sweepCtl(w), sc);
+}
+static void launchBwd(DeviceMesh& m, PcgWorkspace& w, const double* rA, PcgScalars* sc, double* part, unsigned* cnt) {
+    B200_LAUNCH_SMEM(k_dic_bwd, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), (const double*)w.cb.p, rA, w.y.p, w.z.p,
+                     sweepCtl(w), sc, part, cnt);
 }
 
 void amulDevice(DeviceMesh& m, const double* diag, const double* upS, const double* loS, const double* psi, double* Apsi,
@@ -77,22 +100,15 @@ void dicCalcReciprocalD(DeviceMesh& m, const double* diag, const double* upS, do
     PcgWorkspace& w = pcgWorkspace(m);
     ScopedTimer t(T_DIC_RD);
     if (!m.N) return;
-    fillSentinel(w.Dt, m.N);
-    int nChunks = gridFor(m.N);
-    B200_LAUNCH(k_dic_fwd_tiled<1>, sweepGridOf(m, w), SWEEP_BLOCK, rt().stream, m.view(), m.tiles(), diag, (const double*)nullptr, upS, w.Dt.p, rD,
-                sweepCtl(w), (const PcgScalars*)nullptr);
+    launchCalcRD(m, w, diag, upS, rD);
 }
 
 void dicPrecondition(DeviceMesh& m, const double* rD, const double* upS, const double* rA, double* wA) {
     PcgWorkspace& w = pcgWorkspace(m);
     if (!m.N) return;
-    int nChunks = gridFor(m.N);
-    { ScopedTimer t(T_DIC_FWD);
-      B200_LAUNCH(k_dic_fwd_tiled<0>, sweepGridOf(m, w), SWEEP_BLOCK, rt().stream, m.view(), m.tiles(), rD, rA, upS, w.y.p, (double*)nullptr, sweepCtl(w),
-                  (const PcgScalars*)nullptr); }
-    { ScopedTimer t(T_DIC_BWD);
-      B200_LAUNCH(k_dic_bwd_tiled, sweepGridOf(m, w), SWEEP_BLOCK, rt().stream, m.view(), m.tiles(), rD, upS, rA, w.y.p, w.z.p, sweepCtl(w),
-                  (PcgScalars*)nullptr, (double*)nullptr, (unsigned*)nullptr); }
+    { ScopedTimer t(T_DIC_RD); launchCoeffs(m, w, rD, upS); }
+    { ScopedTimer t(T_DIC_FWD); launchFwd(m, w, rD, rA, nullptr); }
+    { ScopedTimer t(T_DIC_BWD); launchBwd(m, w, rA, nullptr, nullptr, nullptr); }
     B200_CHECK_CUDA(cudaMemcpyAsync(wA, w.z.p, 8 * (size_t)m.N, cudaMemcpyDeviceToDevice, rt().stream));
     fillSentinel(w.z, m.N);
 }
@@ -134,7 +150,7 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
     B200_CHECK_CUDA(cudaMemcpyAsync(&w.hsc[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
     B200_CHECK_CUDA(cudaEventRecord(w.ev[0], st));
     // calcReciprocalD is enqueued before the host learns whether it is needed (one sweep; keeps the GPU busy)
-    if (N) { fillSentinel(w.Dt, N); B200_LAUNCH(k_dic_fwd_tiled<1>, sweepGridOf(m, w), SWEEP_BLOCK, st, mv, m.tiles(), diag, (const double*)nullptr, upS, w.Dt.p, w.rD.p, sweepCtl(w), (const PcgScalars*)nullptr); }
+    if (N) { ScopedTimer t(T_DIC_RD); launchCalcRD(m, w, diag, upS, w.rD.p); launchCoeffs(m, w, w.rD.p, upS); }
     B200_CHECK_CUDA(cudaEventSynchronize(w.ev[0]));
     bool stopped = w.hsc[0].stop != 0;
     const int BATCH = 8;
@@ -143,10 +159,8 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
 #define KT(id) std::unique_ptr<ScopedTimer> _kt(kt ? new ScopedTimer(id) : nullptr)
     auto enqueueIteration = [&]() {
         if (N) {
-            { KT(T_DIC_FWD);
-              B200_LAUNCH(k_dic_fwd_tiled<0>, sweepGridOf(m, w), SWEEP_BLOCK, st, mv, m.tiles(), (const double*)w.rD.p, (const double*)w.rA.p, upS, w.y.p, (double*)nullptr, sweepCtl(w), (const PcgScalars*)sc); }
-            { KT(T_DIC_BWD);
-              B200_LAUNCH(k_dic_bwd_tiled, sweepGridOf(m, w), SWEEP_BLOCK, st, mv, m.tiles(), (const double*)w.rD.p, upS, (const double*)w.rA.p, w.y.p, w.z.p, sweepCtl(w), sc, part, cnt); }
+            { KT(T_DIC_FWD); launchFwd(m, w, w.rD.p, w.rA.p, sc); }
+            { KT(T_DIC_BWD); launchBwd(m, w, w.rA.p, sc, part, cnt); }
         }
         if (multi) allReduce(&sc->wArA, 1, RED_SUM);
         { KT(T_PCG_VEC);

@@ -9,6 +9,7 @@ struct Halo;  // comm.cuh
 
 struct PcgWorkspace {
     DevBuf<double> pA, wA, rA, y, z, rD, Dt, partials, hist;
+    DevBuf<double> cf, cb;                     // per-solve DIC coefficients rD[row]*upper in the sweep tiles' ELL layout
     DevBuf<double> diag, upS, x, b, bou;       // staging for the host-pointer API
     DevBuf<double> sendBuf, recvBuf;           // processor-patch halo
     DevBuf<PcgScalars> sc;

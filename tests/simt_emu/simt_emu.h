@@ -27,6 +27,8 @@
 #define __launch_bounds__(...)
 
 struct uint3 { unsigned x, y, z; };
+struct uint2 { unsigned x, y; };
+inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 
 namespace emu {
@@ -46,8 +48,11 @@ inline void trampoline() {
     if (s.live > 0 && s.barCount == s.live) { s.barCount = 0; s.barGen++; }  // exited threads release the barrier
     swapcontext(&s.cur->ctx, &s.sched);
 }
-inline void launch(dim3 grid, dim3 block, std::function<void()> body) {
+inline std::vector<unsigned char>& dynSmemBuf() { static std::vector<unsigned char> b; return b; }
+inline unsigned char* dynSmem() { return dynSmemBuf().data(); }
+inline void launch(dim3 grid, dim3 block, std::function<void()> body, size_t smemBytes = 0) {
     State& s = S();
+    if (dynSmemBuf().size() < smemBytes + 16) dynSmemBuf().resize(smemBytes + 16);
     const size_t STK = 256 * 1024;
     unsigned nt = block.x;
     while (s.stacks.size() < nt) s.stacks.push_back((char*)malloc(STK));

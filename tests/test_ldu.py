@@ -21,12 +21,22 @@ def test_renumbering_and_addressing_bit_exact(lib, oracle, dims, weir):
     F = pm.nInternalFaces
     rowCell, level, nLevels = ldu.renumbering()
     band_levels, tile_rows, tile_start = ldu.tiling()
-    lev, perm, inv, ts = mo.tile_renumbering(pm.owner[:F], pm.neighbour, pm.nCells, band_levels, tile_rows)
+    plan = mo.sweep_plan(pm.owner[:F], pm.neighbour, pm.nCells, band_levels, tile_rows)
+    lev, perm, inv, ts = plan["level"], plan["rowCell"], plan["cellRow"], plan["tileStart"]
     assert np.array_equal(level, lev) and np.array_equal(rowCell, perm) and np.array_equal(tile_start, ts)
-    # tile order is a topological order of the tile graph: every dependency goes to the same or a later tile
+    # ticket order is a topological order of the tile graph: every dependency goes to the same or a later tile,
+    # and to a strictly higher tile level when it leaves the tile
     tile_of_row = np.searchsorted(tile_start, np.arange(pm.nCells), side="right") - 1
     if F:
-        assert np.all(tile_of_row[inv[pm.owner[:F]]] <= tile_of_row[inv[pm.neighbour]])
+        ta, tb = tile_of_row[inv[pm.owner[:F]]], tile_of_row[inv[pm.neighbour]]
+        assert np.all(ta <= tb)
+        assert np.all(plan["tileLevel"][ta[ta != tb]] < plan["tileLevel"][tb[ta != tb]])
+        # the potentials never decrease along a dependency (what makes the tile graph acyclic on any mesh)
+        for k in ("level", "potJ", "potK"):
+            assert np.all(plan[k][pm.owner[:F]] <= plan[k][pm.neighbour])
+    if weir is None and min(dims) > 1:
+        i, j, k = np.unravel_index(np.arange(pm.nCells), dims[::-1])[::-1]
+        assert np.array_equal(plan["potJ"], j) and np.array_equal(plan["potK"], k)   # stride classes recover (j, k) of a hex block
     assert sorted(rowCell.tolist()) == list(range(pm.nCells))          # a permutation
     assert nLevels == (lev.max() + 1 if pm.nCells else 0)
     if weir is None:
@@ -129,20 +139,21 @@ def test_bad_addressing_is_rejected(lib):
         lib.ldu_create(3, [0, 2], [1, 1])      # lower >= upper
 
 
-@pytest.mark.parametrize("band,rows", [(1, 32), (3, 64), (5, 96), (64, 2048)])
-def test_dic_tiling_variants_bitwise(lib, oracle, band, rows):
-    """small tiles force cross-tile (polled) dependencies at every level; huge tiles keep everything in one CTA"""
+@pytest.mark.parametrize("band,rows,smem", [(1, 8, 110 * 1024), (3, 64, 110 * 1024), (5, 96, 110 * 1024), (64, 4096, 200 * 1024), (16, 2048, 12000)])
+def test_dic_tiling_variants_bitwise(lib, oracle, band, rows, smem):
+    """small tiles: almost every dependency is a polled halo value; huge tiles keep everything in one CTA; a tiny shared-memory
+    budget forces the piece-halving path"""
     from oracle import mesh_oracle as mo
-    lib.set_option("sweep_band_levels", band); lib.set_option("sweep_tile_rows", rows)
+    lib.set_option("sweep_band_levels", band); lib.set_option("sweep_tile_rows", rows); lib.set_option("sweep_smem_bytes", smem)
     try:
         pm, ldu = make(lib, (14, 9, 11), (0.45, 0.6, 0.3))
         m = oracle_mesh_of(pm)
         F = pm.nInternalFaces
         bl, tr, ts = ldu.tiling()
         assert (bl, tr) == (band, rows)
-        lev, perm, inv, ts_ref = mo.tile_renumbering(pm.owner[:F], pm.neighbour, pm.nCells, band, rows)
+        plan = mo.sweep_plan(pm.owner[:F], pm.neighbour, pm.nCells, band, rows, smem)
         rowCell, level, _ = ldu.renumbering()
-        assert np.array_equal(rowCell, perm) and np.array_equal(ts, ts_ref)
+        assert np.array_equal(rowCell, plan["rowCell"]) and np.array_equal(ts, plan["tileStart"])
         diag, upper = random_spd(m, seed=21)
         rng = np.random.default_rng(22)
         rA = rng.uniform(-1, 1, m.N)
@@ -157,4 +168,4 @@ def test_dic_tiling_variants_bitwise(lib, oracle, band, rows):
         assert pg.nIterations == po.nIterations and np.allclose(hg, ho, rtol=1e-8, atol=1e-13 * ho[0])
         ldu.release()
     finally:
-        lib.set_option("sweep_band_levels", 16); lib.set_option("sweep_tile_rows", 1024)
+        lib.set_option("sweep_band_levels", 16); lib.set_option("sweep_tile_rows", 2048); lib.set_option("sweep_smem_bytes", 110 * 1024)
