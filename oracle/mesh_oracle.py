@@ -327,7 +327,7 @@ def sweep_smem_bytes(n_rows, n_slots, n_halo, d):
     return 8 * ((n_rows + n_halo + 4) // 2 * 2) + 8 * n_slots * (d + (d + 3) // 4) + 64
 
 
-def sweep_plan(lower, upper, N, band_levels=16, max_rows=2048, smem_budget=110 * 1024, lanes=128):
+def sweep_plan(lower, upper, N, band_levels=16, max_rows=4096, smem_budget=225000, lanes=256):
     """DIC sweep plan of the device rows (this repo's own design; restates csrc/host_mesh.cpp buildSweepPlan).
     Three potentials that never decrease along a dependency l -> u: level, potJ / potK = most faces of stride class 1 / 2 on any
     path (stride classes = the three dominant magnitudes of upper - lower).  Tile class = (level // band, potK // binK, potJ // binJ);

@@ -12,8 +12,8 @@ upper = -rng.uniform(0.5, 1.5, F)
 diag = np.zeros(N); np.add.at(diag, pm.owner[:F], -upper); np.add.at(diag, pm.neighbour, -upper); diag += 1e-4
 b = rng.uniform(-1, 1, N)
 rD = ldu.dic_calc_rd(diag, upper)
-for grid in (0, 37, 74, 148, 222, 296):
-    for ns in (0, 50, 200, 1000):
+for grid, ns in [(0, 0), (0, 20), (0, 100), (0, 300), (148, 0), (148, 100), (100, 0), (200, 0)]:
+    if True:
         lib.set_option("sweep_grid", grid); lib.set_option("sweep_poll_ns", ns)
         ldu.dic_precondition(rD, upper, b)
         lib.timers_reset()

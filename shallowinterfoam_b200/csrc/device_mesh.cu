@@ -53,9 +53,9 @@ void DeviceMesh::build(int32_t nCells, int32_t nFaces, const int32_t* lo, const 
         B200_REQUIRE(lower[f] >= 0 && upper[f] < N, B200_ERR_ARG, "lduAddressing label out of range");
     for (int b = 0; b < B; b++) B200_REQUIRE(fc[b] >= 0 && fc[b] < N, B200_ERR_ARG, "faceCells label out of range");
     int bandLevels = std::min(SWEEP_MAX_STEPS, std::max(1, (int)rt().opt("sweep_band_levels", 16)));
-    int lanes = std::max(32, std::min(SWEEP_THREADS, (int)rt().opt("sweep_threads", 128))) / 32 * 32;
-    int tileRows = std::max(8, (int)rt().opt("sweep_tile_rows", 2048));
-    int smemBudget = std::min(227 * 1024, std::max(4096, (int)rt().opt("sweep_smem_bytes", 110 * 1024)));
+    int lanes = std::max(32, std::min(SWEEP_THREADS, (int)rt().opt("sweep_threads", 256))) / 32 * 32;
+    int tileRows = std::max(8, (int)rt().opt("sweep_tile_rows", 4096));
+    int smemBudget = std::min(227 * 1024, std::max(4096, (int)rt().opt("sweep_smem_bytes", 225000)));
     try {
         buildSweepPlan(N, lower.data(), upper.data(), F, bandLevels, tileRows, smemBudget, lanes, plan);
     } catch (const std::exception& e) { throw Error(B200_ERR_ARG, e.what()); }

@@ -198,13 +198,15 @@ __device__ __forceinline__ void sweepSteps(const TileSmem& s, const SweepTile& t
     }
 }
 
-// stage the operand block of a tile: one elected thread issues the TMA bulk copies (the whole block is contiguous)
-__device__ __forceinline__ void stageBlock(const TileSmem& s, const SweepTile& t, const double* __restrict__ blocks, TileBar* bar) {
+// stage the operand block of a tile: one elected thread issues the TMA bulk copies (the whole block is contiguous).
+// offsetsOnly: just the packed-offset columns (calcReciprocalD gathers its coefficients itself)
+__device__ __forceinline__ void stageBlock(const TileSmem& s, const SweepTile& t, const double* __restrict__ blocks, TileBar* bar, bool offsetsOnly) {
     if (threadIdx.x == 0) {
-        const size_t bytes = (size_t)(t.d + ((t.d + 3) >> 2)) * s.S * 8;
+        const size_t skip = offsetsOnly ? (size_t)t.d * s.S : 0;
+        const size_t bytes = ((size_t)(t.d + ((t.d + 3) >> 2)) * s.S - skip) * 8;
         fenceAsyncProxy();
         barExpect(bar, (unsigned)bytes);
-        bulkLoadChunks(s.blk, blocks + t.blk, bytes, bar);
+        bulkLoadChunks(s.blk + skip, blocks + t.blk + skip, bytes, bar);
     }
 }
 // step table of the tile -> shared memory (global first row, length)
@@ -225,16 +227,39 @@ __device__ __forceinline__ void publishTile(const TileSmem& s, const SweepTile& 
     if (e < t.nRows && e >= a) stPublish(out + t.row0 + t.nRows - 1, s.vals[t.nRows - 1]);
 }
 
+// The tail of upstream's PCG iteration, fused into the staging of the next forward sweep (the sweep reads rA anyway):
+//   alpha = wArA/wApA ; x += alpha*pA ; rA -= alpha*wA ; sum|rA|  ->  finalResidual, nIter++, stop  [UPSTREAM PCG.C]
+// The last CTA of the sweep finishes the (fixed-order) residual sum and runs the convergence test (single rank), or leaves the
+// local sum for the all-reduce + k_pcg_check (multi-rank).  When the test says stop, this sweep was the one wasted pass.
+struct PcgFuse {
+    double* x;            // null: plain sweep (b200_dic_precondition)
+    double* rA;
+    const double *pA, *wA;
+    PcgScalars* sc;
+    double* partials; unsigned* counter; double* hist;
+    int doCheck;
+};
+
 // MODE 0: forward precondition sweep: y[row] = rD*rA - sum_j cf_j * y[src_j]              (cf = rD[row]*upper, per solve)
 // MODE 1: calcReciprocalD           : Dt[row] = diag - sum_j up_j*up_j / Dt[src_j] ; rD = 1/Dt (up gathered through fwdPos)
 template <int MODE>
 static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, const double* __restrict__ a0,
-        const double* __restrict__ a1, const double* __restrict__ coef, const double* __restrict__ blocks, double* y,
-        double* __restrict__ rDout, SweepCtl ctl, const PcgScalars* sc) {
+        const double* a1, const double* __restrict__ coef, const double* __restrict__ blocks, double* y,
+        double* __restrict__ rDout, SweepCtl ctl, const PcgScalars* sc, PcgFuse fz) {
     B200_DYN_SMEM(smem);
     __shared__ int sRow[SWEEP_MAX_STEPS], sLen[SWEEP_MAX_STEPS];
     __shared__ TileBar sBar;
     if (sc && sc->stop) return;
+    const bool fused = MODE == 0 && fz.x != nullptr;
+    const bool upd = fused && fz.sc->nFwd > 0;          // an iteration's x / rA update is pending
+    double alpha = 0.0;
+    if (upd) {
+        if (fabs(fz.sc->wApA) / fz.sc->normFactor <= 1.0e-300) {   // checkSingularity [UPSTREAM PCG.C]: leave x, rA, nIter untouched
+            if (blockIdx.x == 0 && threadIdx.x == 0) { fz.sc->singular = 1; fz.sc->stop = 1; }
+            return;
+        }
+        alpha = fz.sc->wArA / fz.sc->wApA;
+    }
     if (threadIdx.x == 0) barInit(&sBar);
     unsigned phase = 0;
     const int W = blockDim.x, tid = threadIdx.x;
@@ -246,33 +271,47 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
         TileSmem s = carveTile(smem, t, W);
         const int n = t.nRows;
         // 1. row-independent operands: the operand block by TMA bulk copy, start values by batched loads
-        stageBlock(s, t, blocks, &sBar);
-        for (int r0 = tid; r0 < n; r0 += 8 * W) {
-            double a[8], b[8];
+        stageBlock(s, t, blocks, &sBar, MODE == 1);
+        if (MODE == 1) {   // the block's coefficient columns are not valid yet: gather upper through the face slots
+            const int tot = t.d * s.S;
+            for (int e0 = tid; e0 < tot; e0 += 8 * W) {
+                int pos[8]; double c[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) { int r = r0 + k * W; if (r < n) { a[k] = a0[t.row0 + r]; b[k] = (MODE == 0) ? a1[t.row0 + r] : 1.0; } }
+                for (int k = 0; k < 8; k++) { int e = e0 + k * W; pos[k] = e < tot ? sv.fwdPos[t.blk + e] : -1; }
 #pragma unroll
-            for (int k = 0; k < 8; k++) { int r = r0 + k * W; if (r < n) s.vals[r] = (MODE == 0) ? a[k] * b[k] : a[k]; }
+                for (int k = 0; k < 8; k++) c[k] = pos[k] >= 0 ? coef[pos[k]] : 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) { int e = e0 + k * W; if (e < tot) s.blk[e] = c[k]; }
+            }
         }
+        double mag = 0.0;
+        for (int r0 = tid; r0 < n; r0 += 8 * W) {
+            double a[8], b[8], wa[8], xv[8], pv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                int r = r0 + k * W;
+                if (r < n) {
+                    a[k] = a0[t.row0 + r]; b[k] = (MODE == 0) ? a1[t.row0 + r] : 1.0;
+                    if (upd) { wa[k] = fz.wA[t.row0 + r]; xv[k] = fz.x[t.row0 + r]; pv[k] = fz.pA[t.row0 + r]; }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                int r = r0 + k * W;
+                if (r < n) {
+                    if (upd) { fz.x[t.row0 + r] = xv[k] + alpha * pv[k]; b[k] = b[k] - alpha * wa[k]; fz.rA[t.row0 + r] = b[k]; }
+                    if (fused) mag = mag + fabs(b[k]);
+                    s.vals[r] = (MODE == 0) ? a[k] * b[k] : a[k];
+                }
+            }
+        }
+        if (fused) { double v[1] = {mag}; gridReduce<1, OpSum>(v, ti, sv.nTiles, fz.partials, fz.counter, nullptr); }
         stageSteps(sv, t, sRow, sLen);
         if (tid == 0) { s.vals[n + t.nHalo] = 1.0; s.vals[n + t.nHalo + 1] = 0.0; }
         // 2. external inputs
         if (sv.trace) { __syncthreads(); SWEEP_TRACE(1); }
         pollHalo(t, s, sv.fwdHaloRow, y, sv.pollNs);
         barWait(&sBar, phase); phase ^= 1u;
-        if (MODE == 1) {   // the block's coefficient columns are not valid yet: gather upper through the face slots
-            __syncthreads();
-            const int tot = t.d * s.S;
-            for (int e0 = tid; e0 < tot; e0 += 4 * W) {
-                int pos[4]; double c[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) { int e = e0 + k * W; if (e < tot) pos[k] = sv.fwdPos[t.blk + e]; }
-#pragma unroll
-                for (int k = 0; k < 4; k++) { int e = e0 + k * W; if (e < tot) c[k] = pos[k] >= 0 ? coef[pos[k]] : 0.0; }
-#pragma unroll
-                for (int k = 0; k < 4; k++) { int e = e0 + k * W; if (e < tot) s.blk[e] = c[k]; }
-            }
-        }
         __syncthreads();
         SWEEP_TRACE(2);
         // 3. the steps, then publish
@@ -282,6 +321,13 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
         if (MODE == 1) for (int r = tid; r < n; r += W) rDout[t.row0 + r] = 1.0 / s.vals[r];
         if (tid == 0) bulkStoreWaitRead();   // the value array is reused by the next tile
         SWEEP_TRACE(4);
+    }
+    if (fused) {
+        const bool last = gridFinalizeLast<OpSum>(sv.nTiles, fz.partials, fz.counter, &fz.sc->sumMagR);
+        if (last && threadIdx.x == 0) {
+            if (upd) { if (fz.doCheck) pcgEndOfIteration(fz.sc, fz.hist); else fz.sc->pendingCheck = 1; }
+            fz.sc->nFwd = fz.sc->nFwd + 1;
+        }
     }
     sweepExit(ctl);
 }
@@ -304,7 +350,7 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
         const SweepTile t = sv.bwd[ti];
         TileSmem s = carveTile(smem, t, W);
         const int n = t.nRows;
-        stageBlock(s, t, blocks, &sBar);
+        stageBlock(s, t, blocks, &sBar, false);
         for (int r0 = tid; r0 < n; r0 += 8 * W) {
             double a[8];
 #pragma unroll

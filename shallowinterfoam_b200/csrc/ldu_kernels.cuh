@@ -80,10 +80,34 @@ __device__ __forceinline__ void gridFinalize(int nSlots, const double* partials,
     }
 }
 
+// same, but every thread of the block learns whether it was the last block (after the result was written)
+template <class Op0>
+__device__ __forceinline__ bool gridFinalizeLast(int nSlots, const double* partials, unsigned* counter, double* out0) {
+    __shared__ double sh[32];
+    __shared__ int isLast;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned t = atomicInc(counter, gridDim.x - 1);
+        isLast = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!isLast) return false;
+    __threadfence();
+    const volatile double* vp = partials;
+    double a0 = Op0::id();
+    for (int j = threadIdx.x; j < nSlots; j += blockDim.x) a0 = Op0::op(a0, vp[j]);
+    a0 = blockReduce<Op0>(a0, sh);
+    if (threadIdx.x == 0) *out0 = a0;
+    __syncthreads();
+    return true;
+}
+
 // ----------------------------------------------------------------------------- PCG device scalars
 struct PcgScalars {
     double sumX, sumMagR, nfSum, wArA, wArAold, wApA, normFactor, initialResidual, finalResidual, tol, relTol, nGlobal;
-    int nIter, minIter, maxIter, stop, singular, converged, histCap, pad;
+    int nIter, minIter, maxIter, stop, singular, converged, histCap, nFwd;   // nFwd: forward sweeps run in this solve
+    int pendingCheck, pad;   // multi-rank: the forward sweep left a residual sum for k_pcg_check
 };
 
 __device__ __forceinline__ bool isSentinel(double v) { return (unsigned long long)__double_as_longlong(v) == SENTINEL_BITS; }
@@ -221,11 +245,8 @@ static __global__ void k_pcg_check0(PcgScalars* sc, double* hist) {
     sc->wArA = 1.0e20; sc->wArAold = 1.0e20;
     if (hist && sc->histCap > 0) hist[0] = sc->initialResidual;
 }
-// end of an iteration: residual, convergence, iteration count
-static __global__ void k_pcg_check(PcgScalars* sc, double* hist) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (sc->stop) return;
-    if (fabs(sc->wApA) / sc->normFactor <= 1.0e-300) { sc->singular = 1; sc->stop = 1; return; }
+// end of an iteration (x, rA updated, sum|rA| known): residual, convergence, iteration count
+__device__ __forceinline__ void pcgEndOfIteration(PcgScalars* sc, double* hist) {
     sc->finalResidual = sc->sumMagR / sc->normFactor;
     sc->nIter = sc->nIter + 1;
     sc->wArAold = sc->wArA;
@@ -233,7 +254,13 @@ static __global__ void k_pcg_check(PcgScalars* sc, double* hist) {
     sc->converged = pcgConverged(sc) ? 1 : 0;
     sc->stop = (sc->nIter >= sc->minIter) && (sc->nIter >= sc->maxIter || sc->converged);
 }
-
+// multi-rank: runs after the all-reduce of the sum|rA| the forward sweep left behind
+static __global__ void k_pcg_check(PcgScalars* sc, double* hist) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (sc->stop || !sc->pendingCheck) return;
+    sc->pendingCheck = 0;
+    pcgEndOfIteration(sc, hist);
+}
 // pA = z + beta*pA (first iteration: pA = z);  z <- sentinel (re-armed for the next sweep)
 static __global__ void __launch_bounds__(BLOCK) k_pcg_p_update(int N, double* __restrict__ z, double* __restrict__ pA,
                                                          const PcgScalars* sc) {
@@ -245,27 +272,7 @@ static __global__ void __launch_bounds__(BLOCK) k_pcg_p_update(int N, double* __
     else { double beta = sc->wArA / sc->wArAold; pA[row] = zv + beta * pA[row]; }
     z[row] = sentinel();
 }
-// x += alpha*pA ; rA -= alpha*wA ; partial sum|rA|
-static __global__ void __launch_bounds__(BLOCK) k_pcg_xr_update(int N, double* __restrict__ x, double* __restrict__ rA,
-                                                          const double* __restrict__ pA, const double* __restrict__ wA,
-                                                          PcgScalars* sc, double* partials, unsigned* counter) {
-    if (sc->stop) return;
-    bool singular = fabs(sc->wApA) / sc->normFactor <= 1.0e-300;
-    int row = blockIdx.x * blockDim.x + threadIdx.x;
-    double v[1] = {0.0};
-    if (row < N) {
-        double r = rA[row];
-        if (!singular) {
-            double alpha = sc->wArA / sc->wApA;
-            x[row] = x[row] + alpha * pA[row];
-            r = r - alpha * wA[row];
-            rA[row] = r;
-        }
-        v[0] = fabs(r);
-    }
-    gridReduce<1, OpSum>(v, blockIdx.x, gridDim.x, partials, counter, nullptr);
-    gridFinalize<1, OpSum>(gridDim.x, partials, counter, &sc->sumMagR);
-}
+// (x += alpha*pA ; rA -= alpha*wA ; sum|rA| of upstream's loop tail are fused into the NEXT forward sweep: dic_kernels.cuh)
 
 }  // namespace b200
 

@@ -68,14 +68,14 @@ static int sweepThreads(const DeviceMesh& m) { return m.plan.lanes; }   // one r
 static void launchCalcRD(DeviceMesh& m, PcgWorkspace& w, const double* diag, const double* upS, double* rD) {
     fillSentinel(w.Dt, m.N);
     B200_LAUNCH_SMEM(k_dic_fwd<1>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), diag, (const double*)nullptr, upS,
-                     (const double*)w.cf.p, w.Dt.p, rD, sweepCtl(w), (const PcgScalars*)nullptr);
+                     (const double*)w.cf.p, w.Dt.p, rD, sweepCtl(w), (const PcgScalars*)nullptr, PcgFuse{});
 }
 static void launchCoeffs(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* upS) {
     B200_LAUNCH(k_dic_coeffs, 2 * m.nTiles, sweepThreads(m), rt().stream, m.sweep(), rD, upS, w.cf.p, w.cb.p);
 }
-static void launchFwd(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* rA, const PcgScalars* sc) {
+static void launchFwd(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* rA, const PcgScalars* sc, PcgFuse fz = PcgFuse{}) {
     B200_LAUNCH_SMEM(k_dic_fwd<0>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), rD, rA, (const double*)nullptr,
-                     (const double*)w.cf.p, w.y.p, (double*)nullptr, sweepCtl(w), sc);
+                     (const double*)w.cf.p, w.y.p, (double*)nullptr, sweepCtl(w), sc, fz);
 }
 static void launchBwd(DeviceMesh& m, PcgWorkspace& w, const double* rA, PcgScalars* sc, double* part, unsigned* cnt) {
     B200_LAUNCH_SMEM(k_dic_bwd, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), (const double*)w.cb.p, rA, w.y.p, w.z.p,
@@ -150,7 +150,7 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
     B200_CHECK_CUDA(cudaMemcpyAsync(&w.hsc[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
     B200_CHECK_CUDA(cudaEventRecord(w.ev[0], st));
     // calcReciprocalD is enqueued before the host learns whether it is needed (one sweep; keeps the GPU busy)
-    if (N) { ScopedTimer t(T_DIC_RD); launchCalcRD(m, w, diag, upS, w.rD.p); launchCoeffs(m, w, w.rD.p, upS); }
+    if (N) { ScopedTimer t(T_DIC_RD); launchCalcRD(m, w, diag, upS, w.rD.p); launchCoeffs(m, w, w.rD.p, upS); fillSentinel(w.y, N); }
     B200_CHECK_CUDA(cudaEventSynchronize(w.ev[0]));
     bool stopped = w.hsc[0].stop != 0;
     const int BATCH = 8;
@@ -158,10 +158,11 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
     const bool kt = timers().enabled && rt().opt("pcg_kernel_timers", 0) > 0;   // per-kernel-class events (roofline pass)
 #define KT(id) std::unique_ptr<ScopedTimer> _kt(kt ? new ScopedTimer(id) : nullptr)
     auto enqueueIteration = [&]() {
-        if (N) {
-            { KT(T_DIC_FWD); launchFwd(m, w, w.rD.p, w.rA.p, sc); }
-            { KT(T_DIC_BWD); launchBwd(m, w, w.rA.p, sc, part, cnt); }
-        }
+        // (an empty rank still runs the sweeps: they carry the iteration's residual sum / convergence test and the wArA sum)
+        { KT(T_DIC_FWD);   // + the previous iteration's x / rA update, residual sum and convergence test (fused)
+          launchFwd(m, w, w.rD.p, w.rA.p, sc, PcgFuse{x, w.rA.p, w.pA.p, w.wA.p, sc, part, cnt, hist, multi ? 0 : 1}); }
+        if (multi) { allReduce(&sc->sumMagR, 1, RED_SUM); B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist); }
+        { KT(T_DIC_BWD); launchBwd(m, w, w.rA.p, sc, part, cnt); }
         if (multi) allReduce(&sc->wArA, 1, RED_SUM);
         { KT(T_PCG_VEC);
           B200_LAUNCH(k_pcg_p_update, grid, BLOCK, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc); }
@@ -177,10 +178,6 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
             B200_LAUNCH(k_amul<1>, grid, BLOCK, st, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt);
         }
         if (multi) allReduce(&sc->wApA, 1, RED_SUM);
-        { KT(T_PCG_VEC);
-          B200_LAUNCH(k_pcg_xr_update, grid, BLOCK, st, N, x, w.rA.p, (const double*)w.pA.p, (const double*)w.wA.p, sc, part, cnt); }
-        if (multi) allReduce(&sc->sumMagR, 1, RED_SUM);
-        B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist);
     };
 #undef KT
     // two batches in flight: while the host waits for batch i's flag, batch i+1 is already queued

@@ -139,19 +139,21 @@ def test_bad_addressing_is_rejected(lib):
         lib.ldu_create(3, [0, 2], [1, 1])      # lower >= upper
 
 
-@pytest.mark.parametrize("band,rows,smem", [(1, 8, 110 * 1024), (3, 64, 110 * 1024), (5, 96, 110 * 1024), (64, 4096, 200 * 1024), (16, 2048, 12000)])
-def test_dic_tiling_variants_bitwise(lib, oracle, band, rows, smem):
+@pytest.mark.parametrize("band,rows,smem,lanes", [(1, 8, 110 * 1024, 256), (3, 64, 110 * 1024, 32), (5, 96, 110 * 1024, 64), (64, 4096, 200 * 1024, 128),
+                                                  (16, 2048, 24000, 256)])
+def test_dic_tiling_variants_bitwise(lib, oracle, band, rows, smem, lanes):
     """small tiles: almost every dependency is a polled halo value; huge tiles keep everything in one CTA; a tiny shared-memory
     budget forces the piece-halving path"""
     from oracle import mesh_oracle as mo
     lib.set_option("sweep_band_levels", band); lib.set_option("sweep_tile_rows", rows); lib.set_option("sweep_smem_bytes", smem)
+    lib.set_option("sweep_threads", lanes)
     try:
         pm, ldu = make(lib, (14, 9, 11), (0.45, 0.6, 0.3))
         m = oracle_mesh_of(pm)
         F = pm.nInternalFaces
         bl, tr, ts = ldu.tiling()
         assert (bl, tr) == (band, rows)
-        plan = mo.sweep_plan(pm.owner[:F], pm.neighbour, pm.nCells, band, rows, smem)
+        plan = mo.sweep_plan(pm.owner[:F], pm.neighbour, pm.nCells, band, rows, smem, lanes)
         rowCell, level, _ = ldu.renumbering()
         assert np.array_equal(rowCell, plan["rowCell"]) and np.array_equal(ts, plan["tileStart"])
         diag, upper = random_spd(m, seed=21)
@@ -168,4 +170,5 @@ def test_dic_tiling_variants_bitwise(lib, oracle, band, rows, smem):
         assert pg.nIterations == po.nIterations and np.allclose(hg, ho, rtol=1e-8, atol=1e-13 * ho[0])
         ldu.release()
     finally:
-        lib.set_option("sweep_band_levels", 16); lib.set_option("sweep_tile_rows", 2048); lib.set_option("sweep_smem_bytes", 110 * 1024)
+        lib.set_option("sweep_band_levels", 16); lib.set_option("sweep_tile_rows", 4096); lib.set_option("sweep_smem_bytes", 225000)
+        lib.set_option("sweep_threads", 256)
