@@ -54,6 +54,7 @@ __device__ __forceinline__ void fenceAsyncProxy() {}
 __device__ __forceinline__ void bulkStore(void* dst, const void* src, unsigned bytes) { memcpy(dst, src, bytes); }
 __device__ __forceinline__ void bulkStoreCommit() {}
 __device__ __forceinline__ void bulkStoreWaitRead() {}
+__device__ __forceinline__ void bulkStoreWaitAll() {}
 #else
 struct TileBar { unsigned long long word; };
 __device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -83,6 +84,7 @@ __device__ __forceinline__ void bulkStore(void* dst, const void* src, unsigned b
 }
 __device__ __forceinline__ void bulkStoreCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulkStoreWaitRead() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulkStoreWaitAll() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 #endif
 constexpr unsigned BULK_MAX = 32768;   // bytes per cp.async.bulk (multiple of 16)
 __device__ __forceinline__ void bulkLoadChunks(void* dst, const void* src, size_t bytes, TileBar* b) {
@@ -316,12 +318,15 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
         SWEEP_TRACE(2);
         // 3. the steps, then publish
         sweepSteps<MODE, 1>(s, t, sRow, sLen);
+        fenceAsyncProxy();    // this thread's results, for the TMA store below (writers fence, barrier, one thread stores)
+        __syncthreads();
         SWEEP_TRACE(3);
         if (tid == 0) publishTile(s, t, y);
         if (MODE == 1) for (int r = tid; r < n; r += W) rDout[t.row0 + r] = 1.0 / s.vals[r];
         if (tid == 0) bulkStoreWaitRead();   // the value array is reused by the next tile
         SWEEP_TRACE(4);
     }
+    if (threadIdx.x == 0) bulkStoreWaitAll();   // this CTA's TMA stores must have landed before the kernel ends
     if (fused) {
         const bool last = gridFinalizeLast<OpSum>(sv.nTiles, fz.partials, fz.counter, &fz.sc->sumMagR);
         if (last && threadIdx.x == 0) {
@@ -364,6 +369,8 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
         barWait(&sBar, phase); phase ^= 1u;
         __syncthreads();
         sweepSteps<0, -1>(s, t, sRow, sLen);
+        fenceAsyncProxy();
+        __syncthreads();
         if (tid == 0) publishTile(s, t, z);
         if (partials) {
             double dotv = 0.0;
@@ -373,6 +380,7 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
         }
         if (tid == 0) bulkStoreWaitRead();
     }
+    if (threadIdx.x == 0) bulkStoreWaitAll();
     if (partials) gridFinalize<1, OpSum>(sv.nTiles, partials, counter, &sc->wArA);
     sweepExit(ctl);
 }
