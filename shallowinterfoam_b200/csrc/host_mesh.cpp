@@ -414,7 +414,7 @@ void buildSweepPlan(int32_t N, const int32_t* lower, const int32_t* upper, int32
                 next.push_back({pieces[p].b, mid}); next.push_back({mid, pieces[p].e});
                 changed = true;
             } else {
-                if (tooBig) throw std::runtime_error("DIC sweep plan: a single row exceeds the shared-memory budget");
+                if (tooBig) throw std::runtime_error("DIC sweep plan: a single row exceeds the shared-memory budget (more than ~" + std::to_string(smemBudget / (10 * W)) + " lower or upper neighbours with " + std::to_string(W) + " lanes; lower the option sweep_threads)");
                 next.push_back(pieces[p]);
             }
         }
