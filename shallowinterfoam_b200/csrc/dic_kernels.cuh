@@ -243,7 +243,7 @@ struct PcgFuse {
 };
 
 // MODE 0: forward precondition sweep: y[row] = rD*rA - sum_j cf_j * y[src_j]              (cf = rD[row]*upper, per solve)
-// MODE 1: calcReciprocalD           : Dt[row] = diag - sum_j up_j*up_j / Dt[src_j] ; rD = 1/Dt (up gathered through fwdPos)
+// MODE 1: calcReciprocalD           : Dt[row] = diag - sum_j up_j*up_j / Dt[src_j] ; rD = 1/Dt (operand block = plain upper)
 template <int MODE>
 static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, const double* __restrict__ a0,
         const double* a1, const double* __restrict__ coef, const double* __restrict__ blocks, double* y,
@@ -273,19 +273,7 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
         TileSmem s = carveTile(smem, t, W);
         const int n = t.nRows;
         // 1. row-independent operands: the operand block by TMA bulk copy, start values by batched loads
-        stageBlock(s, t, blocks, &sBar, MODE == 1);
-        if (MODE == 1) {   // the block's coefficient columns are not valid yet: gather upper through the face slots
-            const int tot = t.d * s.S;
-            for (int e0 = tid; e0 < tot; e0 += 8 * W) {
-                int pos[8]; double c[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) { int e = e0 + k * W; pos[k] = e < tot ? sv.fwdPos[t.blk + e] : -1; }
-#pragma unroll
-                for (int k = 0; k < 8; k++) c[k] = pos[k] >= 0 ? coef[pos[k]] : 0.0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) { int e = e0 + k * W; if (e < tot) s.blk[e] = c[k]; }
-            }
-        }
+        stageBlock(s, t, blocks, &sBar, false);   // MODE 1: the coefficient columns hold the plain upper coefficients (k_dic_coeffs, rD = null)
         double mag = 0.0;
         for (int r0 = tid; r0 < n; r0 += 8 * W) {
             double a[8], b[8], wa[8], xv[8], pv[8];
@@ -386,7 +374,8 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
 }
 
 // per solve: coefficient columns of the operand blocks: cf = rD[row]*upper (forward), cb = rD[row]*upper (backward).
-// grid = 2*nTiles (forward tiles, then backward tiles); block = lanes
+// rD == null: the plain upper coefficients (what calcReciprocalD sweeps with; 1.0*upper is exact).
+// grid = 2*nTiles (forward tiles, then backward tiles) or nTiles (forward only); block = lanes
 static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_coeffs(SweepView sv, const double* __restrict__ rD,
         const double* __restrict__ upS, double* __restrict__ cf, double* __restrict__ cb) {
     const bool bw = (int)blockIdx.x >= sv.nTiles;
@@ -396,7 +385,7 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_coeffs(SweepView s
     const int W = blockDim.x, S = t.nSteps * W;
     for (int k = 0; k < t.nSteps; k++) {
         const bool valid = (int)threadIdx.x < sv.stepLen[t.step0 + k];
-        const double rd = valid ? rD[sv.stepRow[t.step0 + k] + threadIdx.x] : 0.0;
+        const double rd = !valid ? 0.0 : rD ? rD[sv.stepRow[t.step0 + k] + threadIdx.x] : 1.0;
         for (int j = 0; j < t.d; j++) {
             const int e = t.blk + j * S + k * W + threadIdx.x;
             const int p = valid ? pos[e] : -1;

@@ -67,6 +67,8 @@ static int sweepGridOf(const DeviceMesh& m, const PcgWorkspace&) {
 static int sweepThreads(const DeviceMesh& m) { return m.plan.lanes; }   // one row per thread per step
 static void launchCalcRD(DeviceMesh& m, PcgWorkspace& w, const double* diag, const double* upS, double* rD) {
     fillSentinel(w.Dt, m.N);
+    // forward operand blocks <- plain upper coefficients (fully parallel), so that the sweep stages them with one TMA copy per tile
+    B200_LAUNCH(k_dic_coeffs, m.nTiles, sweepThreads(m), rt().stream, m.sweep(), (const double*)nullptr, upS, w.cf.p, w.cb.p);
     B200_LAUNCH_SMEM(k_dic_fwd<1>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), diag, (const double*)nullptr, upS,
                      (const double*)w.cf.p, w.Dt.p, rD, sweepCtl(w), (const PcgScalars*)nullptr, PcgFuse{});
 }
