@@ -324,10 +324,11 @@ def level_renumbering(lower, upper, N):
 
 
 def sweep_smem_bytes(n_rows, n_slots, n_halo, d):
-    return 8 * ((n_rows + n_halo + 4) // 2 * 2) + 8 * n_slots * (d + (d + 3) // 4) + 64
+    return (8 * ((n_rows + n_halo + 6) // 2 * 2) + 8 * ((n_rows + 3) // 2 * 2) + 4 * ((n_halo + 3) // 4 * 4)
+            + 8 * n_slots * (d + (d + 3) // 4) + 64)
 
 
-def sweep_plan(lower, upper, N, band_levels=16, max_rows=4096, smem_budget=225000, lanes=256):
+def sweep_plan(lower, upper, N, band_levels=16, max_rows=2048, smem_budget=225000, lanes=128):
     """DIC sweep plan of the device rows (this repo's own design; restates csrc/host_mesh.cpp buildSweepPlan).
     Three potentials that never decrease along a dependency l -> u: level, potJ / potK = most faces of stride class 1 / 2 on any
     path (stride classes = the three dominant magnitudes of upper - lower).  Tile class = (level // band, potK // binK, potJ // binJ);
@@ -382,10 +383,21 @@ def sweep_plan(lower, upper, N, band_levels=16, max_rows=4096, smem_budget=22500
             best = (cost, prod, bj, bk)
     binJ, binK = best[2], best[3]
     nJb, nKb = -(-extJ // binJ), -(-extK // binK)
-    # 4. sort + pieces
+    # 4. classes split into connected components (root = smallest cell), sort, pieces
     cls_key = ((lev // band_levels) * nKb + potK // binK) * nJb + potJ // binJ
-    order = np.lexsort((np.arange(N), lev, cls_key))
-    ck = cls_key[order]
+    same = cls_key[lower] == cls_key[upper]
+    if same.any():
+        from scipy.sparse import coo_matrix
+        from scipy.sparse.csgraph import connected_components
+        g = coo_matrix((np.ones(int(same.sum()), dtype=np.int8), (lower[same], upper[same])), shape=(N, N))
+        _, lab = connected_components(g, directed=False)
+    else:
+        lab = np.arange(N)
+    root = np.full(lab.max() + 1, N, dtype=np.int64)
+    np.minimum.at(root, lab, np.arange(N))
+    root = root[lab]
+    order = np.lexsort((np.arange(N), lev, root, cls_key))
+    ck = cls_key[order] * (N + 1) + root[order]
     bounds = np.concatenate([[0], np.nonzero(np.diff(ck))[0] + 1, [N]])
     pieces = []
     for b0, e0 in zip(bounds[:-1], bounds[1:]):
@@ -408,7 +420,7 @@ def sweep_plan(lower, upper, N, band_levels=16, max_rows=4096, smem_budget=22500
             runs = np.diff(np.concatenate([[0], np.nonzero(np.diff(lev[cells]))[0] + 1, [n]]))   # rows per level of the piece
             n_steps = int((-(-runs // lanes)).sum()); S = n_steps * lanes                        # steps of <= lanes rows
             need = max(sweep_smem_bytes(n, S, hF, dF), sweep_smem_bytes(n, S, hB, dB))
-            if (need > smem_budget or n + max(hF, hB) + 2 > 8191 or n_steps > 256) and n > 1:
+            if (need > smem_budget // 2 or n + max(hF, hB) + 4 > 8191 or n_steps > 256) and n > 1:
                 mid = b + n // 2; nxt += [(b, mid), (mid, e)]; changed = True
             else:
                 nxt.append((b, e))
