@@ -48,6 +48,7 @@ __device__ __forceinline__ int facePosOf(const MeshView& mv, int pk, int& l) {
 }
 
 constexpr int SWEEP_THREADS = 256;    // most threads (= lanes) of a sweep CTA
+constexpr int SWEEP_HELPERS = 128;    // helper threads of a sweep CTA (TMA staging / publishing, halo prefetch)
 constexpr int SWEEP_MAX_CHAIN = 96;   // tiles per chain (their descriptors are staged in shared memory)
 // DIC sweep tiles (host_mesh.h SweepPlan, uploaded).  One descriptor per tile and sweep direction.
 struct SweepTile {

@@ -287,19 +287,21 @@ __device__ __forceinline__ void publishTile(const TileSmem& s, const SweepTile& 
 // MODE 1, DIR +1: calcReciprocalD       Dt = diag - sum_j up_j^2/Dt[src_j] ; rD = 1/Dt   (operand block = plain upper)
 // MODE 0, DIR -1: backward              z = y - sum_{owner faces DESC} cb_j*z[u_j] ; per-chain partial of sum(z*rA) -> sc->wArA
 template <int MODE, int DIR>
-static __global__ void __launch_bounds__(SWEEP_THREADS + 32) k_dic_sweep(SweepView sv, const double* __restrict__ start,
+static __global__ void __launch_bounds__(SWEEP_THREADS + SWEEP_HELPERS) k_dic_sweep(SweepView sv, const double* __restrict__ start,
         const double* __restrict__ auxSrc, const double* __restrict__ blocks, double* out, double* __restrict__ rDout,
         SweepCtl ctl, PcgScalars* sc, double* partials, unsigned* counter) {
     B200_DYN_SMEM(smem);
     __shared__ TileBar sBar[2];
     __shared__ SweepTile sTile[SWEEP_MAX_CHAIN];   // the chain's tile descriptors, in execution order
-    __shared__ int sDone;                          // tiles of the chain the compute warps have finished
+    __shared__ int sDone, sPubd, sHaloIn[8];       // tiles of the chain: finished by the compute warps / published / halo share of helper warp w in
     if (sc && sc->stop) return;
     const int tid = threadIdx.x, W = sv.lanes;      // threads [0, W): compute warps (named barrier 1); last warp: DMA
     const bool dma = tid >= W;
     const SweepTile* tiles = DIR > 0 ? sv.fwd : sv.bwd;
     const int* haloRow = DIR > 0 ? sv.fwdHaloRow : sv.bwdHaloRow;
     volatile int* done = &sDone;
+    volatile int* haloIn = sHaloIn;
+    volatile int* pubd = &sPubd;
     if (tid == 0) { barInit(&sBar[0]); barInit(&sBar[1]); }
     unsigned phase[2] = {0u, 0u};
     for (;;) {
@@ -308,31 +310,76 @@ static __global__ void __launch_bounds__(SWEEP_THREADS + 32) k_dic_sweep(SweepVi
         const int c = DIR > 0 ? tk : sv.nChains - 1 - tk;
         const int cs = sv.chainStart[c], m = sv.chainStart[c + 1] - cs;
         for (int i = tid; i < m; i += blockDim.x) sTile[i] = tiles[sv.chainTiles[DIR > 0 ? cs + i : cs + m - 1 - i]];
-        if (tid == 0) sDone = 0;
+        if (tid < 8) sHaloIn[tid] = 0;
+        if (tid == 0) { sDone = 0; sPubd = 0; }
         __syncthreads();
         double dotv = 0.0;
         if (dma) {
-            // ---- DMA warp: keeps the TMA busy, off the compute warps' critical path.  Tile i+2 goes into tile i's buffer as soon
-            //      as tile i is finished (compute warps raise `done`) and its TMA store has read the buffer.
-            const bool lead = tid == W;
-            if (lead) {
+            // ---- helper warps, off the compute warps' critical path.
+            //   * publish (helper warp 0): as soon as the compute warps have finished tile i (`done`), one TMA store sends its rows
+            //     to L2, then tile i+2 is staged into its buffer (operand block, halo list, start values: TMA); `pubd` counts;
+            //   * halo prefetch (all helper warps, entries dealt out statically): the transverse halo of the next tile is polled
+            //     out of L2 and written into the tile's halo slots; `haloIn[w]` = tiles whose share of warp w is complete.
+            //     One pass keeps up to 8 loads per lane in flight, so a tile's ~700 entries take one L2 round trip.
+            const int hw = (tid - W) >> 5, lane = tid & 31, nhw = (blockDim.x - W) >> 5, hid = tid - W, nh = blockDim.x - W;
+            if (hid == 0) {
                 stageTile(sv, sTile[0], smem, haloRow, blocks, start, auxSrc, &sBar[0]);
                 if (m > 1) stageTile(sv, sTile[1], smem + sv.bufBytes, haloRow, blocks, start, auxSrc, &sBar[1]);
             }
-            for (int i = 0; i < m; i++) {
-                waitFlag<20>(done, i + 1);
-                if (lead) {
-                    unsigned char* buf = smem + (i & 1) * sv.bufBytes;
-                    const SweepTile t = sTile[i];
-                    const int ti = sv.trace ? sv.chainTiles[DIR > 0 ? cs + i : cs + m - 1 - i] : 0;
-                    fenceAsyncProxy();
-                    publishTile(carveTile(buf, t, W), t, out);
-                    SWEEP_TRACE(4);
-                    if (i + 2 < m) { bulkStoreWaitRead(); stageTile(sv, sTile[i + 2], buf, haloRow, blocks, start, auxSrc, &sBar[i & 1]); }
+            __syncwarp();
+            int pub = 0, pol = 0;            // next tile to publish (warp 0) / tile whose halo is being fetched
+            unsigned pending = 0; bool armed = false;   // per-lane bit mask of the entries (hid + nh*k) still to arrive
+            while (hw == 0 ? pub < m : pol < m) {
+                if (hw == 0 && *done > pub) {           // (warp-uniform: every lane reads the same word)
+                    if (lane == 0) {
+                        unsigned char* buf = smem + (pub & 1) * sv.bufBytes;
+                        const SweepTile t = sTile[pub];
+                        fenceAsyncProxy();
+                        publishTile(carveTile(buf, t, W), t, out);
+                        if (pub + 2 < m) { bulkStoreWaitRead(); stageTile(sv, sTile[pub + 2], buf, haloRow, blocks, start, auxSrc, &sBar[pub & 1]); }
+                        *pubd = pub + 1;
+                    }
+                    __syncwarp();
+                    pub++;
+                    continue;
                 }
-                __syncwarp();
+                const int pubNow = hw == 0 ? pub : *pubd;
+                if (pol < m && pol <= pubNow + 1) {    // tile pol owns its buffer (tile pol-2 has been published and re-staged)
+                    const SweepTile t = sTile[pol];
+                    double* hv = carveTile(smem + (pol & 1) * sv.bufBytes, t, W).vals + t.nRows + 1;
+                    if (!armed) {
+                        pending = 0;
+                        for (int k = 0; k < 32; k++) { int h = hid + nh * k; if (h < t.nHalo && haloRow[t.halo + h] >= 0) pending |= 1u << k; }
+                        armed = true;
+                    }
+                    unsigned left = pending;
+                    while (left) {              // one pass: up to 8 loads in flight per lane
+                        constexpr int U = 8;
+                        int k[U]; double v[U];
+#pragma unroll
+                        for (int q = 0; q < U; q++) { k[q] = left ? __ffs(left) - 1 : -1; if (left) left &= left - 1; }
+#pragma unroll
+                        for (int q = 0; q < U; q++) if (k[q] >= 0) v[q] = ldPoll(out + haloRow[t.halo + hid + nh * k[q]]);
+#pragma unroll
+                        for (int q = 0; q < U; q++) if (k[q] >= 0 && !isSentinel(v[q])) { hv[hid + nh * k[q]] = v[q]; pending &= ~(1u << k[q]); }
+                    }
+                    if (__all_sync(0xffffffffu, pending == 0)) {
+                        __syncwarp();
+                        if (lane == 0) haloIn[hw] = pol + 1;
+                        pol++; armed = false;
+                    }
+#ifdef B200_EMU
+                    else emu::yield();
+#endif
+                } else {
+#ifdef B200_EMU
+                    emu::yield();
+#else
+                    __nanosleep(20);
+#endif
+                }
             }
-            if (lead) bulkStoreWaitRead();   // both buffers are re-staged by the next chain
+            if (hid == 0) bulkStoreWaitRead();   // both buffers are re-staged by the next chain
         } else {
             // ---- compute warps
             barWait(&sBar[0], phase[0]); phase[0] ^= 1u;
@@ -345,8 +392,10 @@ static __global__ void __launch_bounds__(SWEEP_THREADS + 32) k_dic_sweep(SweepVi
                 unsigned char* other = smem + (b ^ 1) * sv.bufBytes;
                 const TileSmem s = carveTile(buf, t, W);
                 const int n = t.nRows;
-                // A. the transverse halo: polled from L2 (the chain neighbour's values were handed over in shared memory)
-                pollHalo(t, s, out, W, sv.pollNs);
+                // A. the transverse halo was fetched by the DMA warp (tiles with more than 1024 entries poll it themselves);
+                //    the chain neighbour's values were handed over in shared memory
+                if (t.nHalo > 32 * (int)(blockDim.x - W)) pollHalo(t, s, out, W, sv.pollNs);
+                else for (int w = 0; w < (int)(blockDim.x - W) >> 5; w++) waitFlag<0>(haloIn + w, i + 1);
                 if (tid == 0) { s.vals[n + 1 + t.nHalo] = 1.0; s.vals[n + 2 + t.nHalo] = 0.0; }
                 SWEEP_TRACE(1);
                 namedBarSync(1, W);
@@ -372,7 +421,7 @@ static __global__ void __launch_bounds__(SWEEP_THREADS + 32) k_dic_sweep(SweepVi
         }
         if (DIR < 0 && partials) { double v[1] = {dotv}; gridReduce<1, OpSum>(v, c, sv.nChains, partials, counter, nullptr); }
     }
-    if (tid == W) bulkStoreWaitAll();   // this CTA's TMA stores must have landed before the kernel ends
+    if (tid == W) bulkStoreWaitAll();   // this CTA's TMA stores (helper thread 0) must have landed before the kernel ends
     if (DIR < 0 && partials) gridFinalize<1, OpSum>(sv.nChains, partials, counter, &sc->wArA);
     sweepExit(ctl);
 }

@@ -63,7 +63,7 @@ static int sweepGridOf(const DeviceMesh& m, const PcgWorkspace&) {
     int g = forced > 0 ? forced : rt().numSMs * perSM;
     return std::max(1, std::min(g, std::max(1, m.plan.nChains)));
 }
-static int sweepThreads(const DeviceMesh& m) { return m.plan.lanes + 32; }   // compute warps (one row per thread per step) + the DMA warp
+static int sweepThreads(const DeviceMesh& m) { return m.plan.lanes + std::max(32, std::min(SWEEP_HELPERS, (int)rt().opt("sweep_helpers", SWEEP_HELPERS))) / 32 * 32; }   // compute warps + helper warps
 static int coeffThreads(const DeviceMesh& m) { return m.plan.lanes; }
 static void launchCoeffs(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* upS) {
     B200_LAUNCH(k_dic_coeffs, 2 * m.nTiles, coeffThreads(m), rt().stream, m.sweep(), rD, upS, w.cf.p, w.cb.p);

@@ -132,6 +132,7 @@ inline unsigned __ballot_sync(unsigned, int p) { return emu::ballot(p); }
 inline int __all_sync(unsigned, int p) { return emu::ballot(p) == 0xffffffffu; }
 inline int __any_sync(unsigned, int p) { return emu::ballot(p) != 0u; }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 inline unsigned atomicInc(unsigned* p, unsigned lim) { unsigned o = *p; *p = (o >= lim) ? 0 : o + 1; return o; }
