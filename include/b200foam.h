@@ -108,8 +108,8 @@ int b200_ldu_get_renumbering(const b200_ldu_t* ldu, int32_t* rowCell, int32_t* c
  * Pass tileStart = NULL to query the sizes only. */
 int b200_ldu_get_tiling(const b200_ldu_t* ldu, int32_t* bandLevels, int32_t* tileRows, int32_t* nTiles, int32_t* tileStart);
 /* debug: with option "sweep_trace" > 0 the forward sweep stamps %globaltimer per tile (ticket, staged, halo ready, done);
- * out[8*nTiles] ns (5 stamps used), tileLevel[nTiles] = level of the tile in the tile graph, tileChain[nTiles] = its chain (ticket order) */
-int b200_debug_get_sweep_trace(const b200_ldu_t* ldu, unsigned long long* out, int32_t cap, int32_t* tileLevel, int32_t* tileChain);
+ * out[8*nTiles] ns (5 stamps used), tileLevel[nTiles] = level of the tile in the tile graph */
+int b200_debug_get_sweep_trace(const b200_ldu_t* ldu, unsigned long long* out, int32_t cap, int32_t* tileLevel);
 /* derived addressing, for bit-exact parity with lduAddressing::ownerStartAddr/losortAddr/losortStartAddr */
 int b200_ldu_get_addressing(const b200_ldu_t* ldu, int32_t* ownerStart, int32_t* losort, int32_t* losortStart);
 

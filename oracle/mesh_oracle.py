@@ -324,11 +324,10 @@ def level_renumbering(lower, upper, N):
 
 
 def sweep_smem_bytes(n_rows, n_slots, n_halo, d):
-    return (8 * ((n_rows + n_halo + 6) // 2 * 2) + 8 * ((n_rows + 3) // 2 * 2) + 4 * ((n_halo + 3) // 4 * 4)
-            + 8 * n_slots * (d + (d + 3) // 4) + 64)
+    return 8 * ((n_rows + n_halo + 4) // 2 * 2) + 8 * n_slots * (d + (d + 3) // 4) + 64
 
 
-def sweep_plan(lower, upper, N, band_levels=16, max_rows=2048, smem_budget=225000, lanes=128):
+def sweep_plan(lower, upper, N, band_levels=16, max_rows=4096, smem_budget=225000, lanes=256):
     """DIC sweep plan of the device rows (this repo's own design; restates csrc/host_mesh.cpp buildSweepPlan).
     Three potentials that never decrease along a dependency l -> u: level, potJ / potK = most faces of stride class 1 / 2 on any
     path (stride classes = the three dominant magnitudes of upper - lower).  Tile class = (level // band, potK // binK, potJ // binJ);
@@ -420,7 +419,7 @@ def sweep_plan(lower, upper, N, band_levels=16, max_rows=2048, smem_budget=22500
             runs = np.diff(np.concatenate([[0], np.nonzero(np.diff(lev[cells]))[0] + 1, [n]]))   # rows per level of the piece
             n_steps = int((-(-runs // lanes)).sum()); S = n_steps * lanes                        # steps of <= lanes rows
             need = max(sweep_smem_bytes(n, S, hF, dF), sweep_smem_bytes(n, S, hB, dB))
-            if (need > smem_budget // 2 or n + max(hF, hB) + 4 > 8191 or n_steps > 256) and n > 1:
+            if (need > smem_budget or n + max(hF, hB) + 2 > 8191 or n_steps > 256) and n > 1:
                 mid = b + n // 2; nxt += [(b, mid), (mid, e)]; changed = True
             else:
                 nxt.append((b, e))

@@ -5,13 +5,14 @@ import numpy as np
 from shallowinterfoam_b200 import capi
 lib = capi.load(); lib.init(0, 0, 1)
 sizes = [(200, 50, 100)] + ([(400, 100, 200)] if "--big" in sys.argv else [])
-combos = [(16, 2048, 225, 128), (8, 1024, 225, 128), (12, 1536, 225, 128), (16, 1024, 225, 64), (24, 3072, 225, 128), (8, 2048, 225, 256), (32, 2048, 225, 64)]
+combos = [(16, 2048, 110, 128), (16, 4096, 220, 256), (8, 1024, 72, 128), (12, 1536, 110, 128), (24, 3072, 220, 128), (32, 4096, 220, 128),
+          (16, 1024, 72, 64), (8, 512, 36, 64), (16, 1536, 110, 96), (20, 2560, 150, 128), (32, 2048, 110, 64)]
 if "--quick" in sys.argv:
     combos = combos[:3]
 for dims in sizes:
     ref = None
     for band, rows, kb, lanes in combos:
-        lib.set_option("sweep_band_levels", band); lib.set_option("sweep_tile_rows", rows); lib.set_option("sweep_smem_bytes", kb * 1000)
+        lib.set_option("sweep_band_levels", band); lib.set_option("sweep_tile_rows", rows); lib.set_option("sweep_smem_bytes", kb * 1024)
         lib.set_option("sweep_threads", lanes)
         t0 = time.time()
         pm = lib.polymesh_box(*dims, 20.0, 5.0, 10.0, weir=(0.45, 0.5, 0.3))

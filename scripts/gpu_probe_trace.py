@@ -13,29 +13,41 @@ diag = np.zeros(N); np.add.at(diag, pm.owner[:F], -upper); np.add.at(diag, pm.ne
 b = rng.uniform(-1, 1, N)
 rD = ldu.dic_calc_rd(diag, upper)
 ref = ldu.dic_precondition(rD, upper, b)
-for wk in (0,):
+for wk in (0, 1):
+    lib.set_option("sweep_weak_publish", wk)
     assert np.array_equal(ldu.dic_precondition(rD, upper, b), ref)
     lib.timers_reset()
     for i in range(10):
         ldu.dic_precondition(rD, upper, b)
     tm = lib.timers()
-    print("run %d: fwd %6.1f bwd %6.1f us" % (wk, 1e3 * tm["dic_fwd"][0] / tm["dic_fwd"][1], 1e3 * tm["dic_bwd"][0] / tm["dic_bwd"][1]), flush=True)
+    print("weak_publish %d: fwd %6.1f bwd %6.1f us" % (wk, 1e3 * tm["dic_fwd"][0] / tm["dic_fwd"][1], 1e3 * tm["dic_bwd"][0] / tm["dic_bwd"][1]), flush=True)
+lib.set_option("sweep_weak_publish", int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 lib.set_option("sweep_trace", 1)
 ldu.dic_precondition(rD, upper, b)
 tr, tl, ts = ldu.sweep_trace()
 lib.set_option("sweep_trace", 0)
 tr = tr.astype(np.int64); t0 = tr[:, 0].min(); tr -= t0
-print("tiles %d, sweep span %.1f us" % (tr.shape[0], tr[:, 4].max() / 1e3))
-print("per-tile mean (us): start->halo in (poll + staging of the next tile) %.2f, steps %.2f, hand-over + epilogue + publish %.2f" % (
-    (tr[:, 2] - tr[:, 0]).mean() / 1e3, (tr[:, 3] - tr[:, 2]).mean() / 1e3, (tr[:, 4] - tr[:, 3]).mean() / 1e3))
+print("tiles %d, sweep span %.1f us" % (tr.shape[0], tr[:, 3].max() / 1e3))
+print("per-tile mean (us): ticket->staged %.2f, staged->halo ready %.2f, levels %.2f" % (
+    (tr[:, 1] - tr[:, 0]).mean() / 1e3, (tr[:, 2] - tr[:, 1]).mean() / 1e3, (tr[:, 3] - tr[:, 2]).mean() / 1e3))
 rows = np.diff(ts)
-ch = ldu.tile_chain
-print("chains %d" % (ch.max() + 1))
-for c in (0, 5, 20, 40, 60):
-    if c > ch.max():
-        continue
-    tiles = np.nonzero(ch == c)[0]
-    tiles = tiles[np.argsort(tr[tiles, 0])]
-    print("chain %d: (tile, level, rows | start, t0 at barrier, halo in, steps done, t0 at final barrier, published)" % c)
-    for t in tiles:
-        print("  %4d L%2d %5d | %7.2f %7.2f %7.2f %7.2f %7.2f %7.2f" % (t, tl[t], rows[t], tr[t, 0] / 1e3, tr[t, 1] / 1e3, tr[t, 2] / 1e3, tr[t, 3] / 1e3, tr[t, 5] / 1e3, tr[t, 4] / 1e3))
+# per-tile lag: halo ready - latest "steps done" / "published" among the tiles it depends on
+rowCell, level, _ = ldu.renumbering()
+cellRow = np.empty(N, dtype=np.int64); cellRow[rowCell] = np.arange(N)
+tile_of_row = np.searchsorted(ts, np.arange(N), side="right") - 1
+ta, tb = tile_of_row[cellRow[pm.owner[:F]]], tile_of_row[cellRow[pm.neighbour]]
+m = ta != tb
+dep_done = np.zeros(tr.shape[0], dtype=np.int64); dep_pub = np.zeros(tr.shape[0], dtype=np.int64)
+np.maximum.at(dep_done, tb[m], tr[ta[m], 3]); np.maximum.at(dep_pub, tb[m], tr[ta[m], 4])
+has = np.zeros(tr.shape[0], dtype=bool); has[tb[m]] = True
+lag_done = (tr[has, 2] - dep_done[has]) / 1e3; lag_pub = (tr[has, 2] - dep_pub[has]) / 1e3
+print("publish pass (us): mean %.2f max %.2f" % ((tr[:, 4] - tr[:, 3]).mean() / 1e3, (tr[:, 4] - tr[:, 3]).max() / 1e3))
+print("ready - last dep steps-done (us): min %.2f median %.2f mean %.2f max %.2f" % (lag_done.min(), np.median(lag_done), lag_done.mean(), lag_done.max()))
+print("ready - last dep published  (us): min %.2f median %.2f mean %.2f max %.2f" % (lag_pub.min(), np.median(lag_pub), lag_pub.mean(), lag_pub.max()))
+late = tr[has, 1] > dep_pub[has]
+print("tiles whose staging finished after their deps were published: %d of %d" % (late.sum(), has.sum()))
+print("level: nTiles  ticket(min)  staged(max)  ready(min..max)  done(max)  levels_us(mean)  rows(mean)")
+for l in range(tl.max() + 1):
+    m = tl == l
+    print("%3d: %3d  %8.1f  %8.1f  %8.1f..%8.1f  %8.1f  %6.2f  %6.0f" % (l, m.sum(), tr[m, 0].min() / 1e3, tr[m, 1].max() / 1e3, tr[m, 2].min() / 1e3,
+          tr[m, 2].max() / 1e3, tr[m, 3].max() / 1e3, (tr[m, 3] - tr[m, 2]).mean() / 1e3, rows[m].mean()))

@@ -218,8 +218,8 @@ class Ldu:
     def sweep_trace(self):
         _, _, ts = self.tiling()
         nt = ts.size - 1
-        out = np.zeros(8 * nt, dtype=np.uint64); tl = np.zeros(nt, dtype=np.int32); self.tile_chain = np.zeros(nt, dtype=np.int32)
-        self.lib.check(self.lib.c.b200_debug_get_sweep_trace(self.h, out.ctypes.data_as(C.POINTER(C.c_ulonglong)), C.c_int32(out.size), _i(tl), _i(self.tile_chain)))
+        out = np.zeros(8 * nt, dtype=np.uint64); tl = np.zeros(nt, dtype=np.int32)
+        self.lib.check(self.lib.c.b200_debug_get_sweep_trace(self.h, out.ctypes.data_as(C.POINTER(C.c_ulonglong)), C.c_int32(out.size), _i(tl)))
         return out.reshape(nt, 8), tl, ts
 
     def addressing(self):

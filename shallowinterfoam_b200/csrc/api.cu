@@ -162,16 +162,13 @@ int b200_ldu_get_tiling(const b200_ldu_t* ldu, int32_t* bandLevels, int32_t* til
     if (tileStart) memcpy(tileStart, m->plan.tileStart.data(), 4 * m->plan.tileStart.size());
     API_END
 }
-int b200_debug_get_sweep_trace(const b200_ldu_t* ldu, unsigned long long* out, int32_t cap, int32_t* tileLevel, int32_t* tileChain) {
+int b200_debug_get_sweep_trace(const b200_ldu_t* ldu, unsigned long long* out, int32_t cap, int32_t* tileLevel) {
     API_BEGIN
     const DeviceMesh* m = asMesh(ldu);
     size_t n = std::min<size_t>((size_t)cap, 8 * (size_t)m->nTiles);
     syncStream();
     B200_CHECK_CUDA(cudaMemcpy(out, m->dTrace.p, 8 * n, cudaMemcpyDeviceToHost));
     if (tileLevel) memcpy(tileLevel, m->plan.tileLevel.data(), 4 * (size_t)m->nTiles);
-    if (tileChain)
-        for (int c = 0; c < m->plan.nChains; c++)
-            for (int q = m->plan.chainStart[c]; q < m->plan.chainStart[c + 1]; q++) tileChain[m->plan.chainTiles[q]] = c;
     API_END
 }
 int b200_ldu_get_addressing(const b200_ldu_t* ldu, int32_t* ownerStart, int32_t* losort, int32_t* losortStart) {

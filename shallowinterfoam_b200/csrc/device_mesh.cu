@@ -53,16 +53,15 @@ void DeviceMesh::build(int32_t nCells, int32_t nFaces, const int32_t* lo, const 
         B200_REQUIRE(lower[f] >= 0 && upper[f] < N, B200_ERR_ARG, "lduAddressing label out of range");
     for (int b = 0; b < B; b++) B200_REQUIRE(fc[b] >= 0 && fc[b] < N, B200_ERR_ARG, "faceCells label out of range");
     int bandLevels = std::min(SWEEP_MAX_STEPS, std::max(1, (int)rt().opt("sweep_band_levels", 16)));
-    int lanes = std::max(32, std::min(SWEEP_THREADS, (int)rt().opt("sweep_threads", 128))) / 32 * 32;
-    int tileRows = std::max(8, (int)rt().opt("sweep_tile_rows", 2048));
+    int lanes = std::max(32, std::min(SWEEP_THREADS, (int)rt().opt("sweep_threads", 256))) / 32 * 32;
+    int tileRows = std::max(8, (int)rt().opt("sweep_tile_rows", 4096));
     int smemBudget = std::min(227 * 1024, std::max(4096, (int)rt().opt("sweep_smem_bytes", 225000)));
     try {
         buildSweepPlan(N, lower.data(), upper.data(), F, bandLevels, tileRows, smemBudget, lanes, plan);
     } catch (const std::exception& e) { throw Error(B200_ERR_ARG, e.what()); }
     level = plan.level; rowCell = plan.rowCell; cellRow = plan.cellRow; nLevels = plan.nLevels;
     nTiles = plan.nTiles;
-    bufBytes = (std::max(plan.smemFwd, plan.smemBwd) + 127) / 128 * 128;   // one tile buffer; a CTA double-buffers
-    sweepSmem = 2 * bufBytes;
+    sweepSmem = std::max(plan.smemFwd, plan.smemBwd);
     lduDerived(N, lower, upper, ownerStart, losort, losortStart);
     levelStart.assign(nLevels + 1, 0);
     for (int c = 0; c < N; c++) levelStart[level[c] + 1]++;
@@ -109,8 +108,8 @@ void DeviceMesh::build(int32_t nCells, int32_t nFaces, const int32_t* lo, const 
             d.step0 = plan.tileStepStart[t]; d.nSteps = plan.tileStepStart[t + 1] - d.step0;
             const size_t S = (size_t)d.nSteps * plan.lanes;
             tf[t] = d; tb[t] = d;
-            tf[t].d = plan.fwdD[t]; tf[t].halo = plan.fwdHalo[t]; tf[t].nHalo = plan.fwdNHalo[t];
-            tb[t].d = plan.bwdD[t]; tb[t].halo = plan.bwdHalo[t]; tb[t].nHalo = plan.bwdNHalo[t];
+            tf[t].d = plan.fwdD[t]; tf[t].halo = plan.fwdHalo[t]; tf[t].nHalo = plan.fwdHalo[t + 1] - plan.fwdHalo[t];
+            tb[t].d = plan.bwdD[t]; tb[t].halo = plan.bwdHalo[t]; tb[t].nHalo = plan.bwdHalo[t + 1] - plan.bwdHalo[t];
             tf[t].blk = (int)blkF; tb[t].blk = (int)blkB;
             blkF += (size_t)(tf[t].d + (tf[t].d + 3) / 4) * S; blkB += (size_t)(tb[t].d + (tb[t].d + 3) / 4) * S;
             B200_REQUIRE(blkF < ((size_t)1 << 31) && blkB < ((size_t)1 << 31), B200_ERR_UNSUPPORTED, "mesh too large for 32-bit sweep block offsets");
@@ -129,7 +128,7 @@ void DeviceMesh::build(int32_t nCells, int32_t nFaces, const int32_t* lo, const 
                 const size_t S = (size_t)d.nSteps * plan.lanes;
                 uint16_t* offs = reinterpret_cast<uint16_t*>(blk0.data() + d.blk + (size_t)d.d * S);
                 const int nq = (d.d + 3) / 4;
-                const uint16_t padOff = (uint16_t)(8 * (d.nRows + 1 + d.nHalo)), trashOff = (uint16_t)(8 * (d.nRows + 2 + d.nHalo));
+                const uint16_t padOff = (uint16_t)(8 * (d.nRows + d.nHalo)), trashOff = (uint16_t)(8 * (d.nRows + d.nHalo + 1));
                 for (size_t e = 0; e < (size_t)nq * S * 4; e++) offs[e] = padOff;
                 for (int j = 0; j < d.d; j++)
                     for (size_t sl = 0; sl < S; sl++) {
@@ -150,7 +149,6 @@ void DeviceMesh::build(int32_t nCells, int32_t nFaces, const int32_t* lo, const 
         }
         dTilesF.upload(tf); dTilesB.upload(tb); dStepRow.upload(plan.stepRow); dStepLen.upload(plan.stepLen);
         dFwdHaloRow.upload(plan.fwdHaloRow); dBwdHaloRow.upload(plan.bwdHaloRow);
-        dChainStart.upload(plan.chainStart); dChainTiles.upload(plan.chainTiles);
         dTrace.alloc(8 * (size_t)nTiles + 8); dTrace.zero();
         syncStream();   // the host vectors above go out of scope
         plan.fwdFace.clear(); plan.fwdFace.shrink_to_fit(); plan.bwdFace.clear(); plan.bwdFace.shrink_to_fit();

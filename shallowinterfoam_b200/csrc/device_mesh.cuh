@@ -48,28 +48,25 @@ __device__ __forceinline__ int facePosOf(const MeshView& mv, int pk, int& l) {
 }
 
 constexpr int SWEEP_THREADS = 256;    // most threads (= lanes) of a sweep CTA
-constexpr int SWEEP_HELPERS = 128;    // helper threads of a sweep CTA (TMA staging / publishing, halo prefetch)
-constexpr int SWEEP_MAX_CHAIN = 96;   // tiles per chain (their descriptors are staged in shared memory)
 // DIC sweep tiles (host_mesh.h SweepPlan, uploaded).  One descriptor per tile and sweep direction.
 struct SweepTile {
     int row0, nRows;       // device rows [row0, row0+nRows)
-    int step0, nSteps;     // steps: stepRow/stepLen[step0 .. step0+nSteps); S = nSteps*lanes operand slots
+    int step0, nSteps;     // steps: stepRow/stepLen[step0 .. step0+nSteps); S = nSteps*lanes value slots
     int blk, d;            // operand block offset (doubles) and ELL width; block = d coefficient columns [S] followed by
                            // ceil(d/4) columns of packed 16-bit BYTE offsets of the sources in the tile's value array
-    int halo, nHalo;       // halo list offset (multiple of 4) and length
+    int halo, nHalo;       // halo list offset and length
     int pad[4];
 };
 struct SweepView {
-    int nTiles, nChains, nRows;
-    const SweepTile *fwd, *bwd;              // [nTiles]
-    const int *chainStart, *chainTiles;      // CSR: tiles of each chain, chains in ticket order
+    int nTiles;
+    const SweepTile *fwd, *bwd;              // [nTiles] in ticket order
     const int *stepRow, *stepLen;            // first device row / rows of each step
     int lanes;                               // rows per step = threads of a sweep CTA
     const int *fwdPos, *bwdPos;              // face slot of each coefficient entry of the operand blocks (-1 = padding)
-    const int *fwdHaloRow, *bwdHaloRow;      // per halo entry: device row to poll, or -(r+1) = local row r of the chain neighbour
-    unsigned bufBytes;                       // shared-memory bytes of one tile buffer (a CTA holds two)
+    const int *fwdHaloRow, *bwdHaloRow;      // device rows a tile polls
     int pollNs;                              // back-off between polls of a not-yet-published halo value
-    unsigned long long* trace;               // debug: [8*nTiles] globaltimer stamps per tile or null
+    int weakPublish;                         // experiment: publish with plain stores
+    unsigned long long* trace;               // debug: [8*nTiles] globaltimer stamps per tile (ticket, staged, halo ready, steps done, published) or null
 };
 
 struct PcgWorkspace;  // pcg.cu
@@ -89,8 +86,7 @@ struct DeviceMesh {
     int nTiles = 0;
     size_t sweepSmem = 0;                  // dynamic shared memory of the sweep kernels (bytes)
     DevBuf<SweepTile> dTilesF, dTilesB;
-    DevBuf<int> dStepRow, dStepLen, dFwdPos, dBwdPos, dFwdHaloRow, dBwdHaloRow, dChainStart, dChainTiles;
-    size_t bufBytes = 0;                   // one tile buffer (sweepSmem = 2 buffers)
+    DevBuf<int> dStepRow, dStepLen, dFwdPos, dBwdPos, dFwdHaloRow, dBwdHaloRow;
     DevBuf<double> dFwdBlk0, dBwdBlk0;     // operand-block templates: coefficient columns 0, source-offset columns filled
     size_t fwdBlkSize = 0, bwdBlkSize = 0; // doubles
     DevBuf<unsigned long long> dTrace;     // debug trace of the last sweep (option sweep_trace)
@@ -113,8 +109,7 @@ struct DeviceMesh {
                      const double* w, const double* dc);
     MeshView view() const;
     SweepView sweep() const {
-        return SweepView{nTiles, plan.nChains, N, dTilesF.p, dTilesB.p, dChainStart.p, dChainTiles.p, dStepRow.p, dStepLen.p, plan.lanes, dFwdPos.p, dBwdPos.p,
-                         dFwdHaloRow.p, dBwdHaloRow.p, (unsigned)bufBytes, (int)rt().opt("sweep_poll_ns", 0),
+        return SweepView{nTiles, dTilesF.p, dTilesB.p, dStepRow.p, dStepLen.p, plan.lanes, dFwdPos.p, dBwdPos.p, dFwdHaloRow.p, dBwdHaloRow.p, (int)rt().opt("sweep_poll_ns", 0), (int)rt().opt("sweep_weak_publish", 0),
                          rt().opt("sweep_trace", 0) > 0 ? dTrace.p : nullptr};
     }
     void coupleGeometry();   // collective: processor-face weights/deltaCoeffs/neighbour centres from a halo swap of C

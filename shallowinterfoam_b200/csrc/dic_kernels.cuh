@@ -45,13 +45,11 @@ __device__ __forceinline__ void sweepExit(SweepCtl c) {
 // ---- TMA bulk copies (cp.async.bulk, 1-D) + mbarrier: one elected thread streams a tile's operand block into shared memory
 // while the other threads compute rD*rA and poll the halo.
 #ifdef B200_EMU
-// emulator: the copies are synchronous; the barrier counts completed stagings so that waiting threads really wait
-struct TileBar { volatile unsigned completed; };
-__device__ __forceinline__ void barInit(TileBar* b) { b->completed = 0; }
+struct TileBar { int dummy; };
+__device__ __forceinline__ void barInit(TileBar*) {}
 __device__ __forceinline__ void barExpect(TileBar*, unsigned) {}
 __device__ __forceinline__ void bulkLoad(void* dst, const void* src, unsigned bytes, TileBar*) { memcpy(dst, src, bytes); }
-__device__ __forceinline__ void barStaged(TileBar* b) { b->completed = b->completed + 1; }
-__device__ __forceinline__ void barWait(TileBar* b, unsigned parity) { while ((b->completed & 1u) == parity) emu::yield(); }
+__device__ __forceinline__ void barWait(TileBar*, unsigned) {}
 __device__ __forceinline__ void fenceAsyncProxy() {}
 __device__ __forceinline__ void bulkStore(void* dst, const void* src, unsigned bytes) { memcpy(dst, src, bytes); }
 __device__ __forceinline__ void bulkStoreCommit() {}
@@ -59,7 +57,6 @@ __device__ __forceinline__ void bulkStoreWaitRead() {}
 __device__ __forceinline__ void bulkStoreWaitAll() {}
 #else
 struct TileBar { unsigned long long word; };
-__device__ __forceinline__ void barStaged(TileBar*) {}   // (emulator hook: the hardware mbarrier completes by transaction count)
 __device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void barInit(TileBar* b) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(b)) : "memory");
@@ -99,64 +96,34 @@ __device__ __forceinline__ unsigned long long globalTimerNs() { return 0; }
 #else
 __device__ __forceinline__ unsigned long long globalTimerNs() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #endif
-#define SWEEP_TRACE(slot) do { if (sv.trace && DIR > 0 && threadIdx.x == 0) sv.trace[8 * ti + (slot)] = globalTimerNs(); } while (0)
-
-#ifdef B200_EMU
-__device__ __forceinline__ void namedBarSync(int id, int n) { emu::namedBarrier(id, n); }
-#else
-__device__ __forceinline__ void namedBarSync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-#endif
-
-// spin on a shared-memory counter raised by another warp of the CTA (its data stores precede the counter store: barrier among
-// the writers, then one thread raises the counter); a waiting helper warp sleeps between looks so that it does not steal issue slots
-template <int SLEEP_NS>
-__device__ __forceinline__ void waitFlag(volatile int* flag, int need) {
-    while (*flag < need) {
-#ifdef B200_EMU
-        emu::yield();
-#else
-        if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
-#endif
-    }
-#ifndef B200_EMU
-    asm volatile("" ::: "memory");
-#endif
-}
+#define SWEEP_TRACE(slot) do { if (sv.trace && threadIdx.x == 0) sv.trace[8 * ti + (slot)] = globalTimerNs(); } while (0)
 
 struct TileSmem {
-    double* vals;          // [nRows + 1 + nHalo + 2] rows of the tile (start values, overwritten in place by the results), one gap
-                           // slot, halo values, padding slot (1.0), trash slot (0.0).  &vals[r] is 16-byte aligned iff row0+r is even.
-    double* aux;           // [nRows] auxiliary row values (backward sweep: rA for the fused dot product), same alignment rule
-    int* halo;             // [nHalo] halo list of the tile (device row to poll, or -(r+1) = local row r of the chain neighbour)
+    double* vals;          // [nRows + nHalo + 2] rows of the tile (start values, overwritten in place by the results), halo values,
+                           // padding slot (1.0), trash slot (0.0).  &vals[r] is 16-byte aligned iff device row row0+r is even.
     double* blk;           // [(d + ceil(d/4)) * S] coefficient columns, then packed 16-bit byte offsets into vals (slot layout)
     int S;
 };
-__device__ __forceinline__ TileSmem carveTile(unsigned char* buf, const SweepTile& t, int lanes) {
+__device__ __forceinline__ TileSmem carveTile(unsigned char* smem, const SweepTile& t, int lanes) {
     TileSmem s;
-    const int nv = (t.nRows + t.nHalo + 6) & ~1, na = (t.nRows + 3) & ~1;
     s.S = t.nSteps * lanes;
-    s.vals = (double*)buf + (t.row0 & 1);
-    s.aux = (double*)buf + nv + (t.row0 & 1);
-    s.halo = (int*)((double*)buf + nv + na);
-    s.blk = (double*)(s.halo + ((t.nHalo + 3) & ~3));
+    s.vals = (double*)smem + (t.row0 & 1);
+    s.blk = (double*)smem + ((t.nRows + t.nHalo + 4) & ~1);
     return s;
 }
 __device__ __forceinline__ double ldsAt(const double* vals, unsigned byteOff) { return *(const double*)((const char*)vals + byteOff); }
 __device__ __forceinline__ void stsAt(double* vals, unsigned byteOff, double v) { *(double*)((char*)vals + byteOff) = v; }
 
-// poll the tile's external halo entries (list in shared memory; negative entries were handed over along the chain) out of `src`
-// (sentinel = not yet published) into vals[nRows + 1 ..); the loads of one pass are independent
-__device__ __forceinline__ void pollHalo(const SweepTile& t, const TileSmem& s, const double* src, int np, int pollNs) {
+// poll the tile's halo rows out of `src` (sentinel = not yet published) into vals[nRows ..); loads of one pass are independent
+__device__ __forceinline__ void pollHalo(const SweepTile& t, const TileSmem& s, const int* __restrict__ haloRow, const double* src, int pollNs) {
     constexpr int U = 4;
-    const int pid = threadIdx.x;
-    for (int h0 = pid; h0 < t.nHalo; h0 += U * np) {
+    for (int h0 = threadIdx.x; h0 < t.nHalo; h0 += U * blockDim.x) {
         const double* p[U]; double v[U]; bool need[U];
 #pragma unroll
         for (int q = 0; q < U; q++) {
-            int h = h0 + q * np;
-            int hr = h < t.nHalo ? s.halo[h] : -1;
-            need[q] = hr >= 0;
-            p[q] = src + (need[q] ? hr : 0);
+            int h = h0 + q * blockDim.x;
+            need[q] = h < t.nHalo;
+            p[q] = src + (need[q] ? haloRow[t.halo + h] : 0);
         }
         bool pending;
         do {
@@ -167,7 +134,7 @@ __device__ __forceinline__ void pollHalo(const SweepTile& t, const TileSmem& s, 
             for (int q = 0; q < U; q++)
                 if (need[q]) {
                     if (isSentinel(v[q])) pending = true;
-                    else { s.vals[t.nRows + 1 + h0 + q * np] = v[q]; need[q] = false; }
+                    else { s.vals[t.nRows + h0 + q * blockDim.x] = v[q]; need[q] = false; }
                 }
 #ifdef B200_EMU
             if (pending) emu::yield();
@@ -188,8 +155,8 @@ __device__ __forceinline__ void pollHalo(const SweepTile& t, const TileSmem& s, 
 // No global access inside the loop: bar.sync would wait for the L2 acknowledge of a gpu-scope store (~400 cycles per step).
 // OP 0: w -= c*v ; OP 1: w -= c*c/v (calcReciprocalD).  DIR +1: steps upwards (forward sweep), -1: downwards (backward).
 template <int OP, int DIR, int D>
-__device__ __forceinline__ void sweepStepsD(const TileSmem& s, const SweepTile& t, const int W) {
-    const int S = s.S;
+__device__ __forceinline__ void sweepStepsD(const TileSmem& s, const SweepTile& t) {
+    const int W = blockDim.x, S = s.S;
     int slot = (DIR > 0 ? 0 : (t.nSteps - 1) * W) + (int)threadIdx.x;
     const double* C = s.blk;
     const uint2* PK = (const uint2*)(s.blk + D * S);
@@ -207,21 +174,21 @@ __device__ __forceinline__ void sweepStepsD(const TileSmem& s, const SweepTile& 
         if (OP == 0) { w = w - c0 * v0; if (D > 1) w = w - c1 * v1; if (D > 2) w = w - c2 * v2; }
         else { w = w - c0 * c0 / v0; if (D > 1) w = w - c1 * c1 / v1; if (D > 2) w = w - c2 * c2 / v2; }
         stsAt(s.vals, pk.y >> 16, w);
-        namedBarSync(1, W);
+        __syncthreads();
         c0 = n0; c1 = n1; c2 = n2; w = nw; pk = npk; slot = nslot;
     }
 }
 template <int OP, int DIR>
-__device__ __forceinline__ void sweepSteps(const SweepView& sv, const TileSmem& s, const SweepTile& t, const int W) {
+__device__ __forceinline__ void sweepSteps(const TileSmem& s, const SweepTile& t, const int* sRow, const int* sLen) {
     if (t.nSteps == 0) return;
-    if (t.d == 3) { sweepStepsD<OP, DIR, 3>(s, t, W); return; }
-    if (t.d == 2) { sweepStepsD<OP, DIR, 2>(s, t, W); return; }
-    if (t.d == 1) { sweepStepsD<OP, DIR, 1>(s, t, W); return; }
-    const int S = s.S;
+    if (t.d == 3) { sweepStepsD<OP, DIR, 3>(s, t); return; }
+    if (t.d == 2) { sweepStepsD<OP, DIR, 2>(s, t); return; }
+    if (t.d == 1) { sweepStepsD<OP, DIR, 1>(s, t); return; }
+    const int W = blockDim.x, S = s.S;
     const unsigned short* OFF = (const unsigned short*)(s.blk + t.d * S);   // [ceil(d/4)][S][4]
     for (int k = DIR > 0 ? 0 : t.nSteps - 1; k >= 0 && k < t.nSteps; k += DIR) {   // polyhedral rows (d > 3), isolated rows (d = 0)
-        if ((int)threadIdx.x < sv.stepLen[t.step0 + k]) {
-            const int slot = k * W + threadIdx.x, r = sv.stepRow[t.step0 + k] - t.row0 + threadIdx.x;
+        if ((int)threadIdx.x < sLen[k]) {
+            const int slot = k * W + threadIdx.x, r = sRow[k] - t.row0 + threadIdx.x;
             double w = s.vals[r];
             for (int j = 0; j < t.d; j++) {
                 double c = s.blk[j * S + slot], v = ldsAt(s.vals, OFF[((j >> 2) * S + slot) * 4 + (j & 3)]);
@@ -229,43 +196,32 @@ __device__ __forceinline__ void sweepSteps(const SweepView& sv, const TileSmem& 
             }
             s.vals[r] = w;
         }
-        namedBarSync(1, W);
+        __syncthreads();
     }
 }
 
-// rows [row0, row0+n) of a global array -> shared memory at dst[0..n), by TMA: the 16-byte aligned hull [lo, hi) of the range is
-// copied (dst[-1] and dst[n] exist and are scratch); an odd very last row of the array is copied by the calling thread.
-__device__ __forceinline__ unsigned rowsBytes(const SweepTile& t, int nTotal) {
-    const int lo = t.row0 & ~1, end = t.row0 + t.nRows;
-    int hi = end + (end & 1); if (hi > nTotal) hi = end & ~1;
-    return (unsigned)((hi - lo) * 8);
+// stage the operand block of a tile: one elected thread issues the TMA bulk copies (the whole block is contiguous).
+// offsetsOnly: just the packed-offset columns (calcReciprocalD gathers its coefficients itself)
+__device__ __forceinline__ void stageBlock(const TileSmem& s, const SweepTile& t, const double* __restrict__ blocks, TileBar* bar, bool offsetsOnly) {
+    if (threadIdx.x == 0) {
+        const size_t skip = offsetsOnly ? (size_t)t.d * s.S : 0;
+        const size_t bytes = ((size_t)(t.d + ((t.d + 3) >> 2)) * s.S - skip) * 8;
+        fenceAsyncProxy();
+        barExpect(bar, (unsigned)bytes);
+        bulkLoadChunks(s.blk + skip, blocks + t.blk + skip, bytes, bar);
+    }
 }
-__device__ __forceinline__ void stageRows(double* dst, const double* __restrict__ src, const SweepTile& t, int nTotal, TileBar* bar) {
-    const int lo = t.row0 & ~1, end = t.row0 + t.nRows;
-    int hi = end + (end & 1); if (hi > nTotal) hi = end & ~1;
-    if (hi > lo) bulkLoadChunks(dst + (lo - t.row0), src + lo, (size_t)(hi - lo) * 8, bar);
-    if (hi < end) dst[t.nRows - 1] = src[end - 1];
-}
-// stage one tile into a buffer (one thread): operand block, halo list, start values (+ auxiliary rows)
-__device__ __forceinline__ void stageTile(const SweepView& sv, const SweepTile& t, unsigned char* buf, const int* __restrict__ haloRow,
-                                          const double* __restrict__ blocks, const double* __restrict__ start, const double* __restrict__ auxSrc, TileBar* bar) {
-    TileSmem s = carveTile(buf, t, sv.lanes);
-    const size_t blkBytes = (size_t)(t.d + ((t.d + 3) >> 2)) * s.S * 8, haloBytes = (size_t)((t.nHalo + 3) & ~3) * 4;
-    const unsigned rb = rowsBytes(t, sv.nRows);
-    fenceAsyncProxy();   // generic-proxy accesses of the buffer's previous tenant (ordered by the CTA barrier) before the async writes
-    barExpect(bar, (unsigned)(blkBytes + haloBytes + rb + (auxSrc ? rb : 0u)));
-    bulkLoadChunks(s.blk, blocks + t.blk, blkBytes, bar);
-    if (haloBytes) bulkLoadChunks(s.halo, haloRow + t.halo, haloBytes, bar);
-    stageRows(s.vals, start, t, sv.nRows, bar);
-    if (auxSrc) stageRows(s.aux, auxSrc, t, sv.nRows, bar);
-    barStaged(bar);
+// step table of the tile -> shared memory (global first row, length)
+__device__ __forceinline__ void stageSteps(const SweepView& sv, const SweepTile& t, int* sRow, int* sLen) {
+    for (int k = threadIdx.x; k < t.nSteps; k += blockDim.x) { sRow[k] = sv.stepRow[t.step0 + k]; sLen[k] = sv.stepLen[t.step0 + k]; }
 }
 // publish the tile's rows: the results sit contiguously in vals[0..nRows) = device rows [row0, row0+nRows): one TMA bulk
-// store for the 16-byte aligned middle (it lands in L2, where the dependants poll), scalar gpu-scope stores for an odd first /
-// last row.  Writers have fenced (fence.proxy.async) and passed a CTA barrier; called by one thread.
+// store for the 16-byte aligned middle, scalar gpu-scope stores for an odd first / last row.  Called by one thread after the
+// CTA barrier that ends the last step.
 __device__ __forceinline__ void publishTile(const TileSmem& s, const SweepTile& t, double* out) {
     const int a = t.row0 & 1, e = t.nRows - ((t.row0 + t.nRows) & 1);   // local range [a, e) is aligned
     if (e > a) {
+        fenceAsyncProxy();
         for (int o = a; o < e; o += (int)(BULK_MAX / 8)) bulkStore(out + t.row0 + o, s.vals + o, (unsigned)((e - o < (int)(BULK_MAX / 8) ? e - o : (int)(BULK_MAX / 8)) * 8));
         bulkStoreCommit();
     }
@@ -273,156 +229,147 @@ __device__ __forceinline__ void publishTile(const TileSmem& s, const SweepTile& 
     if (e < t.nRows && e >= a) stPublish(out + t.row0 + t.nRows - 1, s.vals[t.nRows - 1]);
 }
 
-// One sweep.  A CTA takes a CHAIN of tiles by ticket (the tiles of one (binK, binJ) column band after band, or a single tile)
-// and runs them in order, double-buffered in shared memory:
-//   * one thread keeps the TMA busy: while tile i runs, tile i+1's operand block, halo list and start values stream into the
-//     other buffer (cp.async.bulk + mbarrier);
-//   * the values tile i+1 needs from tile i (the band direction: the true critical path of the triangular solve) are copied
-//     from buffer to buffer -- no L2 round trip along the chain; only the transverse halo (from chains with an earlier ticket,
-//     which run ahead) is polled from L2, once per tile, the data being its own ready flag (NaN sentinel);
-//   * a tile's results leave with ONE TMA bulk store right after its last step.
-// Chains are ticketed in a topological order of the chain graph, so a running CTA only waits on CTAs that are already running:
-// no grid barrier, no co-residency requirement, deadlock-free for any grid size.
-// MODE 0, DIR +1: forward precondition  y = w0 - sum_j cf_j*y[src_j]          (w0 = rD*rA from k_pcg_xr_w0, cf = rD[row]*upper)
-// MODE 1, DIR +1: calcReciprocalD       Dt = diag - sum_j up_j^2/Dt[src_j] ; rD = 1/Dt   (operand block = plain upper)
-// MODE 0, DIR -1: backward              z = y - sum_{owner faces DESC} cb_j*z[u_j] ; per-chain partial of sum(z*rA) -> sc->wArA
-template <int MODE, int DIR>
-static __global__ void __launch_bounds__(SWEEP_THREADS + SWEEP_HELPERS) k_dic_sweep(SweepView sv, const double* __restrict__ start,
-        const double* __restrict__ auxSrc, const double* __restrict__ blocks, double* out, double* __restrict__ rDout,
-        SweepCtl ctl, PcgScalars* sc, double* partials, unsigned* counter) {
+// The tail of upstream's PCG iteration, fused into the staging of the next forward sweep (the sweep reads rA anyway):
+//   alpha = wArA/wApA ; x += alpha*pA ; rA -= alpha*wA ; sum|rA|  ->  finalResidual, nIter++, stop  [UPSTREAM PCG.C]
+// The last CTA of the sweep finishes the (fixed-order) residual sum and runs the convergence test (single rank), or leaves the
+// local sum for the all-reduce + k_pcg_check (multi-rank).  When the test says stop, this sweep was the one wasted pass.
+struct PcgFuse {
+    double* x;            // null: plain sweep (b200_dic_precondition)
+    double* rA;
+    const double *pA, *wA;
+    PcgScalars* sc;
+    double* partials; unsigned* counter; double* hist;
+    int doCheck;
+};
+
+// MODE 0: forward precondition sweep: y[row] = rD*rA - sum_j cf_j * y[src_j]              (cf = rD[row]*upper, per solve)
+// MODE 1: calcReciprocalD           : Dt[row] = diag - sum_j up_j*up_j / Dt[src_j] ; rD = 1/Dt (operand block = plain upper)
+template <int MODE>
+static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, const double* __restrict__ a0,
+        const double* a1, const double* __restrict__ coef, const double* __restrict__ blocks, double* y,
+        double* __restrict__ rDout, SweepCtl ctl, const PcgScalars* sc, PcgFuse fz) {
     B200_DYN_SMEM(smem);
-    __shared__ TileBar sBar[2];
-    __shared__ SweepTile sTile[SWEEP_MAX_CHAIN];   // the chain's tile descriptors, in execution order
-    __shared__ int sDone, sPubd, sHaloIn[8];       // tiles of the chain: finished by the compute warps / published / halo share of helper warp w in
+    __shared__ int sRow[SWEEP_MAX_STEPS], sLen[SWEEP_MAX_STEPS];
+    __shared__ TileBar sBar;
     if (sc && sc->stop) return;
-    const int tid = threadIdx.x, W = sv.lanes;      // threads [0, W): compute warps (named barrier 1); last warp: DMA
-    const bool dma = tid >= W;
-    const SweepTile* tiles = DIR > 0 ? sv.fwd : sv.bwd;
-    const int* haloRow = DIR > 0 ? sv.fwdHaloRow : sv.bwdHaloRow;
-    volatile int* done = &sDone;
-    volatile int* haloIn = sHaloIn;
-    volatile int* pubd = &sPubd;
-    if (tid == 0) { barInit(&sBar[0]); barInit(&sBar[1]); }
-    unsigned phase[2] = {0u, 0u};
+    const bool fused = MODE == 0 && fz.x != nullptr;
+    const bool upd = fused && fz.sc->nFwd > 0;          // an iteration's x / rA update is pending
+    double alpha = 0.0;
+    if (upd) {
+        if (fabs(fz.sc->wApA) / fz.sc->normFactor <= 1.0e-300) {   // checkSingularity [UPSTREAM PCG.C]: leave x, rA, nIter untouched
+            if (blockIdx.x == 0 && threadIdx.x == 0) { fz.sc->singular = 1; fz.sc->stop = 1; }
+            return;
+        }
+        alpha = fz.sc->wArA / fz.sc->wApA;
+    }
+    if (threadIdx.x == 0) barInit(&sBar);
+    unsigned phase = 0;
+    const int W = blockDim.x, tid = threadIdx.x;
     for (;;) {
-        const int tk = nextTicket(ctl);
-        if (tk >= sv.nChains) break;
-        const int c = DIR > 0 ? tk : sv.nChains - 1 - tk;
-        const int cs = sv.chainStart[c], m = sv.chainStart[c + 1] - cs;
-        for (int i = tid; i < m; i += blockDim.x) sTile[i] = tiles[sv.chainTiles[DIR > 0 ? cs + i : cs + m - 1 - i]];
-        if (tid < 8) sHaloIn[tid] = 0;
-        if (tid == 0) { sDone = 0; sPubd = 0; }
-        __syncthreads();
-        double dotv = 0.0;
-        if (dma) {
-            // ---- helper warps, off the compute warps' critical path.
-            //   * publish (helper warp 0): as soon as the compute warps have finished tile i (`done`), one TMA store sends its rows
-            //     to L2, then tile i+2 is staged into its buffer (operand block, halo list, start values: TMA); `pubd` counts;
-            //   * halo prefetch (all helper warps, entries dealt out statically): the transverse halo of the next tile is polled
-            //     out of L2 and written into the tile's halo slots; `haloIn[w]` = tiles whose share of warp w is complete.
-            //     One pass keeps up to 8 loads per lane in flight, so a tile's ~700 entries take one L2 round trip.
-            const int hw = (tid - W) >> 5, lane = tid & 31, nhw = (blockDim.x - W) >> 5, hid = tid - W, nh = blockDim.x - W;
-            if (hid == 0) {
-                stageTile(sv, sTile[0], smem, haloRow, blocks, start, auxSrc, &sBar[0]);
-                if (m > 1) stageTile(sv, sTile[1], smem + sv.bufBytes, haloRow, blocks, start, auxSrc, &sBar[1]);
-            }
-            __syncwarp();
-            int pub = 0, pol = 0;            // next tile to publish (warp 0) / tile whose halo is being fetched
-            unsigned pending = 0; bool armed = false;   // per-lane bit mask of the entries (hid + nh*k) still to arrive
-            while (hw == 0 ? pub < m : pol < m) {
-                if (hw == 0 && *done > pub) {           // (warp-uniform: every lane reads the same word)
-                    if (lane == 0) {
-                        unsigned char* buf = smem + (pub & 1) * sv.bufBytes;
-                        const SweepTile t = sTile[pub];
-                        fenceAsyncProxy();
-                        publishTile(carveTile(buf, t, W), t, out);
-                        if (pub + 2 < m) { bulkStoreWaitRead(); stageTile(sv, sTile[pub + 2], buf, haloRow, blocks, start, auxSrc, &sBar[pub & 1]); }
-                        *pubd = pub + 1;
-                    }
-                    __syncwarp();
-                    pub++;
-                    continue;
-                }
-                const int pubNow = hw == 0 ? pub : *pubd;
-                if (pol < m && pol <= pubNow + 1) {    // tile pol owns its buffer (tile pol-2 has been published and re-staged)
-                    const SweepTile t = sTile[pol];
-                    double* hv = carveTile(smem + (pol & 1) * sv.bufBytes, t, W).vals + t.nRows + 1;
-                    if (!armed) {
-                        pending = 0;
-                        for (int k = 0; k < 32; k++) { int h = hid + nh * k; if (h < t.nHalo && haloRow[t.halo + h] >= 0) pending |= 1u << k; }
-                        armed = true;
-                    }
-                    unsigned left = pending;
-                    while (left) {              // one pass: up to 8 loads in flight per lane
-                        constexpr int U = 8;
-                        int k[U]; double v[U];
+        int ti = nextTicket(ctl);
+        if (ti >= sv.nTiles) break;
+        const SweepTile t = sv.fwd[ti];
+        SWEEP_TRACE(0);
+        TileSmem s = carveTile(smem, t, W);
+        const int n = t.nRows;
+        // 1. row-independent operands: the operand block by TMA bulk copy, start values by batched loads
+        stageBlock(s, t, blocks, &sBar, false);   // MODE 1: the coefficient columns hold the plain upper coefficients (k_dic_coeffs, rD = null)
+        double mag = 0.0;
+        for (int r0 = tid; r0 < n; r0 += 8 * W) {
+            double a[8], b[8], wa[8], xv[8], pv[8];
 #pragma unroll
-                        for (int q = 0; q < U; q++) { k[q] = left ? __ffs(left) - 1 : -1; if (left) left &= left - 1; }
-#pragma unroll
-                        for (int q = 0; q < U; q++) if (k[q] >= 0) v[q] = ldPoll(out + haloRow[t.halo + hid + nh * k[q]]);
-#pragma unroll
-                        for (int q = 0; q < U; q++) if (k[q] >= 0 && !isSentinel(v[q])) { hv[hid + nh * k[q]] = v[q]; pending &= ~(1u << k[q]); }
-                    }
-                    if (__all_sync(0xffffffffu, pending == 0)) {
-                        __syncwarp();
-                        if (lane == 0) haloIn[hw] = pol + 1;
-                        pol++; armed = false;
-                    }
-#ifdef B200_EMU
-                    else emu::yield();
-#endif
-                } else {
-#ifdef B200_EMU
-                    emu::yield();
-#else
-                    __nanosleep(20);
-#endif
+            for (int k = 0; k < 8; k++) {
+                int r = r0 + k * W;
+                if (r < n) {
+                    a[k] = a0[t.row0 + r]; b[k] = (MODE == 0) ? a1[t.row0 + r] : 1.0;
+                    if (upd) { wa[k] = fz.wA[t.row0 + r]; xv[k] = fz.x[t.row0 + r]; pv[k] = fz.pA[t.row0 + r]; }
                 }
             }
-            if (hid == 0) bulkStoreWaitRead();   // both buffers are re-staged by the next chain
-        } else {
-            // ---- compute warps
-            barWait(&sBar[0], phase[0]); phase[0] ^= 1u;
-            for (int i = 0; i < m; i++) {
-                const int b = i & 1;
-                const SweepTile t = sTile[i];
-                const int ti = sv.trace ? sv.chainTiles[DIR > 0 ? cs + i : cs + m - 1 - i] : 0;
-                SWEEP_TRACE(0);
-                unsigned char* buf = smem + b * sv.bufBytes;
-                unsigned char* other = smem + (b ^ 1) * sv.bufBytes;
-                const TileSmem s = carveTile(buf, t, W);
-                const int n = t.nRows;
-                // A. the transverse halo was fetched by the DMA warp (tiles with more than 1024 entries poll it themselves);
-                //    the chain neighbour's values were handed over in shared memory
-                if (t.nHalo > 32 * (int)(blockDim.x - W)) pollHalo(t, s, out, W, sv.pollNs);
-                else for (int w = 0; w < (int)(blockDim.x - W) >> 5; w++) waitFlag<0>(haloIn + w, i + 1);
-                if (tid == 0) { s.vals[n + 1 + t.nHalo] = 1.0; s.vals[n + 2 + t.nHalo] = 0.0; }
-                SWEEP_TRACE(1);
-                namedBarSync(1, W);
-                if (sv.trace && DIR > 0 && tid == 0 && s.vals[n + 1 + t.nHalo] == 1.0) SWEEP_TRACE(2);
-                // B. the steps
-                sweepSteps<MODE, DIR>(sv, s, t, W);
-                fenceAsyncProxy();    // this thread's results, for the DMA warp's TMA store (writers fence, barrier, one thread stores)
-                SWEEP_TRACE(3);
-                // C. hand the chain values over to tile i+1 (its buffer was staged while this tile ran)
-                if (i + 1 < m) {
-                    barWait(&sBar[b ^ 1], phase[b ^ 1]); phase[b ^ 1] ^= 1u;
-                    const SweepTile t2 = sTile[i + 1];
-                    const TileSmem s2 = carveTile(other, t2, W);
-                    for (int h = tid; h < t2.nHalo; h += W) { int hr = s2.halo[h]; if (hr < 0) s2.vals[t2.nRows + 1 + h] = s.vals[-hr - 1]; }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                int r = r0 + k * W;
+                if (r < n) {
+                    if (upd) { fz.x[t.row0 + r] = xv[k] + alpha * pv[k]; b[k] = b[k] - alpha * wa[k]; fz.rA[t.row0 + r] = b[k]; }
+                    if (fused) mag = mag + fabs(b[k]);
+                    s.vals[r] = (MODE == 0) ? a[k] * b[k] : a[k];
                 }
-                // D. epilogue out of shared memory (before the barrier: the buffer is re-staged once `done` is raised)
-                if (MODE == 1) for (int r = tid; r < n; r += W) rDout[t.row0 + r] = 1.0 / s.vals[r];
-                if (DIR < 0 && partials) for (int r = tid; r < n; r += W) dotv = dotv + s.vals[r] * s.aux[r];
-                SWEEP_TRACE(5);
-                namedBarSync(1, W);
-                if (tid == 0) *done = i + 1;
             }
         }
-        if (DIR < 0 && partials) { double v[1] = {dotv}; gridReduce<1, OpSum>(v, c, sv.nChains, partials, counter, nullptr); }
+        if (fused) { double v[1] = {mag}; gridReduce<1, OpSum>(v, ti, sv.nTiles, fz.partials, fz.counter, nullptr); }
+        stageSteps(sv, t, sRow, sLen);
+        if (tid == 0) { s.vals[n + t.nHalo] = 1.0; s.vals[n + t.nHalo + 1] = 0.0; }
+        // 2. external inputs
+        if (sv.trace) { __syncthreads(); SWEEP_TRACE(1); }
+        pollHalo(t, s, sv.fwdHaloRow, y, sv.pollNs);
+        barWait(&sBar, phase); phase ^= 1u;
+        __syncthreads();
+        SWEEP_TRACE(2);
+        // 3. the steps, then publish
+        sweepSteps<MODE, 1>(s, t, sRow, sLen);
+        fenceAsyncProxy();    // this thread's results, for the TMA store below (writers fence, barrier, one thread stores)
+        __syncthreads();
+        SWEEP_TRACE(3);
+        if (tid == 0) publishTile(s, t, y);
+        if (MODE == 1) for (int r = tid; r < n; r += W) rDout[t.row0 + r] = 1.0 / s.vals[r];
+        if (tid == 0) bulkStoreWaitRead();   // the value array is reused by the next tile
+        SWEEP_TRACE(4);
     }
-    if (tid == W) bulkStoreWaitAll();   // this CTA's TMA stores (helper thread 0) must have landed before the kernel ends
-    if (DIR < 0 && partials) gridFinalize<1, OpSum>(sv.nChains, partials, counter, &sc->wArA);
+    if (threadIdx.x == 0) bulkStoreWaitAll();   // this CTA's TMA stores must have landed before the kernel ends
+    if (fused) {
+        const bool last = gridFinalizeLast<OpSum>(sv.nTiles, fz.partials, fz.counter, &fz.sc->sumMagR);
+        if (last && threadIdx.x == 0) {
+            if (upd) { if (fz.doCheck) pcgEndOfIteration(fz.sc, fz.hist); else fz.sc->pendingCheck = 1; }
+            fz.sc->nFwd = fz.sc->nFwd + 1;
+        }
+    }
+    sweepExit(ctl);
+}
+
+// backward: z[row] = y[row] - sum_{owner faces DESC} cb_j * z[u_j]   (cb = rD[row]*upper) ; y[row] <- sentinel (re-armed) ;
+// per-tile partial of sum(z*rA) (fixed rows per partial, fixed order => deterministic) -> sc->wArA
+static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, const double* __restrict__ blocks,
+        const double* __restrict__ rA, double* y, double* z, SweepCtl ctl, PcgScalars* sc, double* partials, unsigned* counter) {
+    B200_DYN_SMEM(smem);
+    __shared__ int sRow[SWEEP_MAX_STEPS], sLen[SWEEP_MAX_STEPS];
+    __shared__ TileBar sBar;
+    if (sc && sc->stop) return;
+    if (threadIdx.x == 0) barInit(&sBar);
+    unsigned phase = 0;
+    const int W = blockDim.x, tid = threadIdx.x;
+    for (;;) {
+        int tk = nextTicket(ctl);
+        if (tk >= sv.nTiles) break;
+        const int ti = sv.nTiles - 1 - tk;
+        const SweepTile t = sv.bwd[ti];
+        TileSmem s = carveTile(smem, t, W);
+        const int n = t.nRows;
+        stageBlock(s, t, blocks, &sBar, false);
+        for (int r0 = tid; r0 < n; r0 += 8 * W) {
+            double a[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) { int r = r0 + k * W; if (r < n) a[k] = y[t.row0 + r]; }
+#pragma unroll
+            for (int k = 0; k < 8; k++) { int r = r0 + k * W; if (r < n) { s.vals[r] = a[k]; y[t.row0 + r] = sentinel(); } }
+        }
+        stageSteps(sv, t, sRow, sLen);
+        if (tid == 0) { s.vals[n + t.nHalo] = 1.0; s.vals[n + t.nHalo + 1] = 0.0; }
+        pollHalo(t, s, sv.bwdHaloRow, z, sv.pollNs);
+        barWait(&sBar, phase); phase ^= 1u;
+        __syncthreads();
+        sweepSteps<0, -1>(s, t, sRow, sLen);
+        fenceAsyncProxy();
+        __syncthreads();
+        if (tid == 0) publishTile(s, t, z);
+        if (partials) {
+            double dotv = 0.0;
+            for (int r = tid; r < n; r += W) dotv = dotv + s.vals[r] * rA[t.row0 + r];
+            double v[1] = {dotv};
+            gridReduce<1, OpSum>(v, ti, sv.nTiles, partials, counter, nullptr);
+        }
+        if (tid == 0) bulkStoreWaitRead();
+    }
+    if (threadIdx.x == 0) bulkStoreWaitAll();
+    if (partials) gridFinalize<1, OpSum>(sv.nTiles, partials, counter, &sc->wArA);
     sweepExit(ctl);
 }
 
@@ -444,43 +391,6 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_coeffs(SweepView s
             const int p = valid ? pos[e] : -1;
             out[e] = p >= 0 ? rd * upS[p] : 0.0;
         }
-    }
-}
-
-// The tail of upstream's PCG iteration + the start values of the next forward sweep, one streaming pass over the rows:
-//   alpha = wArA/wApA ; x += alpha*pA ; rA -= alpha*wA ; sum|rA|  ->  finalResidual, nIter++, stop  [UPSTREAM PCG.C]
-//   w0 = rD*rA (the forward sweep's start values) ; y <- sentinel (re-armed for the sweep)
-// The last block finishes the (fixed-order) residual sum and runs the convergence test (single rank), or leaves the local sum for
-// the all-reduce + k_pcg_check (multi-rank).  x == null: only w0 = rD*rA and the re-arming (b200_dic_precondition).
-static __global__ void __launch_bounds__(BLOCK) k_pcg_xr_w0(int N, double* __restrict__ x, double* rA, const double* __restrict__ pA,
-        const double* __restrict__ wA, const double* __restrict__ rD, double* __restrict__ w0, double* __restrict__ y,
-        PcgScalars* sc, double* partials, unsigned* counter, double* hist, int doCheck) {
-    if (sc && sc->stop) return;
-    const bool fused = x != nullptr;
-    const bool upd = fused && sc->nFwd > 0;          // an iteration's x / rA update is pending
-    double alpha = 0.0;
-    if (upd) {
-        if (fabs(sc->wApA) / sc->normFactor <= 1.0e-300) {   // checkSingularity [UPSTREAM PCG.C]: leave x, rA, nIter untouched
-            if (blockIdx.x == 0 && threadIdx.x == 0) { sc->singular = 1; sc->stop = 1; }
-            return;
-        }
-        alpha = sc->wArA / sc->wApA;
-    }
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    double v[1] = {0.0};
-    if (row < N) {
-        double r = rA[row];
-        if (upd) { x[row] = x[row] + alpha * pA[row]; r = r - alpha * wA[row]; rA[row] = r; }
-        w0[row] = rD[row] * r;
-        y[row] = sentinel();
-        v[0] = fabs(r);
-    }
-    if (!fused) return;
-    gridReduce<1, OpSum>(v, blockIdx.x, gridDim.x, partials, counter, nullptr);
-    const bool last = gridFinalizeLast<OpSum>(gridDim.x, partials, counter, &sc->sumMagR);
-    if (last && threadIdx.x == 0) {
-        if (upd) { if (doCheck) pcgEndOfIteration(sc, hist); else sc->pendingCheck = 1; }
-        sc->nFwd = sc->nFwd + 1;
     }
 }
 

@@ -367,9 +367,9 @@ void buildSweepPlan(int32_t N, const int32_t* lower, const int32_t* upper, int32
     }
     const long long nJb = (extJ + P.binJ - 1) / P.binJ, nKb = (extK + P.binK - 1) / P.binK;
     // ---- 4. classes (band, binK, binJ) are split into their connected components (a weir makes two disjoint sets of cells share
-    //         a class: before and behind it); cells sorted by (class, component, level, index); components -> pieces of at most
-    //         maxRows cells.  Components of one class have no path between them (any connecting tile would have the same key),
-    //         so the tile graph stays acyclic.
+    //         a class: before and behind it; together they would need two steps per level); cells sorted by (class, component,
+    //         level, index); components -> pieces of at most maxRows cells.  Components of one class have no path between them
+    //         (any connecting tile would have the same key), so the tile graph stays acyclic.
     std::vector<long long> ckey(N);
     for (int32_t c = 0; c < N; c++)
         ckey[c] = ((((long long)(P.level[c] / B) * nKb + P.potK[c] / P.binK) * nJb + P.potJ[c] / P.binJ) * P.nLevels) + P.level[c];
@@ -426,7 +426,7 @@ void buildSweepPlan(int32_t N, const int32_t* lower, const int32_t* upper, int32
             nSteps += (run + W - 1) / W;
             const int S = nSteps * W;
             size_t need = std::max(sweepSmemBytes(n, S, hF, dF), sweepSmemBytes(n, S, hB, dB));
-            bool tooBig = need > (size_t)smemBudget / 2 || n + std::max(hF, hB) + 4 > SWEEP_MAX_SLOTS || nSteps > SWEEP_MAX_STEPS;
+            bool tooBig = need > (size_t)smemBudget || n + std::max(hF, hB) + 2 > SWEEP_MAX_SLOTS || nSteps > SWEEP_MAX_STEPS;
             if (tooBig && n > 1) {
                 int32_t mid = pieces[p].b + n / 2;
                 next.push_back({pieces[p].b, mid}); next.push_back({mid, pieces[p].e});
@@ -480,60 +480,6 @@ void buildSweepPlan(int32_t N, const int32_t* lower, const int32_t* upper, int32
         P.tileStart.push_back(row);
         P.tileStepStart.push_back((int32_t)P.stepRow.size());
     }
-    // ---- 7b. chains: the tiles of one (binK, binJ) column, band after band, when every band of the column is one tile
-    std::vector<int32_t> chainPrev(nT, -1), chainNext(nT, -1);
-    {
-        const long long nCols = nKb * nJb;
-        std::vector<long long> colOf(nT), bandOf(nT);
-        for (int t = 0; t < nT; t++) { long long cls = ckey[order[pieces[ticket[t]].b]] / P.nLevels; colOf[t] = cls % nCols; bandOf[t] = cls / nCols; }
-        std::vector<int32_t> tileOfPiece0(nT);
-        for (int t = 0; t < nT; t++) tileOfPiece0[ticket[t]] = t;
-        // link a -> b when b is a's only successor in the same column one band up, and a is b's only predecessor there
-        std::vector<int32_t> nSucc(nT, 0), nPred(nT, 0), succ(nT, -1);
-        for (long long e : edges) {
-            int32_t a = tileOfPiece0[e >> 32], b = tileOfPiece0[(int32_t)(e & 0xffffffff)];
-            if (colOf[a] == colOf[b] && bandOf[b] == bandOf[a] + 1) { nSucc[a]++; nPred[b]++; succ[a] = b; }
-        }
-        std::vector<int32_t> len(nT, 1);   // chains are cut after SWEEP_CHAIN_MAX tiles
-        for (int t = 0; t < nT; t++) {     // tiles are in ticket order = ascending tile level: predecessors come first
-            int32_t b = succ[t];
-            if (b >= 0 && nSucc[t] == 1 && nPred[b] == 1 && len[t] < SWEEP_CHAIN_MAX) { chainNext[t] = b; chainPrev[b] = t; len[b] = len[t] + 1; }
-        }
-        // chain graph (edges of the tile graph between different chains); a cycle (cannot happen when the potentials are
-        // monotone; checked anyway) falls back to one chain per tile
-        for (int attempt = 0; attempt < 2; attempt++) {
-            std::vector<int32_t> headOf(nT, -1), heads;
-            for (int t = 0; t < nT; t++) if (chainPrev[t] < 0) { heads.push_back(t); for (int32_t u = t; u >= 0; u = chainNext[u]) headOf[u] = (int32_t)heads.size() - 1; }
-            const int nC = (int)heads.size();
-            std::vector<long long> ce;
-            std::vector<int32_t> tileOfPiece(nT);
-            for (int t = 0; t < nT; t++) tileOfPiece[ticket[t]] = t;
-            for (long long e : edges) { int32_t a = headOf[tileOfPiece[e >> 32]], b = headOf[tileOfPiece[(int32_t)(e & 0xffffffff)]]; if (a != b) ce.push_back(((long long)a << 32) | (unsigned)b); }
-            std::sort(ce.begin(), ce.end()); ce.erase(std::unique(ce.begin(), ce.end()), ce.end());
-            std::vector<int32_t> cs(nC + 1, 0), deg(nC, 0), cl(nC, 0), q2;
-            for (long long e : ce) { cs[(e >> 32) + 1]++; deg[(int32_t)(e & 0xffffffff)]++; }
-            for (int c = 0; c < nC; c++) cs[c + 1] += cs[c];
-            for (int c = 0; c < nC; c++) if (deg[c] == 0) q2.push_back(c);
-            for (size_t h = 0; h < q2.size(); h++) {
-                int32_t c = q2[h];
-                for (int32_t q = cs[c]; q < cs[c + 1]; q++) { int32_t v = (int32_t)(ce[q] & 0xffffffff); cl[v] = std::max(cl[v], cl[c] + 1); if (--deg[v] == 0) q2.push_back(v); }
-            }
-            if ((int)q2.size() != nC) {
-                if (attempt == 1) throw std::runtime_error("DIC sweep plan: chain graph is cyclic (internal error)");
-                std::fill(chainPrev.begin(), chainPrev.end(), -1); std::fill(chainNext.begin(), chainNext.end(), -1);
-                continue;
-            }
-            std::vector<int32_t> corder(nC);
-            std::iota(corder.begin(), corder.end(), 0);
-            std::stable_sort(corder.begin(), corder.end(), [&](int32_t a, int32_t b) { return cl[a] < cl[b]; });
-            P.nChains = nC; P.chainStart.assign(1, 0); P.chainTiles.clear(); P.chainLevel.clear();
-            for (int32_t c : corder) {
-                for (int32_t u = heads[c]; u >= 0; u = chainNext[u]) P.chainTiles.push_back(u);
-                P.chainStart.push_back((int32_t)P.chainTiles.size()); P.chainLevel.push_back(cl[c]);
-            }
-            break;
-        }
-    }
     // ---- 8. per-tile ELL (slot layout) + halo lists of the two sweeps
     P.fwdD.resize(nT); P.bwdD.resize(nT);
     std::vector<int32_t> slot(N, -1), slotOfRow(N);
@@ -569,20 +515,14 @@ void buildSweepPlan(int32_t N, const int32_t* lower, const int32_t* upper, int32
                     int32_t id;
                     if (tileOfCell[o] == t) id = P.cellRow[o] - r0;
                     else {
-                        if (stamp[o] != st) {
-                            stamp[o] = st; slot[o] = nHalo++;
-                            const int32_t nb = dir == 0 ? chainPrev[t] : chainNext[t];   // handed over in shared memory along the chain
-                            haloRow.push_back(nb >= 0 && tileOfCell[o] == nb ? -(P.cellRow[o] - P.tileStart[nb] + 1) : P.cellRow[o]);
-                        }
-                        id = n + 1 + slot[o];
+                        if (stamp[o] != st) { stamp[o] = st; slot[o] = nHalo++; haloRow.push_back(P.cellRow[o]); }
+                        id = n + slot[o];
                     }
                     idx[e0 + (size_t)j * S + sl] = (uint16_t)id; face[e0 + (size_t)j * S + sl] = f;
                 }
             }
-            for (size_t e = e0; e < idx.size(); e++) if (face[e] < 0) idx[e] = (uint16_t)(n + 1 + nHalo);
-            while (haloRow.size() % 4) haloRow.push_back(0);   // 16-byte granules for the TMA staging of the list
+            for (size_t e = e0; e < idx.size(); e++) if (face[e] < 0) idx[e] = (uint16_t)(n + nHalo);
             ell.push_back((int32_t)idx.size()); halo.push_back((int32_t)haloRow.size());
-            (dir == 0 ? P.fwdNHalo : P.bwdNHalo).push_back(nHalo);
             size_t need = sweepSmemBytes(n, S, nHalo, D);
             if (dir == 0) P.smemFwd = std::max(P.smemFwd, need); else P.smemBwd = std::max(P.smemBwd, need);
         }

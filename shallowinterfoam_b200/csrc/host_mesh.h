@@ -87,34 +87,21 @@ struct SweepPlan {
     // idx: source in the tile's value array (0..nRows-1 = row of this tile, nRows+h = halo entry h, nRows+nHalo = padding);
     // face: ORIGINAL face index of the coefficient (-1 = padding).  Forward columns are in ascending face order, backward
     // columns in descending face order = the order upstream's sequential loops apply them to the row.
-    std::vector<int32_t> fwdEll, fwdD, fwdHalo;     // [nTiles+1] offsets, [nTiles] widths, [nTiles+1] halo offsets (padded lists)
+    std::vector<int32_t> fwdEll, fwdD, fwdHalo;     // [nTiles+1] offsets, [nTiles] widths, [nTiles+1] halo offsets
     std::vector<int32_t> bwdEll, bwdD, bwdHalo;
-    std::vector<int32_t> fwdNHalo, bwdNHalo;        // [nTiles] halo entries of each tile
     std::vector<uint16_t> fwdIdx, bwdIdx;           // [fwdEll.back()], [bwdEll.back()]
     std::vector<int32_t> fwdFace, bwdFace;
-    std::vector<int32_t> fwdHaloRow, bwdHaloRow;    // per halo entry: device row to poll (>= 0), or -(r+1): local row r of the tile's chain
-                                                    // neighbour (previous tile forward, next tile backward), handed over in shared memory.
-                                                    // per-tile lists are padded to multiples of 4 entries (TMA-staged)
-    // chains: a CTA takes a chain by ticket and runs its tiles in order (forward) / reverse order (backward); the values that
-    // cross from one tile of the chain to the next stay in shared memory (no L2 round trip along the chain).
-    // A chain = the tiles of one (binK, binJ) column, band after band, when every band of the column is a single tile; any
-    // other tile is a chain of its own.  Chains are ticketed in a topological order of the chain graph.
-    int nChains = 0;
-    std::vector<int32_t> chainStart, chainTiles;    // CSR: tiles of each chain (ticket order of chains)
-    std::vector<int32_t> chainLevel;                // longest-path level of the chain in the chain graph
+    std::vector<int32_t> fwdHaloRow, bwdHaloRow;    // device rows polled by the tile
     size_t smemFwd = 0, smemBwd = 0;                // largest per-tile shared-memory need (bytes)
 };
-// shared-memory bytes of ONE tile buffer (the formula the kernels use; a CTA holds two): the value array (rows -- start values
-// overwritten in place by the results --, one gap slot, halo, padding, trash, +1 alignment shift), the auxiliary row array (rA of
-// the backward sweep's dot product), the halo list, and the operand block: d coefficient columns + ceil(d/4) columns of packed
-// 16-bit offsets
+// shared-memory bytes of one tile (the formula the kernels use): the value array (rows, start values overwritten in place by the
+// results; halo; padding; trash; +1 alignment shift) and the operand block: d coefficient columns and ceil(d/4) columns of
+// packed 16-bit offsets
 inline size_t sweepSmemBytes(int nRows, int nSlots, int nHalo, int d) {
-    return 8 * ((size_t)((nRows + nHalo + 5 + 1) / 2 * 2)) + 8 * ((size_t)((nRows + 2 + 1) / 2 * 2)) + 4 * ((size_t)((nHalo + 3) / 4 * 4)) +
-           8 * (size_t)nSlots * (size_t)(d + (d + 3) / 4) + 64;
+    return 8 * ((size_t)((nRows + nHalo + 3 + 1) / 2 * 2)) + 8 * (size_t)nSlots * (size_t)(d + (d + 3) / 4) + 64;
 }
-constexpr int SWEEP_MAX_SLOTS = 8191;   // nRows + nHalo + 4 (sources are stored as 16-bit BYTE offsets into the value array)
-constexpr int SWEEP_MAX_STEPS = 256;    // steps per tile
-constexpr int SWEEP_CHAIN_MAX = 96;     // tiles per chain (longer columns are cut into several chains)
+constexpr int SWEEP_MAX_SLOTS = 8191;   // nRows + nHalo + 2 (sources are stored as 16-bit BYTE offsets into the value array)
+constexpr int SWEEP_MAX_STEPS = 256;    // steps per tile (staged in shared memory)
 void buildSweepPlan(int32_t nCells, const int32_t* lower, const int32_t* upper, int32_t nFaces, int bandLevels, int maxRows,
                     int smemBudget, int lanes, SweepPlan& plan);
 

@@ -34,9 +34,9 @@ PcgWorkspace& pcgWorkspace(DeviceMesh& m) {
     PcgWorkspace* w = new PcgWorkspace();
     m.pcg = w;
     size_t N = m.N;
-    w->pA.alloc(N); w->wA.alloc(N); w->rA.alloc(N); w->y.alloc(N); w->z.alloc(N); w->rD.alloc(N); w->Dt.alloc(N); w->w0.alloc(N);
+    w->pA.alloc(N); w->wA.alloc(N); w->rA.alloc(N); w->y.alloc(N); w->z.alloc(N); w->rD.alloc(N); w->Dt.alloc(N);
     int nBlocks = gridFor(m.N) + 1;
-    w->partials.alloc(3 * (size_t)std::max(nBlocks, std::max(m.nTiles, m.plan.nChains)) + 8);
+    w->partials.alloc(3 * (size_t)std::max(nBlocks, m.nTiles) + 8);
     w->cf.alloc(m.fwdBlkSize); w->cb.alloc(m.bwdBlkSize);   // operand blocks: templates carry the (static) source offsets
     if (m.fwdBlkSize) B200_CHECK_CUDA(cudaMemcpyAsync(w->cf.p, m.dFwdBlk0.p, 8 * m.fwdBlkSize, cudaMemcpyDeviceToDevice, rt().stream));
     if (m.bwdBlkSize) B200_CHECK_CUDA(cudaMemcpyAsync(w->cb.p, m.dBwdBlk0.p, 8 * m.bwdBlkSize, cudaMemcpyDeviceToDevice, rt().stream));
@@ -55,38 +55,33 @@ PcgWorkspace& pcgWorkspace(DeviceMesh& m) {
 }
 
 static SweepCtl sweepCtl(PcgWorkspace& w) { return SweepCtl{w.counters.p + 1, w.counters.p + 2}; }
-// CTAs of a sweep: one per SM (a CTA double-buffers two tiles in shared memory); chains are handed out in ticket order, so any
-// grid size is deadlock-free
+// CTAs of a tiled sweep: as many as fit (shared memory bound); tiles are handed out in ticket order, so any grid size is deadlock-free
 static int sweepGridOf(const DeviceMesh& m, const PcgWorkspace&) {
     int forced = (int)rt().opt("sweep_grid", 0);
-    int perSM = std::max(1, std::min(8, (int)((size_t)(227 * 1024) / (m.sweepSmem + 6144))));
+    int perSM = std::max(1, std::min(8, (int)((size_t)(227 * 1024) / (m.sweepSmem + 2048))));
+    int cap = (int)rt().opt("sweep_ctas_per_sm", 0);
+    if (cap > 0) perSM = std::min(perSM, cap);
     int g = forced > 0 ? forced : rt().numSMs * perSM;
-    return std::max(1, std::min(g, std::max(1, m.plan.nChains)));
+    return std::max(1, std::min(g, std::max(1, m.nTiles)));
 }
-static int sweepThreads(const DeviceMesh& m) { return m.plan.lanes + std::max(32, std::min(SWEEP_HELPERS, (int)rt().opt("sweep_helpers", SWEEP_HELPERS))) / 32 * 32; }   // compute warps + helper warps
-static int coeffThreads(const DeviceMesh& m) { return m.plan.lanes; }
-static void launchCoeffs(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* upS) {
-    B200_LAUNCH(k_dic_coeffs, 2 * m.nTiles, coeffThreads(m), rt().stream, m.sweep(), rD, upS, w.cf.p, w.cb.p);
-}
+static int sweepThreads(const DeviceMesh& m) { return m.plan.lanes; }   // one row per thread per step
 static void launchCalcRD(DeviceMesh& m, PcgWorkspace& w, const double* diag, const double* upS, double* rD) {
     fillSentinel(w.Dt, m.N);
     // forward operand blocks <- plain upper coefficients (fully parallel), so that the sweep stages them with one TMA copy per tile
-    B200_LAUNCH(k_dic_coeffs, m.nTiles, coeffThreads(m), rt().stream, m.sweep(), (const double*)nullptr, upS, w.cf.p, w.cb.p);
-    B200_LAUNCH_SMEM((k_dic_sweep<1, 1>), sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), diag, (const double*)nullptr,
-                     (const double*)w.cf.p, w.Dt.p, rD, sweepCtl(w), (PcgScalars*)nullptr, (double*)nullptr, (unsigned*)nullptr);
+    B200_LAUNCH(k_dic_coeffs, m.nTiles, sweepThreads(m), rt().stream, m.sweep(), (const double*)nullptr, upS, w.cf.p, w.cb.p);
+    B200_LAUNCH_SMEM(k_dic_fwd<1>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), diag, (const double*)nullptr, upS,
+                     (const double*)w.cf.p, w.Dt.p, rD, sweepCtl(w), (const PcgScalars*)nullptr, PcgFuse{});
 }
-// start values of the forward sweep (+ the pending x / rA update of the PCG iteration): k_pcg_xr_w0
-static void launchXrW0(DeviceMesh& m, PcgWorkspace& w, double* x, double* rA, const double* rD, PcgScalars* sc, double* hist, int doCheck) {
-    B200_LAUNCH(k_pcg_xr_w0, std::max(1, gridFor(m.N)), BLOCK, rt().stream, m.N, x, rA, (const double*)w.pA.p, (const double*)w.wA.p, rD, w.w0.p, w.y.p,
-                sc, w.partials.p, w.counters.p, hist, doCheck);
+static void launchCoeffs(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* upS) {
+    B200_LAUNCH(k_dic_coeffs, 2 * m.nTiles, sweepThreads(m), rt().stream, m.sweep(), rD, upS, w.cf.p, w.cb.p);
 }
-static void launchFwd(DeviceMesh& m, PcgWorkspace& w, PcgScalars* sc) {
-    B200_LAUNCH_SMEM((k_dic_sweep<0, 1>), sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), (const double*)w.w0.p, (const double*)nullptr,
-                     (const double*)w.cf.p, w.y.p, (double*)nullptr, sweepCtl(w), sc, (double*)nullptr, (unsigned*)nullptr);
+static void launchFwd(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* rA, const PcgScalars* sc, PcgFuse fz = PcgFuse{}) {
+    B200_LAUNCH_SMEM(k_dic_fwd<0>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), rD, rA, (const double*)nullptr,
+                     (const double*)w.cf.p, w.y.p, (double*)nullptr, sweepCtl(w), sc, fz);
 }
 static void launchBwd(DeviceMesh& m, PcgWorkspace& w, const double* rA, PcgScalars* sc, double* part, unsigned* cnt) {
-    B200_LAUNCH_SMEM((k_dic_sweep<0, -1>), sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), (const double*)w.y.p, rA,
-                     (const double*)w.cb.p, w.z.p, (double*)nullptr, sweepCtl(w), sc, part, cnt);
+    B200_LAUNCH_SMEM(k_dic_bwd, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), (const double*)w.cb.p, rA, w.y.p, w.z.p,
+                     sweepCtl(w), sc, part, cnt);
 }
 
 void amulDevice(DeviceMesh& m, const double* diag, const double* upS, const double* loS, const double* psi, double* Apsi,
@@ -113,8 +108,8 @@ void dicCalcReciprocalD(DeviceMesh& m, const double* diag, const double* upS, do
 void dicPrecondition(DeviceMesh& m, const double* rD, const double* upS, const double* rA, double* wA) {
     PcgWorkspace& w = pcgWorkspace(m);
     if (!m.N) return;
-    { ScopedTimer t(T_DIC_RD); launchCoeffs(m, w, rD, upS); launchXrW0(m, w, nullptr, const_cast<double*>(rA), rD, nullptr, nullptr, 0); }
-    { ScopedTimer t(T_DIC_FWD); launchFwd(m, w, nullptr); }
+    { ScopedTimer t(T_DIC_RD); launchCoeffs(m, w, rD, upS); }
+    { ScopedTimer t(T_DIC_FWD); launchFwd(m, w, rD, rA, nullptr); }
     { ScopedTimer t(T_DIC_BWD); launchBwd(m, w, rA, nullptr, nullptr, nullptr); }
     B200_CHECK_CUDA(cudaMemcpyAsync(wA, w.z.p, 8 * (size_t)m.N, cudaMemcpyDeviceToDevice, rt().stream));
     fillSentinel(w.z, m.N);
@@ -166,10 +161,9 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
 #define KT(id) std::unique_ptr<ScopedTimer> _kt(kt ? new ScopedTimer(id) : nullptr)
     auto enqueueIteration = [&]() {
         // (an empty rank still runs the sweeps: they carry the iteration's residual sum / convergence test and the wArA sum)
-        { KT(T_PCG_VEC);   // the previous iteration's x / rA update, residual sum and convergence test + this sweep's start values
-          launchXrW0(m, w, x, w.rA.p, w.rD.p, sc, hist, multi ? 0 : 1); }
+        { KT(T_DIC_FWD);   // + the previous iteration's x / rA update, residual sum and convergence test (fused)
+          launchFwd(m, w, w.rD.p, w.rA.p, sc, PcgFuse{x, w.rA.p, w.pA.p, w.wA.p, sc, part, cnt, hist, multi ? 0 : 1}); }
         if (multi) { allReduce(&sc->sumMagR, 1, RED_SUM); B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist); }
-        { KT(T_DIC_FWD); launchFwd(m, w, sc); }
         { KT(T_DIC_BWD); launchBwd(m, w, w.rA.p, sc, part, cnt); }
         if (multi) allReduce(&sc->wArA, 1, RED_SUM);
         { KT(T_PCG_VEC);

@@ -8,7 +8,7 @@ namespace b200 {
 struct Halo;  // comm.cuh
 
 struct PcgWorkspace {
-    DevBuf<double> pA, wA, rA, y, z, rD, Dt, w0, partials, hist;   // w0 = rD*rA: start values of the forward sweep
+    DevBuf<double> pA, wA, rA, y, z, rD, Dt, partials, hist;
     DevBuf<double> cf, cb;                     // per-solve DIC coefficients rD[row]*upper in the sweep tiles' ELL layout
     DevBuf<double> diag, upS, x, b, bou;       // staging for the host-pointer API
     DevBuf<double> sendBuf, recvBuf;           // processor-patch halo

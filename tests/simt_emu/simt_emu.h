@@ -34,12 +34,10 @@ struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c 
 namespace emu {
 struct Fiber { ucontext_t ctx; uint3 tid; bool done; };
 struct WarpState { int count = 0, gen = 0; unsigned long long buf[32]; unsigned ballot = 0, ballotOut = 0; };
-struct NamedBar { int count = 0, gen = 0; };
 struct State {
     std::vector<Fiber> fibers; std::vector<char*> stacks; std::vector<WarpState> warps;
     ucontext_t sched; Fiber* cur = nullptr; int live = 0, barCount = 0, barGen = 0;
     uint3 blockIdx; dim3 blockDim, gridDim; std::function<void()> body;
-    NamedBar named[16];
 };
 inline State& S() { static State s; return s; }
 inline void yield() { State& s = S(); swapcontext(&s.cur->ctx, &s.sched); }
@@ -64,7 +62,6 @@ inline void launch(dim3 grid, dim3 block, std::function<void()> body, size_t sme
         s.fibers.assign(nt, Fiber());
         s.warps.assign((nt + 31) / 32, WarpState());
         s.live = nt; s.barCount = 0;
-        for (auto& nb : s.named) nb = NamedBar();
         for (unsigned t = 0; t < nt; t++) {
             Fiber& f = s.fibers[t];
             getcontext(&f.ctx);
@@ -82,12 +79,6 @@ inline void syncthreads() {
     State& s = S(); int gen = s.barGen;
     if (++s.barCount == s.live) { s.barCount = 0; s.barGen++; }
     else while (s.barGen == gen) yield();
-}
-// bar.sync id, n : barrier among the n threads that name it (warp-specialised kernels)
-inline void namedBarrier(int id, int n) {
-    NamedBar& b = S().named[id & 15]; int gen = b.gen;
-    if (++b.count == n) { b.count = 0; b.gen++; }
-    else while (b.gen == gen) yield();
 }
 inline WarpState& warp() { State& s = S(); return s.warps[s.cur->tid.x / 32]; }
 inline void warpBarrier() {
@@ -132,7 +123,6 @@ inline unsigned __ballot_sync(unsigned, int p) { return emu::ballot(p); }
 inline int __all_sync(unsigned, int p) { return emu::ballot(p) == 0xffffffffu; }
 inline int __any_sync(unsigned, int p) { return emu::ballot(p) != 0u; }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
-inline int __ffs(int x) { return __builtin_ffs(x); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 inline unsigned atomicInc(unsigned* p, unsigned lim) { unsigned o = *p; *p = (o >= lim) ? 0 : o + 1; return o; }

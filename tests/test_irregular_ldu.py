@@ -95,4 +95,4 @@ def test_irregular_small_tiles(lib, oracle):
         assert np.array_equal(fo.dic_precondition(m, rD, upper, rA), ldu.dic_precondition(rD, upper, rA))
         ldu.release()
     finally:
-        lib.set_option("sweep_band_levels", 16); lib.set_option("sweep_tile_rows", 2048); lib.set_option("sweep_threads", 128)
+        lib.set_option("sweep_band_levels", 16); lib.set_option("sweep_tile_rows", 4096); lib.set_option("sweep_threads", 256)

@@ -170,5 +170,5 @@ def test_dic_tiling_variants_bitwise(lib, oracle, band, rows, smem, lanes):
         assert pg.nIterations == po.nIterations and np.allclose(hg, ho, rtol=1e-8, atol=1e-13 * ho[0])
         ldu.release()
     finally:
-        lib.set_option("sweep_band_levels", 16); lib.set_option("sweep_tile_rows", 2048); lib.set_option("sweep_smem_bytes", 225000)
-        lib.set_option("sweep_threads", 128)
+        lib.set_option("sweep_band_levels", 16); lib.set_option("sweep_tile_rows", 4096); lib.set_option("sweep_smem_bytes", 225000)
+        lib.set_option("sweep_threads", 256)
