@@ -42,7 +42,7 @@ def spd(m, seed):
     return diag, upper
 
 
-@pytest.mark.parametrize("n,seed,max_deg,window", [(300, 1, 6, 40), (1500, 2, 12, 200), (800, 3, 3, 5), (64, 4, 2, 64)])
+@pytest.mark.parametrize("n,seed,max_deg,window", [(300, 1, 6, 40), (1500, 2, 12, 200), (400, 3, 3, 5), (64, 4, 2, 64)])
 def test_irregular_ldu_parity(lib, oracle, n, seed, max_deg, window):
     lower, upper_addr = random_ldu(n, seed, max_deg, window)
     ldu = lib.ldu_create(n, lower, upper_addr)

@@ -139,7 +139,7 @@ def test_bad_addressing_is_rejected(lib):
         lib.ldu_create(3, [0, 2], [1, 1])      # lower >= upper
 
 
-@pytest.mark.parametrize("band,rows,smem,lanes", [(1, 8, 110 * 1024, 256), (3, 64, 110 * 1024, 32), (5, 96, 110 * 1024, 64), (64, 4096, 200 * 1024, 128),
+@pytest.mark.parametrize("band,rows,smem,lanes", [(1, 8, 110 * 1024, 32), (3, 64, 110 * 1024, 32), (5, 96, 110 * 1024, 64), (64, 4096, 200 * 1024, 128),
                                                   (16, 2048, 24000, 256)])
 def test_dic_tiling_variants_bitwise(lib, oracle, band, rows, smem, lanes):
     """small tiles: almost every dependency is a polled halo value; huge tiles keep everything in one CTA; a tiny shared-memory
