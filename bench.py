@@ -174,6 +174,8 @@ def run_ours(args):
     from shallowinterfoam_b200 import capi
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     lib = capi.load()
+    for o in args.opt:          # tuning knobs of the library (b200_set_option), e.g. --opt p2p_allreduce=0
+        k, v = o.split("="); lib.set_option(k, float(v))
     dist = None
     nccl_id = None
     if world > 1:
@@ -316,6 +318,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (repeatable)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

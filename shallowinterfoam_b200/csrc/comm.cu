@@ -51,6 +51,86 @@ void haloPack(const DeviceMesh& m, const double* cellField, double* send) {
 }
 
 #ifdef B200_WITH_NCCL
+// ---- scalar all-reduce over NVLink peer memory (gSum / gMax / gMin of PCG and MULES: 1-4 doubles, pure latency).
+// Every rank owns a mailbox; an all-reduce = each rank stores its values + an epoch tag into its slot of EVERY rank's mailbox
+// (peer stores over NVLink), spins on its own mailbox until all tags of this epoch are in, and combines the values in rank order
+// (same order on every rank => identical result everywhere).  One 32-thread kernel, ~5 us, instead of an NCCL launch (~20 us).
+// Slots are 4-deep: a rank can be at most one all-reduce ahead of its slowest peer.
+constexpr int P2P_MAX_RANKS = 16, P2P_SLOTS = 4, P2P_ENTRY = 8;   // entry = 7 values + tag
+struct P2PView { double* mbox; double* peer[P2P_MAX_RANKS]; int rank, nRanks; };
+struct P2PState { bool ok = false; P2PView v; unsigned long long epoch = 0; void* opened[P2P_MAX_RANKS] = {nullptr}; double* own = nullptr; };
+static P2PState g_p2p;
+
+__global__ void k_p2p_allreduce(double* data, int count, int op, P2PView pv, unsigned long long epoch) {
+    const int lane = threadIdx.x, slot = (int)(epoch & (P2P_SLOTS - 1));
+    const double tag = (double)epoch;
+    if (lane < pv.nRanks) {
+        volatile double* dst = pv.peer[lane] + ((size_t)slot * pv.nRanks + pv.rank) * P2P_ENTRY;
+        for (int i = 0; i < count; i++) dst[i] = data[i];
+        __threadfence_system();
+        dst[P2P_ENTRY - 1] = tag;
+        volatile double* src = pv.mbox + ((size_t)slot * pv.nRanks + lane) * P2P_ENTRY;
+        while (src[P2P_ENTRY - 1] != tag) {}
+        __threadfence_system();
+    }
+    __syncwarp();
+    if (lane < count) {
+        volatile double* base = pv.mbox + (size_t)slot * pv.nRanks * P2P_ENTRY;
+        double acc = base[lane];
+        for (int r = 1; r < pv.nRanks; r++) {
+            double v = base[(size_t)r * P2P_ENTRY + lane];
+            acc = op == 0 ? acc + v : op == 1 ? (acc > v ? acc : v) : (acc < v ? acc : v);
+        }
+        data[lane] = acc;
+    }
+}
+
+static void p2pInit(int rank, int nRanks) {
+    g_p2p = P2PState();
+    if (nRanks > P2P_MAX_RANKS || rt().opt("p2p_allreduce", 1) <= 0) return;
+    cudaStream_t st = rt().stream;
+    const size_t bytes = sizeof(double) * P2P_SLOTS * nRanks * P2P_ENTRY;
+    if (cudaMalloc((void**)&g_p2p.own, bytes) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaMemsetAsync(g_p2p.own, 0, bytes, st);
+    cudaIpcMemHandle_t mine;
+    bool good = cudaIpcGetMemHandle(&mine, g_p2p.own) == cudaSuccess;
+    if (!good) cudaGetLastError();
+    // exchange the handles (and whether every rank got one) through the NCCL communicator
+    char* dAll = nullptr; char* dMine = nullptr;
+    const size_t hb = sizeof(cudaIpcMemHandle_t) + 8;
+    std::vector<char> hMine(hb, 0), hAll(hb * nRanks, 0);
+    memcpy(hMine.data(), &mine, sizeof(mine)); hMine[sizeof(mine)] = good ? 1 : 0;
+    B200_CHECK_CUDA(cudaMalloc((void**)&dAll, hb * nRanks)); B200_CHECK_CUDA(cudaMalloc((void**)&dMine, hb));
+    B200_CHECK_CUDA(cudaMemcpyAsync(dMine, hMine.data(), hb, cudaMemcpyHostToDevice, st));
+    B200_CHECK_NCCL(ncclAllGather(dMine, dAll, hb, ncclChar, (ncclComm_t)rt().nccl, st));
+    B200_CHECK_CUDA(cudaMemcpyAsync(hAll.data(), dAll, hb * nRanks, cudaMemcpyDeviceToHost, st));
+    B200_CHECK_CUDA(cudaStreamSynchronize(st));
+    cudaFree(dAll); cudaFree(dMine);
+    for (int r = 0; r < nRanks; r++) good = good && hAll[hb * r + sizeof(mine)] == 1;
+    g_p2p.v.rank = rank; g_p2p.v.nRanks = nRanks; g_p2p.v.mbox = g_p2p.own;
+    for (int r = 0; r < nRanks && good; r++) {
+        if (r == rank) { g_p2p.v.peer[r] = g_p2p.own; continue; }
+        cudaIpcMemHandle_t h; memcpy(&h, &hAll[hb * r], sizeof(h));
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = false; break; }
+        g_p2p.opened[r] = ptr; g_p2p.v.peer[r] = (double*)ptr;
+    }
+    // every rank must agree (a rank that could not map a peer sends everybody back to NCCL)
+    double flag = good ? 1.0 : 0.0, *dFlag = nullptr;
+    B200_CHECK_CUDA(cudaMalloc((void**)&dFlag, 8));
+    B200_CHECK_CUDA(cudaMemcpyAsync(dFlag, &flag, 8, cudaMemcpyHostToDevice, st));
+    B200_CHECK_NCCL(ncclAllReduce(dFlag, dFlag, 1, ncclDouble, ncclMin, (ncclComm_t)rt().nccl, st));
+    B200_CHECK_CUDA(cudaMemcpyAsync(&flag, dFlag, 8, cudaMemcpyDeviceToHost, st));
+    B200_CHECK_CUDA(cudaStreamSynchronize(st));
+    cudaFree(dFlag);
+    g_p2p.ok = flag > 0.5;
+}
+static void p2pFinalize() {
+    for (auto& p : g_p2p.opened) if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
+    if (g_p2p.own) { cudaFree(g_p2p.own); g_p2p.own = nullptr; }
+    g_p2p.ok = false;
+}
+
 void commInit(int rank, int nRanks, const void* id, size_t idBytes) {
     if (nRanks <= 1) return;
     B200_REQUIRE(id && idBytes >= sizeof(ncclUniqueId), B200_ERR_ARG, "b200_init: ncclUniqueId missing");
@@ -58,10 +138,13 @@ void commInit(int rank, int nRanks, const void* id, size_t idBytes) {
     ncclComm_t comm;
     B200_CHECK_NCCL(ncclCommInitRank(&comm, nRanks, uid, rank));
     rt().nccl = comm;
+    p2pInit(rank, nRanks);
 }
 void commFinalize() {
+    p2pFinalize();
     if (rt().nccl) { ncclCommDestroy((ncclComm_t)rt().nccl); rt().nccl = nullptr; }
 }
+bool commUsesPeerMemory() { return g_p2p.ok; }
 int commUniqueId(void* out128) {
     ncclUniqueId uid;
     B200_CHECK_NCCL(ncclGetUniqueId(&uid));
@@ -70,6 +153,11 @@ int commUniqueId(void* out128) {
 }
 void allReduce(double* p, int count, ReduceOp op) {
     if (rt().nRanks <= 1) return;
+    if (g_p2p.ok && count <= P2P_ENTRY - 1) {
+        g_p2p.epoch++;
+        B200_LAUNCH(k_p2p_allreduce, 1, 32, rt().stream, p, count, (int)op, g_p2p.v, g_p2p.epoch);
+        return;
+    }
     ncclRedOp_t o = op == RED_SUM ? ncclSum : op == RED_MAX ? ncclMax : ncclMin;
     B200_CHECK_NCCL(ncclAllReduce(p, p, count, ncclDouble, o, (ncclComm_t)rt().nccl, rt().stream));
 }
@@ -96,6 +184,7 @@ void commInit(int, int nRanks, const void*, size_t) {
     B200_REQUIRE(nRanks <= 1 || (g_emuAllreduce && g_emuSendrecv), B200_ERR_STATE, "emulated build: register b200_emu_set_comm first");
 }
 void commFinalize() {}
+bool commUsesPeerMemory() { return false; }
 int commUniqueId(void* out128) { memset(out128, 0, 128); return 128; }
 void allReduce(double* p, int count, ReduceOp op) { if (rt().nRanks > 1) g_emuAllreduce(p, count, (int)op); }
 void haloExchange(const DeviceMesh& m, const double* send, double* recv) {
@@ -111,6 +200,7 @@ void commInit(int, int nRanks, const void*, size_t) {
     B200_REQUIRE(nRanks <= 1, B200_ERR_UNSUPPORTED, "this build has no NCCL: nRanks must be 1");
 }
 void commFinalize() {}
+bool commUsesPeerMemory() { return false; }
 int commUniqueId(void* out128) { memset(out128, 0, 128); return 128; }
 void allReduce(double*, int, ReduceOp) {}
 void haloExchange(const DeviceMesh&, const double*, double*) {}

@@ -9,6 +9,7 @@ void commFinalize();
 int commUniqueId(void* out128);
 enum ReduceOp { RED_SUM = 0, RED_MAX = 1, RED_MIN = 2 };
 void allReduce(double* devPtr, int count, ReduceOp op);  // in place on rt().stream; no-op when nRanks == 1
+bool commUsesPeerMemory();   // scalar all-reduces run over NVLink peer memory (mailboxes) instead of NCCL
 // exchange per-boundary-face values on processor patches: recv[b] = neighbour rank's send[b'] (same face)
 void haloExchange(const DeviceMesh& m, const double* send, double* recv);
 bool meshHasProcessorPatches(const DeviceMesh& m);

@@ -326,9 +326,10 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
 }
 
 // backward: z[row] = y[row] - sum_{owner faces DESC} cb_j * z[u_j]   (cb = rD[row]*upper) ; y[row] <- sentinel (re-armed) ;
-// per-tile partial of sum(z*rA) (fixed rows per partial, fixed order => deterministic) -> sc->wArA
+// per-tile partial of sum(z*rA) (fixed rows per partial, fixed order => deterministic) -> *dotOut (sc->wArA; multi-rank: sc->wArAnew)
 static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, const double* __restrict__ blocks,
-        const double* __restrict__ rA, double* y, double* z, SweepCtl ctl, PcgScalars* sc, double* partials, unsigned* counter) {
+        const double* __restrict__ rA, double* y, double* z, SweepCtl ctl, PcgScalars* sc, double* partials, unsigned* counter,
+        double* dotOut) {
     B200_DYN_SMEM(smem);
     __shared__ int sRow[SWEEP_MAX_STEPS], sLen[SWEEP_MAX_STEPS];
     __shared__ TileBar sBar;
@@ -369,7 +370,7 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
         if (tid == 0) bulkStoreWaitRead();
     }
     if (threadIdx.x == 0) bulkStoreWaitAll();
-    if (partials) gridFinalize<1, OpSum>(sv.nTiles, partials, counter, &sc->wArA);
+    if (partials) gridFinalize<1, OpSum>(sv.nTiles, partials, counter, dotOut);
     sweepExit(ctl);
 }
 

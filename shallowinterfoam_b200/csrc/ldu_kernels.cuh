@@ -105,7 +105,8 @@ __device__ __forceinline__ bool gridFinalizeLast(int nSlots, const double* parti
 
 // ----------------------------------------------------------------------------- PCG device scalars
 struct PcgScalars {
-    double sumX, sumMagR, nfSum, wArA, wArAold, wApA, normFactor, initialResidual, finalResidual, tol, relTol, nGlobal;
+    double sumX, sumMagR, wArAnew, nfSum, wArA, wArAold, wApA, normFactor, initialResidual, finalResidual, tol, relTol, nGlobal;
+    // (sumMagR, wArAnew are adjacent: the multi-rank path all-reduces them in one call)
     int nIter, minIter, maxIter, stop, singular, converged, histCap, nFwd;   // nFwd: forward sweeps run in this solve
     int pendingCheck, pad;   // multi-rank: the forward sweep left a residual sum for k_pcg_check
 };
@@ -254,12 +255,37 @@ __device__ __forceinline__ void pcgEndOfIteration(PcgScalars* sc, double* hist) 
     sc->converged = pcgConverged(sc) ? 1 : 0;
     sc->stop = (sc->nIter >= sc->minIter) && (sc->nIter >= sc->maxIter || sc->converged);
 }
-// multi-rank: runs after the all-reduce of the sum|rA| the forward sweep left behind
+// multi-rank: runs after the ONE all-reduce of (sum|rA| left behind by the forward sweep, sum(wA*rA) of the backward sweep):
+// closes the previous iteration (residual, convergence, wArAold = wArA), then adopts the new wArA
 static __global__ void k_pcg_check(PcgScalars* sc, double* hist) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (sc->stop || !sc->pendingCheck) return;
-    sc->pendingCheck = 0;
-    pcgEndOfIteration(sc, hist);
+    if (sc->stop) return;
+    if (sc->pendingCheck) { sc->pendingCheck = 0; pcgEndOfIteration(sc, hist); }
+    if (!sc->stop) sc->wArA = sc->wArAnew;
+}
+// multi-rank tail of Amul: processor-interface update  Apsi[faceCells] -= bouCoeffs*psiNbr  (per boundary row in patch order)
+// fused with sum(Apsi*psi) -> sc->wApA
+static __global__ void __launch_bounds__(BLOCK) k_iface_dot(MeshView mv, const double* __restrict__ bou, const double* __restrict__ psiNbr,
+                                                      double* __restrict__ Apsi, const double* __restrict__ psi, PcgScalars* sc,
+                                                      double* partials, unsigned* counter) {
+    if (sc->stop) return;
+    int row = blockIdx.x * blockDim.x + threadIdx.x, s = row >> 5, lane = row & 31;
+    double v[1] = {0.0};
+    if (row < mv.N) {
+        double acc = Apsi[row];
+        if ((mv.bMask[s] >> lane) & 1u) {
+            int i = mv.bBase[s] + __popc(mv.bMask[s] & ((1u << lane) - 1u));
+            bool any = false;
+            for (int q = mv.bRowStart[i]; q < mv.bRowStart[i + 1]; q++) {
+                int b = mv.bRowFaces[q];
+                if (mv.bCoupled[b]) { acc = acc - bou[b] * psiNbr[b]; any = true; }
+            }
+            if (any) Apsi[row] = acc;
+        }
+        v[0] = acc * psi[row];
+    }
+    gridReduce<1, OpSum>(v, blockIdx.x, gridDim.x, partials, counter, nullptr);
+    gridFinalize<1, OpSum>(gridDim.x, partials, counter, &sc->wApA);
 }
 // pA = z + beta*pA (first iteration: pA = z);  z <- sentinel (re-armed for the next sweep)
 static __global__ void __launch_bounds__(BLOCK) k_pcg_p_update(int N, double* __restrict__ z, double* __restrict__ pA,

@@ -79,9 +79,9 @@ static void launchFwd(DeviceMesh& m, PcgWorkspace& w, const double* rD, const do
     B200_LAUNCH_SMEM(k_dic_fwd<0>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), rD, rA, (const double*)nullptr,
                      (const double*)w.cf.p, w.y.p, (double*)nullptr, sweepCtl(w), sc, fz);
 }
-static void launchBwd(DeviceMesh& m, PcgWorkspace& w, const double* rA, PcgScalars* sc, double* part, unsigned* cnt) {
+static void launchBwd(DeviceMesh& m, PcgWorkspace& w, const double* rA, PcgScalars* sc, double* part, unsigned* cnt, double* dotOut = nullptr) {
     B200_LAUNCH_SMEM(k_dic_bwd, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), (const double*)w.cb.p, rA, w.y.p, w.z.p,
-                     sweepCtl(w), sc, part, cnt);
+                     sweepCtl(w), sc, part, cnt, dotOut ? dotOut : (sc ? &sc->wArA : nullptr));
 }
 
 void amulDevice(DeviceMesh& m, const double* diag, const double* upS, const double* loS, const double* psi, double* Apsi,
@@ -163,9 +163,10 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
         // (an empty rank still runs the sweeps: they carry the iteration's residual sum / convergence test and the wArA sum)
         { KT(T_DIC_FWD);   // + the previous iteration's x / rA update, residual sum and convergence test (fused)
           launchFwd(m, w, w.rD.p, w.rA.p, sc, PcgFuse{x, w.rA.p, w.pA.p, w.wA.p, sc, part, cnt, hist, multi ? 0 : 1}); }
-        if (multi) { allReduce(&sc->sumMagR, 1, RED_SUM); B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist); }
-        { KT(T_DIC_BWD); launchBwd(m, w, w.rA.p, sc, part, cnt); }
-        if (multi) allReduce(&sc->wArA, 1, RED_SUM);
+        { KT(T_DIC_BWD); launchBwd(m, w, w.rA.p, sc, part, cnt, multi ? &sc->wArAnew : &sc->wArA); }
+        // multi-rank: ONE all-reduce carries the previous iteration's sum|rA| and this iteration's sum(wA*rA); the convergence
+        // test therefore runs after the backward sweep (one wasted sweep at the end of a solve)
+        if (multi) { allReduce(&sc->sumMagR, 2, RED_SUM); B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist); }
         { KT(T_PCG_VEC);
           B200_LAUNCH(k_pcg_p_update, grid, BLOCK, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc); }
         if (halo) {
@@ -173,8 +174,7 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
             { KT(T_AMUL);
               B200_LAUNCH(k_amul<0>, grid, BLOCK, st, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt); }
             haloExchange(m, w.sendBuf, w.recvBuf);
-            B200_LAUNCH(k_interface_update, gridFor(m.nBRows), BLOCK, st, mv, bou, w.recvBuf.p, w.wA.p, m.nBRows, w.bRowOfSlot.p);
-            B200_LAUNCH(k_dot, grid, BLOCK, st, N, (const double*)w.wA.p, (const double*)w.pA.p, &sc->wApA, part, cnt, (const PcgScalars*)sc);
+            B200_LAUNCH(k_iface_dot, grid, BLOCK, st, mv, bou, (const double*)w.recvBuf.p, w.wA.p, (const double*)w.pA.p, sc, part, cnt);
         } else {
             KT(T_AMUL);
             B200_LAUNCH(k_amul<1>, grid, BLOCK, st, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt);
