@@ -241,16 +241,18 @@ def run_ours(args):
     hb[0][:] = f["alpha1"]; hb[1][:] = f["U"].reshape(-1); hb[2][:] = f["pd"]; hb[3][:] = f["phi"]; hb[4][:] = f["p"]
     e2e_steps = max(2, min(args.steps, 5))
     reg.step_host(*hb)
+    reg.clear_log()
     barrier(); t0 = time.time()
     for _ in range(e2e_steps):
         reg.step_host(*hb)
     e2e_s = time.time() - t0
+    e2e_iters = sum(p[2] for p in reg.perfs()) / e2e_steps   # (later time steps than the `value` leg: the flow has settled a little)
     barrier()
     if dist:
         import torch
         t = torch.tensor([e2e_s], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t[0])
     e2e = {"value": total_cells * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * (5 * N + nF) * world,
-           "d2h_bytes_per_step": 8 * (6 * N + nF) * world, "steps": e2e_steps,
+           "d2h_bytes_per_step": 8 * (6 * N + nF) * world, "steps": e2e_steps, "pcg_iterations_per_step": e2e_iters,
            "api": "b200_region3d_step_host (host buffers in, host buffers out)"}
 
     # ---- roofline of the dominant kernel class, measured live with CUDA events (separate pass, per-kernel timers on)
@@ -288,8 +290,12 @@ def run_ours(args):
         kernels["mules_explicitSolve"] = {"us": 1e6 * t_mules, "GBps": alg["mules"] / t_mules / 1e9, "share_of_step": tk["mules"][0] / step_ms}
     dom = "dic_precondition" if "dic_precondition" in kernels else "amul"
     ach = kernels[dom]["GBps"] if dom in kernels else None
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
+    # (profiles/r1c_ncu_full_raw.csv: k_dic_fwd 98.9 + 4.5 MB, k_dic_bwd 75.1 + 1.6 MB, k_amul 63.3 + 1.4 MB); only valid for N = 1
+    ncu_traffic = {"dic_precondition": 180.1e6, "amul": 64.7e6}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                "frac_of_8TBps_nominal": (ach / 8000.0) if ach else None, "peak_source": peak_src, "traffic": None,
+                "frac_of_8TBps_nominal": (ach / 8000.0) if ach else None, "peak_source": peak_src,
+                "traffic": ncu_traffic.get(dom) if world == 1 else None,
                 "algorithmic_bytes_per_launch": alg[dom], "kernels": kernels,
                 "pcg_iterations_in_pass": n_iter,
                 "note": "DIC sweeps are bound by the dependency chain (348 wavefronts -> ~41 tile hops of ~3 us), not by bandwidth; the "
