@@ -155,7 +155,7 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
     if (N) { ScopedTimer t(T_DIC_RD); launchCalcRD(m, w, diag, upS, w.rD.p); launchCoeffs(m, w, w.rD.p, upS); fillSentinel(w.y, N); }
     B200_CHECK_CUDA(cudaEventSynchronize(w.ev[0]));
     bool stopped = w.hsc[0].stop != 0;
-    const int BATCH = 8;
+    const int BATCH = (int)std::max(1.0, rt().opt("pcg_batch", 4));   // iterations enqueued per host poll (two batches in flight)
     int slot = 0, enq = 0;
     const bool kt = timers().enabled && rt().opt("pcg_kernel_timers", 0) > 0;   // per-kernel-class events (roofline pass)
 #define KT(id) std::unique_ptr<ScopedTimer> _kt(kt ? new ScopedTimer(id) : nullptr)
