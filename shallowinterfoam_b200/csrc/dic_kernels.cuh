@@ -378,7 +378,8 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
 // rD == null: the plain upper coefficients (what calcReciprocalD sweeps with; 1.0*upper is exact).
 // grid = 2*nTiles (forward tiles, then backward tiles) or nTiles (forward only); block = lanes
 static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_coeffs(SweepView sv, const double* __restrict__ rD,
-        const double* __restrict__ upS, double* __restrict__ cf, double* __restrict__ cb) {
+        const double* __restrict__ upS, double* __restrict__ cf, double* __restrict__ cb, const PcgScalars* gate) {
+    if (gate && gate->stop) return;
     const bool bw = (int)blockIdx.x >= sv.nTiles;
     const SweepTile t = bw ? sv.bwd[blockIdx.x - sv.nTiles] : sv.fwd[blockIdx.x];
     const int* pos = bw ? sv.bwdPos : sv.fwdPos;
@@ -393,6 +394,22 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_coeffs(SweepView s
             out[e] = p >= 0 ? rd * upS[p] : 0.0;
         }
     }
+}
+
+// DIC reuse (pcg.cuh): compares this solve's diag / upper with the kept copies bit by bit, refreshes the copies, and opens the gate
+// (gate->stop = 0) when anything differs.  k_gate_close runs first.
+static __global__ void k_gate_close(PcgScalars* gate) { if (threadIdx.x == 0 && blockIdx.x == 0) gate->stop = 1; }
+static __global__ void __launch_bounds__(BLOCK) k_matrix_changed(int N, int Fs, const double* __restrict__ diag, const double* __restrict__ upS,
+        double* __restrict__ keptDiag, double* __restrict__ keptUp, PcgScalars* gate) {
+    bool diff = false;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N + Fs; i += stride) {
+        const double* src = i < N ? diag + i : upS + (i - N);
+        double* kept = i < N ? keptDiag + i : keptUp + (i - N);
+        const long long a = __double_as_longlong(*src);
+        if (a != __double_as_longlong(*kept)) { *kept = __longlong_as_double(a); diff = true; }
+    }
+    if (diff) gate->stop = 0;
 }
 
 }  // namespace b200

@@ -130,37 +130,76 @@ __device__ __forceinline__ void stPublish(double* p, double v) {
 
 // ----------------------------------------------------------------------------- a1: Amul (row gather)
 // Apsi[row] = diag*psi + sum_{nbr-side faces asc} lower_f*psi[l] + sum_{owner faces asc} upper_f*psi[u]
+// The row's off-diagonal products, accumulated onto acc in upstream's order.  Slices of up to GW faces per side (every
+// hex / prism / tet mesh) take the batched path: all index loads are issued first, then all coefficient and psi loads,
+// and only the FP64 additions stay sequential -- three dependent memory round trips per row instead of 3 x (faces of the
+// row), which is what keeps enough bytes in flight to load HBM.  Wider slices (polyhedra) finish in the generic loops.
+constexpr int GW = 4;
+template <bool WITH_SUM>
+__device__ __forceinline__ double rowOffDiag(const MeshView& mv, const double* __restrict__ upS, const double* __restrict__ loS,
+                                             const double* __restrict__ psi, int s, int lane, double acc, double& sA) {
+    const int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5;
+    const int so0 = mv.sliceOff[s], ow = (mv.sliceOff[s + 1] - so0) >> 5;
+    int pk[GW], u[GW];
+    double cu[GW], pu[GW], cl[GW], pl[GW];
+#pragma unroll
+    for (int i = 0; i < GW; i++) pk[i] = i < nbw ? mv.loPk[nb0 + (i << 5) + lane] : -1;
+#pragma unroll
+    for (int i = 0; i < GW; i++) {
+        u[i] = -1; cu[i] = 0.0;
+        if (i < ow) { u[i] = mv.upIdx[so0 + (i << 5) + lane]; cu[i] = upS[so0 + (i << 5) + lane]; }
+    }
+#pragma unroll
+    for (int i = 0; i < GW; i++) {
+        cl[i] = 0.0; pl[i] = 0.0;
+        if (pk[i] >= 0) { int l; int pos = facePosOf(mv, pk[i], l); cl[i] = loS[pos]; pl[i] = psi[l]; }
+    }
+#pragma unroll
+    for (int i = 0; i < GW; i++) pu[i] = u[i] >= 0 ? psi[u[i]] : 0.0;
+#pragma unroll
+    for (int i = 0; i < GW; i++)
+        if (pk[i] >= 0) { acc = acc + cl[i] * pl[i]; if (WITH_SUM) sA = sA + cl[i]; }
+    for (int j = GW; j < nbw; j++) {
+        int q = mv.loPk[nb0 + (j << 5) + lane];
+        if (q >= 0) { int l; int pos = facePosOf(mv, q, l); double c = loS[pos]; acc = acc + c * psi[l]; if (WITH_SUM) sA = sA + c; }
+    }
+#pragma unroll
+    for (int i = 0; i < GW; i++)
+        if (u[i] >= 0) { acc = acc + cu[i] * pu[i]; if (WITH_SUM) sA = sA + cu[i]; }
+    for (int k = GW; k < ow; k++) {
+        int pos = so0 + (k << 5) + lane;
+        int v = mv.upIdx[pos];
+        if (v >= 0) { double c = upS[pos]; acc = acc + c * psi[v]; if (WITH_SUM) sA = sA + c; }
+    }
+    return acc;
+}
+
 // MODE 0: plain; MODE 1: also accumulates sum(Apsi*psi) into sc->wApA (PCG); skips everything when sc->stop.
+// Persistent: the grid is a fixed number of CTAs per SM and every CTA walks chunks of BLOCK rows with a grid stride, so there is
+// no barrier, fence or atomic per chunk (a CTA that ends after each chunk idles its warps for the ~2 us of the reduction tail) and
+// the warps of an SM drift apart, which keeps loads in flight all the time.  One partial per CTA, summed in a fixed order.
 template <int MODE>
 static __global__ void __launch_bounds__(BLOCK) k_amul(MeshView mv, const double* __restrict__ diag,
                                                  const double* __restrict__ upS, const double* __restrict__ loS,
                                                  const double* __restrict__ psi, double* __restrict__ Apsi,
                                                  PcgScalars* sc, double* partials, unsigned* counter) {
     if (MODE == 1 && sc->stop) return;
-    int row = blockIdx.x * blockDim.x + threadIdx.x, s = row >> 5, lane = row & 31;
-    double acc = 0.0, p = 0.0;
-    if (row < mv.N) {
-        p = psi[row];
-        acc = diag[row] * p;
-        int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5;
-        for (int j = 0; j < nbw; j++) {
-            int pk = mv.loPk[nb0 + (j << 5) + lane];
-            if (pk >= 0) { int l; int pos = facePosOf(mv, pk, l); acc = acc + loS[pos] * psi[l]; }
-        }
-        int so0 = mv.sliceOff[s], ow = (mv.sliceOff[s + 1] - so0) >> 5;
-        for (int k = 0; k < ow; k++) {
-            int pos = so0 + (k << 5) + lane;
-            int u = mv.upIdx[pos];
-            if (u >= 0) acc = acc + upS[pos] * psi[u];
-        }
+    double dot = 0.0;
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < mv.N; row += gridDim.x * blockDim.x) {
+        const double p = psi[row];
+        double unused = 0.0;
+        const double acc = rowOffDiag<false>(mv, upS, loS, psi, row >> 5, row & 31, diag[row] * p, unused);
         Apsi[row] = acc;
+        if (MODE == 1) dot = dot + acc * p;
     }
     if (MODE == 1) {
-        double v[1] = {row < mv.N ? acc * p : 0.0};
+        double v[1] = {dot};
         gridReduce<1, OpSum>(v, blockIdx.x, gridDim.x, partials, counter, nullptr);
         gridFinalize<1, OpSum>(gridDim.x, partials, counter, &sc->wApA);
     }
 }
+// CTAs of the persistent row kernels: as many as are resident at once (k_amul: 48 registers -> 5 CTAs of 256 threads per SM)
+inline int persistentGrid(int nRows) { return std::max(1, std::min(gridFor(nRows), rt().numSMs * (int)rt().opt("amul_ctas_per_sm", 5))); }
 
 // processor-interface update  Apsi[faceCells] -= bouCoeffs*psiNbr, per boundary row in patch order
 static __global__ void k_interface_update(MeshView mv, const double* __restrict__ bou, const double* __restrict__ psiNbr,
@@ -189,18 +228,8 @@ static __global__ void __launch_bounds__(BLOCK) k_pcg_init1(MeshView mv, const d
     double v[2] = {0.0, 0.0};
     if (row < mv.N) {
         double xr = x[row], d = diag[row];
-        double acc = d * xr, sA = d;
-        int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5;
-        for (int j = 0; j < nbw; j++) {
-            int pk = mv.loPk[nb0 + (j << 5) + lane];
-            if (pk >= 0) { int l; int pos = facePosOf(mv, pk, l); double c = upS[pos]; acc = acc + c * x[l]; sA = sA + c; }
-        }
-        int so0 = mv.sliceOff[s], ow = (mv.sliceOff[s + 1] - so0) >> 5;
-        for (int k = 0; k < ow; k++) {
-            int pos = so0 + (k << 5) + lane;
-            int u = mv.upIdx[pos];
-            if (u >= 0) { double c = upS[pos]; acc = acc + c * x[u]; sA = sA + c; }
-        }
+        double sA = d;
+        double acc = rowOffDiag<true>(mv, upS, upS, x, s, lane, d * xr, sA);
         if (bou && ((mv.bMask[s] >> lane) & 1u)) {  // sumA: coupled patches subtract bouCoeffs
             int i = mv.bBase[s] + __popc(mv.bMask[s] & ((1u << lane) - 1u));
             for (int q = mv.bRowStart[i]; q < mv.bRowStart[i + 1]; q++) { int bf = mv.bRowFaces[q]; if (mv.bCoupled[bf]) sA = sA - bou[bf]; }

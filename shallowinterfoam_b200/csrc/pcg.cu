@@ -65,15 +65,30 @@ static int sweepGridOf(const DeviceMesh& m, const PcgWorkspace&) {
     return std::max(1, std::min(g, std::max(1, m.nTiles)));
 }
 static int sweepThreads(const DeviceMesh& m) { return m.plan.lanes; }   // one row per thread per step
-static void launchCalcRD(DeviceMesh& m, PcgWorkspace& w, const double* diag, const double* upS, double* rD) {
+// gate (optional): device flag of the DIC reuse; when it says "unchanged" the kernels return at once and rD / cf / cb stay as they are
+static void launchCalcRD(DeviceMesh& m, PcgWorkspace& w, const double* diag, const double* upS, double* rD, const PcgScalars* gate = nullptr) {
     fillSentinel(w.Dt, m.N);
     // forward operand blocks <- plain upper coefficients (fully parallel), so that the sweep stages them with one TMA copy per tile
-    B200_LAUNCH(k_dic_coeffs, m.nTiles, sweepThreads(m), rt().stream, m.sweep(), (const double*)nullptr, upS, w.cf.p, w.cb.p);
+    B200_LAUNCH(k_dic_coeffs, m.nTiles, sweepThreads(m), rt().stream, m.sweep(), (const double*)nullptr, upS, w.cf.p, w.cb.p, gate);
     B200_LAUNCH_SMEM(k_dic_fwd<1>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), diag, (const double*)nullptr, upS,
-                     (const double*)w.cf.p, w.Dt.p, rD, sweepCtl(w), (const PcgScalars*)nullptr, PcgFuse{});
+                     (const double*)w.cf.p, w.Dt.p, rD, sweepCtl(w), gate, PcgFuse{});
 }
-static void launchCoeffs(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* upS) {
-    B200_LAUNCH(k_dic_coeffs, 2 * m.nTiles, sweepThreads(m), rt().stream, m.sweep(), rD, upS, w.cf.p, w.cb.p);
+static void launchCoeffs(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* upS, const PcgScalars* gate = nullptr) {
+    B200_LAUNCH(k_dic_coeffs, 2 * m.nTiles, sweepThreads(m), rt().stream, m.sweep(), rD, upS, w.cf.p, w.cb.p, gate);
+}
+// DIC reuse: closes the gate, then re-opens it if diag / upper differ from the kept copies (refreshed in the same pass)
+static const PcgScalars* launchMatrixGate(DeviceMesh& m, PcgWorkspace& w, const double* diag, const double* upS) {
+    if (rt().opt("dic_reuse", 1) <= 0) { w.keptValid = false; return nullptr; }
+    if (!w.keptValid) {
+        w.keptDiag.ensure(m.N); w.keptUp.ensure(m.Fs); if (!w.gate.p) w.gate.alloc(1);
+        fillSentinel(w.keptDiag, m.N); fillSentinel(w.keptUp, m.Fs);   // differs from every coefficient
+        w.keptValid = true;
+    }
+    B200_LAUNCH(k_gate_close, 1, 32, rt().stream, w.gate.p);
+    const int n = m.N + m.Fs;
+    B200_LAUNCH(k_matrix_changed, std::max(1, std::min(gridFor(n), rt().numSMs * 8)), BLOCK, rt().stream, m.N, m.Fs, diag, upS, w.keptDiag.p,
+                w.keptUp.p, w.gate.p);
+    return w.gate.p;
 }
 static void launchFwd(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* rA, const PcgScalars* sc, PcgFuse fz = PcgFuse{}) {
     B200_LAUNCH_SMEM(k_dic_fwd<0>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), rD, rA, (const double*)nullptr,
@@ -90,7 +105,7 @@ void amulDevice(DeviceMesh& m, const double* diag, const double* upS, const doub
     ScopedTimer t(T_AMUL);
     bool halo = bou && rt().nRanks > 1 && meshHasProcessorPatches(m);
     if (halo) haloPack(m, psi, w.sendBuf);
-    if (m.N) B200_LAUNCH(k_amul<0>, gridFor(m.N), BLOCK, rt().stream, m.view(), diag, upS, loS, psi, Apsi, (PcgScalars*)nullptr,
+    if (m.N) B200_LAUNCH(k_amul<0>, persistentGrid(m.N), BLOCK, rt().stream, m.view(), diag, upS, loS, psi, Apsi, (PcgScalars*)nullptr,
                          (double*)nullptr, (unsigned*)nullptr);
     if (halo) {
         haloExchange(m, w.sendBuf, w.recvBuf);
@@ -102,12 +117,14 @@ void dicCalcReciprocalD(DeviceMesh& m, const double* diag, const double* upS, do
     PcgWorkspace& w = pcgWorkspace(m);
     ScopedTimer t(T_DIC_RD);
     if (!m.N) return;
+    w.keptValid = false;   // the operand blocks no longer belong to the kept matrix
     launchCalcRD(m, w, diag, upS, rD);
 }
 
 void dicPrecondition(DeviceMesh& m, const double* rD, const double* upS, const double* rA, double* wA) {
     PcgWorkspace& w = pcgWorkspace(m);
     if (!m.N) return;
+    w.keptValid = false;
     { ScopedTimer t(T_DIC_RD); launchCoeffs(m, w, rD, upS); }
     { ScopedTimer t(T_DIC_FWD); launchFwd(m, w, rD, rA, nullptr); }
     { ScopedTimer t(T_DIC_BWD); launchBwd(m, w, rA, nullptr, nullptr, nullptr); }
@@ -152,7 +169,11 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
     B200_CHECK_CUDA(cudaMemcpyAsync(&w.hsc[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
     B200_CHECK_CUDA(cudaEventRecord(w.ev[0], st));
     // calcReciprocalD is enqueued before the host learns whether it is needed (one sweep; keeps the GPU busy)
-    if (N) { ScopedTimer t(T_DIC_RD); launchCalcRD(m, w, diag, upS, w.rD.p); launchCoeffs(m, w, w.rD.p, upS); fillSentinel(w.y, N); }
+    if (N) {
+        ScopedTimer t(T_DIC_RD);
+        const PcgScalars* gate = launchMatrixGate(m, w, diag, upS);
+        launchCalcRD(m, w, diag, upS, w.rD.p, gate); launchCoeffs(m, w, w.rD.p, upS, gate); fillSentinel(w.y, N);
+    }
     B200_CHECK_CUDA(cudaEventSynchronize(w.ev[0]));
     bool stopped = w.hsc[0].stop != 0;
     const int BATCH = (int)std::max(1.0, rt().opt("pcg_batch", 4));   // iterations enqueued per host poll (two batches in flight)
@@ -172,12 +193,12 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
         if (halo) {
             haloPack(m, w.pA, w.sendBuf);
             { KT(T_AMUL);
-              B200_LAUNCH(k_amul<0>, grid, BLOCK, st, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt); }
+              B200_LAUNCH(k_amul<0>, persistentGrid(N), BLOCK, st, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt); }
             haloExchange(m, w.sendBuf, w.recvBuf);
             B200_LAUNCH(k_iface_dot, grid, BLOCK, st, mv, bou, (const double*)w.recvBuf.p, w.wA.p, (const double*)w.pA.p, sc, part, cnt);
         } else {
             KT(T_AMUL);
-            B200_LAUNCH(k_amul<1>, grid, BLOCK, st, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt);
+            B200_LAUNCH(k_amul<1>, persistentGrid(N), BLOCK, st, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt);
         }
         if (multi) allReduce(&sc->wApA, 1, RED_SUM);
     };

@@ -13,6 +13,12 @@ struct PcgWorkspace {
     DevBuf<double> diag, upS, x, b, bou;       // staging for the host-pointer API
     DevBuf<double> sendBuf, recvBuf;           // processor-patch halo
     DevBuf<PcgScalars> sc;
+    // DIC reuse: foam-extend builds a new solver (and calcReciprocalD) per solve, but the PISO correctors of one time step
+    // solve the SAME pd matrix (rUA is fixed when momentumPredictor is off; also every non-orthogonal corrector).  The last
+    // solve's diag / upper are kept; a solve whose coefficients are bitwise the same keeps rD and the sweep operand blocks.
+    DevBuf<double> keptDiag, keptUp;
+    DevBuf<PcgScalars> gate;                   // gate->stop = 1: coefficients unchanged, the calcReciprocalD kernels return at once
+    bool keptValid = false;
     DevBuf<unsigned> counters;                 // [0] reduce counter, [1] sweep ticket, [2] sweep done
     DevBuf<int> bRowOfSlot;
     PcgScalars* hsc = nullptr;                 // pinned mirror (2 slots)
