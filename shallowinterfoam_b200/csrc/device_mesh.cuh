@@ -22,6 +22,7 @@ namespace b200 {
 
 struct MeshView {  // POD handed to kernels by value
     int N, F, B, nSlices, KB, Fs;
+    int uniOw, uniNw;      // > 0: every slice has this many owner / neighbour-side slots per row (positions are arithmetic)
     const int* sliceOff;   // [nSlices+1]
     const int* nbrOff;     // [nSlices+1]
     const int* upIdx;      // [Fs]
@@ -72,7 +73,7 @@ struct SweepView {
 struct PcgWorkspace;  // pcg.cu
 
 struct DeviceMesh {
-    int N = 0, F = 0, B = 0, nSlices = 0, KB = 0, Fs = 0, Ls = 0, nLevels = 0, nBRows = 0;
+    int N = 0, F = 0, B = 0, nSlices = 0, KB = 0, Fs = 0, Ls = 0, nLevels = 0, nBRows = 0, uniOw = 0, uniNw = 0;
     bool hasGeometry = false;
     std::vector<Patch> patches;            // start = boundary-face offset + F (absolute), as given
     std::vector<int32_t> lower, upper;     // original LDU addressing (host)

@@ -134,12 +134,14 @@ __device__ __forceinline__ void stPublish(double* p, double v) {
 // hex / prism / tet mesh) take the batched path: all index loads are issued first, then all coefficient and psi loads,
 // and only the FP64 additions stay sequential -- three dependent memory round trips per row instead of 3 x (faces of the
 // row), which is what keeps enough bytes in flight to load HBM.  Wider slices (polyhedra) finish in the generic loops.
-constexpr int GW = 4;
-template <bool WITH_SUM>
+// UNI: uniform slice widths (device_mesh.cu) -- slot positions are computed, not looked up, which leaves two dependent memory
+// round trips per row: indices, then coefficients / psi.
+template <bool WITH_SUM, bool UNI, int GW>
 __device__ __forceinline__ double rowOffDiag(const MeshView& mv, const double* __restrict__ upS, const double* __restrict__ loS,
                                              const double* __restrict__ psi, int s, int lane, double acc, double& sA) {
-    const int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5;
-    const int so0 = mv.sliceOff[s], ow = (mv.sliceOff[s + 1] - so0) >> 5;
+    int nb0, nbw, so0, ow;
+    if (UNI) { nbw = mv.uniNw; nb0 = s * 32 * nbw; ow = mv.uniOw; so0 = s * 32 * ow; }
+    else { nb0 = mv.nbrOff[s]; nbw = (mv.nbrOff[s + 1] - nb0) >> 5; so0 = mv.sliceOff[s]; ow = (mv.sliceOff[s + 1] - so0) >> 5; }
     int pk[GW], u[GW];
     double cu[GW], pu[GW], cl[GW], pl[GW];
 #pragma unroll
@@ -152,7 +154,12 @@ __device__ __forceinline__ double rowOffDiag(const MeshView& mv, const double* _
 #pragma unroll
     for (int i = 0; i < GW; i++) {
         cl[i] = 0.0; pl[i] = 0.0;
-        if (pk[i] >= 0) { int l; int pos = facePosOf(mv, pk[i], l); cl[i] = loS[pos]; pl[i] = psi[l]; }
+        if (pk[i] >= 0) {
+            int l, pos;
+            if (UNI) { l = pk[i] >> mv.KB; pos = (((l >> 5) * mv.uniOw + (pk[i] & ((1 << mv.KB) - 1))) << 5) + (l & 31); }
+            else pos = facePosOf(mv, pk[i], l);
+            cl[i] = loS[pos]; pl[i] = psi[l];
+        }
     }
 #pragma unroll
     for (int i = 0; i < GW; i++) pu[i] = u[i] >= 0 ? psi[u[i]] : 0.0;
@@ -175,10 +182,11 @@ __device__ __forceinline__ double rowOffDiag(const MeshView& mv, const double* _
 }
 
 // MODE 0: plain; MODE 1: also accumulates sum(Apsi*psi) into sc->wApA (PCG); skips everything when sc->stop.
+// UNI3: the mesh has uniform slice widths <= 3 (every hex mesh).
 // Persistent: the grid is a fixed number of CTAs per SM and every CTA walks chunks of BLOCK rows with a grid stride, so there is
 // no barrier, fence or atomic per chunk (a CTA that ends after each chunk idles its warps for the ~2 us of the reduction tail) and
 // the warps of an SM drift apart, which keeps loads in flight all the time.  One partial per CTA, summed in a fixed order.
-template <int MODE>
+template <int MODE, bool UNI3>
 static __global__ void __launch_bounds__(BLOCK) k_amul(MeshView mv, const double* __restrict__ diag,
                                                  const double* __restrict__ upS, const double* __restrict__ loS,
                                                  const double* __restrict__ psi, double* __restrict__ Apsi,
@@ -188,7 +196,7 @@ static __global__ void __launch_bounds__(BLOCK) k_amul(MeshView mv, const double
     for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < mv.N; row += gridDim.x * blockDim.x) {
         const double p = psi[row];
         double unused = 0.0;
-        const double acc = rowOffDiag<false>(mv, upS, loS, psi, row >> 5, row & 31, diag[row] * p, unused);
+        const double acc = rowOffDiag<false, UNI3, UNI3 ? 3 : 4>(mv, upS, loS, psi, row >> 5, row & 31, diag[row] * p, unused);
         Apsi[row] = acc;
         if (MODE == 1) dot = dot + acc * p;
     }
@@ -198,8 +206,14 @@ static __global__ void __launch_bounds__(BLOCK) k_amul(MeshView mv, const double
         gridFinalize<1, OpSum>(gridDim.x, partials, counter, &sc->wApA);
     }
 }
+inline bool uniform3(const MeshView& mv) { return mv.uniOw > 0 && mv.uniOw <= 3 && mv.uniNw <= 3; }
 // CTAs of the persistent row kernels: as many as are resident at once (k_amul: 48 registers -> 5 CTAs of 256 threads per SM)
-inline int persistentGrid(int nRows) { return std::max(1, std::min(gridFor(nRows), rt().numSMs * (int)rt().opt("amul_ctas_per_sm", 5))); }
+inline int persistentGrid(int nRows) { return std::max(1, std::min(gridFor(nRows), rt().numSMs * (int)rt().opt("amul_ctas_per_sm", 8))); }
+#define B200_LAUNCH_AMUL(MODE, mv, ...)                                                                                       \
+    do {                                                                                                                      \
+        if (uniform3(mv)) B200_LAUNCH((k_amul<MODE, true>), persistentGrid((mv).N), BLOCK, rt().stream, mv, __VA_ARGS__);     \
+        else B200_LAUNCH((k_amul<MODE, false>), persistentGrid((mv).N), BLOCK, rt().stream, mv, __VA_ARGS__);                 \
+    } while (0)
 
 // processor-interface update  Apsi[faceCells] -= bouCoeffs*psiNbr, per boundary row in patch order
 static __global__ void k_interface_update(MeshView mv, const double* __restrict__ bou, const double* __restrict__ psiNbr,
@@ -229,7 +243,7 @@ static __global__ void __launch_bounds__(BLOCK) k_pcg_init1(MeshView mv, const d
     if (row < mv.N) {
         double xr = x[row], d = diag[row];
         double sA = d;
-        double acc = rowOffDiag<true>(mv, upS, upS, x, s, lane, d * xr, sA);
+        double acc = rowOffDiag<true, false, 4>(mv, upS, upS, x, s, lane, d * xr, sA);
         if (bou && ((mv.bMask[s] >> lane) & 1u)) {  // sumA: coupled patches subtract bouCoeffs
             int i = mv.bBase[s] + __popc(mv.bMask[s] & ((1u << lane) - 1u));
             for (int q = mv.bRowStart[i]; q < mv.bRowStart[i + 1]; q++) { int bf = mv.bRowFaces[q]; if (mv.bCoupled[bf]) sA = sA - bou[bf]; }

@@ -105,7 +105,7 @@ void amulDevice(DeviceMesh& m, const double* diag, const double* upS, const doub
     ScopedTimer t(T_AMUL);
     bool halo = bou && rt().nRanks > 1 && meshHasProcessorPatches(m);
     if (halo) haloPack(m, psi, w.sendBuf);
-    if (m.N) B200_LAUNCH(k_amul<0>, persistentGrid(m.N), BLOCK, rt().stream, m.view(), diag, upS, loS, psi, Apsi, (PcgScalars*)nullptr,
+    if (m.N) B200_LAUNCH_AMUL(0, m.view(), diag, upS, loS, psi, Apsi, (PcgScalars*)nullptr,
                          (double*)nullptr, (unsigned*)nullptr);
     if (halo) {
         haloExchange(m, w.sendBuf, w.recvBuf);
@@ -193,12 +193,12 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
         if (halo) {
             haloPack(m, w.pA, w.sendBuf);
             { KT(T_AMUL);
-              B200_LAUNCH(k_amul<0>, persistentGrid(N), BLOCK, st, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt); }
+              B200_LAUNCH_AMUL(0, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt); }
             haloExchange(m, w.sendBuf, w.recvBuf);
             B200_LAUNCH(k_iface_dot, grid, BLOCK, st, mv, bou, (const double*)w.recvBuf.p, w.wA.p, (const double*)w.pA.p, sc, part, cnt);
         } else {
             KT(T_AMUL);
-            B200_LAUNCH(k_amul<1>, persistentGrid(N), BLOCK, st, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt);
+            B200_LAUNCH_AMUL(1, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt);
         }
         if (multi) allReduce(&sc->wApA, 1, RED_SUM);
     };
