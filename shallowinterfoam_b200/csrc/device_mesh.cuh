@@ -66,7 +66,7 @@ struct SweepView {
     const int *fwdPos, *bwdPos;              // face slot of each coefficient entry of the operand blocks (-1 = padding)
     const int *fwdHaloRow, *bwdHaloRow;      // device rows a tile polls
     int pollNs;                              // back-off between polls of a not-yet-published halo value
-    int weakPublish;                         // experiment: publish with plain stores
+    int publishMode;                         // 0: one TMA bulk store per tile after its last step; 1 (default): rows are stored in the step that computes them
     unsigned long long* trace;               // debug: [8*nTiles] globaltimer stamps per tile (ticket, staged, halo ready, steps done, published) or null
 };
 
@@ -110,7 +110,7 @@ struct DeviceMesh {
                      const double* w, const double* dc);
     MeshView view() const;
     SweepView sweep() const {
-        return SweepView{nTiles, dTilesF.p, dTilesB.p, dStepRow.p, dStepLen.p, plan.lanes, dFwdPos.p, dBwdPos.p, dFwdHaloRow.p, dBwdHaloRow.p, (int)rt().opt("sweep_poll_ns", 0), (int)rt().opt("sweep_weak_publish", 0),
+        return SweepView{nTiles, dTilesF.p, dTilesB.p, dStepRow.p, dStepLen.p, plan.lanes, dFwdPos.p, dBwdPos.p, dFwdHaloRow.p, dBwdHaloRow.p, (int)rt().opt("sweep_poll_ns", 0), (int)rt().opt("sweep_publish", 1),
                          rt().opt("sweep_trace", 0) > 0 ? dTrace.p : nullptr};
     }
     void coupleGeometry();   // collective: processor-face weights/deltaCoeffs/neighbour centres from a halo swap of C

@@ -154,9 +154,15 @@ __device__ __forceinline__ void pollHalo(const SweepTile& t, const TileSmem& s, 
 //   BAR -> D x LDS.64 (sources) -> D x DMUL -> D x DADD -> STS -> BAR.
 // No global access inside the loop: bar.sync would wait for the L2 acknowledge of a gpu-scope store (~400 cycles per step).
 // OP 0: w -= c*v ; OP 1: w -= c*c/v (calcReciprocalD).  DIR +1: steps upwards (forward sweep), -1: downwards (backward).
+// out != null: every row is also stored to out[row] (plain write-through store) in the step that computes it, so that when the
+// last step ends only its own rows are still on their way to L2 -- the dependants' polls see the tile ~0.3 us after its last step
+// instead of after a whole-tile publish pass.  Each 8-byte value is its own ready flag, so no ordering between the stores is needed,
+// and a plain store (unlike a gpu-scope one) does not make the following bar.sync wait for the L2 acknowledge.
 template <int OP, int DIR, int D>
-__device__ __forceinline__ void sweepStepsD(const TileSmem& s, const SweepTile& t) {
+__device__ __forceinline__ void sweepStepsD(const TileSmem& s, const SweepTile& t, double* out) {
     const int W = blockDim.x, S = s.S;
+    const unsigned rowBytes = 8u * (unsigned)t.nRows;
+    char* outB = (char*)(out + t.row0);
     int slot = (DIR > 0 ? 0 : (t.nSteps - 1) * W) + (int)threadIdx.x;
     const double* C = s.blk;
     const uint2* PK = (const uint2*)(s.blk + D * S);
@@ -174,16 +180,17 @@ __device__ __forceinline__ void sweepStepsD(const TileSmem& s, const SweepTile& 
         if (OP == 0) { w = w - c0 * v0; if (D > 1) w = w - c1 * v1; if (D > 2) w = w - c2 * v2; }
         else { w = w - c0 * c0 / v0; if (D > 1) w = w - c1 * c1 / v1; if (D > 2) w = w - c2 * c2 / v2; }
         stsAt(s.vals, pk.y >> 16, w);
+        if (out && (pk.y >> 16) < rowBytes) stWeak((double*)(outB + (pk.y >> 16)), w);   // (deferring it past the barrier is slower)
         __syncthreads();
         c0 = n0; c1 = n1; c2 = n2; w = nw; pk = npk; slot = nslot;
     }
 }
 template <int OP, int DIR>
-__device__ __forceinline__ void sweepSteps(const TileSmem& s, const SweepTile& t, const int* sRow, const int* sLen) {
-    if (t.nSteps == 0) return;
-    if (t.d == 3) { sweepStepsD<OP, DIR, 3>(s, t); return; }
-    if (t.d == 2) { sweepStepsD<OP, DIR, 2>(s, t); return; }
-    if (t.d == 1) { sweepStepsD<OP, DIR, 1>(s, t); return; }
+__device__ __forceinline__ bool sweepSteps(const TileSmem& s, const SweepTile& t, const int* sRow, const int* sLen, double* out) {
+    if (t.nSteps == 0) return false;
+    if (t.d == 3) { sweepStepsD<OP, DIR, 3>(s, t, out); return out != nullptr; }
+    if (t.d == 2) { sweepStepsD<OP, DIR, 2>(s, t, out); return out != nullptr; }
+    if (t.d == 1) { sweepStepsD<OP, DIR, 1>(s, t, out); return out != nullptr; }
     const int W = blockDim.x, S = s.S;
     const unsigned short* OFF = (const unsigned short*)(s.blk + t.d * S);   // [ceil(d/4)][S][4]
     for (int k = DIR > 0 ? 0 : t.nSteps - 1; k >= 0 && k < t.nSteps; k += DIR) {   // polyhedral rows (d > 3), isolated rows (d = 0)
@@ -198,6 +205,13 @@ __device__ __forceinline__ void sweepSteps(const TileSmem& s, const SweepTile& t
         }
         __syncthreads();
     }
+    return false;
+}
+// publish of a whole tile by all threads (consecutive threads -> consecutive rows); call after the barrier that ends the steps.
+// Only the variable-width tiles (polyhedral rows) leave this way.  Measured on the 985k-cell channel: a whole-tile publish after the
+// last step, by TMA bulk store or by these stores, is seen by the dependants ~1.0 us after the last step; step-by-step stores ~0.45 us.
+__device__ __forceinline__ void publishTileDirect(const TileSmem& s, const SweepTile& t, double* out) {
+    for (int r = threadIdx.x; r < t.nRows; r += blockDim.x) stWeak(out + t.row0 + r, s.vals[r]);
 }
 
 // stage the operand block of a tile: one elected thread issues the TMA bulk copies (the whole block is contiguous).
@@ -305,13 +319,18 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
         __syncthreads();
         SWEEP_TRACE(2);
         // 3. the steps, then publish
-        sweepSteps<MODE, 1>(s, t, sRow, sLen);
-        fenceAsyncProxy();    // this thread's results, for the TMA store below (writers fence, barrier, one thread stores)
-        __syncthreads();
-        SWEEP_TRACE(3);
-        if (tid == 0) publishTile(s, t, y);
+        const bool inLoop = sweepSteps<MODE, 1>(s, t, sRow, sLen, sv.publishMode == 1 ? y : nullptr);
+        if (sv.publishMode == 0) {
+            fenceAsyncProxy();    // this thread's results, for the TMA store below (writers fence, barrier, one thread stores)
+            __syncthreads();
+            SWEEP_TRACE(3);
+            if (tid == 0) publishTile(s, t, y);
+        } else {
+            SWEEP_TRACE(3);
+            if (!inLoop) publishTileDirect(s, t, y);
+        }
         if (MODE == 1) for (int r = tid; r < n; r += W) rDout[t.row0 + r] = 1.0 / s.vals[r];
-        if (tid == 0) bulkStoreWaitRead();   // the value array is reused by the next tile
+        if (sv.publishMode == 0 && tid == 0) bulkStoreWaitRead();   // the value array is reused by the next tile
         SWEEP_TRACE(4);
     }
     if (threadIdx.x == 0) bulkStoreWaitAll();   // this CTA's TMA stores must have landed before the kernel ends
@@ -357,17 +376,19 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
         pollHalo(t, s, sv.bwdHaloRow, z, sv.pollNs);
         barWait(&sBar, phase); phase ^= 1u;
         __syncthreads();
-        sweepSteps<0, -1>(s, t, sRow, sLen);
-        fenceAsyncProxy();
-        __syncthreads();
-        if (tid == 0) publishTile(s, t, z);
+        const bool inLoop = sweepSteps<0, -1>(s, t, sRow, sLen, sv.publishMode == 1 ? z : nullptr);
+        if (sv.publishMode == 0) {
+            fenceAsyncProxy();
+            __syncthreads();
+            if (tid == 0) publishTile(s, t, z);
+        } else if (!inLoop) publishTileDirect(s, t, z);
         if (partials) {
             double dotv = 0.0;
             for (int r = tid; r < n; r += W) dotv = dotv + s.vals[r] * rA[t.row0 + r];
             double v[1] = {dotv};
             gridReduce<1, OpSum>(v, ti, sv.nTiles, partials, counter, nullptr);
         }
-        if (tid == 0) bulkStoreWaitRead();
+        if (sv.publishMode == 0 && tid == 0) bulkStoreWaitRead();
     }
     if (threadIdx.x == 0) bulkStoreWaitAll();
     if (partials) gridFinalize<1, OpSum>(sv.nTiles, partials, counter, dotOut);
