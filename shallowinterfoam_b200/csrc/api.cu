@@ -202,7 +202,7 @@ int b200_amul(b200_ldu_t* ldu, const double* diag, const double* upper, const do
     m.uploadCells(psi, w.x);
     if (bouCoeffs && psiNbr && m.B) {  // caller-supplied neighbour values (single process, explicit halo)
         { ScopedTimer t(T_AMUL);
-          if (m.N) B200_LAUNCH_AMUL(0, m.view(), (const double*)w.diag.p, (const double*)w.upS.p, lo,
+          if (m.N) B200_LAUNCH_AMUL(0, false, m.view(), (const double*)w.diag.p, (const double*)w.upS.p, lo,
                                (const double*)w.x.p, w.b.p, (PcgScalars*)nullptr, (double*)nullptr, (unsigned*)nullptr); }
         m.uploadBoundary(psiNbr, w.recvBuf);
         B200_LAUNCH(k_interface_update, gridFor(m.nBRows), BLOCK, rt().stream, m.view(), (const double*)w.bou.p, (const double*)w.recvBuf.p, w.b.p,

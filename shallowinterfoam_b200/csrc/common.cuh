@@ -96,6 +96,35 @@ struct ScopedTimer {  // records events around a launch sequence when timers are
     } while (0)
 #endif
 
+// ---- programmatic dependent launch (PDL): a kernel launched with pdl = true may start while its predecessor in the stream is
+// still running; everything it does before pdlWait() must be independent of that predecessor.  Every kernel of the PCG iteration
+// calls pdlWait() and then pdlTrigger(), so when a kernel's prologue runs, the predecessor of its predecessor is complete.
+#ifdef B200_EMU
+#define B200_LAUNCH_PDL(pdl, kernel, grid, block, smem, stream, ...)                    \
+    do {                                                                                \
+        b200::rt().launches++;                                                          \
+        emu::launch(dim3(grid), dim3(block), [&]() { kernel(__VA_ARGS__); }, (smem));   \
+    } while (0)
+__device__ __forceinline__ void pdlWait() {}
+__device__ __forceinline__ void pdlTrigger() {}
+#else
+#define B200_LAUNCH_PDL(pdl_, kernel_, grid_, block_, smem_, stream_, ...)                                                    \
+    do {                                                                                                                      \
+        b200::rt().launches++;                                                                                                \
+        if ((smem_) > 48 * 1024)                                                                                              \
+            B200_CHECK_CUDA(cudaFuncSetAttribute(kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_)));       \
+        cudaLaunchConfig_t _cfg; memset(&_cfg, 0, sizeof(_cfg));                                                              \
+        _cfg.gridDim = dim3(grid_); _cfg.blockDim = dim3(block_); _cfg.dynamicSmemBytes = (smem_); _cfg.stream = (stream_);   \
+        cudaLaunchAttribute _attr[1];                                                                                         \
+        _attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                     \
+        _attr[0].val.programmaticStreamSerializationAllowed = (pdl_) ? 1 : 0;                                                 \
+        _cfg.attrs = _attr; _cfg.numAttrs = 1;                                                                                \
+        B200_CHECK_CUDA(cudaLaunchKernelEx(&_cfg, kernel_, __VA_ARGS__));                                                     \
+    } while (0)
+__device__ __forceinline__ void pdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdlTrigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // ---- device buffer ---------------------------------------------------------------------------------------
 template <class T>
 struct DevBuf {

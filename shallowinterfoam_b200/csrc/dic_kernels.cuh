@@ -265,29 +265,42 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
     B200_DYN_SMEM(smem);
     __shared__ int sRow[SWEEP_MAX_STEPS], sLen[SWEEP_MAX_STEPS];
     __shared__ TileBar sBar;
-    if (sc && sc->stop) return;
-    const bool fused = MODE == 0 && fz.x != nullptr;
-    const bool upd = fused && fz.sc->nFwd > 0;          // an iteration's x / rA update is pending
-    double alpha = 0.0;
-    if (upd) {
-        if (fabs(fz.sc->wApA) / fz.sc->normFactor <= 1.0e-300) {   // checkSingularity [UPSTREAM PCG.C]: leave x, rA, nIter untouched
-            if (blockIdx.x == 0 && threadIdx.x == 0) { fz.sc->singular = 1; fz.sc->stop = 1; }
-            return;
-        }
-        alpha = fz.sc->wArA / fz.sc->wApA;
-    }
     if (threadIdx.x == 0) barInit(&sBar);
     unsigned phase = 0;
     const int W = blockDim.x, tid = threadIdx.x;
-    for (;;) {
-        int ti = nextTicket(ctl);
-        if (ti >= sv.nTiles) break;
-        const SweepTile t = sv.fwd[ti];
-        SWEEP_TRACE(0);
-        TileSmem s = carveTile(smem, t, W);
-        const int n = t.nRows;
-        // 1. row-independent operands: the operand block by TMA bulk copy, start values by batched loads
+    // prologue (may overlap the tail of the previous kernel, PDL): first ticket, tile descriptor, TMA staging of the operand block --
+    // all static during the iterations of a solve.  Nothing the previous kernel writes is touched before pdlWait().
+    int ti = nextTicket(ctl);
+    SweepTile t; TileSmem s;
+    if (ti < sv.nTiles) {
+        t = sv.fwd[ti]; s = carveTile(smem, t, W);
         stageBlock(s, t, blocks, &sBar, false);   // MODE 1: the coefficient columns hold the plain upper coefficients (k_dic_coeffs, rD = null)
+    }
+    pdlWait();
+    pdlTrigger();
+    const bool fused = MODE == 0 && fz.x != nullptr;
+    bool quit = sc && sc->stop;
+    bool upd = false;
+    double alpha = 0.0;
+    if (!quit && fused) {
+        upd = fz.sc->nFwd > 0;          // an iteration's x / rA update is pending
+        if (upd) {
+            if (fabs(fz.sc->wApA) / fz.sc->normFactor <= 1.0e-300) {   // checkSingularity [UPSTREAM PCG.C]: leave x, rA, nIter untouched
+                __syncthreads();   // every thread of the CTA has read the scalars
+                if (blockIdx.x == 0 && threadIdx.x == 0) { fz.sc->singular = 1; fz.sc->stop = 1; }
+                quit = true;
+            } else alpha = fz.sc->wArA / fz.sc->wApA;
+        }
+    }
+    if (quit) {   // hand the ticket back (the last CTA to leave resets the counter) once the staging copy has landed
+        if (ti < sv.nTiles) barWait(&sBar, phase);
+        sweepExit(ctl);
+        return;
+    }
+    while (ti < sv.nTiles) {
+        SWEEP_TRACE(0);
+        const int n = t.nRows;
+        // 1. row-independent operands: the operand block by TMA bulk copy (already on its way), start values by batched loads
         double mag = 0.0;
         for (int r0 = tid; r0 < n; r0 += 8 * W) {
             double a[8], b[8], wa[8], xv[8], pv[8];
@@ -332,6 +345,8 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
         if (MODE == 1) for (int r = tid; r < n; r += W) rDout[t.row0 + r] = 1.0 / s.vals[r];
         if (sv.publishMode == 0 && tid == 0) bulkStoreWaitRead();   // the value array is reused by the next tile
         SWEEP_TRACE(4);
+        ti = nextTicket(ctl);
+        if (ti < sv.nTiles) { t = sv.fwd[ti]; s = carveTile(smem, t, W); stageBlock(s, t, blocks, &sBar, false); }
     }
     if (threadIdx.x == 0) bulkStoreWaitAll();   // this CTA's TMA stores must have landed before the kernel ends
     if (fused) {
@@ -352,18 +367,22 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
     B200_DYN_SMEM(smem);
     __shared__ int sRow[SWEEP_MAX_STEPS], sLen[SWEEP_MAX_STEPS];
     __shared__ TileBar sBar;
-    if (sc && sc->stop) return;
     if (threadIdx.x == 0) barInit(&sBar);
     unsigned phase = 0;
     const int W = blockDim.x, tid = threadIdx.x;
-    for (;;) {
-        int tk = nextTicket(ctl);
-        if (tk >= sv.nTiles) break;
-        const int ti = sv.nTiles - 1 - tk;
-        const SweepTile t = sv.bwd[ti];
-        TileSmem s = carveTile(smem, t, W);
+    // prologue (PDL, see k_dic_fwd): first ticket, descriptor, operand block
+    int tk = nextTicket(ctl), ti = sv.nTiles - 1 - tk;
+    SweepTile t; TileSmem s;
+    if (tk < sv.nTiles) { t = sv.bwd[ti]; s = carveTile(smem, t, W); stageBlock(s, t, blocks, &sBar, false); }
+    pdlWait();
+    pdlTrigger();
+    if (sc && sc->stop) {
+        if (tk < sv.nTiles) barWait(&sBar, phase);
+        sweepExit(ctl);
+        return;
+    }
+    while (tk < sv.nTiles) {
         const int n = t.nRows;
-        stageBlock(s, t, blocks, &sBar, false);
         for (int r0 = tid; r0 < n; r0 += 8 * W) {
             double a[8];
 #pragma unroll
@@ -389,6 +408,8 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
             gridReduce<1, OpSum>(v, ti, sv.nTiles, partials, counter, nullptr);
         }
         if (sv.publishMode == 0 && tid == 0) bulkStoreWaitRead();
+        tk = nextTicket(ctl); ti = sv.nTiles - 1 - tk;
+        if (tk < sv.nTiles) { t = sv.bwd[ti]; s = carveTile(smem, t, W); stageBlock(s, t, blocks, &sBar, false); }
     }
     if (threadIdx.x == 0) bulkStoreWaitAll();
     if (partials) gridFinalize<1, OpSum>(sv.nTiles, partials, counter, dotOut);

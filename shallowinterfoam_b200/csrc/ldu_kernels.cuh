@@ -194,6 +194,8 @@ static __global__ void __launch_bounds__(BLOCK) k_amul(MeshView mv, const double
                                                  const double* __restrict__ upS, const double* __restrict__ loS,
                                                  const double* __restrict__ psi, double* __restrict__ Apsi,
                                                  PcgScalars* sc, double* partials, unsigned* counter) {
+    pdlWait();
+    pdlTrigger();
     if (MODE == 1 && sc->stop) return;
     double dot = 0.0;
     for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < mv.N; row += gridDim.x * blockDim.x) {
@@ -211,11 +213,21 @@ static __global__ void __launch_bounds__(BLOCK) k_amul(MeshView mv, const double
 }
 inline bool uniform3(const MeshView& mv) { return mv.uniOw > 0 && mv.uniOw <= 3 && mv.uniNw <= 3; }
 // CTAs of the persistent row kernels: as many as are resident at once (k_amul: 48 registers -> 5 CTAs of 256 threads per SM)
-inline int persistentGrid(int nRows) { return std::max(1, std::min(gridFor(nRows), rt().numSMs * (int)rt().opt("amul_ctas_per_sm", 8))); }
-#define B200_LAUNCH_AMUL(MODE, mv, ...)                                                                                       \
-    do {                                                                                                                      \
-        if (uniform3(mv)) B200_LAUNCH((k_amul<MODE, true>), persistentGrid((mv).N), BLOCK, rt().stream, mv, __VA_ARGS__);     \
-        else B200_LAUNCH((k_amul<MODE, false>), persistentGrid((mv).N), BLOCK, rt().stream, mv, __VA_ARGS__);                 \
+// CTAs of a persistent row kernel: exactly as many as are resident at once (a PDL successor only starts when every CTA of the
+// grid has started); option amul_ctas_per_sm overrides the occupancy query
+template <class K>
+inline int persistentGrid(int nRows, K kernel) {
+    int perSM = (int)rt().opt("amul_ctas_per_sm", 0);
+#ifndef B200_EMU
+    if (perSM <= 0) B200_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, BLOCK, 0));
+#endif
+    if (perSM <= 0) perSM = 4;
+    return std::max(1, std::min(gridFor(nRows), rt().numSMs * perSM));
+}
+#define B200_LAUNCH_AMUL(MODE, pdl, mv, ...)                                                                                          \
+    do {                                                                                                                              \
+        if (uniform3(mv)) B200_LAUNCH_PDL(pdl, (k_amul<MODE, true>), persistentGrid((mv).N, k_amul<MODE, true>), BLOCK, 0, rt().stream, mv, __VA_ARGS__);    \
+        else B200_LAUNCH_PDL(pdl, (k_amul<MODE, false>), persistentGrid((mv).N, k_amul<MODE, false>), BLOCK, 0, rt().stream, mv, __VA_ARGS__);               \
     } while (0)
 
 // processor-interface update  Apsi[faceCells] -= bouCoeffs*psiNbr, per boundary row in patch order
@@ -336,6 +348,8 @@ static __global__ void __launch_bounds__(BLOCK) k_iface_dot(MeshView mv, const d
 // pA = z + beta*pA (first iteration: pA = z);  z <- sentinel (re-armed for the next sweep)
 static __global__ void __launch_bounds__(BLOCK) k_pcg_p_update(int N, double* __restrict__ z, double* __restrict__ pA,
                                                          const PcgScalars* sc) {
+    pdlWait();
+    pdlTrigger();
     if (sc->stop) return;
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= N) return;

@@ -40,7 +40,7 @@ PcgWorkspace& pcgWorkspace(DeviceMesh& m) {
     w->cf.alloc(m.fwdBlkSize); w->cb.alloc(m.bwdBlkSize);   // operand blocks: templates carry the (static) source offsets
     if (m.fwdBlkSize) B200_CHECK_CUDA(cudaMemcpyAsync(w->cf.p, m.dFwdBlk0.p, 8 * m.fwdBlkSize, cudaMemcpyDeviceToDevice, rt().stream));
     if (m.bwdBlkSize) B200_CHECK_CUDA(cudaMemcpyAsync(w->cb.p, m.dBwdBlk0.p, 8 * m.bwdBlkSize, cudaMemcpyDeviceToDevice, rt().stream));
-    w->sc.alloc(1); w->counters.alloc(4); w->counters.zero();
+    w->sc.alloc(1); w->counters.alloc(8); w->counters.zero();
     B200_CHECK_CUDA(cudaMallocHost((void**)&w->hsc, 2 * sizeof(PcgScalars)));
     for (auto& e : w->ev) B200_CHECK_CUDA(cudaEventCreate(&e));
     fillSentinel(w->y, N); fillSentinel(w->z, N);
@@ -54,7 +54,8 @@ PcgWorkspace& pcgWorkspace(DeviceMesh& m) {
     return *w;
 }
 
-static SweepCtl sweepCtl(PcgWorkspace& w) { return SweepCtl{w.counters.p + 1, w.counters.p + 2}; }
+// separate ticket / done counters per direction: with PDL the backward sweep's CTAs take tickets while the forward sweep still runs
+static SweepCtl sweepCtl(PcgWorkspace& w, bool bwd = false) { return bwd ? SweepCtl{w.counters.p + 3, w.counters.p + 4} : SweepCtl{w.counters.p + 1, w.counters.p + 2}; }
 // CTAs of a tiled sweep: as many as fit (shared memory bound); tiles are handed out in ticket order, so any grid size is deadlock-free
 static int sweepGridOf(const DeviceMesh& m, const PcgWorkspace&) {
     int forced = (int)rt().opt("sweep_grid", 0);
@@ -90,13 +91,14 @@ static const PcgScalars* launchMatrixGate(DeviceMesh& m, PcgWorkspace& w, const 
                 w.keptUp.p, w.gate.p);
     return w.gate.p;
 }
-static void launchFwd(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* rA, const PcgScalars* sc, PcgFuse fz = PcgFuse{}) {
-    B200_LAUNCH_SMEM(k_dic_fwd<0>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), rD, rA, (const double*)nullptr,
-                     (const double*)w.cf.p, w.y.p, (double*)nullptr, sweepCtl(w), sc, fz);
+// pdl: the kernel may start (ticket, descriptor, operand-block staging) while its predecessor in the stream is still running
+static void launchFwd(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* rA, const PcgScalars* sc, PcgFuse fz = PcgFuse{}, bool pdl = false) {
+    B200_LAUNCH_PDL(pdl, k_dic_fwd<0>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), rD, rA, (const double*)nullptr,
+                    (const double*)w.cf.p, w.y.p, (double*)nullptr, sweepCtl(w), sc, fz);
 }
-static void launchBwd(DeviceMesh& m, PcgWorkspace& w, const double* rA, PcgScalars* sc, double* part, unsigned* cnt, double* dotOut = nullptr) {
-    B200_LAUNCH_SMEM(k_dic_bwd, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), (const double*)w.cb.p, rA, w.y.p, w.z.p,
-                     sweepCtl(w), sc, part, cnt, dotOut ? dotOut : (sc ? &sc->wArA : nullptr));
+static void launchBwd(DeviceMesh& m, PcgWorkspace& w, const double* rA, PcgScalars* sc, double* part, unsigned* cnt, double* dotOut = nullptr, bool pdl = false) {
+    B200_LAUNCH_PDL(pdl, k_dic_bwd, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), (const double*)w.cb.p, (const double*)rA, w.y.p, w.z.p,
+                    sweepCtl(w, true), sc, part, cnt, dotOut ? dotOut : (sc ? &sc->wArA : nullptr));
 }
 
 void amulDevice(DeviceMesh& m, const double* diag, const double* upS, const double* loS, const double* psi, double* Apsi,
@@ -105,7 +107,7 @@ void amulDevice(DeviceMesh& m, const double* diag, const double* upS, const doub
     ScopedTimer t(T_AMUL);
     bool halo = bou && rt().nRanks > 1 && meshHasProcessorPatches(m);
     if (halo) haloPack(m, psi, w.sendBuf);
-    if (m.N) B200_LAUNCH_AMUL(0, m.view(), diag, upS, loS, psi, Apsi, (PcgScalars*)nullptr,
+    if (m.N) B200_LAUNCH_AMUL(0, false, m.view(), diag, upS, loS, psi, Apsi, (PcgScalars*)nullptr,
                          (double*)nullptr, (unsigned*)nullptr);
     if (halo) {
         haloExchange(m, w.sendBuf, w.recvBuf);
@@ -180,25 +182,30 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
     int slot = 0, enq = 0;
     const bool kt = timers().enabled && rt().opt("pcg_kernel_timers", 0) > 0;   // per-kernel-class events (roofline pass)
 #define KT(id) std::unique_ptr<ScopedTimer> _kt(kt ? new ScopedTimer(id) : nullptr)
+    // single rank: the four kernels of an iteration are chained by programmatic dependent launch (option pcg_pdl)
+    const bool pdl = !multi && !kt && rt().opt("pcg_pdl", 1) > 0;
+    bool firstIteration = true;
     auto enqueueIteration = [&]() {
         // (an empty rank still runs the sweeps: they carry the iteration's residual sum / convergence test and the wArA sum)
         { KT(T_DIC_FWD);   // + the previous iteration's x / rA update, residual sum and convergence test (fused)
-          launchFwd(m, w, w.rD.p, w.rA.p, sc, PcgFuse{x, w.rA.p, w.pA.p, w.wA.p, sc, part, cnt, hist, multi ? 0 : 1}); }
-        { KT(T_DIC_BWD); launchBwd(m, w, w.rA.p, sc, part, cnt, multi ? &sc->wArAnew : &sc->wArA); }
+          // (the first sweep of a solve follows k_dic_coeffs, which writes the operand blocks the prologue stages: no early start)
+          launchFwd(m, w, w.rD.p, w.rA.p, sc, PcgFuse{x, w.rA.p, w.pA.p, w.wA.p, sc, part, cnt, hist, multi ? 0 : 1}, pdl && !firstIteration); }
+        firstIteration = false;
+        { KT(T_DIC_BWD); launchBwd(m, w, w.rA.p, sc, part, cnt, multi ? &sc->wArAnew : &sc->wArA, pdl); }
         // multi-rank: ONE all-reduce carries the previous iteration's sum|rA| and this iteration's sum(wA*rA); the convergence
         // test therefore runs after the backward sweep (one wasted sweep at the end of a solve)
         if (multi) { allReduce(&sc->sumMagR, 2, RED_SUM); B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist); }
         { KT(T_PCG_VEC);
-          B200_LAUNCH(k_pcg_p_update, grid, BLOCK, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc); }
+          B200_LAUNCH_PDL(pdl, k_pcg_p_update, grid, BLOCK, 0, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc); }
         if (halo) {
             haloPack(m, w.pA, w.sendBuf);
             { KT(T_AMUL);
-              B200_LAUNCH_AMUL(0, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt); }
+              B200_LAUNCH_AMUL(0, false, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt); }
             haloExchange(m, w.sendBuf, w.recvBuf);
             B200_LAUNCH(k_iface_dot, grid, BLOCK, st, mv, bou, (const double*)w.recvBuf.p, w.wA.p, (const double*)w.pA.p, sc, part, cnt);
         } else {
             KT(T_AMUL);
-            B200_LAUNCH_AMUL(1, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt);
+            B200_LAUNCH_AMUL(1, pdl, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt);
         }
         if (multi) allReduce(&sc->wApA, 1, RED_SUM);
     };
