@@ -264,7 +264,7 @@ def run_ours(args):
     lib.set_option("pcg_kernel_timers", 0)
     peak, peak_src = measured_peak()
 
-    # average duration of the launches that did work: the solver enqueues iterations in batches of 8, the ones queued past
+    # average duration of the launches that did work: the solver enqueues iterations in batches of 4, the ones queued past
     # convergence return at once, so per-iteration kernels are averaged over the iterations actually performed
     n_iter = max(1, sum(p[2] for p in reg.perfs()[-(ctl.nCorr * (ctl.nNonOrthCorr + 1)):]))
 
@@ -291,14 +291,14 @@ def run_ours(args):
     dom = "dic_precondition" if "dic_precondition" in kernels else "amul"
     ach = kernels[dom]["GBps"] if dom in kernels else None
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
-    # (profiles/r1c_ncu_full_raw.csv: k_dic_fwd 98.9 + 4.5 MB, k_dic_bwd 75.1 + 1.6 MB, k_amul 63.3 + 1.4 MB); only valid for N = 1
-    ncu_traffic = {"dic_precondition": 180.1e6, "amul": 64.7e6}
+    # (profiles/r1e_ncu_full_raw.csv: k_dic_fwd 98.9 + 4.9 MB, k_dic_bwd 75.0 + 1.9 MB, k_amul 63.1 + 1.6 MB); only valid for N = 1
+    ncu_traffic = {"dic_precondition": 180.7e6, "amul": 64.6e6}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
                 "frac_of_8TBps_nominal": (ach / 8000.0) if ach else None, "peak_source": peak_src,
                 "traffic": ncu_traffic.get(dom) if world == 1 else None,
                 "algorithmic_bytes_per_launch": alg[dom], "kernels": kernels,
                 "pcg_iterations_in_pass": n_iter,
-                "note": "DIC sweeps are bound by the dependency chain (348 wavefronts -> ~41 tile hops of ~3 us), not by bandwidth; the "
+                "note": "DIC sweeps are bound by the dependency chain (348 wavefronts -> 35 tile hops of ~2.4 us), not by bandwidth; the "
                         "per-iteration working set (~180 MB: matrix, sweep operand blocks, 8 vectors) exceeds the 126 MB L2 -- see DESIGN.md"}
 
     if rank != 0:
