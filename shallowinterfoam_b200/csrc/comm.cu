@@ -161,6 +161,130 @@ void allReduce(double* p, int count, ReduceOp op) {
     ncclRedOp_t o = op == RED_SUM ? ncclSum : op == RED_MAX ? ncclMax : ncclMin;
     B200_CHECK_NCCL(ncclAllReduce(p, p, count, ncclDouble, o, (ncclComm_t)rt().nccl, rt().stream));
 }
+// ---- peer-memory halo (comm.cuh).  Own allocation: [2][PEER_MAX_RANKS] epoch flags, then [2][B] receive values (parity = epoch & 1).
+struct PeerHaloPushView {
+    int nNbr, rank;
+    int myOff[PEER_MAX_RANKS], size[PEER_MAX_RANKS];      // this rank's processor-face range [myOff, myOff+size) per neighbour slot
+    double* peerData[PEER_MAX_RANKS];                     // neighbour's receive buffer (parity 0) at the offset of its patch towards this rank
+    long long peerStride[PEER_MAX_RANKS];                 // neighbour's B (distance between its two parity buffers)
+    double* peerFlags[PEER_MAX_RANKS];                    // neighbour's flag array
+};
+struct PeerHalo {
+    PeerHaloPushView v;
+    double* own = nullptr; int B = 0;
+    void* opened[PEER_MAX_RANKS] = {nullptr};
+    unsigned long long epoch = 0;
+    unsigned* counter = nullptr;
+    int maxSize = 0;
+};
+__global__ void k_halo_push(MeshView mv, const double* __restrict__ cf, PeerHaloPushView hv, unsigned long long epoch, unsigned* counter) {
+    const int slot = blockIdx.y, parity = (int)(epoch & 1ull);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < hv.size[slot]) {
+        const int b = hv.myOff[slot] + i;
+        hv.peerData[slot][parity * hv.peerStride[slot] + i] = cf[mv.bFaceRow[b]];     // store over NVLink into the neighbour's HBM
+    }
+    __shared__ int isLast;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        isLast = atomicInc(counter, total - 1) == total - 1;
+    }
+    __syncthreads();
+    if (isLast && (int)threadIdx.x < hv.nNbr) {     // every block's values are out: raise this rank's flag at each neighbour
+        __threadfence_system();
+        volatile double* f = hv.peerFlags[threadIdx.x] + parity * PEER_MAX_RANKS + hv.rank;
+        *f = (double)epoch;
+    }
+}
+PeerHalo* peerHaloGet(DeviceMesh& m) {
+    const int nRanks = rt().nRanks, rank = rt().rank;
+    if (nRanks <= 1) return nullptr;
+    cudaStream_t st = rt().stream;
+    ncclComm_t comm = (ncclComm_t)rt().nccl;
+    PeerHalo* h = new PeerHalo();
+    memset(&h->v, 0, sizeof(h->v));
+    h->B = m.B; h->v.rank = rank;
+    bool good = nRanks <= PEER_MAX_RANKS && rt().opt("p2p_halo", 1) > 0;
+    // this rank's record: IPC handle, ok flag, B, offset of the patch towards every rank (-1: none)
+    struct Rec { cudaIpcMemHandle_t handle; int ok, B; int offTo[PEER_MAX_RANKS], sizeTo[PEER_MAX_RANKS]; };
+    Rec mine; memset(&mine, 0, sizeof(mine));
+    for (int q = 0; q < PEER_MAX_RANKS; q++) { mine.offTo[q] = -1; mine.sizeTo[q] = 0; }
+    for (const Patch& p : m.patches) {
+        if (p.neighbRank < 0 || p.size == 0) continue;
+        if (p.neighbRank >= PEER_MAX_RANKS || mine.offTo[p.neighbRank] >= 0) { good = false; continue; }   // one patch per neighbour (decomposePar)
+        mine.offTo[p.neighbRank] = p.start - m.F; mine.sizeTo[p.neighbRank] = p.size;
+    }
+    const size_t bytes = sizeof(double) * (2 * PEER_MAX_RANKS + 2 * (size_t)std::max(1, m.B));
+    if (good && cudaMalloc((void**)&h->own, bytes) != cudaSuccess) { cudaGetLastError(); good = false; h->own = nullptr; }
+    if (h->own) {
+        cudaMemsetAsync(h->own, 0, bytes, st);
+        if (cudaIpcGetMemHandle(&mine.handle, h->own) != cudaSuccess) { cudaGetLastError(); good = false; }
+    }
+    mine.ok = good ? 1 : 0; mine.B = m.B;
+    std::vector<Rec> all(nRanks);
+    char *dMine = nullptr, *dAll = nullptr;
+    B200_CHECK_CUDA(cudaMalloc((void**)&dMine, sizeof(Rec))); B200_CHECK_CUDA(cudaMalloc((void**)&dAll, sizeof(Rec) * nRanks));
+    B200_CHECK_CUDA(cudaMemcpyAsync(dMine, &mine, sizeof(Rec), cudaMemcpyHostToDevice, st));
+    B200_CHECK_NCCL(ncclAllGather(dMine, dAll, sizeof(Rec), ncclChar, comm, st));
+    B200_CHECK_CUDA(cudaMemcpyAsync(all.data(), dAll, sizeof(Rec) * nRanks, cudaMemcpyDeviceToHost, st));
+    B200_CHECK_CUDA(cudaStreamSynchronize(st));
+    cudaFree(dMine); cudaFree(dAll);
+    for (int r = 0; r < nRanks; r++) good = good && all[r].ok == 1;
+    int n = 0;
+    for (int q = 0; q < nRanks && good; q++) {
+        if (q == rank || mine.offTo[q] < 0) continue;
+        if (all[q].offTo[rank] < 0 || all[q].sizeTo[rank] != mine.sizeTo[q]) { good = false; break; }   // both sides list the same faces
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = false; break; }
+        h->opened[q] = ptr;
+        double* base = (double*)ptr;
+        h->v.myOff[n] = mine.offTo[q]; h->v.size[n] = mine.sizeTo[q];
+        h->v.peerFlags[n] = base;
+        h->v.peerData[n] = base + 2 * PEER_MAX_RANKS + all[q].offTo[rank];
+        h->v.peerStride[n] = all[q].B;
+        h->maxSize = std::max(h->maxSize, mine.sizeTo[q]);
+        h->v.nNbr = ++n;     // slots are in rank order: peerHaloWait lists the opened ranks in the same order
+    }
+    // every rank must agree
+    double flag = good ? 1.0 : 0.0, *dFlag = nullptr;
+    B200_CHECK_CUDA(cudaMalloc((void**)&dFlag, 8));
+    B200_CHECK_CUDA(cudaMemcpyAsync(dFlag, &flag, 8, cudaMemcpyHostToDevice, st));
+    B200_CHECK_NCCL(ncclAllReduce(dFlag, dFlag, 1, ncclDouble, ncclMin, comm, st));
+    B200_CHECK_CUDA(cudaMemcpyAsync(&flag, dFlag, 8, cudaMemcpyDeviceToHost, st));
+    B200_CHECK_CUDA(cudaStreamSynchronize(st));
+    cudaFree(dFlag);
+    if (flag < 0.5) { peerHaloRelease(h); return nullptr; }
+    B200_CHECK_CUDA(cudaMalloc((void**)&h->counter, sizeof(unsigned)));
+    B200_CHECK_CUDA(cudaMemsetAsync(h->counter, 0, sizeof(unsigned), st));
+    B200_CHECK_CUDA(cudaStreamSynchronize(st));
+    return h;
+}
+void peerHaloRelease(PeerHalo* h) {
+    if (!h) return;
+    for (auto& p : h->opened) if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
+    if (h->own) cudaFree(h->own);
+    if (h->counter) cudaFree(h->counter);
+    delete h;
+}
+void peerHaloPush(PeerHalo* h, const DeviceMesh& m, const double* cellField) {
+    h->epoch++;
+    if (h->v.nNbr == 0) return;
+    dim3 grid(std::max(1, gridFor(h->maxSize)), h->v.nNbr);
+    B200_LAUNCH(k_halo_push, grid, BLOCK, rt().stream, m.view(), cellField, h->v, h->epoch, h->counter);
+}
+const double* peerHaloRecv(const PeerHalo* h) { return h->own + 2 * PEER_MAX_RANKS + (size_t)(h->epoch & 1ull) * h->B; }
+PeerHaloWait peerHaloWait(const PeerHalo* h) {
+    PeerHaloWait w; memset(&w, 0, sizeof(w));
+    w.nNbr = h->v.nNbr;
+    int n = 0;
+    for (int q = 0; q < PEER_MAX_RANKS; q++) if (h->opened[q]) w.nbrRank[n++] = q;
+    w.flags = h->own + (size_t)(h->epoch & 1ull) * PEER_MAX_RANKS;
+    w.tag = (double)h->epoch;
+    return w;
+}
+
 void haloExchange(const DeviceMesh& m, const double* send, double* recv) {
     if (rt().nRanks <= 1) return;
     B200_CHECK_NCCL(ncclGroupStart());
@@ -187,6 +311,12 @@ void commFinalize() {}
 bool commUsesPeerMemory() { return false; }
 int commUniqueId(void* out128) { memset(out128, 0, 128); return 128; }
 void allReduce(double* p, int count, ReduceOp op) { if (rt().nRanks > 1) g_emuAllreduce(p, count, (int)op); }
+struct PeerHalo {};
+PeerHalo* peerHaloGet(DeviceMesh&) { return nullptr; }
+void peerHaloRelease(PeerHalo*) {}
+void peerHaloPush(PeerHalo*, const DeviceMesh&, const double*) {}
+const double* peerHaloRecv(const PeerHalo*) { return nullptr; }
+PeerHaloWait peerHaloWait(const PeerHalo*) { PeerHaloWait w; memset(&w, 0, sizeof(w)); return w; }
 void haloExchange(const DeviceMesh& m, const double* send, double* recv) {
     if (rt().nRanks <= 1) return;
     for (const Patch& p : m.patches) {
@@ -204,6 +334,12 @@ bool commUsesPeerMemory() { return false; }
 int commUniqueId(void* out128) { memset(out128, 0, 128); return 128; }
 void allReduce(double*, int, ReduceOp) {}
 void haloExchange(const DeviceMesh&, const double*, double*) {}
+struct PeerHalo {};
+PeerHalo* peerHaloGet(DeviceMesh&) { return nullptr; }
+void peerHaloRelease(PeerHalo*) {}
+void peerHaloPush(PeerHalo*, const DeviceMesh&, const double*) {}
+const double* peerHaloRecv(const PeerHalo*) { return nullptr; }
+PeerHaloWait peerHaloWait(const PeerHalo*) { PeerHaloWait w; memset(&w, 0, sizeof(w)); return w; }
 #endif
 
 }  // namespace b200

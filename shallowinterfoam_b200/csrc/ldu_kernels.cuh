@@ -5,6 +5,7 @@
 // bitwise equal to the sequential loops of lduMatrixATmul.C / DICPreconditioner.C.
 #pragma once
 #include "device_mesh.cuh"
+#include "comm.cuh"
 
 namespace b200 {
 
@@ -129,6 +130,13 @@ __device__ __forceinline__ double ldPoll(const double* p) {
 __device__ __forceinline__ void stPublish(double* p, double v) {
     asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+#endif
+
+// load that is served by L2 (values a peer GPU stored into this GPU's memory must not come from a stale L1 line)
+#ifdef B200_EMU
+__device__ __forceinline__ double ldNoL1(const double* p) { return *p; }
+#else
+__device__ __forceinline__ double ldNoL1(const double* p) { return __ldcg(p); }
 #endif
 
 // ----------------------------------------------------------------------------- a1: Amul (row gather)
@@ -323,10 +331,11 @@ static __global__ void k_pcg_check(PcgScalars* sc, double* hist) {
 }
 // multi-rank tail of Amul: processor-interface update  Apsi[faceCells] -= bouCoeffs*psiNbr  (per boundary row in patch order)
 // fused with sum(Apsi*psi) -> sc->wApA
-static __global__ void __launch_bounds__(BLOCK) k_iface_dot(MeshView mv, const double* __restrict__ bou, const double* __restrict__ psiNbr,
+static __global__ void __launch_bounds__(BLOCK) k_iface_dot(MeshView mv, const double* __restrict__ bou, const double* psiNbr,
                                                       double* __restrict__ Apsi, const double* __restrict__ psi, PcgScalars* sc,
-                                                      double* partials, unsigned* counter) {
+                                                      double* partials, unsigned* counter, PeerHaloWait hw) {
     if (sc->stop) return;
+    peerHaloWaitDevice(hw);    // peer-memory halo: the neighbours' values of this epoch have landed (no-op on the NCCL path)
     int row = blockIdx.x * blockDim.x + threadIdx.x, s = row >> 5, lane = row & 31;
     double v[1] = {0.0};
     if (row < mv.N) {
@@ -336,7 +345,7 @@ static __global__ void __launch_bounds__(BLOCK) k_iface_dot(MeshView mv, const d
             bool any = false;
             for (int q = mv.bRowStart[i]; q < mv.bRowStart[i + 1]; q++) {
                 int b = mv.bRowFaces[q];
-                if (mv.bCoupled[b]) { acc = acc - bou[b] * psiNbr[b]; any = true; }
+                if (mv.bCoupled[b]) { acc = acc - bou[b] * ldNoL1(psiNbr + b); any = true; }
             }
             if (any) Apsi[row] = acc;
         }

@@ -9,6 +9,7 @@
 namespace b200 {
 
 PcgWorkspace::~PcgWorkspace() {
+    peerHaloRelease(peer);
     if (hsc) cudaFreeHost(hsc);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
 }
@@ -184,6 +185,8 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
 #define KT(id) std::unique_ptr<ScopedTimer> _kt(kt ? new ScopedTimer(id) : nullptr)
     // single rank: the four kernels of an iteration are chained by programmatic dependent launch (option pcg_pdl)
     const bool pdl = !multi && !kt && rt().opt("pcg_pdl", 1) > 0;
+    if (multi && !w.peerTried) { w.peerTried = true; w.peer = peerHaloGet(m); }   // collective: every rank reaches its first multi-rank solve
+    PeerHalo* peer = halo ? w.peer : nullptr;
     bool firstIteration = true;
     auto enqueueIteration = [&]() {
         // (an empty rank still runs the sweeps: they carry the iteration's residual sum / convergence test and the wArA sum)
@@ -197,12 +200,17 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
         if (multi) { allReduce(&sc->sumMagR, 2, RED_SUM); B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist); }
         { KT(T_PCG_VEC);
           B200_LAUNCH_PDL(pdl, k_pcg_p_update, grid, BLOCK, 0, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc); }
-        if (halo) {
+        if (halo && peer) {   // halo over NVLink peer memory: push -> Amul (overlaps the transfer) -> wait inside k_iface_dot
+            peerHaloPush(peer, m, w.pA);
+            { KT(T_AMUL);
+              B200_LAUNCH_AMUL(0, false, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt); }
+            B200_LAUNCH(k_iface_dot, grid, BLOCK, st, mv, bou, peerHaloRecv(peer), w.wA.p, (const double*)w.pA.p, sc, part, cnt, peerHaloWait(peer));
+        } else if (halo) {
             haloPack(m, w.pA, w.sendBuf);
             { KT(T_AMUL);
               B200_LAUNCH_AMUL(0, false, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt); }
             haloExchange(m, w.sendBuf, w.recvBuf);
-            B200_LAUNCH(k_iface_dot, grid, BLOCK, st, mv, bou, (const double*)w.recvBuf.p, w.wA.p, (const double*)w.pA.p, sc, part, cnt);
+            B200_LAUNCH(k_iface_dot, grid, BLOCK, st, mv, bou, (const double*)w.recvBuf.p, w.wA.p, (const double*)w.pA.p, sc, part, cnt, PeerHaloWait{});
         } else {
             KT(T_AMUL);
             B200_LAUNCH_AMUL(1, pdl, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt);

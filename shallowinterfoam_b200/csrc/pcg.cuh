@@ -2,10 +2,10 @@
 #pragma once
 #include "device_mesh.cuh"
 #include "ldu_kernels.cuh"
+#include "comm.cuh"
 
 namespace b200 {
 
-struct Halo;  // comm.cuh
 
 struct PcgWorkspace {
     DevBuf<double> pA, wA, rA, y, z, rD, Dt, partials, hist;
@@ -19,6 +19,8 @@ struct PcgWorkspace {
     DevBuf<double> keptDiag, keptUp;
     DevBuf<PcgScalars> gate;                   // gate->stop = 1: coefficients unchanged, the calcReciprocalD kernels return at once
     bool keptValid = false;
+    PeerHalo* peer = nullptr;                  // halo swap of Amul over NVLink peer memory (comm.cuh); null: NCCL
+    bool peerTried = false;
     DevBuf<unsigned> counters;                 // [0] reduce counter, [1] sweep ticket, [2] sweep done
     DevBuf<int> bRowOfSlot;
     PcgScalars* hsc = nullptr;                 // pinned mirror (2 slots)

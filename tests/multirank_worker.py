@@ -1,5 +1,6 @@
-"""Worker of tests/test_multirank.py: one process per rank (gloo, CPU).  Loads the SIMT-emulated test build of the library,
-routes its all-reduces / halo swaps through torch.distributed, and checks the decomposed path against the oracle."""
+"""Worker of tests/test_multirank.py: one process per rank (gloo for the plumbing).  Loads the SIMT-emulated test build of the
+library and routes its all-reduces / halo swaps through torch.distributed -- or, with B200_WORKER_LIB=gpu, the real library with
+one GPU per rank (NCCL + NVLink peer memory) -- and checks the decomposed path against the oracle."""
 import ctypes as C
 import os
 import sys
@@ -18,7 +19,16 @@ from shallowinterfoam_b200 import capi  # noqa: E402
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    lib = capi.B200Lib(os.path.join(ROOT, "tests", "simt_emu", "libb200foam_emu.so"))
+    on_gpu = os.environ.get("B200_WORKER_LIB") == "gpu"     # the real library: one GPU per rank, NCCL + NVLink peer memory
+    if on_gpu:
+        lib = capi.load()
+        for o in os.environ.get("B200_WORKER_OPTS", "").split():
+            k, v = o.split("="); lib.set_option(k, float(v))
+        ids = [lib.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        lib.init(rank, rank, world, ids[0])
+    else:
+        lib = capi.B200Lib(os.path.join(ROOT, "tests", "simt_emu", "libb200foam_emu.so"))
     dp = C.POINTER(C.c_double)
 
     @C.CFUNCTYPE(None, dp, C.c_int, C.c_int)
@@ -35,8 +45,9 @@ def main():
         dist.recv(r, peer)
         req.wait()
 
-    lib.c.b200_emu_set_comm(allreduce, sendrecv)
-    lib.init(0, rank, world)
+    if not on_gpu:
+        lib.c.b200_emu_set_comm(allreduce, sendrecv)
+        lib.init(0, rank, world)
 
     dims = (16, 4, 8); L = (5.0, 1.0, 2.0)
     gpm = lib.polymesh_box(*dims, *L, weir=(0.45, 0.6, 0.3))

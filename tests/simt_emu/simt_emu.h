@@ -115,6 +115,7 @@ inline unsigned ballot(int pred) {
 inline void __syncthreads() { emu::syncthreads(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::warpBarrier(); }
 inline void __threadfence() {}
+inline void __threadfence_system() {}
 inline void __nanosleep(unsigned) { emu::yield(); }
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl(v, src); }
 template <class T> inline T __shfl_down_sync(unsigned, T v, int d) { int l = emu::S().cur->tid.x & 31; return emu::shfl(v, l + d < 32 ? l + d : l); }

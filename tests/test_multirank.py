@@ -17,13 +17,11 @@ def free_port():
     return p
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_decomposed_path_over_gloo(world):
-    subprocess.check_call(["make", "-C", os.path.join(ROOT, "shallowinterfoam_b200", "csrc"), "-j8", "emu"], stdout=subprocess.DEVNULL)
+def run_workers(world, extra_env):
     port = free_port()
     procs = []
     for r in range(world):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1", **extra_env)
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "multirank_worker.py")], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = []
@@ -38,3 +36,20 @@ def test_decomposed_path_over_gloo(world):
     for r, p in enumerate(procs):
         assert p.returncode == 0, "rank %d failed:\n%s" % (r, outs[r][-3000:])
     assert "MULTIRANK_OK" in outs[0]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_decomposed_path_over_gloo(world):
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "shallowinterfoam_b200", "csrc"), "-j8", "emu"], stdout=subprocess.DEVNULL)
+    run_workers(world, {})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("opts", ["", "p2p_halo=0 p2p_allreduce=0"], ids=["peer-memory", "nccl"])
+def test_decomposed_path_on_gpus(opts):
+    """the same checks with the real library, one GPU per rank: halo swap of Amul and scalar all-reduces over NVLink peer memory
+    (default) and over NCCL; needs 2 GPUs (`gpurun --gpus 2`), skipped on a 1-GPU box"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_workers(2, {"B200_WORKER_LIB": "gpu", "B200_WORKER_OPTS": opts})
