@@ -248,6 +248,10 @@ int b200_polymesh_box(int32_t nx, int32_t ny, int32_t nz, double lx, double ly, 
 /* remove cells whose centre has x in [x0,x1)*lx and z < zfrac*lz ("weir"); exposed faces -> last patch "weir" */
 int b200_polymesh_box_weir(int32_t nx, int32_t ny, int32_t nz, double lx, double ly, double lz, double x0, double x1,
                            double zfrac, b200_polymesh_t** out);
+/* skewed mesh (BASELINE configs[3]): moves every vertex that is not on a boundary face by (2u-1)*frac*(dx,dy,dz) with u from the
+ * 64-bit LCG x <- x*6364136223846793005 + 1442695040888963407 (u = (x >> 11) * 2^-53; three draws per vertex, vertices in index order,
+ * x0 = seed).  Addressing is untouched; faces become non-planar and non-orthogonal (what moveDynamicMesh / a skewed blockMesh gives). */
+int b200_polymesh_jitter(b200_polymesh_t* pm, double frac, double dx, double dy, double dz, uint64_t seed);
 int b200_polymesh_release(b200_polymesh_t* pm);
 int b200_polymesh_sizes(const b200_polymesh_t* pm, int32_t* nCells, int32_t* nInternalFaces, int32_t* nBoundaryFaces,
                         int32_t* nPatches, int32_t* nPoints);

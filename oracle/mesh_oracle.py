@@ -161,6 +161,24 @@ def subset_mesh(mesh, keep, exposed_name="weir"):
                 neighbour=nei_i.astype(np.int32), patches=patches, nCells=int(keep.sum()))
 
 
+def jitter_points(mesh, frac, dx, dy, dz, seed=12345):
+    """skewed mesh (BASELINE configs[3]): interior vertices (not on any boundary face) move by (2u-1)*frac*(dx,dy,dz),
+    u from the 64-bit LCG documented in include/b200foam.h (b200_polymesh_jitter); pure-Python integers, so no overflow semantics."""
+    pts = mesh["points"].copy()
+    nI = mesh["neighbour"].size
+    on_b = np.zeros(len(pts), dtype=bool)
+    on_b[np.unique(mesh["faces"][nI:])] = True
+    x = int(seed); M = (1 << 64) - 1
+    d = (dx, dy, dz)
+    for p in np.nonzero(~on_b)[0]:
+        for k in range(3):
+            x = (x * 6364136223846793005 + 1442695040888963407) & M
+            u = float(x >> 11) * (1.0 / 9007199254740992.0)
+            pts[p, k] = pts[p, k] + (2.0 * u - 1.0) * frac * d[k]
+    out = dict(mesh); out["points"] = pts
+    return out
+
+
 def weir_keep_mask(nx, ny, nz, x0=0.45, x1=0.5, zfrac=0.3):
     """cells removed: cell-centre x in [x0,x1)*L and z < zfrac*H  (SURVEY.md section 8(d) cfg2)."""
     ci, cj, ck = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")

@@ -31,7 +31,7 @@ EXPORTS = [
     "b200_region3d_set_patch_mixed", "b200_region3d_get_patch_internal", "b200_region3d_num_solves",
     "b200_region3d_get_perfs", "b200_region3d_get_res_hist", "b200_region3d_get_alpha_stats",
     "b200_region3d_get_cont_errs", "b200_region3d_clear_log",
-    "b200_polymesh_box", "b200_polymesh_box_weir", "b200_polymesh_release", "b200_polymesh_sizes",
+    "b200_polymesh_box", "b200_polymesh_box_weir", "b200_polymesh_jitter", "b200_polymesh_release", "b200_polymesh_sizes",
     "b200_polymesh_get", "b200_polymesh_patch_name", "b200_polymesh_geometry", "b200_decompose_simple",
     "b200_polymesh_submesh", "b200_polymesh_submesh_maps", "b200_mesh_create_from_polymesh",
 ]
@@ -169,7 +169,8 @@ class B200Lib:
         return out
 
     # ------------------------------------------------------------------ host mesh tools
-    def polymesh_box(self, nx, ny, nz, lx, ly, lz, weir=None):
+    def polymesh_box(self, nx, ny, nz, lx, ly, lz, weir=None, jitter=None):
+        """jitter = (frac, seed): skew the mesh by moving interior vertices by up to frac of a cell size (b200_polymesh_jitter)"""
         h = C.c_void_p()
         if weir is None:
             self.check(self.c.b200_polymesh_box(C.c_int32(nx), C.c_int32(ny), C.c_int32(nz), C.c_double(lx), C.c_double(ly),
@@ -178,6 +179,10 @@ class B200Lib:
             x0, x1, zf = weir
             self.check(self.c.b200_polymesh_box_weir(C.c_int32(nx), C.c_int32(ny), C.c_int32(nz), C.c_double(lx), C.c_double(ly),
                                                      C.c_double(lz), C.c_double(x0), C.c_double(x1), C.c_double(zf), C.byref(h)))
+        if jitter is not None:
+            self.c.b200_polymesh_jitter.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64]
+            self.check(self.c.b200_polymesh_jitter(h, C.c_double(jitter[0]), C.c_double(lx / nx), C.c_double(ly / ny), C.c_double(lz / nz),
+                                                   C.c_uint64(jitter[1])))
         return PolyMesh(self, h)
 
     # ------------------------------------------------------------------ lduAddressing-level API

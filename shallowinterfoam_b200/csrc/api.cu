@@ -316,6 +316,12 @@ int b200_polymesh_box_weir(int32_t nx, int32_t ny, int32_t nz, double lx, double
     *out = new b200_polymesh{subsetMesh(box, weirKeepMask(nx, ny, nz, x0, x1, zfrac), "weir")};
     API_END
 }
+int b200_polymesh_jitter(b200_polymesh_t* pm, double frac, double dx, double dy, double dz, uint64_t seed) {
+    API_BEGIN
+    B200_REQUIRE(pm && frac >= 0.0 && frac < 0.5, B200_ERR_ARG, "b200_polymesh_jitter: frac must be in [0, 0.5)");
+    jitterPoints(pm->pm, frac, dx, dy, dz, seed);
+    API_END
+}
 int b200_polymesh_release(b200_polymesh_t* pm) { delete pm; return B200_OK; }
 int b200_polymesh_sizes(const b200_polymesh_t* pm, int32_t* nCells, int32_t* nIF, int32_t* nBF, int32_t* nPatches, int32_t* nPoints) {
     API_BEGIN

@@ -1,5 +1,6 @@
 // comm.cu -- NCCL-backed all-reduce and processor-patch halo exchange (one process per GPU).
 #include "comm.cuh"
+#include "ldu_kernels.cuh"
 #ifdef B200_WITH_NCCL
 #include <nccl.h>
 #define B200_CHECK_NCCL(expr)                                                                              \
@@ -61,7 +62,9 @@ struct P2PView { double* mbox; double* peer[P2P_MAX_RANKS]; int rank, nRanks; };
 struct P2PState { bool ok = false; P2PView v; unsigned long long epoch = 0; void* opened[P2P_MAX_RANKS] = {nullptr}; double* own = nullptr; };
 static P2PState g_p2p;
 
-__global__ void k_p2p_allreduce(double* data, int count, int op, P2PView pv, unsigned long long epoch) {
+// post != 0: the thread that holds the result also runs k_pcg_check's body (closes the previous PCG iteration, adopts the new wArA):
+// one launch less per iteration
+__global__ void k_p2p_allreduce(double* data, int count, int op, P2PView pv, unsigned long long epoch, PcgScalars* post, double* hist) {
     const int lane = threadIdx.x, slot = (int)(epoch & (P2P_SLOTS - 1));
     const double tag = (double)epoch;
     if (lane < pv.nRanks) {
@@ -82,6 +85,13 @@ __global__ void k_p2p_allreduce(double* data, int count, int op, P2PView pv, uns
             acc = op == 0 ? acc + v : op == 1 ? (acc > v ? acc : v) : (acc < v ? acc : v);
         }
         data[lane] = acc;
+    }
+    if (post) {
+        __syncwarp();
+        if (lane == 0 && !post->stop) {
+            if (post->pendingCheck) { post->pendingCheck = 0; pcgEndOfIteration(post, hist); }
+            if (!post->stop) post->wArA = post->wArAnew;
+        }
     }
 }
 
@@ -155,7 +165,7 @@ void allReduce(double* p, int count, ReduceOp op) {
     if (rt().nRanks <= 1) return;
     if (g_p2p.ok && count <= P2P_ENTRY - 1) {
         g_p2p.epoch++;
-        B200_LAUNCH(k_p2p_allreduce, 1, 32, rt().stream, p, count, (int)op, g_p2p.v, g_p2p.epoch);
+        B200_LAUNCH(k_p2p_allreduce, 1, 32, rt().stream, p, count, (int)op, g_p2p.v, g_p2p.epoch, (PcgScalars*)nullptr, (double*)nullptr);
         return;
     }
     ncclRedOp_t o = op == RED_SUM ? ncclSum : op == RED_MAX ? ncclMax : ncclMin;
@@ -285,6 +295,12 @@ PeerHaloWait peerHaloWait(const PeerHalo* h) {
     return w;
 }
 
+bool allReduceSumThenPcgCheck(double* p, int count, PcgScalars* sc, double* hist) {
+    if (!(g_p2p.ok && count <= P2P_ENTRY - 1)) return false;
+    g_p2p.epoch++;
+    B200_LAUNCH(k_p2p_allreduce, 1, 32, rt().stream, p, count, (int)RED_SUM, g_p2p.v, g_p2p.epoch, sc, hist);
+    return true;
+}
 void haloExchange(const DeviceMesh& m, const double* send, double* recv) {
     if (rt().nRanks <= 1) return;
     B200_CHECK_NCCL(ncclGroupStart());
@@ -311,6 +327,7 @@ void commFinalize() {}
 bool commUsesPeerMemory() { return false; }
 int commUniqueId(void* out128) { memset(out128, 0, 128); return 128; }
 void allReduce(double* p, int count, ReduceOp op) { if (rt().nRanks > 1) g_emuAllreduce(p, count, (int)op); }
+bool allReduceSumThenPcgCheck(double*, int, PcgScalars*, double*) { return false; }
 struct PeerHalo {};
 PeerHalo* peerHaloGet(DeviceMesh&) { return nullptr; }
 void peerHaloRelease(PeerHalo*) {}
@@ -334,6 +351,7 @@ bool commUsesPeerMemory() { return false; }
 int commUniqueId(void* out128) { memset(out128, 0, 128); return 128; }
 void allReduce(double*, int, ReduceOp) {}
 void haloExchange(const DeviceMesh&, const double*, double*) {}
+bool allReduceSumThenPcgCheck(double*, int, PcgScalars*, double*) { return false; }
 struct PeerHalo {};
 PeerHalo* peerHaloGet(DeviceMesh&) { return nullptr; }
 void peerHaloRelease(PeerHalo*) {}

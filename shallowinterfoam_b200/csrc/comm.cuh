@@ -9,6 +9,10 @@ void commFinalize();
 int commUniqueId(void* out128);
 enum ReduceOp { RED_SUM = 0, RED_MAX = 1, RED_MIN = 2 };
 void allReduce(double* devPtr, int count, ReduceOp op);  // in place on rt().stream; no-op when nRanks == 1
+struct PcgScalars;
+// sum all-reduce over peer memory whose kernel also runs the PCG convergence check (k_pcg_check's body); false: not available, the
+// caller does allReduce + k_pcg_check
+bool allReduceSumThenPcgCheck(double* devPtr, int count, PcgScalars* sc, double* hist);
 bool commUsesPeerMemory();   // scalar all-reduces run over NVLink peer memory (mailboxes) instead of NCCL
 // exchange per-boundary-face values on processor patches: recv[b] = neighbour rank's send[b'] (same face)
 void haloExchange(const DeviceMesh& m, const double* send, double* recv);

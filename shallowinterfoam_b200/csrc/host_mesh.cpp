@@ -135,6 +135,24 @@ PolyMesh subsetMesh(const PolyMesh& m, const std::vector<uint8_t>& keep, const s
 }
 
 // ------------------------------------------------------------------------------------------- geometry
+// vertex jitter of the interior points (include/b200foam.h b200_polymesh_jitter)
+void jitterPoints(PolyMesh& m, double frac, double dx, double dy, double dz, uint64_t seed) {
+    const size_t nP = m.points.size() / 3;
+    std::vector<uint8_t> onBoundary(nP, 0);
+    for (int32_t f = m.nInternalFaces(); f < m.nFaces(); f++)
+        for (int q = 0; q < 4; q++) onBoundary[m.faces[f][q]] = 1;
+    uint64_t x = seed;
+    const double d[3] = {dx, dy, dz};
+    for (size_t p = 0; p < nP; p++) {
+        if (onBoundary[p]) continue;
+        for (int k = 0; k < 3; k++) {
+            x = x * 6364136223846793005ull + 1442695040888963407ull;
+            const double u = (double)(x >> 11) * (1.0 / 9007199254740992.0);
+            m.points[3 * p + k] = m.points[3 * p + k] + (2.0 * u - 1.0) * frac * d[k];
+        }
+    }
+}
+
 Geometry computeGeometry(const PolyMesh& m) {
     Geometry g;
     int32_t N = m.nCells, F = m.nInternalFaces(), nF = m.nFaces();

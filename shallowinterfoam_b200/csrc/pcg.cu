@@ -197,7 +197,7 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
         { KT(T_DIC_BWD); launchBwd(m, w, w.rA.p, sc, part, cnt, multi ? &sc->wArAnew : &sc->wArA, pdl); }
         // multi-rank: ONE all-reduce carries the previous iteration's sum|rA| and this iteration's sum(wA*rA); the convergence
         // test therefore runs after the backward sweep (one wasted sweep at the end of a solve)
-        if (multi) { allReduce(&sc->sumMagR, 2, RED_SUM); B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist); }
+        if (multi && !allReduceSumThenPcgCheck(&sc->sumMagR, 2, sc, hist)) { allReduce(&sc->sumMagR, 2, RED_SUM); B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist); }
         { KT(T_PCG_VEC);
           B200_LAUNCH_PDL(pdl, k_pcg_p_update, grid, BLOCK, 0, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc); }
         if (halo && peer) {   // halo over NVLink peer memory: push -> Amul (overlaps the transfer) -> wait inside k_iface_dot
