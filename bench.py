@@ -288,6 +288,10 @@ def run_ours(args):
         kernels["amul"] = {"us": 1e6 * t_amul, "GBps": alg["amul"] / t_amul / 1e9, "share_of_step": tk["amul"][0] / step_ms}
     if t_mules:
         kernels["mules_explicitSolve"] = {"us": 1e6 * t_mules, "GBps": alg["mules"] / t_mules / 1e9, "share_of_step": tk["mules"][0] / step_ms}
+    for name in ("pcg_vec", "allreduce", "halo"):     # the rest of a PCG iteration (multi-rank: scalar all-reduces incl. the wait for the slowest rank; halo push + interface update)
+        t = per_iter(name)
+        if t:
+            kernels[name] = {"us": 1e6 * t, "share_of_step": tk[name][0] / step_ms}
     dom = "dic_precondition" if "dic_precondition" in kernels else "amul"
     ach = kernels[dom]["GBps"] if dom in kernels else None
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload

@@ -48,7 +48,7 @@ Runtime& rt();
 void requireDevice();  // throws B200_ERR_NO_DEVICE when no CUDA device is usable
 
 // ---- kernel-class timers (CUDA events on the launching stream) -------------------------------------------
-enum TimerId { T_AMUL = 0, T_DIC_FWD, T_DIC_BWD, T_DIC_RD, T_PCG_VEC, T_PCG_SOLVE, T_MULES, T_FLUX, T_ASSEMBLY, T_UEQN, T_MISC, T_STEP, T_COUNT };
+enum TimerId { T_AMUL = 0, T_DIC_FWD, T_DIC_BWD, T_DIC_RD, T_PCG_VEC, T_PCG_SOLVE, T_MULES, T_FLUX, T_ASSEMBLY, T_UEQN, T_MISC, T_STEP, T_ALLREDUCE, T_HALO, T_COUNT };
 const char* timerName(int i);
 struct Timers {
     bool enabled = false;

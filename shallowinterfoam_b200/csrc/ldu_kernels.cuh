@@ -132,6 +132,16 @@ __device__ __forceinline__ void stPublish(double* p, double v) {
 }
 #endif
 
+// read-only loads that stay where the source puts them (volatile asm keeps its program order): the gather kernels issue ALL loads
+// of a row before the first dependent FP64 instruction -- left to itself the compiler sinks each load next to its use to save
+// registers, and the in-order issue then exposes one memory round trip per face
+#ifdef B200_EMU
+__device__ __forceinline__ double ldgOrdered(const double* p) { return *p; }
+__device__ __forceinline__ int ldgOrdered(const int* p) { return *p; }
+#else
+__device__ __forceinline__ double ldgOrdered(const double* p) { double v; asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
+__device__ __forceinline__ int ldgOrdered(const int* p) { int v; asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+#endif
 // load that is served by L2 (values a peer GPU stored into this GPU's memory must not come from a stale L1 line)
 #ifdef B200_EMU
 __device__ __forceinline__ double ldNoL1(const double* p) { return *p; }
@@ -206,12 +216,54 @@ static __global__ void __launch_bounds__(BLOCK) k_amul(MeshView mv, const double
     pdlTrigger();
     if (MODE == 1 && sc->stop) return;
     double dot = 0.0;
-    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < mv.N; row += gridDim.x * blockDim.x) {
-        const double p = psi[row];
-        double unused = 0.0;
-        const double acc = rowOffDiag<false, UNI3, UNI3 ? 3 : 4>(mv, upS, loS, psi, row >> 5, row & 31, diag[row] * p, unused);
-        Apsi[row] = acc;
-        if (MODE == 1) dot = dot + acc * p;
+    const int stride = gridDim.x * blockDim.x;
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (UNI3) {
+        // uniform widths <= 3: the NEXT row's face indices are fetched while this row's coefficients and psi values are in flight,
+        // so a row costs one exposed memory round trip (software pipeline over the persistent loop)
+        const int nbw = mv.uniNw, ow = mv.uniOw, kmask = (1 << mv.KB) - 1;
+        int pk[3], u[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            pk[i] = (row < mv.N && i < nbw) ? mv.loPk[(row >> 5) * 32 * nbw + (i << 5) + (row & 31)] : -1;
+            u[i] = (row < mv.N && i < ow) ? mv.upIdx[(row >> 5) * 32 * ow + (i << 5) + (row & 31)] : -1;
+        }
+        for (; row < mv.N; row += stride) {
+            const int so0 = (row >> 5) * 32 * ow, lane = row & 31, nrow = row + stride;
+            const double p = ldgOrdered(psi + row), dg = ldgOrdered(diag + row);
+            double cu[3], pu[3], cl[3], pl[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) cu[i] = i < ow ? ldgOrdered(upS + so0 + (i << 5) + lane) : 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {      // padding entries load the row's own (valid, cached) data: unconditional loads batch
+                const int l = pk[i] >= 0 ? pk[i] >> mv.KB : row, k = pk[i] >= 0 ? (pk[i] & kmask) : 0;
+                cl[i] = ldgOrdered(loS + (((l >> 5) * ow + k) << 5) + (l & 31)); pl[i] = ldgOrdered(psi + l);
+                pu[i] = ldgOrdered(psi + (u[i] >= 0 ? u[i] : row));
+            }
+            int npk[3], nu[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                npk[i] = (nrow < mv.N && i < nbw) ? ldgOrdered(mv.loPk + (nrow >> 5) * 32 * nbw + (i << 5) + (nrow & 31)) : -1;
+                nu[i] = (nrow < mv.N && i < ow) ? ldgOrdered(mv.upIdx + (nrow >> 5) * 32 * ow + (i << 5) + (nrow & 31)) : -1;
+            }
+            double acc = dg * p;
+#pragma unroll
+            for (int i = 0; i < 3; i++) if (pk[i] >= 0) acc = acc + cl[i] * pl[i];
+#pragma unroll
+            for (int i = 0; i < 3; i++) if (u[i] >= 0) acc = acc + cu[i] * pu[i];
+            Apsi[row] = acc;
+            if (MODE == 1) dot = dot + acc * p;
+#pragma unroll
+            for (int i = 0; i < 3; i++) { pk[i] = npk[i]; u[i] = nu[i]; }
+        }
+    } else {
+        for (; row < mv.N; row += stride) {
+            const double p = psi[row];
+            double unused = 0.0;
+            const double acc = rowOffDiag<false, false, 4>(mv, upS, loS, psi, row >> 5, row & 31, diag[row] * p, unused);
+            Apsi[row] = acc;
+            if (MODE == 1) dot = dot + acc * p;
+        }
     }
     if (MODE == 1) {
         double v[1] = {dot};

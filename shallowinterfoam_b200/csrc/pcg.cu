@@ -197,14 +197,16 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
         { KT(T_DIC_BWD); launchBwd(m, w, w.rA.p, sc, part, cnt, multi ? &sc->wArAnew : &sc->wArA, pdl); }
         // multi-rank: ONE all-reduce carries the previous iteration's sum|rA| and this iteration's sum(wA*rA); the convergence
         // test therefore runs after the backward sweep (one wasted sweep at the end of a solve)
-        if (multi && !allReduceSumThenPcgCheck(&sc->sumMagR, 2, sc, hist)) { allReduce(&sc->sumMagR, 2, RED_SUM); B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist); }
+        if (multi) { KT(T_ALLREDUCE);
+          if (!allReduceSumThenPcgCheck(&sc->sumMagR, 2, sc, hist)) { allReduce(&sc->sumMagR, 2, RED_SUM); B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist); } }
         { KT(T_PCG_VEC);
           B200_LAUNCH_PDL(pdl, k_pcg_p_update, grid, BLOCK, 0, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc); }
         if (halo && peer) {   // halo over NVLink peer memory: push -> Amul (overlaps the transfer) -> wait inside k_iface_dot
-            peerHaloPush(peer, m, w.pA);
+            { KT(T_HALO); peerHaloPush(peer, m, w.pA); }
             { KT(T_AMUL);
               B200_LAUNCH_AMUL(0, false, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt); }
-            B200_LAUNCH(k_iface_dot, grid, BLOCK, st, mv, bou, peerHaloRecv(peer), w.wA.p, (const double*)w.pA.p, sc, part, cnt, peerHaloWait(peer));
+            { KT(T_HALO);
+              B200_LAUNCH(k_iface_dot, grid, BLOCK, st, mv, bou, peerHaloRecv(peer), w.wA.p, (const double*)w.pA.p, sc, part, cnt, peerHaloWait(peer)); }
         } else if (halo) {
             haloPack(m, w.pA, w.sendBuf);
             { KT(T_AMUL);
@@ -215,7 +217,7 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
             KT(T_AMUL);
             B200_LAUNCH_AMUL(1, pdl, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt);
         }
-        if (multi) allReduce(&sc->wApA, 1, RED_SUM);
+        if (multi) { KT(T_ALLREDUCE); allReduce(&sc->wApA, 1, RED_SUM); }
     };
 #undef KT
     // two batches in flight: while the host waits for batch i's flag, batch i+1 is already queued

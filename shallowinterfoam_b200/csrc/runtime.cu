@@ -24,7 +24,7 @@ void requireDevice() {
 }
 
 static const char* kTimerNames[T_COUNT] = {"amul", "dic_fwd", "dic_bwd", "dic_calc_rD", "pcg_vec", "pcg_solve",
-                                           "mules", "flux", "assembly", "ueqn", "misc", "step"};
+                                           "mules", "flux", "assembly", "ueqn", "misc", "step", "allreduce", "halo"};
 const char* timerName(int i) { return (i >= 0 && i < T_COUNT) ? kTimerNames[i] : ""; }
 Timers& timers() { static Timers t; return t; }
 cudaEvent_t Timers::get() {

@@ -49,7 +49,7 @@ def test_decomposed_path_over_gloo(world):
 def test_decomposed_path_on_gpus(opts):
     """the same checks with the real library, one GPU per rank: halo swap of Amul and scalar all-reduces over NVLink peer memory
     (default) and over NCCL; needs 2 GPUs (`gpurun --gpus 2`), skipped on a 1-GPU box"""
-    import torch
-    if torch.cuda.device_count() < 2:
+    from shallowinterfoam_b200 import capi      # (not torch: importing it after libb200foam.so would clash over libnccl)
+    if capi.load().device_count() < 2:
         pytest.skip("needs 2 GPUs")
     run_workers(2, {"B200_WORKER_LIB": "gpu", "B200_WORKER_OPTS": opts})
