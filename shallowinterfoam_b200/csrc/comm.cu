@@ -195,9 +195,9 @@ __global__ void k_halo_push(MeshView mv, const double* __restrict__ cf, PeerHalo
         hv.peerData[slot][parity * hv.peerStride[slot] + i] = cf[mv.bFaceRow[b]];     // store over NVLink into the neighbour's HBM
     }
     __shared__ int isLast;
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();     // cumulative: the block's stores (ordered before this by the barrier) precede the flag
         const unsigned total = gridDim.x * gridDim.y;
         isLast = atomicInc(counter, total - 1) == total - 1;
     }

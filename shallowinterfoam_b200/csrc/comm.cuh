@@ -22,7 +22,7 @@ void haloPack(const DeviceMesh& m, const double* cellField, double* send);
 
 // ---- halo swap over NVLink peer memory, fused into the producer / consumer kernels of the PCG iteration (no NCCL launch):
 // the producer kernel (k_halo_push) gathers the processor-face values and stores them straight into the NEIGHBOUR rank's receive
-// buffer (cudaIpc-mapped), then raises an epoch flag there; the consumer kernel (k_iface_dot) spins on its own flags before it reads.
+// buffer (cudaIpc-mapped), then raises an epoch flag there; the consumer kernel (k_iface_rows) spins on its own flags before it reads.
 // Amul runs between the two, so the NVLink transfer overlaps it.  [UPSTREAM processorFvPatchField::initInterfaceMatrixUpdate /
 // updateInterfaceMatrix: the same non-blocking send ... compute ... receive split]
 constexpr int PEER_MAX_RANKS = 16;

@@ -381,30 +381,33 @@ static __global__ void k_pcg_check(PcgScalars* sc, double* hist) {
     if (sc->pendingCheck) { sc->pendingCheck = 0; pcgEndOfIteration(sc, hist); }
     if (!sc->stop) sc->wArA = sc->wArAnew;
 }
-// multi-rank tail of Amul: processor-interface update  Apsi[faceCells] -= bouCoeffs*psiNbr  (per boundary row in patch order)
-// fused with sum(Apsi*psi) -> sc->wApA
-static __global__ void __launch_bounds__(BLOCK) k_iface_dot(MeshView mv, const double* __restrict__ bou, const double* psiNbr,
-                                                      double* __restrict__ Apsi, const double* __restrict__ psi, PcgScalars* sc,
-                                                      double* partials, unsigned* counter, PeerHaloWait hw) {
+// multi-rank tail of Amul: processor-interface update  Apsi[faceCells] -= bouCoeffs*psiNbr  over the rows that own boundary faces
+// only (per row in patch order), and the matching correction of sum(Apsi*psi): k_amul<1> has left the sum over the un-updated Apsi
+// in sc->wApA, this kernel adds sum((Apsi_new - Apsi_old)*psi) over the updated rows.  hw: peer-memory halo -- wait for the
+// neighbours' values of this epoch first (no-op on the NCCL path).
+static __global__ void __launch_bounds__(BLOCK) k_iface_rows(MeshView mv, const double* __restrict__ bou, const double* psiNbr,
+                                                       double* __restrict__ Apsi, const double* __restrict__ psi, int nBRows,
+                                                       const int* __restrict__ bRowOfSlot, PcgScalars* sc, double* partials,
+                                                       unsigned* counter, PeerHaloWait hw) {
     if (sc->stop) return;
-    peerHaloWaitDevice(hw);    // peer-memory halo: the neighbours' values of this epoch have landed (no-op on the NCCL path)
-    int row = blockIdx.x * blockDim.x + threadIdx.x, s = row >> 5, lane = row & 31;
+    peerHaloWaitDevice(hw);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double v[1] = {0.0};
-    if (row < mv.N) {
-        double acc = Apsi[row];
-        if ((mv.bMask[s] >> lane) & 1u) {
-            int i = mv.bBase[s] + __popc(mv.bMask[s] & ((1u << lane) - 1u));
-            bool any = false;
-            for (int q = mv.bRowStart[i]; q < mv.bRowStart[i + 1]; q++) {
-                int b = mv.bRowFaces[q];
-                if (mv.bCoupled[b]) { acc = acc - bou[b] * ldNoL1(psiNbr + b); any = true; }
-            }
-            if (any) Apsi[row] = acc;
+    if (i < nBRows) {
+        const int row = bRowOfSlot[i];
+        const double old = Apsi[row];
+        double acc = old;
+        bool any = false;
+        for (int q = mv.bRowStart[i]; q < mv.bRowStart[i + 1]; q++) {
+            const int b = mv.bRowFaces[q];
+            if (mv.bCoupled[b]) { acc = acc - bou[b] * ldNoL1(psiNbr + b); any = true; }
         }
-        v[0] = acc * psi[row];
+        if (any) { Apsi[row] = acc; v[0] = (acc - old) * psi[row]; }
     }
     gridReduce<1, OpSum>(v, blockIdx.x, gridDim.x, partials, counter, nullptr);
-    gridFinalize<1, OpSum>(gridDim.x, partials, counter, &sc->wApA);
+    __shared__ double corr;
+    const bool last = gridFinalizeLast<OpSum>(gridDim.x, partials, counter, &corr);
+    if (last && threadIdx.x == 0) sc->wApA = sc->wApA + corr;
 }
 // pA = z + beta*pA (first iteration: pA = z);  z <- sentinel (re-armed for the next sweep)
 static __global__ void __launch_bounds__(BLOCK) k_pcg_p_update(int N, double* __restrict__ z, double* __restrict__ pA,
