@@ -295,8 +295,8 @@ def run_ours(args):
     dom = "dic_precondition" if "dic_precondition" in kernels else "amul"
     ach = kernels[dom]["GBps"] if dom in kernels else None
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
-    # (profiles/r1e_ncu_full_raw.csv: k_dic_fwd 98.9 + 4.9 MB, k_dic_bwd 75.0 + 1.9 MB, k_amul 63.1 + 1.6 MB); only valid for N = 1
-    ncu_traffic = {"dic_precondition": 180.7e6, "amul": 64.6e6}
+    # (profiles/r1f_ncu_full_raw.csv: k_dic_fwd 98.9 + 4.6 MB, k_dic_bwd 75.0 + 1.7 MB, k_amul 63.1 + 1.4 MB); only valid for N = 1
+    ncu_traffic = {"dic_precondition": 180.2e6, "amul": 64.5e6}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
                 "frac_of_8TBps_nominal": (ach / 8000.0) if ach else None, "peak_source": peak_src,
                 "traffic": ncu_traffic.get(dom) if world == 1 else None,
