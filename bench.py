@@ -147,7 +147,7 @@ def run_reference(args):
             "data": "synthetic", "config": WORKLOAD,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -319,10 +319,28 @@ def run_ours(args):
         t1 = time.time(); r.step(); dt = time.time() - t1
         line["cpu_baseline"] = {"value": m.N / dt, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": "1 step of the same 985000-cell workload after correctPhi (%.1f s; set-up %.1f s untimed), serial oracle" % (dt, t1 - t0)}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result: file descriptor 1 is pointed at stderr for the rest of the process (NCCL
+    prints its version banner with printf, torch.distributed and CUDA libraries may chat too), the JSON goes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n"); out.flush()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
