@@ -252,6 +252,10 @@ int b200_polymesh_box_weir(int32_t nx, int32_t ny, int32_t nz, double lx, double
  * 64-bit LCG x <- x*6364136223846793005 + 1442695040888963407 (u = (x >> 11) * 2^-53; three draws per vertex, vertices in index order,
  * x0 = seed).  Addressing is untouched; faces become non-planar and non-orthogonal (what moveDynamicMesh / a skewed blockMesh gives). */
 int b200_polymesh_jitter(b200_polymesh_t* pm, double frac, double dx, double dy, double dz, uint64_t seed);
+/* polyhedral mesh by agglomeration (BASELINE configs[3], irregular LDU addressing): cells with equal group[cell] merge.  New labels by
+ * first appearance; faces between merged cells vanish; the rest are flipped to owner < neighbour and sorted (owner, neighbour, original
+ * face); boundary faces and patches keep their order.  Two cells may share several faces. */
+int b200_polymesh_agglomerate(const b200_polymesh_t* pm, const int64_t* group, b200_polymesh_t** out);
 int b200_polymesh_release(b200_polymesh_t* pm);
 int b200_polymesh_sizes(const b200_polymesh_t* pm, int32_t* nCells, int32_t* nInternalFaces, int32_t* nBoundaryFaces,
                         int32_t* nPatches, int32_t* nPoints);

@@ -161,6 +161,48 @@ def subset_mesh(mesh, keep, exposed_name="weir"):
                 neighbour=nei_i.astype(np.int32), patches=patches, nCells=int(keep.sum()))
 
 
+def agglomerate(mesh, group):
+    """Polyhedral mesh by agglomeration (BASELINE configs[3]: irregular LDU addressing): cells with the same `group` key merge into
+    one cell.  New cell labels follow the first appearance of a group among the old cells; internal faces between two merged cells
+    vanish; the others keep their points, are flipped when the new owner would exceed the new neighbour, and are sorted by
+    (owner, neighbour, original face) = upper-triangular order (two cells may share several faces: lduAddressing does not mind);
+    boundary faces and patches keep their order.  [UPSTREAM polyMesh ordering rules; restated by b200_polymesh_agglomerate]"""
+    group = np.asarray(group)
+    uniq, first = np.unique(group, return_index=True)
+    rank = np.empty(len(uniq), dtype=np.int64)
+    rank[np.argsort(first, kind="stable")] = np.arange(len(uniq))
+    newid = rank[np.searchsorted(uniq, group)]
+    own, nei = mesh["owner"], mesh["neighbour"]
+    F = nei.size
+    o2, n2 = newid[own[:F]], newid[nei]
+    idx = np.nonzero(o2 != n2)[0]
+    o3, n3 = o2[idx], n2[idx]
+    flip = o3 > n3
+    lo, hi = np.where(flip, n3, o3), np.where(flip, o3, n3)
+    fv = mesh["faces"][:F][idx].copy()
+    fv[flip] = fv[flip][:, ::-1]
+    perm = np.lexsort((idx, hi, lo))
+    shift = F - idx.size
+    patches = [(n, s_ - shift, z) for (n, s_, z) in mesh["patches"]]
+    return dict(points=mesh["points"], faces=np.concatenate([fv[perm], mesh["faces"][F:]]).astype(np.int32),
+                owner=np.concatenate([lo[perm], newid[own[F:]]]).astype(np.int32), neighbour=hi[perm].astype(np.int32),
+                patches=patches, nCells=len(uniq))
+
+
+def block_groups(nx, ny, nz):
+    """group keys that merge the 2x2x2 blocks with (I+J+K) % 3 != 0 of an nx x ny x nz hex box (only complete blocks): new cells are
+    single hexes (6 faces) or 2x2x2 super-cells (24 faces); neighbouring super-cells share 4 faces"""
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    I, J, K = i // 2, j // 2, k // 2
+    full = (2 * I + 1 < nx) & (2 * J + 1 < ny) & (2 * K + 1 < nz)
+    merged = full & ((I + J + K) % 3 != 0)
+    cell = (i + nx * (j + ny * k))
+    key = np.where(merged, nx * ny * nz + (I + (nx // 2 + 1) * (J + (ny // 2 + 1) * K)), cell)
+    out = np.empty(nx * ny * nz, dtype=np.int64)
+    out[cell.ravel()] = key.ravel()
+    return out
+
+
 def jitter_points(mesh, frac, dx, dy, dz, seed=12345):
     """skewed mesh (BASELINE configs[3]): interior vertices (not on any boundary face) move by (2u-1)*frac*(dx,dy,dz),
     u from the 64-bit LCG documented in include/b200foam.h (b200_polymesh_jitter); pure-Python integers, so no overflow semantics."""

@@ -31,7 +31,7 @@ EXPORTS = [
     "b200_region3d_set_patch_mixed", "b200_region3d_get_patch_internal", "b200_region3d_num_solves",
     "b200_region3d_get_perfs", "b200_region3d_get_res_hist", "b200_region3d_get_alpha_stats",
     "b200_region3d_get_cont_errs", "b200_region3d_clear_log",
-    "b200_polymesh_box", "b200_polymesh_box_weir", "b200_polymesh_jitter", "b200_polymesh_release", "b200_polymesh_sizes",
+    "b200_polymesh_box", "b200_polymesh_box_weir", "b200_polymesh_jitter", "b200_polymesh_agglomerate", "b200_polymesh_release", "b200_polymesh_sizes",
     "b200_polymesh_get", "b200_polymesh_patch_name", "b200_polymesh_geometry", "b200_decompose_simple",
     "b200_polymesh_submesh", "b200_polymesh_submesh_maps", "b200_mesh_create_from_polymesh",
 ]
@@ -302,6 +302,13 @@ class PolyMesh:
                                                              _d(g["V"]), _d(g["weights"]), _d(g["deltaCoeffs"])))
             self._geom = g
         return self._geom
+
+    def agglomerate(self, group):
+        """polyhedral mesh: cells with equal group keys merge (b200_polymesh_agglomerate)"""
+        h = C.c_void_p()
+        g = np.ascontiguousarray(group, dtype=np.int64)
+        self.lib.check(self.lib.c.b200_polymesh_agglomerate(self.h, g.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(h)))
+        return PolyMesh(self.lib, h)
 
     def decompose_simple(self, n):
         proc = np.empty(self.nCells, dtype=np.int32)

@@ -322,6 +322,12 @@ int b200_polymesh_jitter(b200_polymesh_t* pm, double frac, double dx, double dy,
     jitterPoints(pm->pm, frac, dx, dy, dz, seed);
     API_END
 }
+int b200_polymesh_agglomerate(const b200_polymesh_t* pm, const int64_t* group, b200_polymesh_t** out) {
+    API_BEGIN
+    B200_REQUIRE(pm && group && out, B200_ERR_ARG, "b200_polymesh_agglomerate: null argument");
+    *out = new b200_polymesh{agglomerate(pm->pm, group)};
+    API_END
+}
 int b200_polymesh_release(b200_polymesh_t* pm) { delete pm; return B200_OK; }
 int b200_polymesh_sizes(const b200_polymesh_t* pm, int32_t* nCells, int32_t* nIF, int32_t* nBF, int32_t* nPatches, int32_t* nPoints) {
     API_BEGIN

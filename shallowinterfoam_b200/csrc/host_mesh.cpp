@@ -1,5 +1,6 @@
 // host_mesh.cpp -- see host_mesh.h.  Plain host C++ (no CUDA).  Compiled with -ffp-contract=off.
 #include "host_mesh.h"
+#include <map>
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -131,6 +132,40 @@ PolyMesh subsetMesh(const PolyMesh& m, const std::vector<uint8_t>& keep, const s
     }
     e.size = (int32_t)s.faces.size() - e.start;
     s.patches.push_back(e);
+    return s;
+}
+
+// polyhedral mesh by agglomeration (include/b200foam.h b200_polymesh_agglomerate)
+PolyMesh agglomerate(const PolyMesh& m, const int64_t* group) {
+    PolyMesh s;
+    const int32_t F = m.nInternalFaces();
+    std::map<int64_t, int32_t> idOf;
+    std::vector<int32_t> newId(m.nCells);
+    for (int32_t c = 0; c < m.nCells; c++) {
+        auto it = idOf.find(group[c]);
+        if (it == idOf.end()) it = idOf.emplace(group[c], (int32_t)idOf.size()).first;
+        newId[c] = it->second;
+    }
+    s.nCells = (int32_t)idOf.size();
+    s.points = m.points;
+    struct Rec { int32_t lo, hi, f; bool flip; };
+    std::vector<Rec> recs;
+    for (int32_t f = 0; f < F; f++) {
+        int32_t o = newId[m.owner[f]], n = newId[m.neighbour[f]];
+        if (o == n) continue;
+        recs.push_back(o < n ? Rec{o, n, f, false} : Rec{n, o, f, true});
+    }
+    std::sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) {
+        return a.lo != b.lo ? a.lo < b.lo : a.hi != b.hi ? a.hi < b.hi : a.f < b.f;
+    });
+    for (const Rec& r : recs) {
+        auto fv = m.faces[r.f];
+        if (r.flip) s.faces.push_back({fv[3], fv[2], fv[1], fv[0]}); else s.faces.push_back(fv);
+        s.owner.push_back(r.lo); s.neighbour.push_back(r.hi);
+    }
+    const int32_t shift = F - (int32_t)recs.size();
+    for (int32_t f = F; f < m.nFaces(); f++) { s.faces.push_back(m.faces[f]); s.owner.push_back(newId[m.owner[f]]); }
+    for (const Patch& p : m.patches) { Patch q = p; q.start = p.start - shift; s.patches.push_back(q); }
     return s;
 }
 

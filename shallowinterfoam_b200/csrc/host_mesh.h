@@ -38,6 +38,7 @@ struct Geometry {
 PolyMesh makeBox(int nx, int ny, int nz, double lx, double ly, double lz);
 // [UPSTREAM subsetMesh semantics] keep[c] != 0 cells survive; exposed faces -> new last patch
 PolyMesh subsetMesh(const PolyMesh& m, const std::vector<uint8_t>& keep, const std::string& exposedName);
+PolyMesh agglomerate(const PolyMesh& m, const int64_t* group);
 void jitterPoints(PolyMesh& m, double frac, double dx, double dy, double dz, uint64_t seed);
 std::vector<uint8_t> weirKeepMask(int nx, int ny, int nz, double x0, double x1, double zfrac);
 
