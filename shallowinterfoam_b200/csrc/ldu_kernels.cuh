@@ -151,53 +151,47 @@ __device__ __forceinline__ double ldNoL1(const double* p) { return __ldcg(p); }
 
 // ----------------------------------------------------------------------------- a1: Amul (row gather)
 // Apsi[row] = diag*psi + sum_{nbr-side faces asc} lower_f*psi[l] + sum_{owner faces asc} upper_f*psi[u]
-// The row's off-diagonal products, accumulated onto acc in upstream's order.  Slices of up to GW faces per side (every
-// hex / prism / tet mesh) take the batched path: all index loads are issued first, then all coefficient and psi loads,
-// and only the FP64 additions stay sequential -- three dependent memory round trips per row instead of 3 x (faces of the
-// row), which is what keeps enough bytes in flight to load HBM.  Wider slices (polyhedra) finish in the generic loops.
-// UNI: uniform slice widths (device_mesh.cu) -- slot positions are computed, not looked up, which leaves two dependent memory
-// round trips per row: indices, then coefficients / psi.
-template <bool WITH_SUM, bool UNI, int GW>
+// rowOffDiag: the row's off-diagonal products, accumulated onto acc in upstream's order.
+// Generic form (any slice widths: polyhedral meshes).  The faces of each side are taken four at a time: four index loads, then the
+// four slice offsets, then coefficients and psi values, all issued in program order before the four additions (ldgOrdered); padding
+// entries load slot 0 / the row's own psi so that no load is predicated.  (Hex meshes take the pipelined loop of k_amul instead.)
+template <bool WITH_SUM>
 __device__ __forceinline__ double rowOffDiag(const MeshView& mv, const double* __restrict__ upS, const double* __restrict__ loS,
-                                             const double* __restrict__ psi, int s, int lane, double acc, double& sA) {
-    int nb0, nbw, so0, ow;
-    if (UNI) { nbw = mv.uniNw; nb0 = s * 32 * nbw; ow = mv.uniOw; so0 = s * 32 * ow; }
-    else { nb0 = mv.nbrOff[s]; nbw = (mv.nbrOff[s + 1] - nb0) >> 5; so0 = mv.sliceOff[s]; ow = (mv.sliceOff[s + 1] - so0) >> 5; }
-    int pk[GW], u[GW];
-    double cu[GW], pu[GW], cl[GW], pl[GW];
+                                             const double* __restrict__ psi, int row, double acc, double& sA) {
+    constexpr int GW = 4;
+    const int s = row >> 5, lane = row & 31, kmask = (1 << mv.KB) - 1;
+    const int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5;
+    const int so0 = mv.sliceOff[s], ow = (mv.sliceOff[s + 1] - so0) >> 5;
+    for (int j0 = 0; j0 < nbw; j0 += GW) {
+        int pk[GW], so[GW];
+        double cl[GW], pl[GW];
 #pragma unroll
-    for (int i = 0; i < GW; i++) pk[i] = i < nbw ? mv.loPk[nb0 + (i << 5) + lane] : -1;
+        for (int i = 0; i < GW; i++) pk[i] = j0 + i < nbw ? ldgOrdered(mv.loPk + nb0 + ((j0 + i) << 5) + lane) : -1;
 #pragma unroll
-    for (int i = 0; i < GW; i++) {
-        u[i] = -1; cu[i] = 0.0;
-        if (i < ow) { u[i] = mv.upIdx[so0 + (i << 5) + lane]; cu[i] = upS[so0 + (i << 5) + lane]; }
-    }
+        for (int i = 0; i < GW; i++) so[i] = pk[i] >= 0 ? ldgOrdered(mv.sliceOff + ((pk[i] >> mv.KB) >> 5)) : 0;
 #pragma unroll
-    for (int i = 0; i < GW; i++) {
-        cl[i] = 0.0; pl[i] = 0.0;
-        if (pk[i] >= 0) {
-            int l, pos;
-            if (UNI) { l = pk[i] >> mv.KB; pos = (((l >> 5) * mv.uniOw + (pk[i] & ((1 << mv.KB) - 1))) << 5) + (l & 31); }
-            else pos = facePosOf(mv, pk[i], l);
-            cl[i] = loS[pos]; pl[i] = psi[l];
+        for (int i = 0; i < GW; i++) {
+            const int l = pk[i] >= 0 ? pk[i] >> mv.KB : row;
+            const int pos = pk[i] >= 0 ? so[i] + ((pk[i] & kmask) << 5) + (l & 31) : 0;
+            cl[i] = ldgOrdered(loS + pos); pl[i] = ldgOrdered(psi + l);
         }
+#pragma unroll
+        for (int i = 0; i < GW; i++)
+            if (pk[i] >= 0) { acc = acc + cl[i] * pl[i]; if (WITH_SUM) sA = sA + cl[i]; }
     }
+    for (int k0 = 0; k0 < ow; k0 += GW) {
+        int u[GW];
+        double cu[GW], pu[GW];
 #pragma unroll
-    for (int i = 0; i < GW; i++) pu[i] = u[i] >= 0 ? psi[u[i]] : 0.0;
+        for (int i = 0; i < GW; i++) u[i] = k0 + i < ow ? ldgOrdered(mv.upIdx + so0 + ((k0 + i) << 5) + lane) : -1;
 #pragma unroll
-    for (int i = 0; i < GW; i++)
-        if (pk[i] >= 0) { acc = acc + cl[i] * pl[i]; if (WITH_SUM) sA = sA + cl[i]; }
-    for (int j = GW; j < nbw; j++) {
-        int q = mv.loPk[nb0 + (j << 5) + lane];
-        if (q >= 0) { int l; int pos = facePosOf(mv, q, l); double c = loS[pos]; acc = acc + c * psi[l]; if (WITH_SUM) sA = sA + c; }
-    }
+        for (int i = 0; i < GW; i++) {
+            cu[i] = ldgOrdered(upS + (k0 + i < ow ? so0 + ((k0 + i) << 5) + lane : 0));
+            pu[i] = ldgOrdered(psi + (u[i] >= 0 ? u[i] : row));
+        }
 #pragma unroll
-    for (int i = 0; i < GW; i++)
-        if (u[i] >= 0) { acc = acc + cu[i] * pu[i]; if (WITH_SUM) sA = sA + cu[i]; }
-    for (int k = GW; k < ow; k++) {
-        int pos = so0 + (k << 5) + lane;
-        int v = mv.upIdx[pos];
-        if (v >= 0) { double c = upS[pos]; acc = acc + c * psi[v]; if (WITH_SUM) sA = sA + c; }
+        for (int i = 0; i < GW; i++)
+            if (u[i] >= 0) { acc = acc + cu[i] * pu[i]; if (WITH_SUM) sA = sA + cu[i]; }
     }
     return acc;
 }
@@ -260,7 +254,7 @@ static __global__ void __launch_bounds__(BLOCK) k_amul(MeshView mv, const double
         for (; row < mv.N; row += stride) {
             const double p = psi[row];
             double unused = 0.0;
-            const double acc = rowOffDiag<false, false, 4>(mv, upS, loS, psi, row >> 5, row & 31, diag[row] * p, unused);
+            const double acc = rowOffDiag<false>(mv, upS, loS, psi, row, diag[row] * p, unused);
             Apsi[row] = acc;
             if (MODE == 1) dot = dot + acc * p;
         }
@@ -318,7 +312,7 @@ static __global__ void __launch_bounds__(BLOCK) k_pcg_init1(MeshView mv, const d
     if (row < mv.N) {
         double xr = x[row], d = diag[row];
         double sA = d;
-        double acc = rowOffDiag<true, false, 4>(mv, upS, upS, x, s, lane, d * xr, sA);
+        double acc = rowOffDiag<true>(mv, upS, upS, x, row, d * xr, sA);
         if (bou && ((mv.bMask[s] >> lane) & 1u)) {  // sumA: coupled patches subtract bouCoeffs
             int i = mv.bBase[s] + __popc(mv.bMask[s] & ((1u << lane) - 1u));
             for (int q = mv.bRowStart[i]; q < mv.bRowStart[i + 1]; q++) { int bf = mv.bRowFaces[q]; if (mv.bCoupled[bf]) sA = sA - bou[bf]; }
