@@ -16,10 +16,12 @@ box = lib.polymesh_box(*dims, *L, jitter=(0.25, 12345))
 pm = box.agglomerate(mo.block_groups(*dims)); box.release()
 N, F = pm.nCells, pm.nInternalFaces
 m = oracle_mesh_of(pm)
-ldu = pm.ldu()
+dm = pm.device_mesh()      # with geometry: the sweep plan may classify faces by their normals
+ldu = dm.ldu
+band, rows_max, tile_start = ldu.tiling()
 nfaces = np.bincount(pm.owner, minlength=N) + np.bincount(pm.neighbour, minlength=N)
 out = {"mesh": "polyhedral box from %dx%dx%d hexes: %d cells, %d internal faces (%.2f per cell), faces per cell %d..%d" % (dims + (N, F, F / N, nfaces.min(), nfaces.max())),
-       "build_s": time.time() - t0}
+       "build_s": time.time() - t0, "sweep_tiles": int(len(tile_start) - 1), "mean_rows_per_tile": float(N / max(1, len(tile_start) - 1))}
 diag, upper = random_spd(m, seed=1)
 rng = np.random.default_rng(2); psi = rng.uniform(0, 1, N); b = rng.uniform(-1, 1, N)
 out["amul_bitwise"] = bool(np.array_equal(fo.amul(m, diag, upper, upper, psi), ldu.amul(diag, upper, psi)))
