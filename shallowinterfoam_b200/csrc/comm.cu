@@ -65,6 +65,8 @@ static P2PState g_p2p;
 // post != 0: the thread that holds the result also runs k_pcg_check's body (closes the previous PCG iteration, adopts the new wArA):
 // one launch less per iteration
 __global__ void k_p2p_allreduce(double* data, int count, int op, P2PView pv, unsigned long long epoch, PcgScalars* post, double* hist) {
+    pdlTrigger();   // (launched without the PDL attribute: everything before it is complete) lets a PDL successor -- the next forward
+                    // sweep -- run its prologue while this warp waits for the peers
     const int lane = threadIdx.x, slot = (int)(epoch & (P2P_SLOTS - 1));
     const double tag = (double)epoch;
     if (lane < pv.nRanks) {

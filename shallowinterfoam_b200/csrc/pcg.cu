@@ -185,6 +185,8 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
 #define KT(id) std::unique_ptr<ScopedTimer> _kt(kt ? new ScopedTimer(id) : nullptr)
     // single rank: the four kernels of an iteration are chained by programmatic dependent launch (option pcg_pdl)
     const bool pdl = !multi && !kt && rt().opt("pcg_pdl", 1) > 0;
+    // multi-rank: only the sweeps start early (the forward sweep's predecessor is the peer-memory all-reduce kernel, which triggers at once)
+    const bool pdlSweeps = !kt && rt().opt("pcg_pdl", 1) > 0;
     if (multi && !w.peerTried) { w.peerTried = true; w.peer = peerHaloGet(m); }   // collective: every rank reaches its first multi-rank solve
     PeerHalo* peer = halo ? w.peer : nullptr;
     bool firstIteration = true;
@@ -192,9 +194,9 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
         // (an empty rank still runs the sweeps: they carry the iteration's residual sum / convergence test and the wArA sum)
         { KT(T_DIC_FWD);   // + the previous iteration's x / rA update, residual sum and convergence test (fused)
           // (the first sweep of a solve follows k_dic_coeffs, which writes the operand blocks the prologue stages: no early start)
-          launchFwd(m, w, w.rD.p, w.rA.p, sc, PcgFuse{x, w.rA.p, w.pA.p, w.wA.p, sc, part, cnt, hist, multi ? 0 : 1}, pdl && !firstIteration); }
+          launchFwd(m, w, w.rD.p, w.rA.p, sc, PcgFuse{x, w.rA.p, w.pA.p, w.wA.p, sc, part, cnt, hist, multi ? 0 : 1}, pdlSweeps && !firstIteration); }
         firstIteration = false;
-        { KT(T_DIC_BWD); launchBwd(m, w, w.rA.p, sc, part, cnt, multi ? &sc->wArAnew : &sc->wArA, pdl); }
+        { KT(T_DIC_BWD); launchBwd(m, w, w.rA.p, sc, part, cnt, multi ? &sc->wArAnew : &sc->wArA, pdlSweeps); }
         // multi-rank: ONE all-reduce carries the previous iteration's sum|rA| and this iteration's sum(wA*rA); the convergence
         // test therefore runs after the backward sweep (one wasted sweep at the end of a solve)
         if (multi) { KT(T_ALLREDUCE);
