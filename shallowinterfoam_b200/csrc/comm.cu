@@ -190,6 +190,8 @@ struct PeerHalo {
     int maxSize = 0;
 };
 __global__ void k_halo_push(MeshView mv, const double* __restrict__ cf, PeerHaloPushView hv, unsigned long long epoch, unsigned* counter) {
+    pdlWait();
+    pdlTrigger();
     const int slot = blockIdx.y, parity = (int)(epoch & 1ull);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < hv.size[slot]) {
@@ -280,11 +282,11 @@ void peerHaloRelease(PeerHalo* h) {
     if (h->counter) cudaFree(h->counter);
     delete h;
 }
-void peerHaloPush(PeerHalo* h, const DeviceMesh& m, const double* cellField) {
+void peerHaloPush(PeerHalo* h, const DeviceMesh& m, const double* cellField, bool pdl) {
     h->epoch++;
     if (h->v.nNbr == 0) return;
     dim3 grid(std::max(1, gridFor(h->maxSize)), h->v.nNbr);
-    B200_LAUNCH(k_halo_push, grid, BLOCK, rt().stream, m.view(), cellField, h->v, h->epoch, h->counter);
+    B200_LAUNCH_PDL(pdl, k_halo_push, grid, BLOCK, 0, rt().stream, m.view(), cellField, h->v, h->epoch, h->counter);
 }
 const double* peerHaloRecv(const PeerHalo* h) { return h->own + 2 * PEER_MAX_RANKS + (size_t)(h->epoch & 1ull) * h->B; }
 PeerHaloWait peerHaloWait(const PeerHalo* h) {
@@ -333,7 +335,7 @@ bool allReduceSumThenPcgCheck(double*, int, PcgScalars*, double*) { return false
 struct PeerHalo {};
 PeerHalo* peerHaloGet(DeviceMesh&) { return nullptr; }
 void peerHaloRelease(PeerHalo*) {}
-void peerHaloPush(PeerHalo*, const DeviceMesh&, const double*) {}
+void peerHaloPush(PeerHalo*, const DeviceMesh&, const double*, bool) {}
 const double* peerHaloRecv(const PeerHalo*) { return nullptr; }
 PeerHaloWait peerHaloWait(const PeerHalo*) { PeerHaloWait w; memset(&w, 0, sizeof(w)); return w; }
 void haloExchange(const DeviceMesh& m, const double* send, double* recv) {
@@ -357,7 +359,7 @@ bool allReduceSumThenPcgCheck(double*, int, PcgScalars*, double*) { return false
 struct PeerHalo {};
 PeerHalo* peerHaloGet(DeviceMesh&) { return nullptr; }
 void peerHaloRelease(PeerHalo*) {}
-void peerHaloPush(PeerHalo*, const DeviceMesh&, const double*) {}
+void peerHaloPush(PeerHalo*, const DeviceMesh&, const double*, bool) {}
 const double* peerHaloRecv(const PeerHalo*) { return nullptr; }
 PeerHaloWait peerHaloWait(const PeerHalo*) { PeerHaloWait w; memset(&w, 0, sizeof(w)); return w; }
 #endif

@@ -202,12 +202,12 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
         if (multi) { KT(T_ALLREDUCE);
           if (!allReduceSumThenPcgCheck(&sc->sumMagR, 2, sc, hist)) { allReduce(&sc->sumMagR, 2, RED_SUM); B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist); } }
         { KT(T_PCG_VEC);
-          B200_LAUNCH_PDL(pdl, k_pcg_p_update, grid, BLOCK, 0, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc); }
+          B200_LAUNCH_PDL(pdl || (pdlSweeps && commUsesPeerMemory()), k_pcg_p_update, grid, BLOCK, 0, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc); }
         if (halo) {
             // Amul of the local block with its dot product, then the interface update (+ dot correction) over the boundary rows only.
             // peer: the halo goes over NVLink peer memory -- push -> Amul (overlaps the transfer) -> wait inside k_iface_rows; else NCCL
-            { KT(T_HALO); if (peer) peerHaloPush(peer, m, w.pA); else haloPack(m, w.pA, w.sendBuf); }
-            { KT(T_AMUL); B200_LAUNCH_AMUL(1, false, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt); }
+            { KT(T_HALO); if (peer) peerHaloPush(peer, m, w.pA, pdlSweeps); else haloPack(m, w.pA, w.sendBuf); }
+            { KT(T_AMUL); B200_LAUNCH_AMUL(1, pdlSweeps && peer != nullptr, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt); }
             { KT(T_HALO);
               if (!peer) haloExchange(m, w.sendBuf, w.recvBuf);
               B200_LAUNCH(k_iface_rows, std::max(1, gridFor(m.nBRows)), BLOCK, st, mv, bou, peer ? peerHaloRecv(peer) : (const double*)w.recvBuf.p, w.wA.p,
