@@ -42,9 +42,11 @@ struct MeshView {  // POD handed to kernels by value
     const double *Cnx, *Cny, *Cnz;   // [B] neighbour cell centre of processor faces
 };
 
+// slot of the face a packed neighbour-side reference names; uniform slice widths make it arithmetic (no look-up of the owner's slice)
 __device__ __forceinline__ int facePosOf(const MeshView& mv, int pk, int& l) {
     l = pk >> mv.KB;
     int k = pk & ((1 << mv.KB) - 1);
+    if (mv.uniOw > 0) return (((l >> 5) * mv.uniOw + k) << 5) + (l & 31);
     return mv.sliceOff[l >> 5] + (k << 5) + (l & 31);
 }
 

@@ -13,14 +13,17 @@ namespace b200 {
 #define FV_SMALL 1.0e-15
 
 // ---- face iteration of one row (thread = row; s = slice = warp; lane) ----------------------------------------
+// (uniform slice widths, device_mesh.cu: the slice offsets are arithmetic -- two dependent loads less per row)
 #define FOR_NBR_FACES(mv, s, lane, pos, l)                                                              \
-    for (int _j = 0, _nb0 = (mv).nbrOff[s], _nbw = ((mv).nbrOff[(s) + 1] - _nb0) >> 5; _j < _nbw; _j++) { \
+    for (int _j = 0, _nb0 = (mv).uniNw > 0 ? (s) * 32 * (mv).uniNw : (mv).nbrOff[s],                    \
+             _nbw = (mv).uniNw > 0 ? (mv).uniNw : ((mv).nbrOff[(s) + 1] - _nb0) >> 5; _j < _nbw; _j++) { \
         int _pk = (mv).loPk[_nb0 + (_j << 5) + (lane)];                                                 \
         if (_pk < 0) break;                                                                             \
         int l;                                                                                          \
         int pos = facePosOf(mv, _pk, l);
 #define FOR_OWN_FACES(mv, s, lane, pos, u)                                                                \
-    for (int _k = 0, _so0 = (mv).sliceOff[s], _ow = ((mv).sliceOff[(s) + 1] - _so0) >> 5; _k < _ow; _k++) { \
+    for (int _k = 0, _so0 = (mv).uniOw > 0 ? (s) * 32 * (mv).uniOw : (mv).sliceOff[s],                    \
+             _ow = (mv).uniOw > 0 ? (mv).uniOw : ((mv).sliceOff[(s) + 1] - _so0) >> 5; _k < _ow; _k++) {  \
         int pos = _so0 + (_k << 5) + (lane);                                                              \
         int u = (mv).upIdx[pos];                                                                          \
         if (u < 0) break;
