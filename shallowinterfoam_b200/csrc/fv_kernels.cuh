@@ -35,10 +35,23 @@ namespace b200 {
 #define END_FACES }
 #define END_BND }}
 
+// L1 prefetch of the row's index lines (uniform slices: their addresses are arithmetic), so that the face loops below find them in
+// L1 instead of paying one DRAM round trip per face; PREFETCH_OWN_FACES does the same for a face field at the row's owner slots
+#ifdef B200_EMU
+__device__ __forceinline__ void prefetchL1(const void*) {}
+#else
+__device__ __forceinline__ void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#endif
+#define PREFETCH_OWN_FACES(mv, s, lane, arr)                                                                       \
+    if ((mv).uniOw > 0 && (arr)) { for (int _k = 0; _k < (mv).uniOw; _k++) prefetchL1((arr) + (((s) * (mv).uniOw + _k) << 5) + (lane)); }
 #define ROW_PROLOGUE(mv)                                               \
     int row = blockIdx.x * blockDim.x + threadIdx.x;                   \
     int s = row >> 5, lane = row & 31;                                 \
-    (void)s; (void)lane;
+    (void)s; (void)lane;                                               \
+    if (row < (mv).N && (mv).uniOw > 0) {                                                                          \
+        for (int _k = 0; _k < (mv).uniOw; _k++) prefetchL1((mv).upIdx + ((s * (mv).uniOw + _k) << 5) + lane);      \
+        for (int _k = 0; _k < (mv).uniNw; _k++) prefetchL1((mv).loPk + ((s * (mv).uniNw + _k) << 5) + lane);       \
+    }
 
 // ---- boundary-condition algebra [UPSTREAM fvPatchField / fixedValue / zeroGradient / mixedFvPatchField] ---------
 struct BCView {
@@ -256,6 +269,10 @@ static __global__ void __launch_bounds__(BLOCK) k_alpha_flux(MeshView mv, const 
     ROW_PROLOGUE(mv)
     double mx = *maxPhic;
     if (row < mv.N) {
+        PREFETCH_OWN_FACES(mv, s, lane, phi)
+        PREFETCH_OWN_FACES(mv, s, lane, mv.w)
+        PREFETCH_OWN_FACES(mv, s, lane, mv.magSf)
+        PREFETCH_OWN_FACES(mv, s, lane, nHatf)
         double a = alpha[row];
         FOR_OWN_FACES(mv, s, lane, pos, u)
             double n = alpha[u], ff = phi[pos], w = mv.w[pos];
@@ -374,6 +391,8 @@ static __global__ void __launch_bounds__(BLOCK) k_mules_iter(MeshView mv, const 
                                                               double* __restrict__ lamPnew, double* __restrict__ lamMnew) {
     ROW_PROLOGUE(mv)
     if (row >= mv.N) return;
+    PREFETCH_OWN_FACES(mv, s, lane, phiCorr)
+    if (!FIRST) { PREFETCH_OWN_FACES(mv, s, lane, lamFacePrev) }
     double sP = 0.0, sM = 0.0, lpMe = 1.0, lmMe = 1.0;
     if (!FIRST) { lpMe = lamPprev[row]; lmMe = lamMprev[row]; }
     FOR_NBR_FACES(mv, s, lane, pos, l)
@@ -416,6 +435,9 @@ static __global__ void __launch_bounds__(BLOCK) k_mules_update(MeshView mv, cons
                                                                 double* __restrict__ fluxOut) {
     ROW_PROLOGUE(mv)
     if (row >= mv.N) return;
+    PREFETCH_OWN_FACES(mv, s, lane, phiCorrRO)
+    PREFETCH_OWN_FACES(mv, s, lane, phiBD)
+    PREFETCH_OWN_FACES(mv, s, lane, lamFacePrev)
     double lpMe = lamP[row], lmMe = lamM[row], a = 0.0;
     FOR_NBR_FACES(mv, s, lane, pos, l)
         double pc = phiCorrRO[pos];
@@ -450,6 +472,10 @@ static __global__ void __launch_bounds__(BLOCK) k_lap_row(MeshView mv, const dou
                                                            double* __restrict__ diag, double* __restrict__ upper, double* __restrict__ source) {
     ROW_PROLOGUE(mv)
     if (row >= mv.N) return;
+    PREFETCH_OWN_FACES(mv, s, lane, gammaf)
+    PREFETCH_OWN_FACES(mv, s, lane, mv.dc)
+    PREFETCH_OWN_FACES(mv, s, lane, mv.magSf)
+    PREFETCH_OWN_FACES(mv, s, lane, phi)
     double d = 0.0, a = 0.0;
     FOR_NBR_FACES(mv, s, lane, pos, l)
         (void)l;
@@ -549,6 +575,13 @@ static __global__ void __launch_bounds__(BLOCK) k_reconstruct(MeshView mv, const
                                                                double* __restrict__ oy, double* __restrict__ oz) {
     ROW_PROLOGUE(mv)
     if (row >= mv.N) return;
+    PREFETCH_OWN_FACES(mv, s, lane, phi)
+    PREFETCH_OWN_FACES(mv, s, lane, phiU)
+    PREFETCH_OWN_FACES(mv, s, lane, rUAf)
+    PREFETCH_OWN_FACES(mv, s, lane, mv.magSf)
+    PREFETCH_OWN_FACES(mv, s, lane, mv.Sfx)
+    PREFETCH_OWN_FACES(mv, s, lane, mv.Sfy)
+    PREFETCH_OWN_FACES(mv, s, lane, mv.Sfz)
     double sx = 0.0, sy = 0.0, sz = 0.0;
 #define RC_ADD(p)                                                                  \
     {                                                                              \
