@@ -149,6 +149,10 @@ static __global__ void k_grad_scalar(MeshView mv, const double* __restrict__ vf,
                                      double* __restrict__ gx, double* __restrict__ gy, double* __restrict__ gz) {
     ROW_PROLOGUE(mv)
     if (row >= mv.N) return;
+    PREFETCH_OWN_FACES(mv, s, lane, mv.w)
+    PREFETCH_OWN_FACES(mv, s, lane, mv.Sfx)
+    PREFETCH_OWN_FACES(mv, s, lane, mv.Sfy)
+    PREFETCH_OWN_FACES(mv, s, lane, mv.Sfz)
     double a = vf[row], x = 0.0, y = 0.0, z = 0.0;
     FOR_NBR_FACES(mv, s, lane, pos, l)
         double o = vf[l];
@@ -218,6 +222,8 @@ static __global__ void k_flux_limited(MeshView mv, int scheme, const double* __r
                                       double* __restrict__ out) {
     ROW_PROLOGUE(mv)
     if (row < mv.N) {
+        PREFETCH_OWN_FACES(mv, s, lane, faceFlux)
+        PREFETCH_OWN_FACES(mv, s, lane, mv.w)
         double a = vf[row];
         FOR_OWN_FACES(mv, s, lane, pos, u)
             double n = vf[u], ff = faceFlux[pos], lim;
@@ -318,6 +324,8 @@ static __global__ void k_mules_bd_corr(MeshView mv, const double* __restrict__ p
                                        const double* __restrict__ psib, double* __restrict__ phiPsi, double* __restrict__ phiBD) {
     ROW_PROLOGUE(mv)
     if (row < mv.N) {
+        PREFETCH_OWN_FACES(mv, s, lane, phi)
+        PREFETCH_OWN_FACES(mv, s, lane, phiPsi)
         double a = psi[row];
         FOR_OWN_FACES(mv, s, lane, pos, u)
             double ff = phi[pos];
@@ -342,6 +350,8 @@ static __global__ void __launch_bounds__(BLOCK) k_mules_bounds(MeshView mv, BCVi
                                                                 double* __restrict__ mSumPhim) {
     ROW_PROLOGUE(mv)
     if (row >= mv.N) return;
+    PREFETCH_OWN_FACES(mv, s, lane, phiBD)
+    PREFETCH_OWN_FACES(mv, s, lane, phiCorr)
     double mxn = psiMin, mnn = psiMax, sBD = 0.0, sP = FV_VSMALL, sM = FV_VSMALL;
     FOR_NBR_FACES(mv, s, lane, pos, l)
         double o = psi[l];
