@@ -121,7 +121,7 @@ __device__ __forceinline__ void stPublish(double* p, double v) { *(volatile doub
 __device__ __forceinline__ void stWeak(double* p, double v) { *(volatile double*)p = v; }
 #else
 // plain (weak) write-through store that the compiler may not drop or move across the step barrier
-__device__ __forceinline__ void stWeak(double* p, double v) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void stWeak(double* p, double v) { asm volatile("st.global.cg.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 __device__ __forceinline__ double ldPoll(const double* p) {
     double v;
     asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
