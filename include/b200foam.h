@@ -102,6 +102,9 @@ const char* b200_timer_name(int i);
 int b200_ldu_get_or_create(const void* key, int32_t nCells, int32_t nFaces, const int32_t* lower, const int32_t* upper,
                            int32_t nPatches, const b200_patch_desc* patches, b200_ldu_t** out);
 int b200_ldu_release(b200_ldu_t* ldu);
+/* drop the cache entry of `key` (mesh motion / topology change: the lduAddressing object was rebuilt at the same address).
+ * A hit in b200_ldu_get_or_create is also validated against a hash of lower/upper/faceCells and rebuilt when it differs. */
+int b200_ldu_invalidate(const void* key);
 /* renumbering used on the device: rowCell[row] = original cell of device row `row`; level[cell] = forward DIC level */
 int b200_ldu_get_renumbering(const b200_ldu_t* ldu, int32_t* rowCell, int32_t* cellLevel, int32_t* nLevels);
 /* DIC tiles of the device row order: rows are ordered (tile, level, original cell); tileStart[nTiles+1].
@@ -211,6 +214,18 @@ typedef struct {
     int32_t adjustPhi;       /* adjustPhi(phiU,U,p): p is `calculated` => needReference() [REF pEqn.H:14]          */
     int32_t mulesIncludeOwn; /* SURVEY.md Appendix C item 2                                                      */
     int32_t divUScheme;      /* div(rhoPhi,U): B200_SCHEME_UPWIND | B200_SCHEME_LINEAR                            */
+    /* [REF region3d/readRegion3dPISOControls.H:9-10  momentumPredictor (default true); region3d/UEqn.H:19-34]
+     * 1: solve(UEqn == reconstruct((sigmaK snGrad(alpha1) - ghf snGrad(rho) - snGrad(pd)) magSf)) with b200PBiCG + DILU            */
+    int32_t momentumPredictor;
+    /* laplacianSchemes / snGradSchemes `corrected` (1) or `uncorrected` (0): explicit non-orthogonal correction of
+     * fvm::laplacian(rUAf, pd) (source term + faceFluxCorrection in pdEqn.flux()) [REF region3d/pEqn.H:23-45]                     */
+    int32_t nonOrthCorrected;
+    /* [REF region3d/pEqn.H:30  pdEqn.setReference(pdRefCell, pdRefValue); create3dFields.H:227-233 setRefCell]
+     * applied only when no pd patch fixes the value (pd.needReference()); pdRefCell < 0: none                                     */
+    int32_t pdRefCell;
+    int32_t reserved0;
+    double pdRefValue;
+    double UTol, URelTol;    /* fvSolution solvers{U{tolerance; relTol}} of the momentum predictor                                 */
 } b200_region3d_controls;
 
 int b200_region3d_create(b200_mesh_t* mesh, const b200_region3d_controls* ctl, const b200_bc* bcAlpha,
@@ -239,6 +254,11 @@ int b200_region3d_get_perfs(b200_region3d_t* r, b200_solver_perf* out, int32_t c
 int b200_region3d_get_res_hist(b200_region3d_t* r, double* out, int32_t cap);
 int b200_region3d_get_alpha_stats(b200_region3d_t* r, double* out, int32_t cap);
 int b200_region3d_get_cont_errs(b200_region3d_t* r, double* out3);
+/* [REF include/CourantNoMultiRegion.H:78-92] out3 = {meanCoNum, CoNum, velMag} of the current phi, reduced on the device
+ * (gMax / gSum over ranks): the host never needs the face field */
+int b200_region3d_get_courant(b200_region3d_t* r, double* out3);
+/* restart from a saved state: set_fields + the fields derived from alpha1 that a step expects to find (rho, interface.correct()) */
+int b200_region3d_restore(b200_region3d_t* r, const double* alpha1, const double* U, const double* pd, const double* phi);
 int b200_region3d_clear_log(b200_region3d_t* r);
 
 /* ---------------------------------------------------------------- host mesh tools (integers bit-exact)

@@ -536,6 +536,12 @@ extern "C" struct OrcControls {
     int adjustPhi;       // Appendix E: adjustPhi(phiU,U,p) with calculated p => active
     int mulesIncludeOwn; // Appendix C item 2
     int divUScheme;      // div(rhoPhi,U): 2 = upwind, 3 = linear
+    int momentumPredictor;   // [REF region3d/readRegion3dPISOControls.H:9-10; UEqn.H:19-34]
+    int nonOrthCorrected;    // laplacian / snGrad `corrected` [REF region3d/pEqn.H:23-45]
+    int pdRefCell;           // [REF region3d/pEqn.H:30; create3dFields.H:227-233]  < 0: none
+    int reserved0;
+    double pdRefValue;
+    double UTol, URelTol;
 };
 
 struct Region {
@@ -554,6 +560,7 @@ struct Region {
     std::vector<OrcPerf> perfs; std::vector<double> resHist; std::vector<double> alphaStats;
     double sumLocalContErr, globalContErr, cumulativeContErr;
     double tPCG, tMULES, tOther;
+    bool pdNeedRef;   // pd.needReference() [UPSTREAM GeometricField::needReference]: no patch fixes the value
 };
 
 static void setBC(OrcBC& bc, std::vector<int>& t, vec& rv, vec& rg, vec& vf) {
@@ -605,6 +612,8 @@ extern "C" Region* orc_region_create(const OrcMesh* m, const OrcControls* ctl, c
     r->nHatf.resize(F + B); r->K.resize(N); r->Kb.resize(B);
     r->cumulativeContErr = 0;
     r->tPCG = r->tMULES = r->tOther = 0;
+    r->pdNeedRef = true;
+    for (int p = 0; p < P; p++) if (bcFixesValue(r->tPd[p]) && m->pSize[p] > 0) r->pdNeedRef = false;
     return r;
 }
 extern "C" void orc_region_destroy(Region* r) { delete r; }
@@ -664,6 +673,13 @@ static void solvePressureLike(Region* r, const OrcBC& bc, const double* gammaf, 
     const OrcMesh* m = r->m; int N = m->N, F = m->F, B = m->B;
     vec diag(N), upper(F), source(N), ic(B), bcv(B);
     orc_laplacian_assemble(m, &bc, gammaf, psib, r->phi.data(), diag.data(), upper.data(), source.data(), ic.data(), bcv.data());
+    // fvMatrix::setReference(celli, value) [REF region3d/pEqn.H:30; correctPhi.H:43] [UPSTREAM fvMatrix.C]: only when the field
+    // needs a reference level (no patch fixes its value): source[celli] += diag[celli]*value ; diag[celli] += diag[celli]
+    if (r->pdNeedRef && r->ctl.pdRefCell >= 0 && r->ctl.pdRefCell < N) {
+        int c0 = r->ctl.pdRefCell;
+        source[c0] += diag[c0] * r->ctl.pdRefValue;
+        diag[c0] += diag[c0];
+    }
     vec sdiag = diag, tsrc = source;
     orc_add_boundary(m, ic.data(), bcv.data(), sdiag.data(), tsrc.data());
     OrcPerf perf;
@@ -951,6 +967,20 @@ extern "C" int orc_region_alpha_stats(Region* r, double* out, int cap) {
     int n = (int)std::min<size_t>(cap, r->alphaStats.size());
     if (out) std::memcpy(out, r->alphaStats.data(), 8 * n);
     return (int)r->alphaStats.size();
+}
+// Courant number of the 3D region [REF include/CourantNoMultiRegion.H:78-92]: out3 = {meanCoNum, CoNum, velMag}
+// max(GeometricField) spans internal + boundary faces, sum(GeometricField) the internal field [UPSTREAM GeometricFieldFunctions]
+extern "C" void orc_region_courant(Region* r, double* out3) {
+    const OrcMesh* m = r->m; int F = m->F, B = m->B;
+    out3[0] = -1.0e15; out3[1] = 0.0; out3[2] = 0.0;
+    if (F == 0) return;
+    double sumS = 0, sumM = 0, mx = 0, vm = 0;
+    for (int f = 0; f < F + B; f++) {
+        double mp = std::fabs(r->phi[f]), sd = m->dc[f] * mp;
+        if (f < F) { sumS += sd; sumM += m->magSf[f]; }
+        mx = std::max(mx, sd / m->magSf[f]); vm = std::max(vm, mp / m->magSf[f]);
+    }
+    out3[0] = (sumS / sumM) * r->ctl.deltaT; out3[1] = mx * r->ctl.deltaT; out3[2] = vm;
 }
 extern "C" void orc_region_cont_errs(Region* r, double* out3) { out3[0] = r->sumLocalContErr; out3[1] = r->globalContErr; out3[2] = r->cumulativeContErr; }
 extern "C" void orc_region_timers(Region* r, double* out3) { out3[0] = r->tPCG; out3[1] = r->tMULES; out3[2] = r->tOther; }

@@ -40,7 +40,14 @@ class OrcControls(C.Structure):
                 ("pdTol", C.c_double), ("pdRelTol", C.c_double), ("pdFinalTol", C.c_double), ("pdFinalRelTol", C.c_double),
                 ("pcorrTol", C.c_double), ("pcorrRelTol", C.c_double),
                 ("maxIter", C.c_int), ("minIter", C.c_int),
-                ("adjustPhi", C.c_int), ("mulesIncludeOwn", C.c_int), ("divUScheme", C.c_int)]
+                ("adjustPhi", C.c_int), ("mulesIncludeOwn", C.c_int), ("divUScheme", C.c_int),
+                ("momentumPredictor", C.c_int), ("nonOrthCorrected", C.c_int), ("pdRefCell", C.c_int), ("reserved0", C.c_int),
+                ("pdRefValue", C.c_double), ("UTol", C.c_double), ("URelTol", C.c_double)]
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        if "pdRefCell" not in k:
+            self.pdRefCell = -1
 
 
 def build(force=False):
@@ -292,6 +299,11 @@ class Region:
     def timers(self):
         out = np.empty(3)
         lib().orc_region_timers(self.h, _d(out))
+        return out
+
+    def courant(self):
+        out = np.empty(3)
+        lib().orc_region_courant(self.h, _d(out))
         return out
 
     def clear_log(self):

@@ -1,0 +1,51 @@
+// plan_model.cpp -- offline cost model of the DIC sweep plan (no GPU needed): builds the channel mesh, runs buildSweepPlan with the
+// given parameters and prints the modelled critical path of a sweep,  max over tile-DAG paths of  sum(nSteps*s + o),  for the measured
+// per-step time s and publish->visible overhead o (profiles/r1e_sweep_trace.log).  Build:
+//   g++ -O2 -std=c++17 -I shallowinterfoam_b200/csrc scripts/plan_model.cpp shallowinterfoam_b200/csrc/host_mesh.cpp -o /tmp/plan_model
+// Usage: plan_model nx ny nz band maxRows smem lanes [s_ns o_ns]
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "host_mesh.h"
+using namespace b200;
+
+int main(int argc, char** argv) {
+    int nx = argc > 1 ? atoi(argv[1]) : 200, ny = argc > 2 ? atoi(argv[2]) : 50, nz = argc > 3 ? atoi(argv[3]) : 100;
+    int band = argc > 4 ? atoi(argv[4]) : 16, maxRows = argc > 5 ? atoi(argv[5]) : 4096, smem = argc > 6 ? atoi(argv[6]) : 225000;
+    int lanes = argc > 7 ? atoi(argv[7]) : 256;
+    double s = argc > 8 ? atof(argv[8]) : 126.0, o = argc > 9 ? atof(argv[9]) : 450.0;
+    PolyMesh box = makeBox(nx, ny, nz, 20.0, 5.0, 10.0);
+    PolyMesh m = subsetMesh(box, weirKeepMask(nx, ny, nz, 0.45, 0.5, 0.3), "weir");
+    int F = m.nInternalFaces();
+    SweepPlan P;
+    buildSweepPlan(m.nCells, m.owner.data(), m.neighbour.data(), F, band, maxRows, smem, lanes, P);
+    int nT = P.nTiles;
+    std::vector<int> tileOfRow(m.nCells);
+    for (int t = 0; t < nT; t++) for (int r = P.tileStart[t]; r < P.tileStart[t + 1]; r++) tileOfRow[r] = t;
+    std::vector<double> cost(nT), done(nT, 0.0);
+    long long totSteps = 0, maxSteps = 0, over16 = 0; double util = 0;
+    for (int t = 0; t < nT; t++) {
+        int ns = P.tileStepStart[t + 1] - P.tileStepStart[t];
+        cost[t] = ns * s + o; totSteps += ns; maxSteps = std::max<long long>(maxSteps, ns); if (ns > 16) over16++;
+        util += (double)(P.tileStart[t + 1] - P.tileStart[t]);
+    }
+    // tiles are in ticket (topological) order: one forward pass gives the longest path
+    std::vector<std::vector<int>> preds(nT);
+    for (int f = 0; f < F; f++) {
+        int a = tileOfRow[P.cellRow[m.owner[f]]], b = tileOfRow[P.cellRow[m.neighbour[f]]];
+        if (a != b) preds[b].push_back(a);
+    }
+    double crit = 0; int maxHalo = 0;
+    for (int t = 0; t < nT; t++) {
+        double start = 0;
+        for (int a : preds[t]) start = std::max(start, done[a]);
+        done[t] = start + cost[t];
+        crit = std::max(crit, done[t]);
+        maxHalo = std::max(maxHalo, P.fwdHalo[t + 1] - P.fwdHalo[t]);
+    }
+    printf("N %d levels %d | band %d maxRows %d lanes %d binJ %d binK %d | tiles %d tileLevels %d | steps/tile mean %.1f max %lld (>16: %lld) lane-util %.2f | smem %zu maxHalo %d | model crit path %.1f us (s=%.0f ns, o=%.0f ns)\n",
+           m.nCells, P.nLevels, band, maxRows, lanes, P.binJ, P.binK, nT, P.nTileLevels, (double)totSteps / nT, maxSteps, over16,
+           util / ((double)totSteps * lanes), std::max(P.smemFwd, P.smemBwd), maxHalo, crit / 1000.0, s, o);
+    return 0;
+}

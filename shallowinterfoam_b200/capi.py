@@ -30,7 +30,7 @@ EXPORTS = [
     "b200_region3d_step_host", "b200_region3d_get_fields", "b200_region3d_set_fields",
     "b200_region3d_set_patch_mixed", "b200_region3d_get_patch_internal", "b200_region3d_num_solves",
     "b200_region3d_get_perfs", "b200_region3d_get_res_hist", "b200_region3d_get_alpha_stats",
-    "b200_region3d_get_cont_errs", "b200_region3d_clear_log",
+    "b200_region3d_get_cont_errs", "b200_region3d_clear_log", "b200_region3d_get_courant", "b200_region3d_restore", "b200_ldu_invalidate",
     "b200_polymesh_box", "b200_polymesh_box_weir", "b200_polymesh_jitter", "b200_polymesh_agglomerate", "b200_polymesh_release", "b200_polymesh_sizes",
     "b200_polymesh_get", "b200_polymesh_patch_name", "b200_polymesh_geometry", "b200_decompose_simple",
     "b200_polymesh_submesh", "b200_polymesh_submesh_maps", "b200_mesh_create_from_polymesh",
@@ -75,7 +75,14 @@ class Region3dControls(C.Structure):
                 ("pdTol", C.c_double), ("pdRelTol", C.c_double), ("pdFinalTol", C.c_double), ("pdFinalRelTol", C.c_double),
                 ("pcorrTol", C.c_double), ("pcorrRelTol", C.c_double),
                 ("maxIter", C.c_int32), ("minIter", C.c_int32),
-                ("adjustPhi", C.c_int32), ("mulesIncludeOwn", C.c_int32), ("divUScheme", C.c_int32)]
+                ("adjustPhi", C.c_int32), ("mulesIncludeOwn", C.c_int32), ("divUScheme", C.c_int32),
+                ("momentumPredictor", C.c_int32), ("nonOrthCorrected", C.c_int32), ("pdRefCell", C.c_int32), ("reserved0", C.c_int32),
+                ("pdRefValue", C.c_double), ("UTol", C.c_double), ("URelTol", C.c_double)]
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        if "pdRefCell" not in k:
+            self.pdRefCell = -1
 
 
 def f64(a):
@@ -500,6 +507,16 @@ class Region3D:
 
     def clear_log(self):
         self.lib.check(self.lib.c.b200_region3d_clear_log(self.h))
+
+    def courant(self):
+        """(meanCoNum, CoNum, velMag) of the current phi, reduced on the device"""
+        out = np.empty(3)
+        self.lib.check(self.lib.c.b200_region3d_get_courant(self.h, _d(out)))
+        return out
+
+    def restore(self, alpha1, U, pd, phi):
+        """restart from saved fields: set_fields + rho + interface.correct()"""
+        self.lib.check(self.lib.c.b200_region3d_restore(self.h, _d(f64(alpha1)), _d(f64(U).reshape(-1)), _d(f64(pd)), _d(f64(phi))))
 
 
 _LIB = None

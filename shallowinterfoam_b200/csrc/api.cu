@@ -12,6 +12,25 @@ using namespace b200;
 static thread_local std::string g_lastError;
 static std::map<const void*, DeviceMesh*> g_registry;
 
+// FNV-1a over the addressing a cache entry was built from: a hit whose arrays hash differently (mesh motion / topology change rebuilt
+// the lduAddressing at the same address) is rebuilt instead of being trusted
+static uint64_t fnv1a(uint64_t h, const void* p, size_t n) {
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+static uint64_t addressingHash(int32_t nCells, int32_t nFaces, const int32_t* lower, const int32_t* upper, int32_t nPatches,
+                               const b200_patch_desc* patches) {
+    uint64_t h = 1469598103934665603ull;
+    h = fnv1a(h, &nCells, 4); h = fnv1a(h, &nFaces, 4); h = fnv1a(h, &nPatches, 4);
+    if (nFaces) { h = fnv1a(h, lower, 4 * (size_t)nFaces); h = fnv1a(h, upper, 4 * (size_t)nFaces); }
+    for (int p = 0; p < nPatches; p++) {
+        h = fnv1a(h, &patches[p].nFaces, 4); h = fnv1a(h, &patches[p].neighbRank, 4);
+        if (patches[p].nFaces) h = fnv1a(h, patches[p].faceCells, 4 * (size_t)patches[p].nFaces);
+    }
+    return h;
+}
+
 #define API_BEGIN try {
 #define API_END                                                      \
     return B200_OK;                                                  \
@@ -115,12 +134,16 @@ int b200_ldu_get_or_create(const void* key, int32_t nCells, int32_t nFaces, cons
     API_BEGIN
     requireDevice();
     B200_REQUIRE(out && nCells >= 0 && nFaces >= 0 && (nFaces == 0 || (lower && upper)), B200_ERR_ARG, "b200_ldu_get_or_create: bad arguments");
+    const uint64_t hash = addressingHash(nCells, nFaces, lower, upper, nPatches, patches);
     if (key) {
         auto it = g_registry.find(key);
         if (it != g_registry.end()) {
-            B200_REQUIRE(it->second->N == nCells && it->second->F == nFaces, B200_ERR_STATE, "lduAddressing key reused with different sizes");
-            *out = reinterpret_cast<b200_ldu_t*>(it->second);
-            return B200_OK;
+            if (it->second->addrHash == hash) {
+                *out = reinterpret_cast<b200_ldu_t*>(it->second);
+                return B200_OK;
+            }
+            delete it->second;          // same address, different addressing: the mesh changed under the key
+            g_registry.erase(it);
         }
     }
     std::vector<Patch> pt; std::vector<int32_t> fc;
@@ -133,7 +156,7 @@ int b200_ldu_get_or_create(const void* key, int32_t nCells, int32_t nFaces, cons
     }
     std::unique_ptr<DeviceMesh> m(new DeviceMesh());
     m->build(nCells, nFaces, lower, upper, pt, fc);
-    m->key = key;
+    m->key = key; m->addrHash = hash;
     DeviceMesh* raw = m.release();
     if (key) g_registry[key] = raw;
     *out = reinterpret_cast<b200_ldu_t*>(raw);
@@ -143,6 +166,12 @@ int b200_ldu_release(b200_ldu_t* ldu) {
     API_BEGIN
     DeviceMesh* m = asMesh(ldu);
     if (m) { if (m->key) g_registry.erase(m->key); delete m; }
+    API_END
+}
+int b200_ldu_invalidate(const void* key) {
+    API_BEGIN
+    auto it = g_registry.find(key);
+    if (it != g_registry.end()) { delete it->second; g_registry.erase(it); }
     API_END
 }
 int b200_ldu_get_renumbering(const b200_ldu_t* ldu, int32_t* rowCell, int32_t* cellLevel, int32_t* nLevels) {
@@ -711,6 +740,20 @@ int b200_region3d_get_cont_errs(b200_region3d_t* rr, double* out3) {
     API_BEGIN
     Region3D& r = *asRegion(rr);
     out3[0] = r.sumLocalContErr; out3[1] = r.globalContErr; out3[2] = r.cumulativeContErr;
+    API_END
+}
+int b200_region3d_get_courant(b200_region3d_t* rr, double* out3) {
+    API_BEGIN
+    B200_REQUIRE(rr && out3, B200_ERR_ARG, "b200_region3d_get_courant: null argument");
+    asRegion(rr)->courant(out3);
+    API_END
+}
+int b200_region3d_restore(b200_region3d_t* rr, const double* alpha1, const double* U, const double* pd, const double* phi) {
+    API_BEGIN
+    B200_REQUIRE(rr && alpha1 && U && pd && phi, B200_ERR_ARG, "b200_region3d_restore: null argument");
+    int rc = b200_region3d_set_fields(rr, alpha1, U, pd, phi);
+    if (rc != B200_OK) return rc;
+    asRegion(rr)->refreshDerived();
     API_END
 }
 int b200_region3d_clear_log(b200_region3d_t* rr) {

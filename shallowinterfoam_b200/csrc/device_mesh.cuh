@@ -68,6 +68,7 @@ struct SweepView {
     const int *fwdPos, *bwdPos;              // face slot of each coefficient entry of the operand blocks (-1 = padding)
     const int *fwdHaloRow, *bwdHaloRow;      // device rows a tile polls
     int pollNs;                              // back-off between polls of a not-yet-published halo value
+    int regOps;                              // 1 (default): tiles with <= 3 sources per row and <= 16 steps keep their operands in registers (dic_kernels.cuh)
     int publishMode;                         // 0: one TMA bulk store per tile after its last step; 1 (default): rows are stored in the step that computes them
     unsigned long long* trace;               // debug: [8*nTiles] globaltimer stamps per tile (ticket, staged, halo ready, steps done, published) or null
 };
@@ -104,6 +105,7 @@ struct DeviceMesh {
     std::shared_ptr<void> fvHolder;        // FvWorkspace (region3d.cu)
     std::vector<double> hostV;             // cell volumes, original order (deltaN of interfaceProperties)
     const void* key = nullptr;
+    uint64_t addrHash = 0;                 // hash of the addressing this cache was built from (api.cu registry validation)
 
     ~DeviceMesh();
     void build(int32_t nCells, int32_t nFaces, const int32_t* lower, const int32_t* upper,
@@ -112,7 +114,7 @@ struct DeviceMesh {
                      const double* w, const double* dc);
     MeshView view() const;
     SweepView sweep() const {
-        return SweepView{nTiles, dTilesF.p, dTilesB.p, dStepRow.p, dStepLen.p, plan.lanes, dFwdPos.p, dBwdPos.p, dFwdHaloRow.p, dBwdHaloRow.p, (int)rt().opt("sweep_poll_ns", 0), (int)rt().opt("sweep_publish", 1),
+        return SweepView{nTiles, dTilesF.p, dTilesB.p, dStepRow.p, dStepLen.p, plan.lanes, dFwdPos.p, dBwdPos.p, dFwdHaloRow.p, dBwdHaloRow.p, (int)rt().opt("sweep_poll_ns", 0), (int)rt().opt("sweep_reg_ops", 1), (int)rt().opt("sweep_publish", 1),
                          rt().opt("sweep_trace", 0) > 0 ? dTrace.p : nullptr};
     }
     void coupleGeometry();   // collective: processor-face weights/deltaCoeffs/neighbour centres from a halo swap of C

@@ -185,6 +185,63 @@ __device__ __forceinline__ void sweepStepsD(const TileSmem& s, const SweepTile& 
         c0 = n0; c1 = n1; c2 = n2; w = nw; pk = npk; slot = nslot;
     }
 }
+// ---- register-resident operands (the default for tiles with 1..3 sources per row and at most SWEEP_REG_STEPS steps: every hex mesh).
+// Per step the shared-memory loop above moves 72 bytes per row through the SM's 128 B/clk shared-memory pipe (3 sources, 3 coefficients,
+// the packed offsets, the next start value, the result): 256 rows x 72 B = 144 cycles, more than the dependent-instruction chain of the
+// step.  Coefficients and offsets are constant while the tile runs, so each thread loads those of ITS rows (one per step) straight from
+// global memory into registers when it takes the tile -- before the halo wait, off the critical path -- and the step loop, fully
+// unrolled, touches shared memory only for the three source values, the start value and the result (40 B per row).  Tiles with fewer
+// than three sources carry zero coefficients that point at the padding slot (w - 0*1 = w exactly): one code path for d = 1..3.
+constexpr int SWEEP_REG_STEPS = 16;
+struct RegOps { double c[SWEEP_REG_STEPS][3]; uint2 pk[SWEEP_REG_STEPS]; };
+#ifdef B200_EMU
+__device__ __forceinline__ double ldgStream(const double* p) { return *p; }
+__device__ __forceinline__ uint2 ldgStream(const uint2* p) { return *p; }
+#else
+__device__ __forceinline__ double ldgStream(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ uint2 ldgStream(const uint2* p) { return __ldcs(p); }
+#endif
+// register index `it` = the it-th step in processing order (DIR < 0: the tile's steps downwards)
+template <int DIR>
+__device__ __forceinline__ void loadRegOps(RegOps& o, const double* __restrict__ blk, const SweepTile& t) {
+    const int W = blockDim.x, S = t.nSteps * W;
+    const uint2* PK = (const uint2*)(blk + t.d * S);
+#pragma unroll
+    for (int it = 0; it < SWEEP_REG_STEPS; it++) {
+        const bool on = it < t.nSteps;
+        const int slot = (on ? (DIR > 0 ? it : t.nSteps - 1 - it) * W : 0) + (int)threadIdx.x;
+        o.c[it][0] = on ? ldgStream(blk + slot) : 0.0;
+        o.c[it][1] = (on && t.d > 1) ? ldgStream(blk + S + slot) : 0.0;
+        o.c[it][2] = (on && t.d > 2) ? ldgStream(blk + 2 * S + slot) : 0.0;
+        o.pk[it] = on ? ldgStream(PK + slot) : make_uint2(0u, 0u);
+    }
+}
+template <int DIR>
+__device__ __forceinline__ void sweepStepsReg(const TileSmem& s, const SweepTile& t, const RegOps& o, double* out) {
+    const unsigned rowBytes = 8u * (unsigned)t.nRows;
+    char* outB = (char*)(out + t.row0);
+    double w = ldsAt(s.vals, o.pk[0].y >> 16);
+#pragma unroll
+    for (int it = 0; it < SWEEP_REG_STEPS; it++) {
+        if (it < t.nSteps) {   // (uniform: no divergence; the unrolled body indexes the register arrays statically)
+            const uint2 pk = o.pk[it];
+            const double v0 = ldsAt(s.vals, pk.x & 0xffffu);
+            const double v1 = ldsAt(s.vals, pk.x >> 16);
+            const double v2 = ldsAt(s.vals, pk.y & 0xffffu);
+            // the next step's own rows still hold their start values
+            const int nit = it + 1 < SWEEP_REG_STEPS ? it + 1 : it;   // (compile-time after unrolling)
+            const double nw = (nit != it && nit < t.nSteps) ? ldsAt(s.vals, o.pk[nit].y >> 16) : 0.0;
+            w = w - o.c[it][0] * v0; w = w - o.c[it][1] * v1; w = w - o.c[it][2] * v2;
+            stsAt(s.vals, pk.y >> 16, w);
+            if (out && (pk.y >> 16) < rowBytes) stWeak((double*)(outB + (pk.y >> 16)), w);
+            __syncthreads();
+            w = nw;
+        }
+    }
+}
+__device__ __forceinline__ bool tileUsesRegOps(const SweepView& sv, const SweepTile& t) {
+    return sv.regOps && t.d >= 1 && t.d <= 3 && t.nSteps >= 1 && t.nSteps <= SWEEP_REG_STEPS;
+}
 template <int OP, int DIR>
 __device__ __forceinline__ bool sweepSteps(const TileSmem& s, const SweepTile& t, const int* sRow, const int* sLen, double* out) {
     if (t.nSteps == 0) return false;
@@ -272,9 +329,13 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
     // all static during the iterations of a solve.  Nothing the previous kernel writes is touched before pdlWait().
     int ti = nextTicket(ctl);
     SweepTile t; TileSmem s;
+    RegOps ro;
+    bool viaReg = false;   // this tile's operands live in registers (no TMA staging in flight)
     if (ti < sv.nTiles) {
         t = sv.fwd[ti]; s = carveTile(smem, t, W);
-        stageBlock(s, t, blocks, &sBar, false);   // MODE 1: the coefficient columns hold the plain upper coefficients (k_dic_coeffs, rD = null)
+        viaReg = MODE == 0 && tileUsesRegOps(sv, t);
+        if (viaReg) loadRegOps<1>(ro, blocks + t.blk, t);
+        else stageBlock(s, t, blocks, &sBar, false);   // MODE 1: the coefficient columns hold the plain upper coefficients (k_dic_coeffs, rD = null)
     }
     pdlWait();
     pdlTrigger();
@@ -293,7 +354,7 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
         }
     }
     if (quit) {   // hand the ticket back (the last CTA to leave resets the counter) once the staging copy has landed
-        if (ti < sv.nTiles) barWait(&sBar, phase);
+        if (ti < sv.nTiles && !viaReg) barWait(&sBar, phase);
         sweepExit(ctl);
         return;
     }
@@ -302,10 +363,11 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
         const int n = t.nRows;
         // 1. row-independent operands: the operand block by TMA bulk copy (already on its way), start values by batched loads
         double mag = 0.0;
-        for (int r0 = tid; r0 < n; r0 += 8 * W) {
-            double a[8], b[8], wa[8], xv[8], pv[8];
+        constexpr int SU = MODE == 0 ? 4 : 8;   // loads in flight per thread (MODE 0 shares the register file with the tile's operands)
+        for (int r0 = tid; r0 < n; r0 += SU * W) {
+            double a[SU], b[SU], wa[SU], xv[SU], pv[SU];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
+            for (int k = 0; k < SU; k++) {
                 int r = r0 + k * W;
                 if (r < n) {
                     a[k] = a0[t.row0 + r]; b[k] = (MODE == 0) ? a1[t.row0 + r] : 1.0;
@@ -313,7 +375,7 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
+            for (int k = 0; k < SU; k++) {
                 int r = r0 + k * W;
                 if (r < n) {
                     if (upd) { fz.x[t.row0 + r] = xv[k] + alpha * pv[k]; b[k] = b[k] - alpha * wa[k]; fz.rA[t.row0 + r] = b[k]; }
@@ -328,11 +390,13 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
         // 2. external inputs
         if (sv.trace) { __syncthreads(); SWEEP_TRACE(1); }
         pollHalo(t, s, sv.fwdHaloRow, y, sv.pollNs);
-        barWait(&sBar, phase); phase ^= 1u;
+        if (!viaReg) { barWait(&sBar, phase); phase ^= 1u; }
         __syncthreads();
         SWEEP_TRACE(2);
         // 3. the steps, then publish
-        const bool inLoop = sweepSteps<MODE, 1>(s, t, sRow, sLen, sv.publishMode == 1 ? y : nullptr);
+        bool inLoop;
+        if (viaReg) { sweepStepsReg<1>(s, t, ro, sv.publishMode == 1 ? y : nullptr); inLoop = sv.publishMode == 1; }
+        else inLoop = sweepSteps<MODE, 1>(s, t, sRow, sLen, sv.publishMode == 1 ? y : nullptr);
         if (sv.publishMode == 0) {
             fenceAsyncProxy();    // this thread's results, for the TMA store below (writers fence, barrier, one thread stores)
             __syncthreads();
@@ -346,7 +410,11 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
         if (sv.publishMode == 0 && tid == 0) bulkStoreWaitRead();   // the value array is reused by the next tile
         SWEEP_TRACE(4);
         ti = nextTicket(ctl);
-        if (ti < sv.nTiles) { t = sv.fwd[ti]; s = carveTile(smem, t, W); stageBlock(s, t, blocks, &sBar, false); }
+        if (ti < sv.nTiles) {
+            t = sv.fwd[ti]; s = carveTile(smem, t, W);
+            viaReg = MODE == 0 && tileUsesRegOps(sv, t);
+            if (viaReg) loadRegOps<1>(ro, blocks + t.blk, t); else stageBlock(s, t, blocks, &sBar, false);
+        }
     }
     if (threadIdx.x == 0) bulkStoreWaitAll();   // this CTA's TMA stores must have landed before the kernel ends
     if (fused) {
@@ -373,11 +441,17 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
     // prologue (PDL, see k_dic_fwd): first ticket, descriptor, operand block
     int tk = nextTicket(ctl), ti = sv.nTiles - 1 - tk;
     SweepTile t; TileSmem s;
-    if (tk < sv.nTiles) { t = sv.bwd[ti]; s = carveTile(smem, t, W); stageBlock(s, t, blocks, &sBar, false); }
+    RegOps ro;
+    bool viaReg = false;
+    if (tk < sv.nTiles) {
+        t = sv.bwd[ti]; s = carveTile(smem, t, W);
+        viaReg = tileUsesRegOps(sv, t);
+        if (viaReg) loadRegOps<-1>(ro, blocks + t.blk, t); else stageBlock(s, t, blocks, &sBar, false);
+    }
     pdlWait();
     pdlTrigger();
     if (sc && sc->stop) {
-        if (tk < sv.nTiles) barWait(&sBar, phase);
+        if (tk < sv.nTiles && !viaReg) barWait(&sBar, phase);
         sweepExit(ctl);
         return;
     }
@@ -393,9 +467,11 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
         stageSteps(sv, t, sRow, sLen);
         if (tid == 0) { s.vals[n + t.nHalo] = 1.0; s.vals[n + t.nHalo + 1] = 0.0; }
         pollHalo(t, s, sv.bwdHaloRow, z, sv.pollNs);
-        barWait(&sBar, phase); phase ^= 1u;
+        if (!viaReg) { barWait(&sBar, phase); phase ^= 1u; }
         __syncthreads();
-        const bool inLoop = sweepSteps<0, -1>(s, t, sRow, sLen, sv.publishMode == 1 ? z : nullptr);
+        bool inLoop;
+        if (viaReg) { sweepStepsReg<-1>(s, t, ro, sv.publishMode == 1 ? z : nullptr); inLoop = sv.publishMode == 1; }
+        else inLoop = sweepSteps<0, -1>(s, t, sRow, sLen, sv.publishMode == 1 ? z : nullptr);
         if (sv.publishMode == 0) {
             fenceAsyncProxy();
             __syncthreads();
@@ -409,7 +485,11 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
         }
         if (sv.publishMode == 0 && tid == 0) bulkStoreWaitRead();
         tk = nextTicket(ctl); ti = sv.nTiles - 1 - tk;
-        if (tk < sv.nTiles) { t = sv.bwd[ti]; s = carveTile(smem, t, W); stageBlock(s, t, blocks, &sBar, false); }
+        if (tk < sv.nTiles) {
+            t = sv.bwd[ti]; s = carveTile(smem, t, W);
+            viaReg = tileUsesRegOps(sv, t);
+            if (viaReg) loadRegOps<-1>(ro, blocks + t.blk, t); else stageBlock(s, t, blocks, &sBar, false);
+        }
     }
     if (threadIdx.x == 0) bulkStoreWaitAll();
     if (partials) gridFinalize<1, OpSum>(sv.nTiles, partials, counter, dotOut);

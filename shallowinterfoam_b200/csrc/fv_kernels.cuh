@@ -647,4 +647,49 @@ static __global__ void k_alpha_stats(MeshView mv, const double* __restrict__ a, 
     if (threadIdx.x == 0) { out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3; }
 }
 
+// ---- a11: fvMatrix::setReference [REF region3d/pEqn.H:30] [UPSTREAM fvMatrix.C setReference]:
+//   source[celli] += diag[celli]*value ; diag[celli] += diag[celli]   (before addBoundaryDiag / addBoundarySource)
+static __global__ void k_set_reference(int row, double value, double* __restrict__ diag, double* __restrict__ source) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { double d = diag[row]; source[row] = source[row] + d * value; diag[row] = d + d; }
+}
+
+// ---- f3: Courant number [REF include/CourantNoMultiRegion.H:78-92]: SfUfbyDelta = deltaCoeffs*|phi| ;
+//   out = {sum(SfUfbyDelta) over internal faces, sum(magSf) over internal faces, max(SfUfbyDelta/magSf), max(|phi|/magSf)}
+//   (max(GeometricField) takes internal and boundary faces, sum(GeometricField) the internal field only [UPSTREAM GeometricFieldFunctions])
+static __global__ void k_courant(MeshView mv, const double* __restrict__ phi, double* out /*[4]*/, double* partials, unsigned* counter) {
+    ROW_PROLOGUE(mv)
+    double v[2] = {0.0, 0.0}, m0 = 0.0, m1 = 0.0;
+    if (row < mv.N) {
+        FOR_OWN_FACES(mv, s, lane, pos, u)
+            (void)u;
+            double mp = fabs(phi[pos]), ms = mv.magSf[pos], sd = mv.dc[pos] * mp;
+            v[0] = v[0] + sd; v[1] = v[1] + ms;
+            m0 = fmax(m0, sd / ms); m1 = fmax(m1, mp / ms);
+        END_FACES
+    }
+    if (row < mv.B) {
+        int p = mv.Fs + row;
+        double mp = fabs(phi[p]), ms = mv.magSf[p];
+        m0 = fmax(m0, mv.dc[p] * mp / ms); m1 = fmax(m1, mp / ms);
+    }
+    gridReduce<2, OpSum>(v, blockIdx.x, gridDim.x, partials, counter, nullptr);
+    double w[2] = {m0, m1};
+    gridReduce<2, OpMax>(w, blockIdx.x, gridDim.x, partials + 2 * (size_t)gridDim.x, counter, nullptr);
+    __shared__ double sh[32];
+    __shared__ int isLast;
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); unsigned t = atomicInc(counter, gridDim.x - 1); isLast = (t == gridDim.x - 1); }
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    const volatile double* vp = partials;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x) {
+        a0 += vp[2 * (size_t)j]; a1 += vp[2 * (size_t)j + 1];
+        a2 = fmax(a2, vp[2 * (size_t)gridDim.x + 2 * (size_t)j]); a3 = fmax(a3, vp[2 * (size_t)gridDim.x + 2 * (size_t)j + 1]);
+    }
+    a0 = blockReduce<OpSum>(a0, sh); a1 = blockReduce<OpSum>(a1, sh); a2 = blockReduce<OpMax>(a2, sh); a3 = blockReduce<OpMax>(a3, sh);
+    if (threadIdx.x == 0) { out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3; }
+}
+
 }  // namespace b200

@@ -128,6 +128,9 @@ void dicPrecondition(DeviceMesh& m, const double* rD, const double* upS, const d
     PcgWorkspace& w = pcgWorkspace(m);
     if (!m.N) return;
     w.keptValid = false;
+    // y / z double as ready flags (NaN sentinel = not yet published).  A PCG solve that stopped leaves whichever sweep ran last fully
+    // populated (the kernels after the stop flag return at once and never re-arm it), so every entry point re-arms both first.
+    fillSentinel(w.y, m.N); fillSentinel(w.z, m.N);
     { ScopedTimer t(T_DIC_RD); launchCoeffs(m, w, rD, upS); }
     { ScopedTimer t(T_DIC_FWD); launchFwd(m, w, rD, rA, nullptr); }
     { ScopedTimer t(T_DIC_BWD); launchBwd(m, w, rA, nullptr, nullptr, nullptr); }
@@ -175,7 +178,8 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
     if (N) {
         ScopedTimer t(T_DIC_RD);
         const PcgScalars* gate = launchMatrixGate(m, w, diag, upS);
-        launchCalcRD(m, w, diag, upS, w.rD.p, gate); launchCoeffs(m, w, w.rD.p, upS, gate); fillSentinel(w.y, N);
+        launchCalcRD(m, w, diag, upS, w.rD.p, gate); launchCoeffs(m, w, w.rD.p, upS, gate);
+        fillSentinel(w.y, N); fillSentinel(w.z, N);   // re-arm both ready-flag vectors (see dicPrecondition): the previous solve's stop path left one dirty
     }
     B200_CHECK_CUDA(cudaEventSynchronize(w.ev[0]));
     bool stopped = w.hsc[0].stop != 0;

@@ -559,6 +559,20 @@ void Region3D::create(DeviceMesh* mesh, const b200_region3d_controls& c, const b
         sV = h2[0]; nGlobal = h2[1];
     }
     deltaN = 1e-8 / std::pow(sV / nGlobal, 1.0 / 3.0);
+    // pd.needReference(): true when no patch fixes the value on any rank; the reference cell label is local (every rank that holds a
+    // cell with that label applies it, which is what setRefCell's label form does under decomposition) [REF create3dFields.H:227-233]
+    {
+        double anyFixes = 0.0;
+        for (size_t p = 0; p < m->patches.size(); p++) if (bcPd.fixes((int)p) && m->patches[p].size > 0) anyFixes = 1.0;
+        if (rt().nRanks > 1) {
+            B200_CHECK_CUDA(cudaMemcpyAsync(scal.p + 42, &anyFixes, 8, cudaMemcpyHostToDevice, st));
+            allReduce(scal.p + 42, 1, RED_MAX);
+            B200_CHECK_CUDA(cudaMemcpyAsync(&anyFixes, scal.p + 42, 8, cudaMemcpyDeviceToHost, st));
+            syncStream();
+        }
+        pdNeedRef = anyFixes == 0.0;
+        refRow = (c.pdRefCell >= 0 && c.pdRefCell < m->N) ? m->cellRow[c.pdRefCell] : -1;
+    }
     calculateK();   // interfaceProperties constructor [REF region3d/create3dFields.H:254-263]
     syncStream();
 }
@@ -638,6 +652,8 @@ void Region3D::solvePressureLike(const DevBC& bc, const double* gammaf, double* 
     int N = m->N, B = m->B, nmax = std::max(std::max(N, B), 1);
     { ScopedTimer t(T_ASSEMBLY);
       B200_LAUNCH(k_lap_row, gridFor(N), BLOCK, st, mv, gammaf, (const double*)phi.p, pdDiag.p, pdUpper.p, pdSource.p);
+      // pdEqn.setReference(pdRefCell, pdRefValue) [REF region3d/pEqn.H:30; correctPhi.H:43]
+      if (pdNeedRef && refRow >= 0) B200_LAUNCH(k_set_reference, 1, 32, st, refRow, ctl.pdRefValue, pdDiag.p, pdSource.p);
       if (B) {
           B200_LAUNCH(k_lap_boundary, gridFor(B), BLOCK, st, mv, bc.view(), gammaf, (const double*)psib, ic.p, bcv.p);
           B200_LAUNCH(k_add_boundary, gridFor(m->nBRows), BLOCK, st, mv, (const double*)ic.p, (const double*)bcv.p, pdDiag.p, pdSource.p, m->nBRows,
@@ -653,6 +669,30 @@ void Region3D::solvePressureLike(const DevBC& bc, const double* gammaf, double* 
       if (subtractFlux)
           B200_LAUNCH(k_matrix_flux<true>, gridFor(nmax), BLOCK, st, mv, (const double*)pdUpper.p, (const double*)pdUpper.p, (const double*)ic.p,
                       (const double*)bcv.p, (const double*)psi, (const double*)psib, phi.p); }
+}
+
+// [REF include/CourantNoMultiRegion.H:78-92]
+void Region3D::courant(double* out3) {
+    FvWorkspace& w = fvWorkspace(*m);
+    cudaStream_t st = rt().stream;
+    int nmax = std::max(std::max(m->N, m->B), 1);
+    B200_LAUNCH(k_courant, gridFor(nmax), BLOCK, st, m->view(), (const double*)phi.p, scal.p + 44, w.partials.p, w.counter.p);
+    if (rt().nRanks > 1) { allReduce(scal.p + 44, 2, RED_SUM); allReduce(scal.p + 46, 2, RED_MAX); }
+    double h[4];
+    B200_CHECK_CUDA(cudaMemcpyAsync(h, scal.p + 44, 32, cudaMemcpyDeviceToHost, st));
+    syncStream();
+    // mesh.nInternalFaces() == 0: the reference leaves meanCoNum = -GREAT, CoNum unchanged (0), velMag = 0
+    bool any = h[1] > 0.0;
+    out3[0] = any ? (h[0] / h[1]) * ctl.deltaT : -1.0e15;
+    out3[1] = any ? h[2] * ctl.deltaT : 0.0;
+    out3[2] = any ? h[3] : 0.0;
+}
+
+void Region3D::refreshDerived() {
+    int N = m->N, B = m->B, nmax = std::max(std::max(N, B), 1);
+    B200_LAUNCH(k_rho, gridFor(nmax), BLOCK, rt().stream, N, B, (const double*)alpha.p, (const double*)alphab.p, ctl.rho1, ctl.rho2, rho.p, rhob.p);
+    calculateK();
+    syncStream();
 }
 
 // [REF region3d/correctPhi.H]

@@ -58,6 +58,8 @@ struct Region3D {
     std::vector<double> resHist, alphaStats;
     std::vector<size_t> pendingStats;
     bool keepHist = true;
+    bool pdNeedRef = false;      // pd.needReference(): no patch of pd fixes the value, on any rank  [UPSTREAM GeometricField::needReference]
+    int refRow = -1;             // device row of pdRefCell (-1: not on this rank / none)
     double sumLocalContErr = 0, globalContErr = 0, cumulativeContErr = 0;
 
     ~Region3D();
@@ -72,6 +74,8 @@ struct Region3D {
     void correctPhi();
     void step();
     void resolveStats();
+    void courant(double* out3);                             // {meanCoNum, CoNum, velMag} [REF include/CourantNoMultiRegion.H:78-92]
+    void refreshDerived();                                  // rho and interface.correct() from the current alpha1 (restart)
     bool coupled() const;                                   // nRanks > 1 and the mesh has processor patches
     void haloScalar(const double* cellField, double* bdst);  // patchNeighbourField of processor faces -> bdst[b]
     void evalPdBC(const DevBC& bc, const double* psi, double* psib);

@@ -88,6 +88,15 @@ def main():
     assert pg.nIterations == po["nIterations"], (pg.nIterations, po["nIterations"])
     assert np.allclose(hg, ho, rtol=1e-8, atol=1e-13 * ho[0])
     assert np.abs(xg - xo[rank]).max() <= 1e-10 * np.abs(xo[rank]).max()
+    # a SECOND solve on the same handle (PISO correctors 2, 3 ...): the first one stopped after a backward sweep and left the
+    # ready-flag vector z populated; stale halo values must not be taken for published ones
+    b2 = rng.uniform(-1, 1, gm.N)
+    xg2, pg2, hg2 = ldu.pcg_solve(d, u, xo[rank], b2[pm.cellMap], tol=1e-9, maxIter=300, bou=bou)
+    xo2, po2, ho2 = mro.pcg_solve_multi(osubs, [m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats],
+                                        [v.copy() for v in xo], [b2[s.cellMap] for s in subs], tol=1e-9, maxIter=300)
+    assert pg2.nIterations == po2["nIterations"], (pg2.nIterations, po2["nIterations"])
+    assert np.allclose(hg2, ho2, rtol=1e-8, atol=1e-13 * ho2[0])
+    assert np.abs(xg2 - xo2[rank]).max() <= 1e-10 * np.abs(xo2[rank]).max()
     xs, ps, hs = fo.pcg_solve(gm, diag, upper, np.zeros(gm.N), b, tol=1e-9, maxIter=300)
     assert np.abs(xg - xs[pm.cellMap]).max() <= 1e-6 * np.abs(xs).max()      # same solution, different (rank-local) preconditioner
 

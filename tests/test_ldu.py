@@ -168,7 +168,34 @@ def test_dic_tiling_variants_bitwise(lib, oracle, band, rows, smem, lanes):
         xo, po, ho = oracle.pcg_solve(m, diag, upper, np.zeros(m.N), b, tol=1e-9, maxIter=300)
         xg, pg, hg = ldu.pcg_solve(diag, upper, np.zeros(m.N), b, tol=1e-9, maxIter=300)
         assert pg.nIterations == po.nIterations and np.allclose(hg, ho, rtol=1e-8, atol=1e-13 * ho[0])
+        # a converged solve leaves one of the ready-flag vectors (y / z) populated; the next entry point must re-arm them
+        # (stale halo values would be taken for published ones): precondition and a second solve on the same handle
+        assert np.array_equal(w, ldu.dic_precondition(rD, upper, rA))
+        xg2, pg2, hg2 = ldu.pcg_solve(diag, upper, np.zeros(m.N), b, tol=1e-9, maxIter=300)
+        assert pg2.nIterations == pg.nIterations and np.array_equal(hg2, hg) and np.array_equal(xg2, xg)
         ldu.release()
     finally:
         lib.set_option("sweep_band_levels", 16); lib.set_option("sweep_tile_rows", 4096); lib.set_option("sweep_smem_bytes", 225000)
         lib.set_option("sweep_threads", 256)
+
+
+def test_registry_key_reuse_with_new_addressing_rebuilds(lib, oracle):
+    """the device cache is keyed by the address of the lduAddressing; when the mesh changes under the same address the entry is
+    validated by a hash of lower/upper/faceCells and rebuilt, and b200_ldu_invalidate drops it explicitly"""
+    import ctypes as C
+    key = 0x5151
+    pm1 = lib.polymesh_box(6, 4, 3, 1.0, 1.0, 1.0)
+    pm2 = lib.polymesh_box(4, 6, 3, 1.0, 1.0, 1.0)          # same cell and face counts, different addressing
+    assert pm1.nCells == pm2.nCells and pm1.nInternalFaces == pm2.nInternalFaces
+    l1 = pm1.ldu(key=key)
+    l1b = pm1.ldu(key=key)
+    assert l1.h.value == l1b.h.value                         # cache hit
+    l2 = pm2.ldu(key=key)                                    # same key, other addressing: rebuilt, not trusted
+    m2 = oracle_mesh_of(pm2)
+    diag, upper = random_spd(m2, seed=3)
+    psi = np.random.default_rng(1).uniform(0, 1, m2.N)
+    assert np.array_equal(oracle.amul(m2, diag, upper, upper, psi), l2.amul(diag, upper, psi))
+    lib.check(lib.c.b200_ldu_invalidate(C.c_void_p(key)))
+    l3 = pm2.ldu(key=key)
+    assert np.array_equal(oracle.amul(m2, diag, upper, upper, psi), l3.amul(diag, upper, psi))
+    l3.release()
