@@ -5,13 +5,19 @@ A "step" is one 3D-region time step (region3d/solve3d.H): nAlphaSubCycles MULES-
 interface.correct(), UEqn assembly (momentumPredictor off), nCorrectors x (pd assembly + b200PCG/DIC solve + flux +
 reconstruct), continuity errors, p = pd + rho*gh -- all device-resident, through the C-ABI of libb200foam.so.
 
-N = 1 workload (BASELINE.json configs[1]): 3D-only hex channel with weir, 200x50x100 minus the weir block = 985 000
-cells, laminar, PCG+DIC (pd: tol 1e-7 relTol 0.05; pdFinal: relTol 0), nCorrectors 3, nAlphaSubCycles 2.
-N > 1: weak scaling -- the same 985k-cell slab per GPU (global mesh (200*N)x50x100, `simple` x-slab decomposition),
-halo swaps + scalar all-reduces over NCCL.
+Workloads
+  --scaling weak (default)  N = 1: BASELINE.json configs[1], 3D-only hex channel with weir, 200x50x100 minus the weir block = 985 000
+                            cells; N > 1: the same 985k-cell slab per GPU (global mesh (200*N)x50x100, `simple` x-slabs).
+  --scaling strong          BASELINE.json configs[2]: ONE 400x100x200 channel with weir (7.88 M cells) decomposed over the N GPUs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
-    python bench.py --impl reference [--steps K] [--warmup W]      # the CPU oracle on the host cores (reference arm)
+Every leg times the SAME time steps from the SAME state: fresh fields -> correctPhi -> W warm-up steps -> checkpoint -> K timed steps
+(the window [W, W+K)).  `value` (device-resident), `e2e` (host buffers, restarted from the checkpoint), the cpu_baseline leg and
+`--impl reference` (the CPU oracle, which replays correctPhi and the W warm-up steps itself) all run that window, so
+pcg_iterations_per_step is the same work everywhere (the N-way CPU run has rank-local DIC like foam-extend under mpirun, hence its own
+iteration counts; us_per_pcg_iteration is reported beside every throughput).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--scaling weak|strong]      # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]                        # the reference's CPU algorithm on the host cores
 """
 import argparse
 import json
@@ -29,10 +35,12 @@ import numpy as np  # noqa: E402
 
 METRIC = "3D-region cell-steps/s (PISO+MULES)"
 UNIT = "cell-steps/s"
-DIMS = (200, 50, 100)
-LENGTHS = (20.0, 5.0, 10.0)
+WEAK = dict(dims=(200, 50, 100), lengths=(20.0, 5.0, 10.0), name="BASELINE configs[1]")
+STRONG = dict(dims=(400, 100, 200), lengths=(40.0, 10.0, 20.0), name="BASELINE configs[2]")
 WEIR = (0.45, 0.5, 0.3)
-DELTA_T = 0.002
+DELTA_T = 0.005         # max Courant number ~0.2-0.4 once the flow over the weir has accelerated to 3-4 m/s on dx = 0.1 m (SURVEY.md
+                        # section 8(d) "Co ~ 0.2"; round 1 ran 0.002 = Co 0.05; 0.02 gives max Co ~1.5, beyond what explicit MULES is run at).
+                        # The line carries the device-reduced Courant numbers of the timed window.
 
 
 # ----------------------------------------------------------------------------------------------- the synthetic case
@@ -58,18 +66,35 @@ def channel_fields(names, C, Cfb, patch_slices, lengths):
     return dict(alpha=alpha, U=U, pd=pd, tA=tA, tU=tU, tP=tP, rvA=rvA, rvU=rvU)
 
 
-def set_controls(c):
-    c.deltaT = DELTA_T; c.nCorr = 3; c.nNonOrthCorr = 0; c.nAlphaCorr = 1; c.nAlphaSubCycles = 2; c.cAlpha = 1.0
+def set_controls(c, delta_t=DELTA_T):
+    c.deltaT = delta_t; c.nCorr = 3; c.nNonOrthCorr = 0; c.nAlphaCorr = 1; c.nAlphaSubCycles = 2; c.cAlpha = 1.0
     c.rho1 = 1000.0; c.rho2 = 1.0; c.nu1 = 1e-6; c.nu2 = 1.48e-5; c.sigma = 0.07
     c.g[0] = 0.0; c.g[1] = 0.0; c.g[2] = -9.81
     c.pdTol = 1e-7; c.pdRelTol = 0.05; c.pdFinalTol = 1e-7; c.pdFinalRelTol = 0.0; c.pcorrTol = 1e-7; c.pcorrRelTol = 0.0
     c.maxIter = 1000; c.minIter = 0; c.adjustPhi = 1; c.mulesIncludeOwn = 0; c.divUScheme = 2
+    c.momentumPredictor = 0; c.nonOrthCorrected = 0; c.pdRefCell = -1; c.pdRefValue = 0.0
     return c
 
 
-WORKLOAD = {"workload": "3D-only hex channel with weir, %dx%dx%d minus weir = 985000 cells per GPU (BASELINE configs[1])" % DIMS,
-            "deltaT": DELTA_T, "nCorrectors": 3, "nAlphaSubCycles": 2, "nAlphaCorr": 1,
-            "pd_solver": "b200PCG+DIC tol 1e-7 relTol 0.05 (pdFinal relTol 0)", "momentumPredictor": "no", "turbulence": "laminar"}
+def problem(args, world):
+    """global mesh of this run: (dims, lengths, weir, decomposition, description)"""
+    if args.scaling == "strong":
+        dims, lengths = STRONG["dims"], STRONG["lengths"]
+        weir = WEIR
+        desc = "3D hex channel with weir, %dx%dx%d minus weir = 7 880 000 cells decomposed over the GPUs (%s)" % (dims + (STRONG["name"],))
+    else:
+        dims = (WEAK["dims"][0] * world, WEAK["dims"][1], WEAK["dims"][2])
+        lengths = (WEAK["lengths"][0] * world, WEAK["lengths"][1], WEAK["lengths"][2])
+        weir = (WEIR[0] / world, WEIR[0] / world + (WEIR[1] - WEIR[0]) / world, WEIR[2]) if world > 1 else WEIR
+        desc = "3D-only hex channel with weir, %dx%dx%d minus weir = 985000 cells per GPU (%s)" % (WEAK["dims"] + (WEAK["name"],))
+    return dims, lengths, weir, desc
+
+
+def workload(args, desc):
+    return {"workload": desc, "deltaT": args.delta_t, "Co_target": "max Co ~0.2-0.4 (see `courant`)", "nCorrectors": 3, "nAlphaSubCycles": 2, "nAlphaCorr": 1,
+            "pd_solver": "b200PCG+DIC tol 1e-7 relTol 0.05 (pdFinal relTol 0)", "momentumPredictor": "no", "turbulence": "laminar",
+            "window": "fresh fields -> correctPhi -> %d warm-up steps -> the %d timed steps (every leg and both arms time these same steps)"
+                      % (args.warmup, args.steps)}
 
 
 # ----------------------------------------------------------------------------------------------- clocks sampler
@@ -105,48 +130,38 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------------------------- reference arm (CPU oracle)
-def build_oracle_region(dims, lengths, weir, n_threads=1):
-    from oracle import foam_oracle as fo, mesh_oracle as mo
-    mesh = mo.block_mesh_box(*dims, *lengths)
-    if weir:
-        mesh = mo.subset_mesh(mesh, mo.weir_keep_mask(*dims, *weir))
-    g = mo.geometry(mesh)
-    m = fo.Mesh(mesh["owner"], mesh["neighbour"], mesh["patches"], g, mesh["nCells"])
-    names = [p[0] for p in mesh["patches"]]
-    slices = {n: m.patch_slice(n) for n in names}
-    cs = channel_fields(names, g["C"], g["Cf"][m.F:], slices, lengths)
-    ctl = set_controls(fo.OrcControls())
-    r = fo.Region(m, ctl, fo.BC(m, cs["tA"], 1, cs["rvA"]), fo.BC(m, cs["tU"], 3, cs["rvU"]), fo.BC(m, cs["tP"], 1),
-                  cs["alpha"], cs["U"], cs["pd"])
-    r.correct_phi(); r.clear_log()
-    return m, r
+# ----------------------------------------------------------------------------------------------- the CPU arm (oracle)
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_window(args, dims, lengths, weir, n_proc, warm, steps, budget_s):
+    """The reference's CPU algorithm (oracle/: restatement of foam-extend-3.1, which is not installable here) on the same window:
+    correctPhi -> `warm` steps -> `steps` timed steps, decomposed `n_proc` ways (one thread per `simple` sub-domain, rank-local DIC,
+    halo swaps and rank-ordered global sums: what `mpirun -np n_proc shallowInterFoam -parallel` does).  The timed steps are cut short
+    when the projected time exceeds budget_s; the sample says how many ran."""
+    from oracle import cpu_run
+    return cpu_run.run_window(dims, lengths, weir, channel_fields, lambda c: set_controls(c, args.delta_t), n_proc, warm, steps, budget_s)
 
 
 def run_reference(args):
-    """bench.py --impl reference: the reference's CPU algorithm (oracle port of foam-extend-3.1: /root/reference is only the
-    40-line call scripts and foam-extend is not installable here -- DESIGN.md section 5) on the host cores."""
+    """bench.py --impl reference: the reference's CPU implementation of the path on the box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3)); warm = min(args.warmup, 1)   # bounded sample: ~12 s of CPU per 985k-cell step
-    m, r = build_oracle_region(DIMS, LENGTHS, WEIR)
-    for _ in range(warm):
-        r.step()
-    r.clear_log()
-    t0 = time.time()
-    for _ in range(steps):
-        r.step()
-    dt = time.time() - t0
-    val = m.N * steps / dt
-    iters = sum(p[2] for p in r.perfs())
-    sample = "%d warm-up + %d timed steps of the same 985000-cell workload (driver asked %d/%d; bounded to keep the run short), " \
-             "%d PCG iterations, serial oracle" % (warm, steps, args.warmup, args.steps, iters)
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-            "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": WORKLOAD,
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    dims, lengths, weir, desc = problem(args, world)
+    n_proc = args.cpu_procs or host_cores()
+    r = cpu_window(args, dims, lengths, weir, n_proc, args.warmup, args.steps, budget_s=args.cpu_budget or 420.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"],
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": dict(workload(args, desc), cells_total=r["cells"]),
+            "pcg_iterations_per_step": r["pcg_iterations_per_step"], "us_per_pcg_iteration": r["us_per_pcg_iteration"],
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
@@ -159,12 +174,50 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the N = 1 workload
+    (profiles/ncu_traffic.json: {"workload": ..., "kernels": {name: bytes}}); None when the file is absent"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return None
+
+
 def pinned(n):
     try:
         import torch
         return torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
     except Exception:
         return np.empty(n)
+
+
+def preflight(lib, rank, world, dist):
+    """untimed: the decomposed small case on these N GPUs against the N-rank / serial CPU oracle, over NVLink peer memory (default) and
+    over NCCL (p2p_*=0).  The oracle is the CHECKER here; nothing of it runs in a timed region."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from multirank_worker import decomposed_checks
+    out = {}
+    for tag, opts in (("peer_memory", {"p2p_halo": 1, "p2p_allreduce": 1}), ("nccl", {"p2p_halo": 0, "p2p_allreduce": 0})):
+        for k, v in opts.items():
+            lib.set_option(k, v)
+        try:
+            res = decomposed_checks(lib, rank, world)
+            res["ok"] = True
+        except AssertionError as e:
+            res = {"ok": False, "error": str(e)[:300]}
+        ok = [res["ok"]]
+        if dist:
+            import torch
+            t = torch.tensor([1 if res["ok"] else 0]); dist.all_reduce(t, op=dist.ReduceOp.MIN); ok = [bool(t.item())]
+        res["ok_all_ranks"] = ok[0]
+        out[tag] = res
+    lib.set_option("p2p_halo", 1); lib.set_option("p2p_allreduce", 1)
+    summary = {"amul_bitwise": all(o.get("amul_bitwise", False) for o in out.values()),
+               "pcg_hist_1e-8": max(o.get("pcg_hist_rel", 1.0) for o in out.values()),
+               "fields_linf": max(o.get("fields_linf", 1.0) for o in out.values()),
+               "ok": all(o["ok_all_ranks"] for o in out.values()), "transports": out,
+               "case": "16x4x8 weir channel over %d ranks: Amul vs N-rank oracle, 2 consecutive PCG solves, correctPhi + 2 region steps vs the serial oracle" % world}
+    return summary
 
 
 def run_ours(args):
@@ -189,13 +242,32 @@ def run_ours(args):
         nccl_id = ids[0]
     lib.init(local, rank, world, nccl_id)
 
-    # ---- mesh: this rank's slab of the (200*N) x 50 x 100 channel
-    dims = (DIMS[0] * world, DIMS[1], DIMS[2]); lengths = (LENGTHS[0] * world, LENGTHS[1], LENGTHS[2])
-    weir = (WEIR[0] / world, WEIR[0] / world + (WEIR[1] - WEIR[0]) / world, WEIR[2]) if world > 1 else WEIR
+    def barrier():
+        if dist:
+            dist.barrier()
+
+    def reduce_max(vals):
+        if not dist:
+            return list(vals)
+        import torch
+        t = torch.tensor(list(vals), dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    parity = None
+    if world > 1 and not args.no_preflight:
+        parity = preflight(lib, rank, world, dist)
+        if not parity["ok"]:
+            if rank == 0:
+                emit({"metric": METRIC, "error": "multi-GPU parity pre-flight failed", "parity_check": parity})
+            sys.exit(3)
+
+    # ---- mesh: this rank's part of the global channel
+    dims, lengths, weir, desc = problem(args, world)
     gpm = lib.polymesh_box(*dims, *lengths, weir=weir)
     if world > 1:
         proc = gpm.decompose_simple((world, 1, 1))
         pm = gpm.submesh(proc, world, rank)
+        gpm.release()
     else:
         pm = gpm
     g = pm.geometry()
@@ -203,7 +275,7 @@ def run_ours(args):
     slices = {n: pm.patch_slice(n) for n in pm.patchNames}
     cs = channel_fields(pm.patchNames, g["C"], g["Cf"][F:], slices, lengths)
     dm = pm.device_mesh()
-    ctl = set_controls(capi.Region3dControls())
+    ctl = set_controls(capi.Region3dControls(), args.delta_t)
     reg = dm.region3d(ctl, dm.bc(cs["tA"], 1, cs["rvA"]), dm.bc(cs["tU"], 3, cs["rvU"]), dm.bc(cs["tP"], 1), cs["alpha"], cs["U"], cs["pd"])
     reg.correct_phi(); reg.clear_log()
     N = pm.nCells
@@ -211,64 +283,64 @@ def run_ours(args):
     if dist:
         import torch
         t = torch.tensor([N], dtype=torch.int64); dist.all_reduce(t); total_cells = int(t.item())
+    K = args.steps
 
-    def barrier():
-        if dist:
-            dist.barrier()
+    # ---- W warm-up steps, then the checkpoint every leg restarts from
+    for _ in range(args.warmup):
+        reg.step()
+    ck = reg.fields()
+    courant0 = reg.courant()
 
     # ---- value: device-resident steps, inputs already in HBM.  Timed on the device with CUDA events on the launching
     #      stream (library timer "step" = events around every step), max over ranks.
-    for _ in range(args.warmup):
-        reg.step()
     reg.clear_log()
     sampler = ClockSampler(local); sampler.start()
     barrier(); lib.timers_reset(); l0 = lib.launches(); t0 = time.time()
-    reg.step(args.steps)
+    reg.step(K)
     tm = lib.timers(); wall = time.time() - t0; launches = lib.launches() - l0
     barrier()
     clocks = sampler.stop()
     dev_s = tm["step"][0] * 1e-3
-    iters = [p[2] for p in reg.perfs()]
-    if dist:
-        import torch
-        t = torch.tensor([dev_s, wall], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); dev_s, wall = float(t[0]), float(t[1])
-    value = total_cells * args.steps / dev_s
+    iters_value = [p[2] for p in reg.perfs()]
+    courant1 = reg.courant()
+    dev_s, wall = reduce_max([dev_s, wall])
+    value = total_cells * K / dev_s
 
-    # ---- e2e: the same step through b200_region3d_step_host with HOST buffers (pinned), H2D + D2H inside the timed region
-    f = reg.fields()
+    # ---- e2e: the SAME K steps from the checkpoint through b200_region3d_step_host with HOST buffers (pinned), H2D + D2H inside the timed region
     nF = F + pm.nBoundaryFaces
     hb = [pinned(N), pinned(3 * N), pinned(N), pinned(nF), pinned(N)]
-    hb[0][:] = f["alpha1"]; hb[1][:] = f["U"].reshape(-1); hb[2][:] = f["pd"]; hb[3][:] = f["phi"]; hb[4][:] = f["p"]
-    e2e_steps = max(2, min(args.steps, 5))
-    reg.step_host(*hb)
+    reg.restore(ck["alpha1"], ck["U"], ck["pd"], ck["phi"])
+    hb[0][:] = ck["alpha1"]; hb[1][:] = ck["U"].reshape(-1); hb[2][:] = ck["pd"]; hb[3][:] = ck["phi"]; hb[4][:] = ck["p"]
     reg.clear_log()
     barrier(); t0 = time.time()
-    for _ in range(e2e_steps):
+    for _ in range(K):
         reg.step_host(*hb)
     e2e_s = time.time() - t0
-    e2e_iters = sum(p[2] for p in reg.perfs()) / e2e_steps   # (later time steps than the `value` leg: the flow has settled a little)
+    iters_e2e = [p[2] for p in reg.perfs()]
     barrier()
-    if dist:
-        import torch
-        t = torch.tensor([e2e_s], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t[0])
-    e2e = {"value": total_cells * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * (5 * N + nF) * world,
-           "d2h_bytes_per_step": 8 * (6 * N + nF) * world, "steps": e2e_steps, "pcg_iterations_per_step": e2e_iters,
-           "api": "b200_region3d_step_host (host buffers in, host buffers out)"}
+    e2e_s, = reduce_max([e2e_s])
+    e2e = {"value": total_cells * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * (5 * N + nF) * world,
+           "d2h_bytes_per_step": 8 * (6 * N + nF) * world, "steps": K, "pcg_iterations_per_step": sum(iters_e2e) / K,
+           "same_iterations_as_value_leg": iters_e2e == iters_value,
+           "api": "b200_region3d_step_host (host buffers in, host buffers out), restarted from the same checkpoint as `value`"}
 
-    # ---- roofline of the dominant kernel class, measured live with CUDA events (separate pass, per-kernel timers on)
+    # ---- roofline of the dominant kernel class, measured live with CUDA events (separate pass: first step of the window again,
+    #      per-kernel timers on) -- and, at N = 1, the plug-point replay of that step (e2e_plugin)
+    reg.restore(ck["alpha1"], ck["U"], ck["pd"], ck["phi"])
     lib.set_option("pcg_kernel_timers", 1)
     lib.timers_reset()
     reg.clear_log()
+    if world == 1:
+        reg.capture(True)
     reg.step(1)
     tk = lib.timers()
     lib.set_option("pcg_kernel_timers", 0)
     peak, peak_src = measured_peak()
+    n_solves = ctl.nCorr * (ctl.nNonOrthCorr + 1)
+    pass_perfs = reg.perfs()[-n_solves:]
+    n_iter = max(1, sum(p[2] for p in pass_perfs))
 
-    # average duration of the launches that did work: the solver enqueues iterations in batches of 4, the ones queued past
-    # convergence return at once, so per-iteration kernels are averaged over the iterations actually performed
-    n_iter = max(1, sum(p[2] for p in reg.perfs()[-(ctl.nCorr * (ctl.nNonOrthCorr + 1)):]))
-
-    def per_iter(name):
+    def per_iter(name):      # per-iteration kernels: averaged over the iterations actually performed (launches queued past convergence return at once)
         ms, calls = tk.get(name, (0.0, 0))
         return (ms / n_iter * 1e-3) if calls else None
 
@@ -279,46 +351,93 @@ def run_ours(args):
     alg = {"dic_precondition": 48 * N + 32 * F, "amul": 8 * (3 * N + F) + 8 * F, "mules": 424 * N + 288 * F}
     t_fwd, t_bwd, t_amul, t_mules = per_iter("dic_fwd"), per_iter("dic_bwd"), per_iter("amul"), per_launch("mules")
     step_ms = tk["step"][0]
+    traffic = ncu_traffic() if (world == 1 and args.scaling == "weak") else None
+    tr = (traffic or {}).get("kernels", {})
     kernels = {}
+
+    def add(name, t, share_ms, note=None, alg_bytes=None):
+        k = {"us": 1e6 * t, "share_of_step": share_ms / step_ms}
+        if alg_bytes:
+            k["GBps"] = alg_bytes / t / 1e9
+            k["frac_of_measured_peak"] = k["GBps"] / peak
+        if name in tr:     # real DRAM traffic of this kernel class per launch (ncu) over the live duration
+            k["dram_bytes_ncu"] = tr[name]; k["dram_GBps"] = tr[name] / t / 1e9
+        if note:
+            k["note"] = note
+        kernels[name] = k
+
     if t_fwd and t_bwd:
-        kernels["dic_precondition"] = {"us": 1e6 * (t_fwd + t_bwd), "GBps": alg["dic_precondition"] / (t_fwd + t_bwd) / 1e9,
-                                       "share_of_step": (tk["dic_fwd"][0] + tk["dic_bwd"][0]) / step_ms,
-                                       "note": "k_dic_fwd (+ fused x/rA update and residual sum) + k_dic_bwd (+ fused wArA sum), per PCG iteration"}
+        add("dic_precondition", t_fwd + t_bwd, tk["dic_fwd"][0] + tk["dic_bwd"][0],
+            "k_dic_fwd (+ fused x/rA update and residual sum) + k_dic_bwd (+ fused wArA sum), per PCG iteration", alg["dic_precondition"])
     if t_amul:
-        kernels["amul"] = {"us": 1e6 * t_amul, "GBps": alg["amul"] / t_amul / 1e9, "share_of_step": tk["amul"][0] / step_ms}
+        add("amul", t_amul, tk["amul"][0], None, alg["amul"])
     if t_mules:
-        kernels["mules_explicitSolve"] = {"us": 1e6 * t_mules, "GBps": alg["mules"] / t_mules / 1e9, "share_of_step": tk["mules"][0] / step_ms}
+        add("mules_explicitSolve", t_mules, tk["mules"][0],
+            "GBps counts upstream's 14-pass byte structure (424N+288F); the 6 fused kernels move about half of it: see dram_GBps", alg["mules"])
     for name in ("pcg_vec", "allreduce", "halo"):     # the rest of a PCG iteration (multi-rank: scalar all-reduces incl. the wait for the slowest rank; halo push + interface update)
         t = per_iter(name)
         if t:
-            kernels[name] = {"us": 1e6 * t, "share_of_step": tk[name][0] / step_ms}
+            add(name, t, tk[name][0])
     dom = "dic_precondition" if "dic_precondition" in kernels else "amul"
     ach = kernels[dom]["GBps"] if dom in kernels else None
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
-    # (profiles/r1f_ncu_full_raw.csv: k_dic_fwd 98.9 + 4.6 MB, k_dic_bwd 75.0 + 1.7 MB, k_amul 63.1 + 1.4 MB); only valid for N = 1
-    ncu_traffic = {"dic_precondition": 180.2e6, "amul": 64.5e6}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
                 "frac_of_8TBps_nominal": (ach / 8000.0) if ach else None, "peak_source": peak_src,
-                "traffic": ncu_traffic.get(dom) if world == 1 else None,
+                "traffic": tr.get(dom), "traffic_source": (traffic or {}).get("source"),
                 "algorithmic_bytes_per_launch": alg[dom], "kernels": kernels,
                 "pcg_iterations_in_pass": n_iter,
-                "note": "DIC sweeps are bound by the dependency chain (348 wavefronts -> 35 tile hops of ~2.4 us), not by bandwidth; the "
-                        "per-iteration working set (~180 MB: matrix, sweep operand blocks, 8 vectors) exceeds the 126 MB L2 -- see DESIGN.md"}
+                "note": "DIC sweeps are bound by the dependency chain (wavefronts -> tile hops), not by bandwidth -- see DESIGN.md section 4.1"}
+
+    # ---- e2e_plugin (N = 1): what `solver b200PCG;` + the MULES replacement deliver to an unmodified shallowInterFoam -- every linear
+    #      system and MULES call of that step replayed through the two plug points from PAGEABLE host arrays (H2D/D2H inside)
+    e2e_plugin = None
+    if world == 1:
+        solves, mules = reg.captured_solves(), reg.captured_mules()
+        reg.capture(False)
+        ldu = dm.ldu
+        bcA = dm.bc(cs["tA"], 1, cs["rvA"])
+        t_solve, it_solve, t_mul = [], [], []
+        for s in solves:
+            t0 = time.time()
+            x, pf, _ = ldu.pcg_solve(s["diag"], s["upper"], s["x0"], s["source"], tol=s["tol"], relTol=s["relTol"], maxIter=ctl.maxIter)
+            t_solve.append(time.time() - t0); it_solve.append(int(pf.nIterations))
+        for q in mules:
+            t0 = time.time()
+            dm.mules_explicit_solve(bcA, q["psi"], q["psib"], q["psi0"], q["phi"], q["phiPsi"], q["deltaT"])
+            t_mul.append(time.time() - t0)
+        plug_s = sum(t_solve) + sum(t_mul)
+        resident_ms = tk["pcg_solve"][0] + tk["mules"][0]
+        e2e_plugin = {"ms_per_step_in_plugin_calls": 1e3 * plug_s, "pcg_solve_ms": [1e3 * t for t in t_solve], "pcg_iterations": it_solve,
+                      "same_iterations_as_resident": it_solve == [p[2] for p in pass_perfs],
+                      "mules_ms": [1e3 * t for t in t_mul], "resident_ms_same_calls": resident_ms,
+                      "h2d_bytes_per_step": len(solves) * 8 * (3 * N + F) + len(mules) * 8 * (2 * N + pm.nBoundaryFaces + 2 * nF),
+                      "d2h_bytes_per_step": len(solves) * 8 * N + len(mules) * 8 * (N + nF),
+                      "cell_steps_per_s_of_the_plugged_part": N / plug_s,
+                      "api": "b200_pcg_solve x%d + b200_mules_explicit_solve x%d of one time step, pageable host arrays in foam-extend order "
+                             "(what foam/b200PCG + foam/b200MULES call); the rest of the step stays in foam-extend on the host and is not timed"
+                             % (len(solves), len(mules))}
 
     if rank != 0:
         return
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": dict(WORKLOAD, cells_total=total_cells, l2="inputs (~1 GB of fields+mesh per GPU) exceed the 126 MB L2"),
+    its = sum(iters_value)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": dict(workload(args, desc), cells_total=total_cells, l2="inputs (~1 GB of fields+mesh per GPU) exceed the 126 MB L2"),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "pcg_iterations_per_step": sum(iters) / max(args.steps, 1), "wall_ms_per_step": 1e3 * wall / args.steps}
+            "pcg_iterations_per_step": its / max(K, 1), "us_per_pcg_iteration": 1e6 * dev_s / max(its, 1),
+            "wall_ms_per_step": 1e3 * wall / K,
+            "courant": {"mean_start": courant0[0], "max_start": courant0[1], "mean_end": courant1[0], "max_end": courant1[1],
+                        "api": "b200_region3d_get_courant (device reduction)"}}
+    if e2e_plugin:
+        line["e2e_plugin"] = e2e_plugin
+    if parity:
+        line["parity_check"] = parity
     if world == 1 and not args.no_cpu_baseline:
-        # the oracle ("port") on one host core, on a bounded sample of the same workload: 1 step (about 12 s of CPU)
-        t0 = time.time()
-        m, r = build_oracle_region(DIMS, LENGTHS, WEIR)
-        t1 = time.time(); r.step(); dt = time.time() - t1
-        line["cpu_baseline"] = {"value": m.N / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": "1 step of the same 985000-cell workload after correctPhi (%.1f s; set-up %.1f s untimed), serial oracle" % (dt, t1 - t0)}
+        # the N-way decomposed oracle ("port") on the box's host cores, same window, bounded to ~30 s of timed CPU work
+        dims1, lengths1, weir1, _ = problem(args, 1)
+        n_proc = args.cpu_procs or host_cores()
+        r = cpu_window(args, dims1, lengths1, weir1, n_proc, args.warmup, K, budget_s=args.cpu_budget or 45.0)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                                "pcg_iterations_per_step": r["pcg_iterations_per_step"], "us_per_pcg_iteration": r["us_per_pcg_iteration"]}
     emit(line)
 
 
@@ -346,7 +465,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--delta-t", dest="delta_t", type=float, default=DELTA_T)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-preflight", action="store_true")
+    ap.add_argument("--cpu-procs", type=int, default=0, help="sub-domains (threads) of the CPU arm; default = host cores")
+    ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of timed CPU work before the CPU arm stops early")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (repeatable)")
     args = ap.parse_args()
     if args.impl == "reference":

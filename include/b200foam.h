@@ -260,6 +260,16 @@ int b200_region3d_get_courant(b200_region3d_t* r, double* out3);
 /* restart from a saved state: set_fields + the fields derived from alpha1 that a step expects to find (rho, interface.correct()) */
 int b200_region3d_restore(b200_region3d_t* r, const double* alpha1, const double* U, const double* pd, const double* phi);
 int b200_region3d_clear_log(b200_region3d_t* r);
+/* capture (bench / debugging): with `on`, every later step keeps host copies -- in foam-extend's original cell / face order -- of each
+ * linear system handed to the solver (after addBoundaryDiag/Source: what fvScalarMatrix::solve passes to lduMatrix::solver::solve) and
+ * of each MULES::explicitSolve input: exactly what the two plug points receive from an unmodified shallowInterFoam.  kind 0 = solves,
+ * 1 = MULES calls.  bench.py replays them through b200_pcg_solve / b200_mules_explicit_solve from pageable host arrays ("e2e_plugin"). */
+int b200_region3d_capture(b200_region3d_t* r, int32_t on);
+int b200_region3d_num_captured(b200_region3d_t* r, int32_t kind);
+int b200_region3d_get_captured_solve(b200_region3d_t* r, int32_t i, double* diag, double* upper, double* source, double* x0, double* bou,
+                                     double* tolRelTol);
+int b200_region3d_get_captured_mules(b200_region3d_t* r, int32_t i, double* psi, double* psib, double* psi0, double* phi, double* phiPsi,
+                                     double* deltaT);
 
 /* ---------------------------------------------------------------- host mesh tools (integers bit-exact)
  * [UPSTREAM blockMesh (single hex block ordering), subsetMesh, primitiveMesh geometry, surfaceInterpolation

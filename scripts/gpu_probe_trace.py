@@ -13,15 +13,15 @@ diag = np.zeros(N); np.add.at(diag, pm.owner[:F], -upper); np.add.at(diag, pm.ne
 b = rng.uniform(-1, 1, N)
 rD = ldu.dic_calc_rd(diag, upper)
 ref = ldu.dic_precondition(rD, upper, b)
-for wk in (0, 1):
-    lib.set_option("sweep_publish", wk)
+for ro in (0, 1):     # operands through shared memory (round 1) / register-resident (round 2)
+    lib.set_option("sweep_reg_ops", ro)
     assert np.array_equal(ldu.dic_precondition(rD, upper, b), ref)
     lib.timers_reset()
     for i in range(10):
         ldu.dic_precondition(rD, upper, b)
     tm = lib.timers()
-    print("sweep_publish %d: fwd %6.1f bwd %6.1f us" % (wk, 1e3 * tm["dic_fwd"][0] / tm["dic_fwd"][1], 1e3 * tm["dic_bwd"][0] / tm["dic_bwd"][1]), flush=True)
-lib.set_option("sweep_publish", int(sys.argv[1]) if len(sys.argv) > 1 else 1)
+    print("sweep_reg_ops %d: fwd %6.1f bwd %6.1f us" % (ro, 1e3 * tm["dic_fwd"][0] / tm["dic_fwd"][1], 1e3 * tm["dic_bwd"][0] / tm["dic_bwd"][1]), flush=True)
+lib.set_option("sweep_reg_ops", int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 lib.set_option("sweep_trace", 1)
 ldu.dic_precondition(rD, upper, b)
 tr, tl, ts = ldu.sweep_trace()

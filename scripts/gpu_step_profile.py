@@ -7,10 +7,11 @@ from shallowinterfoam_b200 import capi
 lib = capi.load(); lib.init(0, 0, 1)
 for a in sys.argv[1:]:
     k, v = a.split("="); lib.set_option(k, float(v))
-pm = lib.polymesh_box(*bench.DIMS, *bench.LENGTHS, weir=bench.WEIR)
+DIMS, LENGTHS = bench.WEAK["dims"], bench.WEAK["lengths"]
+pm = lib.polymesh_box(*DIMS, *LENGTHS, weir=bench.WEIR)
 g = pm.geometry(); F = pm.nInternalFaces
 slices = {n: pm.patch_slice(n) for n in pm.patchNames}
-cs = bench.channel_fields(pm.patchNames, g["C"], g["Cf"][F:], slices, bench.LENGTHS)
+cs = bench.channel_fields(pm.patchNames, g["C"], g["Cf"][F:], slices, LENGTHS)
 dm = pm.device_mesh()
 ctl = bench.set_controls(capi.Region3dControls())
 reg = dm.region3d(ctl, dm.bc(cs["tA"], 1, cs["rvA"]), dm.bc(cs["tU"], 3, cs["rvU"]), dm.bc(cs["tP"], 1), cs["alpha"], cs["U"], cs["pd"])

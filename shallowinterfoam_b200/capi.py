@@ -31,6 +31,7 @@ EXPORTS = [
     "b200_region3d_set_patch_mixed", "b200_region3d_get_patch_internal", "b200_region3d_num_solves",
     "b200_region3d_get_perfs", "b200_region3d_get_res_hist", "b200_region3d_get_alpha_stats",
     "b200_region3d_get_cont_errs", "b200_region3d_clear_log", "b200_region3d_get_courant", "b200_region3d_restore", "b200_ldu_invalidate",
+    "b200_region3d_capture", "b200_region3d_num_captured", "b200_region3d_get_captured_solve", "b200_region3d_get_captured_mules",
     "b200_polymesh_box", "b200_polymesh_box_weir", "b200_polymesh_jitter", "b200_polymesh_agglomerate", "b200_polymesh_release", "b200_polymesh_sizes",
     "b200_polymesh_get", "b200_polymesh_patch_name", "b200_polymesh_geometry", "b200_decompose_simple",
     "b200_polymesh_submesh", "b200_polymesh_submesh_maps", "b200_mesh_create_from_polymesh",
@@ -507,6 +508,30 @@ class Region3D:
 
     def clear_log(self):
         self.lib.check(self.lib.c.b200_region3d_clear_log(self.h))
+
+    def capture(self, on=True):
+        self.lib.check(self.lib.c.b200_region3d_capture(self.h, C.c_int32(1 if on else 0)))
+
+    def captured_solves(self):
+        m = self.mesh; out = []
+        for i in range(self.lib.c.b200_region3d_num_captured(self.h, C.c_int32(0))):
+            d = dict(diag=np.empty(m.N), upper=np.empty(m.F), source=np.empty(m.N), x0=np.empty(m.N), bou=np.empty(m.B)); tr = np.empty(2)
+            self.lib.check(self.lib.c.b200_region3d_get_captured_solve(self.h, C.c_int32(i), _d(d["diag"]), _d(d["upper"]), _d(d["source"]),
+                                                                       _d(d["x0"]), _d(d["bou"]), _d(tr)))
+            d["tol"], d["relTol"] = float(tr[0]), float(tr[1])
+            out.append(d)
+        return out
+
+    def captured_mules(self):
+        m = self.mesh; out = []
+        for i in range(self.lib.c.b200_region3d_num_captured(self.h, C.c_int32(1))):
+            d = dict(psi=np.empty(m.N), psib=np.empty(m.B), psi0=np.empty(m.N), phi=np.empty(m.F + m.B), phiPsi=np.empty(m.F + m.B))
+            dt = C.c_double()
+            self.lib.check(self.lib.c.b200_region3d_get_captured_mules(self.h, C.c_int32(i), _d(d["psi"]), _d(d["psib"]), _d(d["psi0"]),
+                                                                       _d(d["phi"]), _d(d["phiPsi"]), C.byref(dt)))
+            d["deltaT"] = dt.value
+            out.append(d)
+        return out
 
     def courant(self):
         """(meanCoNum, CoNum, velMag) of the current phi, reduced on the device"""

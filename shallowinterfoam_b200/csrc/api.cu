@@ -756,6 +756,45 @@ int b200_region3d_restore(b200_region3d_t* rr, const double* alpha1, const doubl
     asRegion(rr)->refreshDerived();
     API_END
 }
+int b200_region3d_capture(b200_region3d_t* rr, int32_t on) {
+    API_BEGIN
+    Region3D& r = *asRegion(rr);
+    r.capture = on != 0;
+    r.capSolves.clear(); r.capMules.clear();
+    API_END
+}
+int b200_region3d_num_captured(b200_region3d_t* rr, int32_t kind) {
+    Region3D& r = *asRegion(rr);
+    return kind == 0 ? (int)r.capSolves.size() : (int)r.capMules.size();
+}
+int b200_region3d_get_captured_solve(b200_region3d_t* rr, int32_t i, double* diag, double* upper, double* source, double* x0, double* bou,
+                                     double* tolRelTol) {
+    API_BEGIN
+    Region3D& r = *asRegion(rr);
+    B200_REQUIRE(i >= 0 && i < (int)r.capSolves.size(), B200_ERR_ARG, "b200_region3d_get_captured_solve: index out of range");
+    const Region3D::CapturedSolve& c = r.capSolves[i];
+    if (diag) memcpy(diag, c.diag.data(), 8 * c.diag.size());
+    if (upper) memcpy(upper, c.upper.data(), 8 * c.upper.size());
+    if (source) memcpy(source, c.source.data(), 8 * c.source.size());
+    if (x0) memcpy(x0, c.x0.data(), 8 * c.x0.size());
+    if (bou) memcpy(bou, c.bou.data(), 8 * c.bou.size());
+    if (tolRelTol) { tolRelTol[0] = c.tol; tolRelTol[1] = c.relTol; }
+    API_END
+}
+int b200_region3d_get_captured_mules(b200_region3d_t* rr, int32_t i, double* psi, double* psib, double* psi0, double* phi, double* phiPsi,
+                                     double* deltaT) {
+    API_BEGIN
+    Region3D& r = *asRegion(rr);
+    B200_REQUIRE(i >= 0 && i < (int)r.capMules.size(), B200_ERR_ARG, "b200_region3d_get_captured_mules: index out of range");
+    const Region3D::CapturedMules& c = r.capMules[i];
+    if (psi) memcpy(psi, c.psi.data(), 8 * c.psi.size());
+    if (psib) memcpy(psib, c.psib.data(), 8 * c.psib.size());
+    if (psi0) memcpy(psi0, c.psi0.data(), 8 * c.psi0.size());
+    if (phi) memcpy(phi, c.phi.data(), 8 * c.phi.size());
+    if (phiPsi) memcpy(phiPsi, c.phiPsi.data(), 8 * c.phiPsi.size());
+    if (deltaT) *deltaT = c.deltaT;
+    API_END
+}
 int b200_region3d_clear_log(b200_region3d_t* rr) {
     API_BEGIN
     Region3D& r = *asRegion(rr);

@@ -99,7 +99,7 @@ __global__ void k_p2p_allreduce(double* data, int count, int op, P2PView pv, uns
 
 static void p2pInit(int rank, int nRanks) {
     g_p2p = P2PState();
-    if (nRanks > P2P_MAX_RANKS || rt().opt("p2p_allreduce", 1) <= 0) return;
+    if (nRanks > P2P_MAX_RANKS) return;
     cudaStream_t st = rt().stream;
     const size_t bytes = sizeof(double) * P2P_SLOTS * nRanks * P2P_ENTRY;
     if (cudaMalloc((void**)&g_p2p.own, bytes) != cudaSuccess) { cudaGetLastError(); return; }
@@ -156,16 +156,18 @@ void commFinalize() {
     p2pFinalize();
     if (rt().nccl) { ncclCommDestroy((ncclComm_t)rt().nccl); rt().nccl = nullptr; }
 }
-bool commUsesPeerMemory() { return g_p2p.ok; }
+bool commUsesPeerMemory() { return g_p2p.ok && rt().opt("p2p_allreduce", 1) > 0; }
 int commUniqueId(void* out128) {
     ncclUniqueId uid;
     B200_CHECK_NCCL(ncclGetUniqueId(&uid));
     memcpy(out128, &uid, sizeof(uid));
     return (int)sizeof(uid);
 }
+// (the option is read per call so that a checker can exercise both transports in one process; every rank must set it alike)
+static bool p2pAllreduceOn() { return g_p2p.ok && rt().opt("p2p_allreduce", 1) > 0; }
 void allReduce(double* p, int count, ReduceOp op) {
     if (rt().nRanks <= 1) return;
-    if (g_p2p.ok && count <= P2P_ENTRY - 1) {
+    if (p2pAllreduceOn() && count <= P2P_ENTRY - 1) {
         g_p2p.epoch++;
         B200_LAUNCH(k_p2p_allreduce, 1, 32, rt().stream, p, count, (int)op, g_p2p.v, g_p2p.epoch, (PcgScalars*)nullptr, (double*)nullptr);
         return;
@@ -300,7 +302,7 @@ PeerHaloWait peerHaloWait(const PeerHalo* h) {
 }
 
 bool allReduceSumThenPcgCheck(double* p, int count, PcgScalars* sc, double* hist) {
-    if (!(g_p2p.ok && count <= P2P_ENTRY - 1)) return false;
+    if (!(p2pAllreduceOn() && count <= P2P_ENTRY - 1)) return false;
     g_p2p.epoch++;
     B200_LAUNCH(k_p2p_allreduce, 1, 32, rt().stream, p, count, (int)RED_SUM, g_p2p.v, g_p2p.epoch, sc, hist);
     return true;

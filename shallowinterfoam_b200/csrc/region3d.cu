@@ -609,6 +609,14 @@ void Region3D::alphaEqn(double dt) {
           B200_LAUNCH(k_alpha_flux, gridFor(nmax), BLOCK, st, mv, (const double*)phi.p, (const double*)alpha.p, (const double*)alphab.p,
                       (const double*)w.gx.p, (const double*)w.gy.p, (const double*)w.gz.p, (const double*)w.gb.p, (const double*)nHatf.p, ctl.cAlpha, (const double*)scal.p, phiAlpha.p); }
         evalAlphaBC();
+        if (capture) {
+            capMules.emplace_back();
+            CapturedMules& c = capMules.back();
+            c.psi.resize(N); c.psib.resize(B); c.psi0.resize(N); c.phi.resize(m->F + B); c.phiPsi.resize(m->F + B); c.deltaT = dt;
+            m->downloadCells(alpha, c.psi.data()); if (B) m->downloadBoundary(alphab, c.psib.data()); m->downloadCells(alpha0, c.psi0.data());
+            m->downloadFaces(phi, c.phi.data(), true); m->downloadFaces(phiAlpha, c.phiPsi.data(), true);
+            syncStream();
+        }
         mulesExplicitDevice(*m, bcAlpha.view(), alpha, alphab, alpha0, phi, phiAlpha, dt, 1.0, 0.0, ctl.mulesIncludeOwn, 3, nullptr);
         evalAlphaBC();
         B200_LAUNCH(k_rhophi, gridFor((long long)nf), BLOCK, st, (int)nf, (const double*)phiAlpha.p, (const double*)phi.p, ctl.rho1, ctl.rho2, rhoPhi.p);
@@ -660,6 +668,14 @@ void Region3D::solvePressureLike(const DevBC& bc, const double* gammaf, double* 
                       (const int*)pw.bRowOfSlot.p);
       } }
     b200_solver_controls sc{tol, relTol, ctl.minIter, ctl.maxIter};
+    if (capture) {
+        capSolves.emplace_back();
+        CapturedSolve& c = capSolves.back();
+        c.diag.resize(N); c.upper.resize(m->F); c.source.resize(N); c.x0.resize(N); c.bou.resize(B); c.tol = tol; c.relTol = relTol;
+        m->downloadCells(pdDiag, c.diag.data()); m->downloadFaces(pdUpper, c.upper.data(), false); m->downloadCells(pdSource, c.source.data());
+        m->downloadCells(psi, c.x0.data()); if (B) m->downloadBoundary(bcv, c.bou.data());
+        syncStream();
+    }
     std::vector<double> hist;
     b200_solver_perf perf = pcgSolveDevice(*m, pdDiag, pdUpper, coupled() ? bcv.p : nullptr, psi, pdSource, sc, keepHist ? &hist : nullptr);
     perfs.push_back(perf);

@@ -58,6 +58,13 @@ struct Region3D {
     std::vector<double> resHist, alphaStats;
     std::vector<size_t> pendingStats;
     bool keepHist = true;
+    // capture (debug / bench): host copies, in foam-extend's ORIGINAL cell / face order, of every linear system handed to the solver
+    // and of every MULES::explicitSolve input -- what the two plug points would receive from an unmodified shallowInterFoam
+    bool capture = false;
+    struct CapturedSolve { std::vector<double> diag, upper, source, x0, bou; double tol, relTol; };
+    struct CapturedMules { std::vector<double> psi, psib, psi0, phi, phiPsi; double deltaT; };
+    std::vector<CapturedSolve> capSolves;
+    std::vector<CapturedMules> capMules;
     bool pdNeedRef = false;      // pd.needReference(): no patch of pd fixes the value, on any rank  [UPSTREAM GeometricField::needReference]
     int refRow = -1;             // device row of pdRefCell (-1: not on this rank / none)
     double sumLocalContErr = 0, globalContErr = 0, cumulativeContErr = 0;

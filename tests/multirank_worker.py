@@ -49,7 +49,19 @@ def main():
         lib.c.b200_emu_set_comm(allreduce, sendrecv)
         lib.init(0, rank, world)
 
-    dims = (16, 4, 8); L = (5.0, 1.0, 2.0)
+    res = decomposed_checks(lib, rank, world)
+    dist.barrier()
+    if rank == 0:
+        print("MULTIRANK_OK world=%d %s" % (world, res))
+
+
+def decomposed_checks(lib, rank, world, dims=(16, 4, 8)):
+    """The decomposed hot path of `lib` (already initialised for `world` ranks) against the N-rank / serial oracle on a small
+    weir channel: Amul bitwise, two consecutive b200PCG solves (rank-local DIC; iteration counts, residual history 1e-8), two
+    region steps (fields 1e-7 with tight solver tolerances).  Collective: every rank calls it.  Returns the measured errors;
+    raises AssertionError on a mismatch.  Also used by bench.py's untimed pre-flight on the real GPUs (N > 1)."""
+    res = {}
+    L = (5.0, 1.0, 2.0)
     gpm = lib.polymesh_box(*dims, *L, weir=(0.45, 0.6, 0.3))
     n = (world, 1, 1) if world != 4 else (2, 1, 2)
     proc = gpm.decompose_simple(n)
@@ -80,6 +92,7 @@ def main():
     A_loc = ldu.amul(d, u, psi[pm.cellMap], bou=bou)                      # halo over the (emulated) comm layer
     A_ref = mro.amul_multi(osubs, [m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], [psi[s.cellMap] for s in subs])[rank]
     assert np.array_equal(A_loc, A_ref), "decomposed Amul differs from the N-rank oracle"
+    res["amul_bitwise"] = True
     A_ser = fo.amul(gm, diag, upper, upper, psi)[pm.cellMap]
     assert np.allclose(A_loc, A_ser, rtol=1e-13, atol=1e-13), "decomposed Amul differs from the serial Amul"
     xg, pg, hg = ldu.pcg_solve(d, u, np.zeros(pm.nCells), b[pm.cellMap], tol=1e-9, maxIter=300, bou=bou)
@@ -88,6 +101,8 @@ def main():
     assert pg.nIterations == po["nIterations"], (pg.nIterations, po["nIterations"])
     assert np.allclose(hg, ho, rtol=1e-8, atol=1e-13 * ho[0])
     assert np.abs(xg - xo[rank]).max() <= 1e-10 * np.abs(xo[rank]).max()
+    res["pcg_iterations"] = [int(pg.nIterations)]
+    res["pcg_hist_rel"] = float(np.max(np.abs(hg - ho) / np.maximum(ho, 1e-13 * ho[0])))
     # a SECOND solve on the same handle (PISO correctors 2, 3 ...): the first one stopped after a backward sweep and left the
     # ready-flag vector z populated; stale halo values must not be taken for published ones
     b2 = rng.uniform(-1, 1, gm.N)
@@ -97,6 +112,8 @@ def main():
     assert pg2.nIterations == po2["nIterations"], (pg2.nIterations, po2["nIterations"])
     assert np.allclose(hg2, ho2, rtol=1e-8, atol=1e-13 * ho2[0])
     assert np.abs(xg2 - xo2[rank]).max() <= 1e-10 * np.abs(xo2[rank]).max()
+    res["pcg_iterations"].append(int(pg2.nIterations))
+    res["pcg_hist_rel"] = max(res["pcg_hist_rel"], float(np.max(np.abs(hg2 - ho2) / np.maximum(ho2, 1e-13 * ho2[0]))))
     xs, ps, hs = fo.pcg_solve(gm, diag, upper, np.zeros(gm.N), b, tol=1e-9, maxIter=300)
     assert np.abs(xg - xs[pm.cellMap]).max() <= 1e-6 * np.abs(xs).max()      # same solution, different (rank-local) preconditioner
 
@@ -119,6 +136,7 @@ def main():
     dm = pm.device_mesh()                                    # collective: halo swap of cell centres
     rg = dm.region3d(tight(default_controls(capi.Region3dControls)), dm.bc(types(cs["tA"]), 1, rvA), dm.bc(types(cs["tU"]), 3, rvU),
                      dm.bc(types(cs["tP"]), 1), cs["alpha"][pm.cellMap], cs["U"][pm.cellMap], cs["pd"][pm.cellMap])
+    res["fields_linf"] = 0.0
     def check(tag, tol):
         fo_, fg = ro.fields(), rg.fields()
         for k in ("alpha1", "U", "pd", "p", "rho"):
@@ -126,9 +144,11 @@ def main():
             scale = max(np.abs(fo_[k]).max(), 1e-300)
             err = np.abs(ref - fg[k]).max() / scale
             assert err <= tol, (tag, k, err)
+            res["fields_linf"] = max(res["fields_linf"], float(err))
         sign = np.where(pm.faceFlip != 0, -1.0, 1.0)
         err = np.abs(fo_["phi"][pm.faceMap] * sign - fg["phi"]).max() / np.abs(fo_["phi"]).max()
         assert err <= tol, (tag, "phi", err)
+        res["fields_linf"] = max(res["fields_linf"], float(err))
     check("init", 1e-13)
     ro.correct_phi(); rg.correct_phi()
     check("correctPhi", 1e-9)
@@ -137,9 +157,8 @@ def main():
         check("step%d" % s, 1e-7)
     so, sg = ro.alpha_stats()[-1], rg.alpha_stats()[-1]
     assert np.allclose(so, sg, rtol=1e-8, atol=1e-12)
-    dist.barrier()
-    if rank == 0:
-        print("MULTIRANK_OK world=%d" % world)
+    rg.release(); dm.release(); ldu.release()
+    return res
 
 
 if __name__ == "__main__":
