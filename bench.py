@@ -38,9 +38,10 @@ UNIT = "cell-steps/s"
 WEAK = dict(dims=(200, 50, 100), lengths=(20.0, 5.0, 10.0), name="BASELINE configs[1]")
 STRONG = dict(dims=(400, 100, 200), lengths=(40.0, 10.0, 20.0), name="BASELINE configs[2]")
 WEIR = (0.45, 0.5, 0.3)
-DELTA_T = 0.005         # max Courant number ~0.2-0.4 once the flow over the weir has accelerated to 3-4 m/s on dx = 0.1 m (SURVEY.md
-                        # section 8(d) "Co ~ 0.2"; round 1 ran 0.002 = Co 0.05; 0.02 gives max Co ~1.5, beyond what explicit MULES is run at).
-                        # The line carries the device-reduced Courant numbers of the timed window.
+DELTA_T = 0.002         # max Courant number 0.21 -> 0.34 over the timed window at 985k cells (mean 0.004): the flow accelerates to 3-4 m/s
+                        # over the weir, so the survey's "Co ~ 0.2"  is met in the max norm.  Measured on the device
+                        # (b200_region3d_get_courant; profiles/bench_r2a_dt.md): deltaT 0.005 gives max Co 0.83 -> 1.03, beyond what explicit
+                        # MULES is run at.  Every line carries the Courant numbers of its own window.
 
 
 # ----------------------------------------------------------------------------------------------- the synthetic case
@@ -91,7 +92,7 @@ def problem(args, world):
 
 
 def workload(args, desc):
-    return {"workload": desc, "deltaT": args.delta_t, "Co_target": "max Co ~0.2-0.4 (see `courant`)", "nCorrectors": 3, "nAlphaSubCycles": 2, "nAlphaCorr": 1,
+    return {"workload": desc, "deltaT": args.delta_t, "Co_target": "max Co ~0.2-0.35 (see `courant`)", "nCorrectors": 3, "nAlphaSubCycles": 2, "nAlphaCorr": 1,
             "pd_solver": "b200PCG+DIC tol 1e-7 relTol 0.05 (pdFinal relTol 0)", "momentumPredictor": "no", "turbulence": "laminar",
             "window": "fresh fields -> correctPhi -> %d warm-up steps -> the %d timed steps (every leg and both arms time these same steps)"
                       % (args.warmup, args.steps)}
@@ -330,8 +331,6 @@ def run_ours(args):
     lib.set_option("pcg_kernel_timers", 1)
     lib.timers_reset()
     reg.clear_log()
-    if world == 1:
-        reg.capture(True)
     reg.step(1)
     tk = lib.timers()
     lib.set_option("pcg_kernel_timers", 0)
@@ -391,6 +390,9 @@ def run_ours(args):
     #      system and MULES call of that step replayed through the two plug points from PAGEABLE host arrays (H2D/D2H inside)
     e2e_plugin = None
     if world == 1:
+        reg.restore(ck["alpha1"], ck["U"], ck["pd"], ck["phi"])      # the same step once more, keeping host copies of what the plug points see
+        reg.capture(True)
+        reg.step(1)
         solves, mules = reg.captured_solves(), reg.captured_mules()
         reg.capture(False)
         ldu = dm.ldu

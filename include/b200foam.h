@@ -139,6 +139,19 @@ int b200_pcg_solve(b200_ldu_t* ldu, const double* diag, const double* upper, con
                    const double* bouCoeffs, double* x, const double* b, const b200_solver_controls* ctl,
                    b200_solver_perf* perf, double* resHist, int32_t histCap);
 
+/* ---------------------------------------------------------------- f1  PBiCG::solve + DILUPreconditioner  ("solver b200PBiCG; preconditioner DILU;")
+ * [REF region3d/UEqn.H:19-34  solve(UEqn == fvc::reconstruct(...)), momentumPredictor defaults to true: readRegion3dPISOControls.H:9-10]
+ * [UPSTREAM PBiCG.C solve; DILUPreconditioner.C calcReciprocalD / precondition / preconditionT; lduMatrixATmul.C Tmul]
+ * Asymmetric matrices (lower != upper).  bouCoeffs / intCoeffs: interfaceBouCoeffs (Amul) and interfaceIntCoeffs (Tmul) of the processor
+ * patches ([nBoundaryFaces] or NULL).  One call per vector component, as fvMatrix<vector>::solve does. */
+int b200_pbicg_solve(b200_ldu_t* ldu, const double* diag, const double* upper, const double* lower, const double* bouCoeffs,
+                     const double* intCoeffs, double* x, const double* b, const b200_solver_controls* ctl, b200_solver_perf* perf,
+                     double* resHist, int32_t histCap);
+int b200_dilu_calc_reciprocal_d(b200_ldu_t* ldu, const double* diag, const double* upper, const double* lower, double* rD);
+/* transpose != 0: preconditionT */
+int b200_dilu_precondition(b200_ldu_t* ldu, const double* rD, const double* upper, const double* lower, const double* rA, double* wA,
+                           int32_t transpose);
+
 /* ---------------------------------------------------------------- mesh (lduAddressing + fvMesh geometry) */
 typedef struct {
     int32_t nCells, nInternalFaces, nBoundaryFaces, nPatches;
@@ -158,6 +171,12 @@ typedef struct {
 int b200_mesh_create(const b200_mesh_desc* desc, b200_mesh_t** out);
 int b200_mesh_release(b200_mesh_t* mesh);
 b200_ldu_t* b200_mesh_ldu(b200_mesh_t* mesh);
+/* [UPSTREAM surfaceInterpolation::makeCorrectionVectors] non-orthogonality measure asin(min(sum(magSf*|corrVec|)/sum(magSf), 1)) in degrees over
+ * the internal faces of all ranks, and mesh.orthogonal() (< 0.1 degrees: the `corrected` schemes are no-ops) */
+int b200_mesh_non_orthogonality(b200_mesh_t* mesh, double* degrees, int32_t* orthogonal);
+/* [UPSTREAM correctedSnGrad::correction; gaussLaplacianScheme::fvmLaplacian faceFluxCorrection] out[nIF+nBF] = (gammaf*magSf) *
+ * (corrVec & linearInterpolate(fvc::grad(vf))) with the Gauss-linear gradient; gammaf == NULL: the bare snGrad correction */
+int b200_non_orth_correction(b200_mesh_t* mesh, const double* gammaf, const double* vf, const double* vfBoundary, double* out);
 
 /* ---------------------------------------------------------------- a13 building blocks (host-pointer forms)
  * [REF region3d/pEqn.H:3,16-20,47] [UPSTREAM linear interpolation, snGradScheme, fvcSurfaceIntegrate, gaussGrad, fvcReconstruct] */
@@ -282,6 +301,8 @@ int b200_polymesh_box_weir(int32_t nx, int32_t ny, int32_t nz, double lx, double
  * 64-bit LCG x <- x*6364136223846793005 + 1442695040888963407 (u = (x >> 11) * 2^-53; three draws per vertex, vertices in index order,
  * x0 = seed).  Addressing is untouched; faces become non-planar and non-orthogonal (what moveDynamicMesh / a skewed blockMesh gives). */
 int b200_polymesh_jitter(b200_polymesh_t* pm, double frac, double dx, double dy, double dz, uint64_t seed);
+/* non-orthogonal (but not skewed) mesh: affine shear of every point, x += sxy*y + sxz*z, y += syz*z */
+int b200_polymesh_shear(b200_polymesh_t* pm, double sxy, double sxz, double syz);
 /* polyhedral mesh by agglomeration (BASELINE configs[3], irregular LDU addressing): cells with equal group[cell] merge.  New labels by
  * first appearance; faces between merged cells vanish; the rest are flipped to owner < neighbour and sorted (owner, neighbour, original
  * face); boundary faces and patches keep their order.  Two cells may share several faces. */

@@ -13,10 +13,12 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load this library.  The product (libb200foam.so) never links or calls it.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 typedef std::vector<double> vec;
@@ -38,7 +40,16 @@ struct OrcMesh {
     const double* C;    // [3N]
     const double* V;    // [N]
     const double* w;    // [F+B] linear weights (boundary = 1)
-    const double* dc;   // [F+B] deltaCoeffs
+    const double* dc;   // [F+B] deltaCoeffs (processor faces: 1/|Cn - C| of the internal face they were)
+    const double* Cn;   // [3B] or null: neighbour-rank cell centre of processor faces (decomposed runs; w/dc of those faces are the
+                        // internal-face values seen from this side)
+};
+
+// N-rank emulation hooks (null = single rank): what Pstream gives foam-extend under mpirun
+struct OrcComm {
+    void* ctx;
+    void (*halo)(void* ctx, const double* cellField, int nc, double* outB);  // patchNeighbourField of processor faces -> outB[nc*b+k]
+    double (*reduce)(void* ctx, double v, int op);                            // 0 = sum in rank order, 1 = max, 2 = min
 };
 
 // patch field types
@@ -125,29 +136,40 @@ static bool pcgStop(int nIter, int minIter, int maxIter, double init, double fin
     return fin < tol || (relTol > 0 && fin < relTol * init);
 }
 
+// comm != null: the decomposed solve -- halo swap of psi before every Amul (interface update with bou), gSum* = per-rank sequential
+// sums reduced in rank order, DIC rank-local (block Jacobi) exactly like foam-extend under MPI
+static void pcgSolve(const OrcMesh* m, const double* diag, const double* upper, const double* bou, double* x, const double* b,
+                     double tol, double relTol, int minIter, int maxIter, OrcPerf* perf, double* resHist, const OrcComm* comm);
 extern "C" void orc_pcg_solve(const OrcMesh* m, const double* diag, const double* upper, const double* bou,
                               double* x, const double* b, double tol, double relTol, int minIter, int maxIter,
                               OrcPerf* perf, double* resHist) {
+    pcgSolve(m, diag, upper, bou, x, b, tol, relTol, minIter, maxIter, perf, resHist, nullptr);
+}
+static void pcgSolve(const OrcMesh* m, const double* diag, const double* upper, const double* bou, double* x, const double* b,
+                     double tol, double relTol, int minIter, int maxIter, OrcPerf* perf, double* resHist, const OrcComm* comm) {
     int N = m->N;
-    vec pA(N), wA(N), rA(N), rD(N);
-    bool hasCoupled = false;
-    for (int p = 0; p < m->nPatches; p++) hasCoupled |= (m->pKind[p] == 1);
-    (void)hasCoupled;  // single-rank oracle: coupled patches are rejected by the callers
-    orc_amul(m, diag, upper, upper, x, wA.data(), nullptr, nullptr);
+    vec pA(N), wA(N), rA(N), rD(N), psiNbr(comm ? m->B : 0);
+    auto gsum = [&](double v) { return comm ? comm->reduce(comm->ctx, v, 0) : v; };
+    auto amul = [&](const double* psi, double* Apsi) {
+        if (comm) { comm->halo(comm->ctx, psi, 1, psiNbr.data()); orc_amul(m, diag, upper, upper, psi, Apsi, bou, psiNbr.data()); }
+        else orc_amul(m, diag, upper, upper, psi, Apsi, nullptr, nullptr);
+    };
+    amul(x, wA.data());
     for (int c = 0; c < N; c++) rA[c] = b[c] - wA[c];
     // normFactor: pA used as scratch for sumA; xRef = gAverage(x)
     orc_sumA(m, diag, upper, upper, pA.data(), bou);
     double xRef = 0;
     for (int c = 0; c < N; c++) xRef += x[c];
-    xRef /= N;
+    xRef = gsum(xRef) / gsum((double)N);
     double nf = 0;
     for (int c = 0; c < N; c++) {
         double t = xRef * pA[c];  // pA *= xRef
         nf += std::fabs(wA[c] - t) + std::fabs(b[c] - t);
     }
-    nf += 1.0e-20;  // lduMatrix::small_
+    nf = gsum(nf) + 1.0e-20;  // lduMatrix::small_
     double s = 0;
     for (int c = 0; c < N; c++) s += std::fabs(rA[c]);
+    s = gsum(s);
     perf->initialResidual = perf->finalResidual = s / nf;
     perf->nIterations = 0; perf->singular = 0;
     if (resHist) resHist[0] = perf->initialResidual;
@@ -159,26 +181,120 @@ extern "C" void orc_pcg_solve(const OrcMesh* m, const double* diag, const double
             orc_dic_precondition(m, rD.data(), upper, rA.data(), wA.data());
             wArA = 0;
             for (int c = 0; c < N; c++) wArA += wA[c] * rA[c];
+            wArA = gsum(wArA);
             if (perf->nIterations == 0) {
                 for (int c = 0; c < N; c++) pA[c] = wA[c];
             } else {
                 double beta = wArA / wArAold;
                 for (int c = 0; c < N; c++) pA[c] = wA[c] + beta * pA[c];
             }
-            orc_amul(m, diag, upper, upper, pA.data(), wA.data(), nullptr, nullptr);
+            amul(pA.data(), wA.data());
             double wApA = 0;
             for (int c = 0; c < N; c++) wApA += wA[c] * pA[c];
+            wApA = gsum(wApA);
             if (std::fabs(wApA) / nf <= VSMALL) { perf->singular = 1; break; }  // checkSingularity
             double alpha = wArA / wApA;
             for (int c = 0; c < N; c++) { x[c] += alpha * pA[c]; rA[c] -= alpha * wA[c]; }
             s = 0;
             for (int c = 0; c < N; c++) s += std::fabs(rA[c]);
+            s = gsum(s);
             perf->finalResidual = s / nf;
             perf->nIterations++;
             if (resHist) resHist[perf->nIterations] = perf->finalResidual;
         } while (!pcgStop(perf->nIterations, minIter, maxIter, perf->initialResidual, perf->finalResidual, tol, relTol));
     }
     perf->converged = (perf->finalResidual < tol || (relTol > 0 && perf->finalResidual < relTol * perf->initialResidual));
+}
+
+// ================================================================== f1: DILUPreconditioner + PBiCG::solve
+// [REF region3d/UEqn.H:19-34] [UPSTREAM DILUPreconditioner.C calcReciprocalD / precondition / preconditionT]
+static void ldu_losort(const OrcMesh* m, std::vector<int>& losort) {   // [UPSTREAM lduAddressing::calcLosort] faces by upper address, stable
+    std::vector<int> start(m->N + 1, 0);
+    for (int f = 0; f < m->F; f++) start[m->nei[f] + 1]++;
+    for (int c = 0; c < m->N; c++) start[c + 1] += start[c];
+    losort.resize(m->F);
+    for (int f = 0; f < m->F; f++) losort[start[m->nei[f]]++] = f;
+}
+extern "C" void orc_dilu_calc_rd(const OrcMesh* m, const double* diag, const double* upper, const double* lower, double* rD) {
+    for (int c = 0; c < m->N; c++) rD[c] = diag[c];
+    for (int f = 0; f < m->F; f++) rD[m->nei[f]] -= upper[f] * lower[f] / rD[m->own[f]];
+    for (int c = 0; c < m->N; c++) rD[c] = 1.0 / rD[c];
+}
+extern "C" void orc_dilu_precondition(const OrcMesh* m, const double* rD, const double* upper, const double* lower, const double* rA,
+                                      double* wA, int transpose) {
+    std::vector<int> losort; ldu_losort(m, losort);
+    for (int c = 0; c < m->N; c++) wA[c] = rD[c] * rA[c];
+    if (!transpose) {
+        for (int face = 0; face < m->F; face++) { int sf = losort[face]; wA[m->nei[sf]] -= rD[m->nei[sf]] * lower[sf] * wA[m->own[sf]]; }
+        for (int f = m->F - 1; f >= 0; f--) wA[m->own[f]] -= rD[m->own[f]] * upper[f] * wA[m->nei[f]];
+    } else {
+        for (int f = 0; f < m->F; f++) wA[m->nei[f]] -= rD[m->nei[f]] * upper[f] * wA[m->own[f]];
+        for (int face = m->F - 1; face >= 0; face--) { int sf = losort[face]; wA[m->own[sf]] -= rD[m->own[sf]] * lower[sf] * wA[m->nei[sf]]; }
+    }
+}
+// [UPSTREAM PBiCG.C solve]  intc: interfaceIntCoeffs (Tmul's interface update); comm as in pcgSolve
+static void pbicgSolve(const OrcMesh* m, const double* diag, const double* upper, const double* lower, const double* bou, const double* intc,
+                       double* x, const double* b, double tol, double relTol, int minIter, int maxIter, OrcPerf* perf, double* resHist,
+                       const OrcComm* comm) {
+    int N = m->N;
+    vec pA(N), pT(N, 0.0), wA(N), wT(N), rA(N), rT(N), rD(N), psiNbr(comm ? m->B : 0);
+    auto gsum = [&](double v) { return comm ? comm->reduce(comm->ctx, v, 0) : v; };
+    auto amul = [&](const double* psi, double* Apsi) {
+        if (comm) { comm->halo(comm->ctx, psi, 1, psiNbr.data()); orc_amul(m, diag, upper, lower, psi, Apsi, bou, psiNbr.data()); }
+        else orc_amul(m, diag, upper, lower, psi, Apsi, nullptr, nullptr);
+    };
+    auto tmul = [&](const double* psi, double* Tpsi) {   // [UPSTREAM lduMatrix::Tmul]: lower and upper swap roles, interfaceIntCoeffs
+        if (comm) { comm->halo(comm->ctx, psi, 1, psiNbr.data()); orc_amul(m, diag, lower, upper, psi, Tpsi, intc, psiNbr.data()); }
+        else orc_amul(m, diag, lower, upper, psi, Tpsi, nullptr, nullptr);
+    };
+    amul(x, wA.data());
+    for (int c = 0; c < N; c++) { rA[c] = b[c] - wA[c]; rT[c] = rA[c]; }
+    orc_sumA(m, diag, upper, lower, pA.data(), comm ? bou : nullptr);
+    double xRef = 0;
+    for (int c = 0; c < N; c++) xRef += x[c];
+    xRef = gsum(xRef) / gsum((double)N);
+    double nf = 0;
+    for (int c = 0; c < N; c++) { double t = xRef * pA[c]; nf += std::fabs(wA[c] - t) + std::fabs(b[c] - t); }
+    nf = gsum(nf) + 1.0e-20;
+    double s = 0;
+    for (int c = 0; c < N; c++) s += std::fabs(rA[c]);
+    s = gsum(s);
+    perf->initialResidual = perf->finalResidual = s / nf;
+    perf->nIterations = 0; perf->singular = 0;
+    if (resHist) resHist[0] = perf->initialResidual;
+    if (!pcgStop(0, minIter, maxIter, perf->initialResidual, perf->finalResidual, tol, relTol)) {
+        orc_dilu_calc_rd(m, diag, upper, lower, rD.data());
+        double wArT = 1e20, wArTold;
+        do {
+            wArTold = wArT;
+            orc_dilu_precondition(m, rD.data(), upper, lower, rA.data(), wA.data(), 0);
+            orc_dilu_precondition(m, rD.data(), upper, lower, rT.data(), wT.data(), 1);
+            wArT = 0;
+            for (int c = 0; c < N; c++) wArT += wA[c] * rT[c];
+            wArT = gsum(wArT);
+            if (perf->nIterations == 0) { for (int c = 0; c < N; c++) { pA[c] = wA[c]; pT[c] = wT[c]; } }
+            else { double beta = wArT / wArTold; for (int c = 0; c < N; c++) { pA[c] = wA[c] + beta * pA[c]; pT[c] = wT[c] + beta * pT[c]; } }
+            amul(pA.data(), wA.data());
+            tmul(pT.data(), wT.data());
+            double wApT = 0;
+            for (int c = 0; c < N; c++) wApT += wA[c] * pT[c];
+            wApT = gsum(wApT);
+            if (std::fabs(wApT) / nf <= VSMALL) { perf->singular = 1; break; }
+            double alpha = wArT / wApT;
+            for (int c = 0; c < N; c++) { x[c] += alpha * pA[c]; rA[c] -= alpha * wA[c]; rT[c] -= alpha * wT[c]; }
+            s = 0;
+            for (int c = 0; c < N; c++) s += std::fabs(rA[c]);
+            s = gsum(s);
+            perf->finalResidual = s / nf;
+            perf->nIterations++;
+            if (resHist) resHist[perf->nIterations] = perf->finalResidual;
+        } while (!pcgStop(perf->nIterations, minIter, maxIter, perf->initialResidual, perf->finalResidual, tol, relTol));
+    }
+    perf->converged = (perf->finalResidual < tol || (relTol > 0 && perf->finalResidual < relTol * perf->initialResidual));
+}
+extern "C" void orc_pbicg_solve(const OrcMesh* m, const double* diag, const double* upper, const double* lower, double* x, const double* b,
+                                double tol, double relTol, int minIter, int maxIter, OrcPerf* perf, double* resHist) {
+    pbicgSolve(m, diag, upper, lower, nullptr, nullptr, x, b, tol, relTol, minIter, maxIter, perf, resHist, nullptr);
 }
 
 // ================================================================== boundary-condition algebra
@@ -247,6 +363,72 @@ extern "C" void orc_interpolate(const OrcMesh* m, const double* vf, const double
     }
     for (int b = 0; b < m->B; b++)
         for (int k = 0; k < nc; k++) out[nc * (m->F + b) + k] = vfb[nc * b + k];
+    // processor (coupled) patches: the linear interpolate with the neighbour-rank cell, vfb = patchNeighbourField
+    // [UPSTREAM surfaceInterpolationScheme::interpolate, coupled branch]
+    for (int p = 0; p < m->nPatches; p++)
+        if (m->pKind[p] == 1)
+            for (int f = m->pStart[p]; f < m->pStart[p] + m->pSize[p]; f++) {
+                int b = f - m->F, c = m->own[f];
+                for (int k = 0; k < nc; k++) out[nc * f + k] = m->w[f] * (vf[nc * c + k] - vfb[nc * b + k]) + vfb[nc * b + k];
+            }
+}
+// value of a field on boundary face f as the Gauss sums see it: the patch value, or the interpolate on a processor face
+static inline double bndFaceValue(const OrcMesh* m, int p, int f, double own, double bv) {
+    return m->pKind[p] == 1 ? m->w[f] * (own - bv) + bv : bv;
+}
+// ---- non-orthogonal correction [UPSTREAM surfaceInterpolation.C makeCorrectionVectors; correctedSnGrad.C correction;
+// gaussLaplacianScheme.C fvmLaplacian]  [REF region3d/pEqn.H:23-45]
+// corrVec_f = Sf/magSf - d*deltaCoeffs, d = C[N] - C[P] (internal faces; processor faces with the neighbour-rank centre Cn; physical
+// boundary faces: zero)
+static inline void corrVec(const OrcMesh* m, int f, double* cv) {
+    cv[0] = cv[1] = cv[2] = 0.0;
+    if (f < m->F) {
+        int o = m->own[f], n = m->nei[f];
+        for (int k = 0; k < 3; k++) cv[k] = m->Sf[3 * f + k] / m->magSf[f] - (m->C[3 * n + k] - m->C[3 * o + k]) * m->dc[f];
+    } else if (m->Cn) {
+        int b = f - m->F;
+        for (int p = 0; p < m->nPatches; p++)
+            if (m->pKind[p] == 1 && f >= m->pStart[p] && f < m->pStart[p] + m->pSize[p]) {
+                int o = m->own[f];
+                for (int k = 0; k < 3; k++) cv[k] = m->Sf[3 * f + k] / m->magSf[f] - (m->Cn[3 * b + k] - m->C[3 * o + k]) * m->dc[f];
+            }
+    }
+}
+// this rank's sums of mesh.orthogonal(): out2 = {sum(magSf*|corrVec|), sum(magSf)} over the internal faces
+extern "C" void orc_non_orth_sums(const OrcMesh* m, double* out2) {
+    double sMC = 0, sM = 0;
+    for (int f = 0; f < m->F; f++) {
+        double c[3]; corrVec(m, f, c);
+        sMC += m->magSf[f] * std::sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+        sM += m->magSf[f];
+    }
+    out2[0] = sMC; out2[1] = sM;
+}
+static inline double nonOrthDegrees(double sMC, double sM) {
+    if (!(sM > 0.0)) return 0.0;
+    return std::asin(std::min(sMC / sM, 1.0)) * 180.0 / 3.14159265358979323846;
+}
+// out[f] = scale_f * (corrVec_f & linearInterpolate(grad)_f), scale = gammaf*magSf (gammaf null: 1); grad [3N], gradB [3B] = the
+// neighbour-rank cell gradient on processor faces (ignored elsewhere)
+extern "C" void orc_non_orth_correction(const OrcMesh* m, const double* gammaf, const double* grad, const double* gradB, double* out) {
+    for (int f = 0; f < m->F + m->B; f++) out[f] = 0.0;
+    for (int f = 0; f < m->F; f++) {
+        int l = m->own[f], u = m->nei[f];
+        double cv[3], gf[3]; corrVec(m, f, cv);
+        for (int k = 0; k < 3; k++) gf[k] = m->w[f] * (grad[3 * l + k] - grad[3 * u + k]) + grad[3 * u + k];
+        double c = (cv[0] * gf[0] + cv[1] * gf[1]) + cv[2] * gf[2];
+        out[f] = gammaf ? (gammaf[f] * m->magSf[f]) * c : c;
+    }
+    if (m->Cn && gradB)
+        for (int p = 0; p < m->nPatches; p++)
+            if (m->pKind[p] == 1)
+                for (int f = m->pStart[p]; f < m->pStart[p] + m->pSize[p]; f++) {
+                    int b = f - m->F, l = m->own[f];
+                    double cv[3], gf[3]; corrVec(m, f, cv);
+                    for (int k = 0; k < 3; k++) gf[k] = m->w[f] * (grad[3 * l + k] - gradB[3 * b + k]) + gradB[3 * b + k];
+                    double c = (cv[0] * gf[0] + cv[1] * gf[1]) + cv[2] * gf[2];
+                    out[f] = gammaf ? (gammaf[f] * m->magSf[f]) * c : c;
+                }
 }
 // snGrad (uncorrected) [UPSTREAM snGradScheme::snGrad; patch snGrad]
 extern "C" void orc_sngrad(const OrcMesh* m, const OrcBC* bc, const double* vf, const double* vfb, double* out) {
@@ -273,8 +455,11 @@ extern "C" void orc_grad_gauss(const OrcMesh* m, const OrcBC* bc, const double* 
         double sf = m->w[f] * (vf[l] - vf[u]) + vf[u];
         for (int k = 0; k < 3; k++) { double t = m->Sf[3 * f + k] * sf; g[3 * l + k] += t; g[3 * u + k] -= t; }
     }
-    for (int f = F; f < F + m->B; f++)
-        for (int k = 0; k < 3; k++) g[3 * m->own[f] + k] += m->Sf[3 * f + k] * vfb[f - F];
+    for (int p = 0; p < m->nPatches; p++)
+        for (int f = m->pStart[p]; f < m->pStart[p] + m->pSize[p]; f++) {
+            double fv = bndFaceValue(m, p, f, vf[m->own[f]], vfb[f - F]);
+            for (int k = 0; k < 3; k++) g[3 * m->own[f] + k] += m->Sf[3 * f + k] * fv;
+        }
     for (int c = 0; c < N; c++)
         for (int k = 0; k < 3; k++) g[3 * c + k] /= m->V[c];
     if (gb)
@@ -302,9 +487,12 @@ static void gradGaussVector(const OrcMesh* m, const double* U, const double* Ub,
             for (int i = 0; i < 3; i++) { double t = m->Sf[3 * f + i] * uf; gradU[9 * l + 3 * i + j] += t; gradU[9 * u + 3 * i + j] -= t; }
         }
     }
-    for (int f = F; f < F + m->B; f++)
-        for (int j = 0; j < 3; j++)
-            for (int i = 0; i < 3; i++) gradU[9 * m->own[f] + 3 * i + j] += m->Sf[3 * f + i] * Ub[3 * (f - F) + j];
+    for (int p = 0; p < m->nPatches; p++)
+        for (int f = m->pStart[p]; f < m->pStart[p] + m->pSize[p]; f++)
+            for (int j = 0; j < 3; j++) {
+                double uf = bndFaceValue(m, p, f, U[3 * m->own[f] + j], Ub[3 * (f - F) + j]);
+                for (int i = 0; i < 3; i++) gradU[9 * m->own[f] + 3 * i + j] += m->Sf[3 * f + i] * uf;
+            }
     for (int c = 0; c < N; c++)
         for (int q = 0; q < 9; q++) gradU[9 * c + q] /= m->V[c];
 }
@@ -365,6 +553,8 @@ static inline double compressionLimiter(double aP, double aN) {
     return 1.0 - std::max(wP * wP, wN * wN);
 }
 // out = faceFlux * interpolate(vf) with the named limited scheme; boundary: faceFlux_b * vf_b
+static void fluxLimitedCoupled(const OrcMesh* m, int scheme, const double* faceFlux, const double* vf, const double* vfb,
+                               const double* grad, const double* gradNbr, double* out);
 extern "C" void orc_flux_limited(const OrcMesh* m, int scheme, const double* faceFlux, const double* vf,
                                  const double* vfb, const double* grad /*3N or null*/, double* out) {
     int F = m->F;
@@ -383,6 +573,27 @@ extern "C" void orc_flux_limited(const OrcMesh* m, int scheme, const double* fac
     }
     for (int b = 0; b < m->B; b++) out[F + b] = faceFlux[F + b] * vfb[b];
 }
+// processor faces of a decomposed run: the internal-face formula with the neighbour-rank cell as N (vfb = patchNeighbourField,
+// gradNbr [3B] = the neighbour cell's gradient, m->Cn its centre) [UPSTREAM limitedSurfaceInterpolationScheme, coupled patches]
+static void fluxLimitedCoupled(const OrcMesh* m, int scheme, const double* faceFlux, const double* vf, const double* vfb,
+                               const double* grad, const double* gradNbr, double* out) {
+    for (int p = 0; p < m->nPatches; p++) {
+        if (m->pKind[p] != 1) continue;
+        for (int f = m->pStart[p]; f < m->pStart[p] + m->pSize[p]; f++) {
+            int b = f - m->F, c = m->own[f];
+            double lim;
+            if (scheme == 0) {
+                double d[3] = {m->Cn[3 * b] - m->C[3 * c], m->Cn[3 * b + 1] - m->C[3 * c + 1], m->Cn[3 * b + 2] - m->C[3 * c + 2]};
+                lim = vanLeerLimiter(vf[c], vfb[b], &grad[3 * c], &gradNbr[3 * b], d, faceFlux[f]);
+            } else if (scheme == 1) lim = compressionLimiter(vf[c], vfb[b]);
+            else if (scheme == 2) lim = 0.0;
+            else lim = 1.0;
+            double pos = faceFlux[f] >= 0 ? 1.0 : 0.0;
+            double wgt = lim * m->w[f] + (1.0 - lim) * pos;
+            out[f] = faceFlux[f] * (wgt * (vf[c] - vfb[b]) + vfb[b]);
+        }
+    }
+}
 
 // ================================================================== a5/a6: MULES
 // [REF region3d/alphaEqn.H:31] [UPSTREAM MULES.C explicitSolve -> MULESTemplates.C explicitSolve/limiter]
@@ -391,7 +602,7 @@ extern "C" void orc_mules_limiter(const OrcMesh* m, double* lambda /*F+B*/, cons
                                   const double* psi0, const double* phiBD, const double* phiCorr, double deltaT,
                                   double psiMax, double psiMin, int nLimiterIter, int includeOwn,
                                   const double* psiNbr /*coupled patchNeighbourField or null*/,
-                                  const OrcBC* bc) {
+                                  const OrcBC* bc, const OrcComm* comm = nullptr) {
     int N = m->N, F = m->F, B = m->B;
     vec psiMaxn(N, psiMin), psiMinn(N, psiMax), sumPhiBD(N, 0.0), sumPhip(N, VSMALL), mSumPhim(N, VSMALL);
     for (int f = 0; f < F + B; f++) lambda[f] = 1.0;
@@ -451,7 +662,17 @@ extern "C" void orc_mules_limiter(const OrcMesh* m, double* lambda /*F+B*/, cons
             if (phiCorr[f] > 0.0) lambda[f] = std::min(lambda[f], lambdap[c]);
             else lambda[f] = std::min(lambda[f], lambdam[c]);
         }
-        // syncTools::syncFaceList(minEqOp) over processor faces: done by the multi-rank driver
+        // syncTools::syncFaceList(mesh, allLambda, minEqOp) over processor faces: the other side limited the same face with ITS cell
+        // (its phiCorr has the opposite sign), so it holds  min(before, pc > 0 ? lambdam_nbr : lambdap_nbr)
+        if (comm) {
+            vec lpN(B), lmN(B);
+            comm->halo(comm->ctx, lambdap.data(), 1, lpN.data());
+            comm->halo(comm->ctx, lambdam.data(), 1, lmN.data());
+            for (int p = 0; p < m->nPatches; p++)
+                if (m->pKind[p] == 1)
+                    for (int f = m->pStart[p]; f < m->pStart[p] + m->pSize[p]; f++)
+                        lambda[f] = std::min(lambda[f], phiCorr[f] > 0.0 ? lmN[f - F] : lpN[f - F]);
+        }
     }
 }
 
@@ -459,15 +680,19 @@ extern "C" void orc_mules_limiter(const OrcMesh* m, double* lambda /*F+B*/, cons
 // the caller, as the adapter does on the host); phiPsi: in = high-order flux, out = limited flux.
 extern "C" void orc_mules_explicit_solve(const OrcMesh* m, double* psi, const double* psib, const double* psi0,
                                          const double* phi, double* phiPsi, double deltaT, double psiMax,
-                                         double psiMin, int includeOwn, double* lambdaOut, const OrcBC* bc) {
+                                         double psiMin, int includeOwn, double* lambdaOut, const OrcBC* bc,
+                                         const OrcComm* comm = nullptr) {
     int N = m->N, F = m->F, B = m->B;
     vec phiBD(F + B), lambda(F + B);
     // upwind(phi).flux(psi)
     for (int f = 0; f < F; f++) phiBD[f] = phi[f] * (phi[f] >= 0 ? psi[m->own[f]] : psi[m->nei[f]]);
     for (int b = 0; b < B; b++) phiBD[F + b] = phi[F + b] * psib[b];
+    for (int p = 0; p < m->nPatches; p++)   // processor faces: upwind between the cell and its neighbour-rank cell (psib = patchNeighbourField)
+        if (m->pKind[p] == 1)
+            for (int f = m->pStart[p]; f < m->pStart[p] + m->pSize[p]; f++) phiBD[f] = phi[f] * (phi[f] >= 0 ? psi[m->own[f]] : psib[f - F]);
     for (int f = 0; f < F + B; f++) phiPsi[f] -= phiBD[f];  // phiCorr, in place
     orc_mules_limiter(m, lambda.data(), psi, psib, psi0, phiBD.data(), phiPsi, deltaT, psiMax, psiMin, 3, includeOwn,
-                      nullptr, bc);
+                      nullptr, bc, comm);
     for (int f = 0; f < F + B; f++) phiPsi[f] = phiBD[f] + lambda[f] * phiPsi[f];
     vec div(N);
     orc_surface_integrate(m, phiPsi, div.data());
@@ -490,6 +715,10 @@ extern "C" void orc_laplacian_assemble(const OrcMesh* m, const OrcBC* bc, const 
         for (int f = m->pStart[p]; f < m->pStart[p] + m->pSize[p]; f++) {
             int b = f - F, t = bc->type[p];
             double pg = gammaf[f] * m->magSf[f];
+            if (t == BC_PROCESSOR) {   // coupledFvPatchField: gradientInternalCoeffs = -deltaCoeffs, gradientBoundaryCoeffs = +deltaCoeffs
+                intCoeffs[b] = pg * (-1.0 * m->dc[f]); bouCoeffs[b] = -pg * m->dc[f];
+                continue;
+            }
             intCoeffs[b] = pg * bcGradIntCoeff(m, *bc, t, b);
             bouCoeffs[b] = -pg * bcGradBouCoeff(m, *bc, t, b, b, pb[b]);
         }
@@ -507,10 +736,20 @@ extern "C" void orc_add_boundary(const OrcMesh* m, const double* intCoeffs, cons
         if (m->pKind[p] == 0)
             for (int f = m->pStart[p]; f < m->pStart[p] + m->pSize[p]; f++) source[m->own[f]] += bouCoeffs[f - m->F];
 }
-extern "C" void orc_matrix_flux(const OrcMesh* m, const double* upper, const double* lower, const double* intCoeffs,
-                                const double* bouCoeffs, const double* psi, double* flux) {
+static void matrixFlux(const OrcMesh* m, const double* upper, const double* lower, const double* intCoeffs,
+                       const double* bouCoeffs, const double* psi, const double* psib /*patchNeighbourField on processor faces, or null*/,
+                       double* flux) {
     for (int f = 0; f < m->F; f++) flux[f] = upper[f] * psi[m->nei[f]] - lower[f] * psi[m->own[f]];
     for (int f = m->F; f < m->F + m->B; f++) flux[f] = intCoeffs[f - m->F] * psi[m->own[f]] - bouCoeffs[f - m->F];
+    if (psib)
+        for (int p = 0; p < m->nPatches; p++)
+            if (m->pKind[p] == 1)
+                for (int f = m->pStart[p]; f < m->pStart[p] + m->pSize[p]; f++)
+                    flux[f] = intCoeffs[f - m->F] * psi[m->own[f]] - bouCoeffs[f - m->F] * psib[f - m->F];
+}
+extern "C" void orc_matrix_flux(const OrcMesh* m, const double* upper, const double* lower, const double* intCoeffs,
+                                const double* bouCoeffs, const double* psi, double* flux) {
+    matrixFlux(m, upper, lower, intCoeffs, bouCoeffs, psi, nullptr, flux);
 }
 
 // ================================================================== a14
@@ -544,8 +783,13 @@ extern "C" struct OrcControls {
     double UTol, URelTol;
 };
 
+struct World;
 struct Region {
     const OrcMesh* m; OrcControls ctl;
+    // decomposed runs (orc_world_*): this rank's hooks, and for every boundary face the neighbour rank (-1: physical) and its cell there
+    OrcComm commS; const OrcComm* comm = nullptr; World* world = nullptr; int rank = 0;
+    std::vector<int> nbrRank, nbrCell;
+    const double* pub = nullptr;   // the cell field this rank currently offers to its neighbours (halo)
     std::vector<int> tAlpha, tU, tPd;
     vec rvAlpha, rgAlpha, vfAlpha, rvU, rgU, vfU, rvPd, rgPd, vfPd;
     OrcBC bcAlpha, bcU, bcPd, bcRho;
@@ -561,7 +805,31 @@ struct Region {
     double sumLocalContErr, globalContErr, cumulativeContErr;
     double tPCG, tMULES, tOther;
     bool pdNeedRef;   // pd.needReference() [UPSTREAM GeometricField::needReference]: no patch fixes the value
+    bool orthogonal;  // mesh.orthogonal() (global): the `corrected` schemes are no-ops when true
 };
+
+// psi.correctBoundaryConditions(): processor patches receive patchNeighbourField through the halo hook
+static void evalBC(Region* r, const OrcBC& bc, const double* internal, double* bval, int nc) {
+    if (r->comm) {
+        vec nbr((size_t)nc * r->m->B);
+        r->comm->halo(r->comm->ctx, internal, nc, nbr.data());
+        bcEvaluate(r->m, bc, internal, bval, nc, nbr.data());
+    } else bcEvaluate(r->m, bc, internal, bval, nc);
+}
+static inline double gSum(Region* r, double v) { return r->comm ? r->comm->reduce(r->comm->ctx, v, 0) : v; }
+static inline double gMax(Region* r, double v) { return r->comm ? r->comm->reduce(r->comm->ctx, v, 1) : v; }
+static inline double gMin(Region* r, double v) { return r->comm ? r->comm->reduce(r->comm->ctx, v, 2) : v; }
+// patchNeighbourField of a cell field on the processor faces of bdst (other faces untouched)
+static void haloInto(Region* r, const double* cellField, int nc, double* bdst) {
+    if (!r->comm) return;
+    const OrcMesh* m = r->m;
+    vec nbr((size_t)nc * m->B);
+    r->comm->halo(r->comm->ctx, cellField, nc, nbr.data());
+    for (int p = 0; p < m->nPatches; p++)
+        if (m->pKind[p] == 1)
+            for (int f = m->pStart[p]; f < m->pStart[p] + m->pSize[p]; f++)
+                for (int k = 0; k < nc; k++) bdst[nc * (f - m->F) + k] = nbr[nc * (f - m->F) + k];
+}
 
 static void setBC(OrcBC& bc, std::vector<int>& t, vec& rv, vec& rg, vec& vf) {
     bc.type = t.data(); bc.refValue = rv.data(); bc.refGrad = rg.data(); bc.valueFraction = vf.data();
@@ -584,20 +852,7 @@ extern "C" Region* orc_region_create(const OrcMesh* m, const OrcControls* ctl, c
     r->bcRho = r->bcAlpha;  // rho takes alpha1's patch types [REF create3dFields.H:147-164]; values are forced (==)
     r->alpha.assign(alpha, alpha + N); r->U.assign(U, U + 3 * N); r->pd.assign(pd, pd + N);
     r->alphab.assign(B, 0); r->Ub.assign(3 * B, 0); r->pdb.assign(B, 0);
-    bcEvaluate(m, r->bcAlpha, r->alpha.data(), r->alphab.data(), 1);
-    bcEvaluate(m, r->bcU, r->U.data(), r->Ub.data(), 3);
-    bcEvaluate(m, r->bcPd, r->pd.data(), r->pdb.data(), 1);
-    // phi = linearInterpolate(U) & Sf  [REF create3dFields.H:99-114]
-    vec Uf(3 * (F + B));
-    orc_interpolate(m, r->U.data(), r->Ub.data(), Uf.data(), 3);
-    r->phi.resize(F + B);
-    for (int f = 0; f < F + B; f++) r->phi[f] = Uf[3 * f] * m->Sf[3 * f] + Uf[3 * f + 1] * m->Sf[3 * f + 1] + Uf[3 * f + 2] * m->Sf[3 * f + 2];
-    // rho [REF create3dFields.H:147-164]
-    r->rho.resize(N); r->rhob.resize(B);
-    for (int c = 0; c < N; c++) r->rho[c] = r->alpha[c] * ctl->rho1 + (1.0 - r->alpha[c]) * ctl->rho2;
-    for (int b = 0; b < B; b++) r->rhob[b] = r->alphab[b] * ctl->rho1 + (1.0 - r->alphab[b]) * ctl->rho2;
-    r->rhoPhi.resize(F + B);
-    for (int f = 0; f < F + B; f++) r->rhoPhi[f] = ctl->rho1 * r->phi[f];
+    r->phi.resize(F + B); r->rho.resize(N); r->rhob.resize(B); r->rhoPhi.resize(F + B);
     // gh, ghf [REF create3dFields.H:188-206]
     r->gh.resize(N); r->ghf.resize(F + B);
     for (int c = 0; c < N; c++) r->gh[c] = ctl->g[0] * m->C[3 * c] + ctl->g[1] * m->C[3 * c + 1] + ctl->g[2] * m->C[3 * c + 2];
@@ -605,16 +860,39 @@ extern "C" Region* orc_region_create(const OrcMesh* m, const OrcControls* ctl, c
     r->p.resize(N); r->pb.resize(B);
     r->invT.resize(6 * N);
     orc_reconstruct_tensor(m, r->invT.data());
-    // interfaceProperties: deltaN = 1e-8/cbrt(average(V))  [UPSTREAM interfaceProperties.C ctor]
-    double sV = 0;
-    for (int c = 0; c < N; c++) sV += m->V[c];
-    r->deltaN = 1e-8 / std::pow(sV / N, 1.0 / 3.0);
     r->nHatf.resize(F + B); r->K.resize(N); r->Kb.resize(B);
     r->cumulativeContErr = 0;
     r->tPCG = r->tMULES = r->tOther = 0;
-    r->pdNeedRef = true;
-    for (int p = 0; p < P; p++) if (bcFixesValue(r->tPd[p]) && m->pSize[p] > 0) r->pdNeedRef = false;
     return r;
+}
+static void calculateK(Region* r);
+// the part of createFields that evaluates boundary conditions (halo swaps on processor patches) and global reductions: run once per
+// region -- directly (single rank, orc_region_init_interface) or by every rank's thread (orc_world_create)
+static void initFields(Region* r) {
+    const OrcMesh* m = r->m; const OrcControls* ctl = &r->ctl; int N = m->N, F = m->F, B = m->B;
+    evalBC(r, r->bcAlpha, r->alpha.data(), r->alphab.data(), 1);
+    evalBC(r, r->bcU, r->U.data(), r->Ub.data(), 3);
+    evalBC(r, r->bcPd, r->pd.data(), r->pdb.data(), 1);
+    // phi = linearInterpolate(U) & Sf  [REF create3dFields.H:99-114]
+    vec Uf(3 * (F + B));
+    orc_interpolate(m, r->U.data(), r->Ub.data(), Uf.data(), 3);
+    for (int f = 0; f < F + B; f++) r->phi[f] = Uf[3 * f] * m->Sf[3 * f] + Uf[3 * f + 1] * m->Sf[3 * f + 1] + Uf[3 * f + 2] * m->Sf[3 * f + 2];
+    // rho [REF create3dFields.H:147-164]
+    for (int c = 0; c < N; c++) r->rho[c] = r->alpha[c] * ctl->rho1 + (1.0 - r->alpha[c]) * ctl->rho2;
+    for (int b = 0; b < B; b++) r->rhob[b] = r->alphab[b] * ctl->rho1 + (1.0 - r->alphab[b]) * ctl->rho2;
+    for (int f = 0; f < F + B; f++) r->rhoPhi[f] = ctl->rho1 * r->phi[f];
+    // interfaceProperties: deltaN = 1e-8/cbrt(average(V)) (a global average)  [UPSTREAM interfaceProperties.C ctor]
+    double sV = 0;
+    for (int c = 0; c < N; c++) sV += m->V[c];
+    r->deltaN = 1e-8 / std::pow(gSum(r, sV) / gSum(r, (double)N), 1.0 / 3.0);
+    // pd.needReference(): no patch fixes the value on any rank
+    double anyFixes = 0.0;
+    for (int p = 0; p < m->nPatches; p++) if (bcFixesValue(r->tPd[p]) && m->pSize[p] > 0) anyFixes = 1.0;
+    r->pdNeedRef = gMax(r, anyFixes) == 0.0;
+    double no[2];
+    orc_non_orth_sums(m, no);
+    r->orthogonal = nonOrthDegrees(gSum(r, no[0]), gSum(r, no[1])) < 0.1;
+    calculateK(r);   // interfaceProperties ctor [REF create3dFields.H:254-263]
 }
 extern "C" void orc_region_destroy(Region* r) { delete r; }
 
@@ -623,6 +901,7 @@ static void calculateK(Region* r) {
     const OrcMesh* m = r->m; int N = m->N, F = m->F, B = m->B;
     vec g(3 * N), gb(3 * B), gf(3 * (F + B));
     orc_grad_gauss(m, &r->bcAlpha, r->alpha.data(), r->alphab.data(), g.data(), gb.data());
+    haloInto(r, g.data(), 3, gb.data());   // processor faces: the neighbour cell's gradient
     orc_interpolate(m, g.data(), gb.data(), gf.data(), 3);
     for (int f = 0; f < F + B; f++) {
         double mg = std::sqrt(gf[3 * f] * gf[3 * f] + gf[3 * f + 1] * gf[3 * f + 1] + gf[3 * f + 2] * gf[3 * f + 2]);
@@ -632,6 +911,7 @@ static void calculateK(Region* r) {
     orc_surface_integrate(m, r->nHatf.data(), r->K.data());
     for (int c = 0; c < N; c++) r->K[c] = -r->K[c];
     for (int b = 0; b < B; b++) r->Kb[b] = r->K[m->own[F + b]];  // zeroGradient patches on the div result
+    haloInto(r, r->K.data(), 1, r->Kb.data());
 }
 
 static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -654,7 +934,8 @@ static void adjustPhi(Region* r, double* phiU) {
     {
         double sAbs = 0;
         for (int f = 0; f < F; f++) sAbs += std::fabs(phiU[f]);
-        totalFlux += sAbs;
+        massIn = gSum(r, massIn); fixedMassOut = gSum(r, fixedMassOut); adjustableMassOut = gSum(r, adjustableMassOut);
+        totalFlux += gSum(r, sAbs);
     }
     double magAdjustableMassOut = std::fabs(adjustableMassOut);
     double massCorr = 1.0;
@@ -668,11 +949,30 @@ static void adjustPhi(Region* r, double* phiU) {
     }
 }
 
+static inline bool nonOrth(const Region* r) { return r->ctl.nonOrthCorrected != 0 && !r->orthogonal; }  // (declared above)
+// (gammaf*magSf) * correctedSnGrad::correction(vf) on every face: Gauss-linear grad(vf) with boundary values vfb
+static void nonOrthCorrection(Region* r, const OrcBC& bc, const double* vf, const double* vfb, const double* gammaf, double* out) {
+    const OrcMesh* m = r->m;
+    vec g(3 * m->N), gN(r->comm ? 3 * m->B : 0);
+    orc_grad_gauss(m, &bc, vf, vfb, g.data(), nullptr);
+    if (r->comm) r->comm->halo(r->comm->ctx, g.data(), 3, gN.data());
+    orc_non_orth_correction(m, gammaf, g.data(), r->comm ? gN.data() : nullptr, out);
+}
 static void solvePressureLike(Region* r, const OrcBC& bc, const double* gammaf, double* psi, double* psib,
                               double tol, double relTol, bool finalFlux, vec& fluxOut) {
     const OrcMesh* m = r->m; int N = m->N, F = m->F, B = m->B;
     vec diag(N), upper(F), source(N), ic(B), bcv(B);
-    orc_laplacian_assemble(m, &bc, gammaf, psib, r->phi.data(), diag.data(), upper.data(), source.data(), ic.data(), bcv.data());
+    // laplacian `corrected`: fvm.faceFluxCorrectionPtr() = gammaMagSf*snGradScheme.correction(vf); fvm.source() -= V*fvc::div(ffc)
+    // -- BEFORE the == fvc::div(phi) term is added to the source [UPSTREAM gaussLaplacianScheme::fvmLaplacian]
+    vec ffc;
+    if (nonOrth(r)) { ffc.resize(F + B); nonOrthCorrection(r, bc, psi, psib, gammaf, ffc.data()); }
+    orc_laplacian_assemble(m, &bc, gammaf, psib, nullptr, diag.data(), upper.data(), source.data(), ic.data(), bcv.data());
+    {
+        vec div(N);
+        if (!ffc.empty()) { orc_surface_integrate(m, ffc.data(), div.data()); for (int c = 0; c < N; c++) source[c] -= m->V[c] * div[c]; }
+        orc_surface_integrate(m, r->phi.data(), div.data());
+        for (int c = 0; c < N; c++) source[c] += m->V[c] * div[c];
+    }
     // fvMatrix::setReference(celli, value) [REF region3d/pEqn.H:30; correctPhi.H:43] [UPSTREAM fvMatrix.C]: only when the field
     // needs a reference level (no patch fixes its value): source[celli] += diag[celli]*value ; diag[celli] += diag[celli]
     if (r->pdNeedRef && r->ctl.pdRefCell >= 0 && r->ctl.pdRefCell < N) {
@@ -686,14 +986,16 @@ static void solvePressureLike(Region* r, const OrcBC& bc, const double* gammaf, 
     size_t h0 = r->resHist.size();
     r->resHist.resize(h0 + r->ctl.maxIter + 2, -1.0);
     double t0 = now();
-    orc_pcg_solve(m, sdiag.data(), upper.data(), nullptr, psi, tsrc.data(), tol, relTol, r->ctl.minIter, r->ctl.maxIter, &perf, &r->resHist[h0]);
+    pcgSolve(m, sdiag.data(), upper.data(), r->comm ? bcv.data() : nullptr, psi, tsrc.data(), tol, relTol, r->ctl.minIter, r->ctl.maxIter, &perf,
+             &r->resHist[h0], r->comm);
     r->tPCG += now() - t0;
     r->resHist.resize(h0 + perf.nIterations + 1);
     r->perfs.push_back(perf);
-    bcEvaluate(m, bc, psi, psib, 1);
+    evalBC(r, bc, psi, psib, 1);
     if (finalFlux) {
         fluxOut.resize(F + B);
-        orc_matrix_flux(m, upper.data(), upper.data(), ic.data(), bcv.data(), psi, fluxOut.data());
+        matrixFlux(m, upper.data(), upper.data(), ic.data(), bcv.data(), psi, r->comm ? psib : nullptr, fluxOut.data());
+        if (!ffc.empty()) for (int f = 0; f < F + B; f++) fluxOut[f] += ffc[f];   // fieldFlux += *faceFluxCorrectionPtr_ [UPSTREAM fvMatrix::flux]
     }
 }
 
@@ -721,29 +1023,40 @@ static void alphaEqn(Region* r, double dt) {
     vec phic(F + B), phir(F + B);
     double mx = -1e300;
     for (int f = 0; f < F + B; f++) { phic[f] = std::fabs(r->phi[f] / m->magSf[f]); mx = std::max(mx, phic[f]); }
+    mx = gMax(r, mx);
     for (int f = 0; f < F + B; f++) { phic[f] = std::min(c.cAlpha * phic[f], mx); phir[f] = phic[f] * r->nHatf[f]; }
     for (int aCorr = 0; aCorr < c.nAlphaCorr; aCorr++) {
         vec g(3 * N), phiAlpha(F + B), t1(F + B), t2(F + B), oneMinus(N), oneMinusB(B), mphir(F + B);
         orc_grad_gauss(m, &r->bcAlpha, r->alpha.data(), r->alphab.data(), g.data(), nullptr);
+        vec gN(r->comm ? 3 * B : 0);
+        if (r->comm) r->comm->halo(r->comm->ctx, g.data(), 3, gN.data());
         orc_flux_limited(m, 0, r->phi.data(), r->alpha.data(), r->alphab.data(), g.data(), phiAlpha.data());
+        if (r->comm) fluxLimitedCoupled(m, 0, r->phi.data(), r->alpha.data(), r->alphab.data(), g.data(), gN.data(), phiAlpha.data());
         for (int i = 0; i < N; i++) oneMinus[i] = 1.0 - r->alpha[i];
         for (int b = 0; b < B; b++) oneMinusB[b] = 1.0 - r->alphab[b];
         for (int f = 0; f < F + B; f++) mphir[f] = -phir[f];
         orc_flux_limited(m, 1, mphir.data(), oneMinus.data(), oneMinusB.data(), nullptr, t1.data());
+        if (r->comm) fluxLimitedCoupled(m, 1, mphir.data(), oneMinus.data(), oneMinusB.data(), nullptr, nullptr, t1.data());
         for (int f = 0; f < F + B; f++) t1[f] = -t1[f];
         orc_flux_limited(m, 1, t1.data(), r->alpha.data(), r->alphab.data(), nullptr, t2.data());
+        if (r->comm) fluxLimitedCoupled(m, 1, t1.data(), r->alpha.data(), r->alphab.data(), nullptr, nullptr, t2.data());
         for (int f = 0; f < F + B; f++) phiAlpha[f] = phiAlpha[f] + t2[f];
         // MULES::explicitSolve(alpha1, phi, phiAlpha, 1, 0): psi.correctBoundaryConditions() first
         double t0 = now();
-        bcEvaluate(m, r->bcAlpha, r->alpha.data(), r->alphab.data(), 1);
+        evalBC(r, r->bcAlpha, r->alpha.data(), r->alphab.data(), 1);
         orc_mules_explicit_solve(m, r->alpha.data(), r->alphab.data(), r->alpha0.data(), r->phi.data(), phiAlpha.data(),
-                                 dt, 1.0, 0.0, c.mulesIncludeOwn, nullptr, &r->bcAlpha);
-        bcEvaluate(m, r->bcAlpha, r->alpha.data(), r->alphab.data(), 1);
+                                 dt, 1.0, 0.0, c.mulesIncludeOwn, nullptr, &r->bcAlpha, r->comm);
+        evalBC(r, r->bcAlpha, r->alpha.data(), r->alphab.data(), 1);
         r->tMULES += now() - t0;
         for (int f = 0; f < F + B; f++) r->rhoPhi[f] = phiAlpha[f] * (c.rho1 - c.rho2) + r->phi[f] * c.rho2;
     }
     double st[3];
     orc_alpha_stats(m, r->alpha.data(), r->alphab.data(), st);
+    if (r->comm) {   // weightedAverage / gMin / gMax over the ranks
+        double sV = 0, sVa = 0;
+        for (int i = 0; i < N; i++) { sVa += m->V[i] * r->alpha[i]; sV += m->V[i]; }
+        st[0] = gSum(r, sVa) / gSum(r, sV); st[1] = gMin(r, st[1]); st[2] = gMax(r, st[2]);
+    }
     r->alphaStats.insert(r->alphaStats.end(), st, st + 3);
 }
 
@@ -782,6 +1095,15 @@ static void assembleUEqn(Region* r) {
         for (int f = m->pStart[p]; f < m->pStart[p] + m->pSize[p]; f++) {
             int b = f - F, t = r->tU[p];
             double pf = r->rhoPhi[f], pg = muf[f] * m->magSf[f];
+            if (t == BC_PROCESSOR) {   // coupledFvPatchField: value coeffs (w, 1-w) with the convection scheme's weights, gradient coeffs (-dc, +dc)
+                double w = (c.divUScheme == 2) ? (pf >= 0 ? 1.0 : 0.0) : m->w[f];
+                for (int k = 0; k < 3; k++) {
+                    double dIC = pf * (1.0 * w), dBC = -pf * (1.0 * (1.0 - w));
+                    double lIC = pg * (-1.0 * m->dc[f]), lBC = -pg * m->dc[f];
+                    r->uIC[3 * b + k] = dIC - lIC; r->uBC[3 * b + k] = dBC - lBC;
+                }
+                continue;
+            }
             for (int k = 0; k < 3; k++) {
                 int idx = 3 * b + k;
                 double dIC = pf * bcValueIntCoeff(r->bcU, t, b);
@@ -798,7 +1120,7 @@ static void assembleUEqn(Region* r) {
     for (int f = 0; f < F; f++)
         for (int k = 0; k < 3; k++) { double t = m->Sf[3 * f + k] * muf[f]; gradMu[3 * m->own[f] + k] += t; gradMu[3 * m->nei[f] + k] -= t; }
     for (int f = F; f < F + B; f++)
-        for (int k = 0; k < 3; k++) gradMu[3 * m->own[f] + k] += m->Sf[3 * f + k] * muf[f];
+        for (int k = 0; k < 3; k++) gradMu[3 * m->own[f] + k] += m->Sf[3 * f + k] * muf[f];   // (muf is a face field: already interpolated on processor faces)
     for (int i = 0; i < N; i++) {
         double gm[3] = {gradMu[3 * i] / m->V[i], gradMu[3 * i + 1] / m->V[i], gradMu[3 * i + 2] / m->V[i]};
         const double* T = &gradU[9 * i];
@@ -806,6 +1128,50 @@ static void assembleUEqn(Region* r) {
             double s = T[3 * k] * gm[0] + T[3 * k + 1] * gm[1] + T[3 * k + 2] * gm[2];
             r->uSource[3 * i + k] += m->V[i] * s;
         }
+    }
+}
+
+// momentum predictor [REF region3d/UEqn.H:19-34]: solve(UEqn == fvc::reconstruct((interpolate(sigmaK)*snGrad(alpha1) - ghf*snGrad(rho)
+// - snGrad(pd))*magSf)) component by component [UPSTREAM fvMatrixSolve.C fvMatrix<Type>::solve: addBoundaryDiag(diag, cmpt),
+// source + boundary source, PBiCG + DILU per component].  The explicit coupled-source add/subtract pair of upstream cancels and is omitted.
+static inline bool nonOrth(const Region* r);
+static void nonOrthCorrection(Region* r, const OrcBC& bc, const double* vf, const double* vfb, const double* gammaf, double* out);
+static void momentumPredictor(Region* r) {
+    const OrcMesh* m = r->m; const OrcControls& c = r->ctl; int N = m->N, F = m->F, B = m->B;
+    vec sK(N), sKb(B), sKf(F + B), sga(F + B), sgr(F + B), sgp(F + B), rf(F + B), R(3 * N);
+    for (int i = 0; i < N; i++) sK[i] = c.sigma * r->K[i];
+    for (int b = 0; b < B; b++) sKb[b] = c.sigma * r->Kb[b];
+    orc_interpolate(m, sK.data(), sKb.data(), sKf.data(), 1);
+    orc_sngrad(m, &r->bcAlpha, r->alpha.data(), r->alphab.data(), sga.data());
+    orc_sngrad(m, &r->bcRho, r->rho.data(), r->rhob.data(), sgr.data());
+    orc_sngrad(m, &r->bcPd, r->pd.data(), r->pdb.data(), sgp.data());
+    if (nonOrth(r)) {
+        vec ca(F + B), cr(F + B), cp(F + B);
+        nonOrthCorrection(r, r->bcAlpha, r->alpha.data(), r->alphab.data(), nullptr, ca.data());
+        nonOrthCorrection(r, r->bcRho, r->rho.data(), r->rhob.data(), nullptr, cr.data());
+        nonOrthCorrection(r, r->bcPd, r->pd.data(), r->pdb.data(), nullptr, cp.data());
+        for (int f = 0; f < F + B; f++) { sga[f] = sga[f] + ca[f]; sgr[f] = sgr[f] + cr[f]; sgp[f] = sgp[f] + cp[f]; }
+    }
+    for (int f = 0; f < F + B; f++) rf[f] = ((sKf[f] * sga[f] - r->ghf[f] * sgr[f]) - sgp[f]) * m->magSf[f];
+    orc_reconstruct(m, r->invT.data(), rf.data(), R.data());
+    for (int k = 0; k < 3; k++) {
+        vec diag = r->uDiag, src(N), x(N), bou(B), intc(B);
+        for (int i = 0; i < N; i++) { src[i] = r->uSource[3 * i + k] + m->V[i] * R[3 * i + k]; x[i] = r->U[3 * i + k]; }
+        for (int p = 0; p < m->nPatches; p++)
+            for (int f = m->pStart[p]; f < m->pStart[p] + m->pSize[p]; f++) {
+                int b = f - F;
+                diag[m->own[f]] += r->uIC[3 * b + k];
+                if (m->pKind[p] == 0) src[m->own[f]] += r->uBC[3 * b + k];
+                bou[b] = r->uBC[3 * b + k]; intc[b] = r->uIC[3 * b + k];
+            }
+        OrcPerf perf;
+        size_t h0 = r->resHist.size();
+        r->resHist.resize(h0 + c.maxIter + 2, -1.0);
+        pbicgSolve(m, diag.data(), r->uUpper.data(), r->uLower.data(), r->comm ? bou.data() : nullptr, r->comm ? intc.data() : nullptr, x.data(), src.data(),
+                   c.UTol, c.URelTol, c.minIter, c.maxIter, &perf, &r->resHist[h0], r->comm);
+        r->resHist.resize(h0 + perf.nIterations + 1);
+        r->perfs.push_back(perf);
+        for (int i = 0; i < N; i++) r->U[3 * i + k] = x[i];
     }
 }
 
@@ -833,9 +1199,11 @@ static void ueqnH(Region* r, vec& H) {
     }
     for (int i = 0; i < 3 * N; i++) H[i] += lh[i] + r->uSource[i];
     for (int p = 0; p < m->nPatches; p++)
-        if (m->pKind[p] == 0)
-            for (int f = m->pStart[p]; f < m->pStart[p] + m->pSize[p]; f++)
-                for (int k = 0; k < 3; k++) H[3 * m->own[f] + k] += r->uBC[3 * (f - F) + k];
+        for (int f = m->pStart[p]; f < m->pStart[p] + m->pSize[p]; f++)
+            for (int k = 0; k < 3; k++) {
+                if (m->pKind[p] == 0) H[3 * m->own[f] + k] += r->uBC[3 * (f - F) + k];
+                else H[3 * m->own[f] + k] += r->uBC[3 * (f - F) + k] * r->Ub[3 * (f - F) + k];   // boundaryCoeffs*patchNeighbourField
+            }
     for (int i = 0; i < N; i++)
         for (int k = 0; k < 3; k++) H[3 * i + k] /= m->V[i];
 }
@@ -848,6 +1216,7 @@ static void pEqn(Region* r, int corr) {
     ueqnA(r, A);
     for (int i = 0; i < N; i++) rUA[i] = 1.0 / A[i];
     for (int b = 0; b < B; b++) rUAb[b] = 1.0 / A[m->own[F + b]];  // A(): zeroGradient patches
+    haloInto(r, rUA.data(), 1, rUAb.data());
     orc_interpolate(m, rUA.data(), rUAb.data(), rUAf.data(), 1);
     ueqnH(r, H);
     for (int i = 0; i < N; i++)
@@ -859,9 +1228,10 @@ static void pEqn(Region* r, int corr) {
     for (int p = 0; p < m->nPatches; p++)
         for (int f = m->pStart[p]; f < m->pStart[p] + m->pSize[p]; f++) {
             int b = f - F, cc = m->own[f];
-            if (r->tU[p] != BC_FIXED_VALUE)
+            if (r->tU[p] != BC_FIXED_VALUE && r->tU[p] != BC_PROCESSOR)
                 for (int k = 0; k < 3; k++) r->Ub[3 * b + k] = rUAb[b] * H[3 * cc + k];
         }
+    haloInto(r, r->U.data(), 3, r->Ub.data());   // processor patches: patchNeighbourField of the new U
     // phiU = (interpolate(U) & Sf) + ddtPhiCorr(rUA, rho, U, phi)
     vec Uf(3 * (F + B)), phiU(F + B);
     orc_interpolate(m, r->U.data(), r->Ub.data(), Uf.data(), 3);
@@ -889,6 +1259,12 @@ static void pEqn(Region* r, int corr) {
     orc_interpolate(m, sK.data(), sKb.data(), sKf.data(), 1);
     orc_sngrad(m, &r->bcAlpha, r->alpha.data(), r->alphab.data(), sga.data());
     orc_sngrad(m, &r->bcRho, r->rho.data(), r->rhob.data(), sgr.data());
+    if (nonOrth(r)) {   // snGrad `corrected`: ssf += correction(vf) on every face (zero on physical boundary faces)
+        vec ca(F + B), cr(F + B);
+        nonOrthCorrection(r, r->bcAlpha, r->alpha.data(), r->alphab.data(), nullptr, ca.data());
+        nonOrthCorrection(r, r->bcRho, r->rho.data(), r->rhob.data(), nullptr, cr.data());
+        for (int f = 0; f < F + B; f++) { sga[f] = sga[f] + ca[f]; sgr[f] = sgr[f] + cr[f]; }
+    }
     for (int f = 0; f < F + B; f++) r->phi[f] = phiU[f] + (sKf[f] * sga[f] - r->ghf[f] * sgr[f]) * rUAf[f] * m->magSf[f];
     for (int nonOrth = 0; nonOrth <= c.nNonOrthCorr; nonOrth++) {
         bool fin = (corr == c.nCorr - 1 && nonOrth == c.nNonOrthCorr);
@@ -904,11 +1280,11 @@ static void pEqn(Region* r, int corr) {
     orc_reconstruct(m, r->invT.data(), s.data(), rec.data());
     for (int i = 0; i < N; i++)
         for (int k = 0; k < 3; k++) r->U[3 * i + k] += rUA[i] * rec[3 * i + k];
-    bcEvaluate(m, r->bcU, r->U.data(), r->Ub.data(), 3);
+    evalBC(r, r->bcU, r->U.data(), r->Ub.data(), 3);
 }
 
 // interfaceProperties ctor [REF create3dFields.H:254-263] -> calculateK(); call once before the first step
-extern "C" void orc_region_init_interface(Region* r) { calculateK(r); }
+extern "C" void orc_region_init_interface(Region* r) { initFields(r); }
 
 extern "C" void orc_region_step(Region* r) {
     const OrcMesh* m = r->m; const OrcControls& c = r->ctl; int N = m->N, F = m->F, B = m->B;
@@ -933,13 +1309,15 @@ extern "C" void orc_region_step(Region* r) {
     for (int i = 0; i < N; i++) r->rho[i] = r->alpha[i] * c.rho1 + (1.0 - r->alpha[i]) * c.rho2;
     for (int b = 0; b < B; b++) r->rhob[b] = r->alphab[b] * c.rho1 + (1.0 - r->alphab[b]) * c.rho2;
     assembleUEqn(r);
-    bcEvaluate(m, r->bcU, r->U.data(), r->Ub.data(), 3);  // UEqn.H last line
+    if (c.momentumPredictor) momentumPredictor(r);
+    evalBC(r, r->bcU, r->U.data(), r->Ub.data(), 3);  // UEqn.H last line
     for (int corr = 0; corr < c.nCorr; corr++) pEqn(r, corr);
     // continuityErrs.H
     vec div(N);
     orc_surface_integrate(m, r->phi.data(), div.data());
     double sV = 0, sA = 0, sG = 0;
     for (int i = 0; i < N; i++) { sV += m->V[i]; sA += m->V[i] * std::fabs(div[i]); sG += m->V[i] * div[i]; }
+    sV = gSum(r, sV); sA = gSum(r, sA); sG = gSum(r, sG);
     r->sumLocalContErr = c.deltaT * (sA / sV); r->globalContErr = c.deltaT * (sG / sV); r->cumulativeContErr += r->globalContErr;
     // p = pd + rho*gh
     for (int i = 0; i < N; i++) r->p[i] = r->pd[i] + r->rho[i] * r->gh[i];
@@ -982,6 +1360,100 @@ extern "C" void orc_region_courant(Region* r, double* out3) {
     }
     out3[0] = (sumS / sumM) * r->ctl.deltaT; out3[1] = mx * r->ctl.deltaT; out3[2] = vm;
 }
+static void courantGlobal(Region* r, double* out3) {   // collective form of the above (every rank's thread calls it)
+    const OrcMesh* m = r->m; int F = m->F, B = m->B;
+    double sumS = 0, sumM = 0, mx = 0, vm = 0;
+    for (int f = 0; f < F + B; f++) {
+        double mp = std::fabs(r->phi[f]), sd = m->dc[f] * mp;
+        if (f < F) { sumS += sd; sumM += m->magSf[f]; }
+        mx = std::max(mx, sd / m->magSf[f]); vm = std::max(vm, mp / m->magSf[f]);
+    }
+    sumS = gSum(r, sumS); sumM = gSum(r, sumM); mx = gMax(r, mx); vm = gMax(r, vm);
+    out3[0] = (sumS / sumM) * r->ctl.deltaT; out3[1] = mx * r->ctl.deltaT; out3[2] = vm;
+}
 extern "C" void orc_region_cont_errs(Region* r, double* out3) { out3[0] = r->sumLocalContErr; out3[1] = r->globalContErr; out3[2] = r->cumulativeContErr; }
 extern "C" void orc_region_timers(Region* r, double* out3) { out3[0] = r->tPCG; out3[1] = r->tMULES; out3[2] = r->tOther; }
 extern "C" void orc_region_clear_log(Region* r) { r->perfs.clear(); r->resHist.clear(); r->alphaStats.clear(); }
+
+// ================================================================== N-rank emulation (decomposed run on the host cores)
+// One Region per `simple` sub-domain, one thread per Region: what `mpirun -np N shallowInterFoam -parallel` does
+// [REF shallowInterFoam.C:66-67], with Pstream replaced by shared memory: a halo swap publishes a pointer to the cell field, meets the
+// other ranks at a barrier and reads the neighbour cells directly; a global reduction leaves every rank's partial in a slot and
+// combines the slots in rank order (the same order on every rank => identical control flow).  DIC stays rank-local.
+struct SpinBarrier {
+    std::atomic<int> count{0}, gen{0};
+    int n = 1;
+    void wait() {
+        int g = gen.load(std::memory_order_acquire);
+        if (count.fetch_add(1, std::memory_order_acq_rel) == n - 1) {
+            count.store(0, std::memory_order_relaxed);
+            gen.fetch_add(1, std::memory_order_release);
+        } else {
+            int spins = 0;
+            while (gen.load(std::memory_order_acquire) == g)
+                if (++spins > 2000) { std::this_thread::yield(); spins = 0; }
+        }
+    }
+};
+struct World {
+    int R = 0;
+    std::vector<Region*> regs;
+    SpinBarrier bar;
+    std::vector<double> slots;   // one cache line per rank
+};
+static void worldHalo(void* ctx, const double* f, int nc, double* out) {
+    Region* r = (Region*)ctx; World* w = r->world;
+    r->pub = f;
+    w->bar.wait();
+    const int B = r->m->B;
+    for (int b = 0; b < B; b++) {
+        int q = r->nbrRank[b];
+        if (q < 0) continue;
+        const double* src = w->regs[q]->pub + (size_t)nc * r->nbrCell[b];
+        for (int k = 0; k < nc; k++) out[(size_t)nc * b + k] = src[k];
+    }
+    w->bar.wait();
+}
+static double worldReduce(void* ctx, double v, int op) {
+    Region* r = (Region*)ctx; World* w = r->world;
+    w->slots[8 * (size_t)r->rank] = v;
+    w->bar.wait();
+    double acc = w->slots[0];
+    for (int q = 1; q < w->R; q++) {
+        double x = w->slots[8 * (size_t)q];
+        acc = op == 0 ? acc + x : op == 1 ? std::max(acc, x) : std::min(acc, x);
+    }
+    w->bar.wait();
+    return acc;
+}
+template <class Fn>
+static void worldRun(World* w, Fn fn) {
+    std::vector<std::thread> th;
+    for (int q = 1; q < w->R; q++) th.emplace_back([=]() { fn(w->regs[q]); });
+    fn(w->regs[0]);
+    for (auto& t : th) t.join();
+}
+// regs[R]: regions created with orc_region_create on the sub-meshes (processor patches: pKind 1, BC_PROCESSOR); nbrRank/nbrCell[r]: per
+// boundary face of rank r.  Links the ranks and (re)runs the field initialisation with halo swaps.
+extern "C" World* orc_world_create(int R, Region** regs, const int* const* nbrRank, const int* const* nbrCell) {
+    World* w = new World();
+    w->R = R; w->regs.assign(regs, regs + R); w->bar.n = R; w->slots.assign(8 * (size_t)R, 0.0);
+    for (int q = 0; q < R; q++) {
+        Region* r = regs[q];
+        r->world = w; r->rank = q;
+        r->nbrRank.assign(nbrRank[q], nbrRank[q] + r->m->B); r->nbrCell.assign(nbrCell[q], nbrCell[q] + r->m->B);
+        r->commS.ctx = r; r->commS.halo = worldHalo; r->commS.reduce = worldReduce; r->comm = &r->commS;
+    }
+    worldRun(w, [](Region* r) { initFields(r); });
+    return w;
+}
+extern "C" void orc_world_destroy(World* w) { delete w; }
+extern "C" void orc_world_correct_phi(World* w) { worldRun(w, [](Region* r) { orc_region_correct_phi(r); }); }
+extern "C" void orc_world_step(World* w, int nSteps) {
+    worldRun(w, [=](Region* r) { for (int i = 0; i < nSteps; i++) orc_region_step(r); });
+}
+extern "C" void orc_world_courant(World* w, double* out3) {
+    std::vector<double> all(3 * (size_t)w->R);
+    worldRun(w, [&](Region* r) { courantGlobal(r, &all[3 * (size_t)r->rank]); });
+    out3[0] = all[0]; out3[1] = all[1]; out3[2] = all[2];
+}

@@ -221,6 +221,16 @@ def jitter_points(mesh, frac, dx, dy, dz, seed=12345):
     return out
 
 
+def shear_points(mesh, sxy, sxz, syz):
+    """affine shear (include/b200foam.h b200_polymesh_shear): x += sxy*y + sxz*z ; y += syz*z -- non-orthogonal, not skewed"""
+    pts = mesh["points"].copy()
+    y, z = pts[:, 1].copy(), pts[:, 2].copy()
+    pts[:, 0] = pts[:, 0] + (sxy * y + sxz * z)
+    pts[:, 1] = y + syz * z
+    out = dict(mesh); out["points"] = pts
+    return out
+
+
 def weir_keep_mask(nx, ny, nz, x0=0.45, x1=0.5, zfrac=0.3):
     """cells removed: cell-centre x in [x0,x1)*L and z < zfrac*H  (SURVEY.md section 8(d) cfg2)."""
     ci, cj, ck = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")

@@ -31,6 +31,7 @@ EXPORTS = [
     "b200_region3d_set_patch_mixed", "b200_region3d_get_patch_internal", "b200_region3d_num_solves",
     "b200_region3d_get_perfs", "b200_region3d_get_res_hist", "b200_region3d_get_alpha_stats",
     "b200_region3d_get_cont_errs", "b200_region3d_clear_log", "b200_region3d_get_courant", "b200_region3d_restore", "b200_ldu_invalidate",
+    "b200_pbicg_solve", "b200_dilu_calc_reciprocal_d", "b200_dilu_precondition", "b200_polymesh_shear", "b200_mesh_non_orthogonality", "b200_non_orth_correction",
     "b200_region3d_capture", "b200_region3d_num_captured", "b200_region3d_get_captured_solve", "b200_region3d_get_captured_mules",
     "b200_polymesh_box", "b200_polymesh_box_weir", "b200_polymesh_jitter", "b200_polymesh_agglomerate", "b200_polymesh_release", "b200_polymesh_sizes",
     "b200_polymesh_get", "b200_polymesh_patch_name", "b200_polymesh_geometry", "b200_decompose_simple",
@@ -177,8 +178,9 @@ class B200Lib:
         return out
 
     # ------------------------------------------------------------------ host mesh tools
-    def polymesh_box(self, nx, ny, nz, lx, ly, lz, weir=None, jitter=None):
-        """jitter = (frac, seed): skew the mesh by moving interior vertices by up to frac of a cell size (b200_polymesh_jitter)"""
+    def polymesh_box(self, nx, ny, nz, lx, ly, lz, weir=None, jitter=None, shear=None):
+        """jitter = (frac, seed): skew the mesh by moving interior vertices by up to frac of a cell size (b200_polymesh_jitter);
+        shear = (sxy, sxz, syz): affine shear, non-orthogonal but not skewed (b200_polymesh_shear)"""
         h = C.c_void_p()
         if weir is None:
             self.check(self.c.b200_polymesh_box(C.c_int32(nx), C.c_int32(ny), C.c_int32(nz), C.c_double(lx), C.c_double(ly),
@@ -191,6 +193,8 @@ class B200Lib:
             self.c.b200_polymesh_jitter.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64]
             self.check(self.c.b200_polymesh_jitter(h, C.c_double(jitter[0]), C.c_double(lx / nx), C.c_double(ly / ny), C.c_double(lz / nz),
                                                    C.c_uint64(jitter[1])))
+        if shear is not None:
+            self.check(self.c.b200_polymesh_shear(h, C.c_double(shear[0]), C.c_double(shear[1]), C.c_double(shear[2])))
         return PolyMesh(self, h)
 
     # ------------------------------------------------------------------ lduAddressing-level API
@@ -271,6 +275,29 @@ class Ldu:
         bou_ = None if bou is None else f64(bou); lower_ = None if lower is None else f64(lower)
         self.lib.check(self.lib.c.b200_pcg_solve(self.h, _d(f64(diag)), _d(f64(upper)), _d(lower_), _d(bou_), _d(x), _d(f64(b)),
                                                  C.byref(ctl), C.byref(perf), _d(hist), C.c_int32(hist.size)))
+        return x, perf, hist[:perf.nIterations + 1].copy()
+
+
+    # ---- f1: b200PBiCG + DILU
+    def dilu_calc_rd(self, diag, upper, lower):
+        out = np.empty(self.N)
+        self.lib.check(self.lib.c.b200_dilu_calc_reciprocal_d(self.h, _d(f64(diag)), _d(f64(upper)), _d(f64(lower)), _d(out)))
+        return out
+
+    def dilu_precondition(self, rD, upper, lower, rA, transpose=False):
+        out = np.empty(self.N)
+        self.lib.check(self.lib.c.b200_dilu_precondition(self.h, _d(f64(rD)), _d(f64(upper)), _d(f64(lower)), _d(f64(rA)), _d(out),
+                                                         C.c_int32(1 if transpose else 0)))
+        return out
+
+    def pbicg_solve(self, diag, upper, lower, x0, b, tol=1e-6, relTol=0.0, minIter=0, maxIter=1000, bou=None, intc=None):
+        x = f64(x0).copy()
+        ctl = SolverControls(tol, relTol, minIter, maxIter)
+        perf = SolverPerf()
+        hist = np.full(maxIter + 2, -1.0)
+        bou_ = None if bou is None else f64(bou); int_ = None if intc is None else f64(intc)
+        self.lib.check(self.lib.c.b200_pbicg_solve(self.h, _d(f64(diag)), _d(f64(upper)), _d(f64(lower)), _d(bou_), _d(int_), _d(x), _d(f64(b)),
+                                                   C.byref(ctl), C.byref(perf), _d(hist), C.c_int32(hist.size)))
         return x, perf, hist[:perf.nIterations + 1].copy()
 
 
@@ -393,6 +420,18 @@ class DeviceMesh:
         out = np.empty(3 * self.N)
         self.lib.check(self.lib.c.b200_reconstruct(self.h, _d(f64(ssf)), _d(out)))
         return out.reshape(-1, 3)
+
+    def non_orthogonality(self):
+        """(degrees over this rank's internal faces, mesh.orthogonal() over all ranks)"""
+        d = C.c_double(); o = C.c_int32()
+        self.lib.check(self.lib.c.b200_mesh_non_orthogonality(self.h, C.byref(d), C.byref(o)))
+        return d.value, bool(o.value)
+
+    def non_orth_correction(self, vf, vfb, gammaf=None):
+        out = np.empty(self.F + self.B)
+        g = None if gammaf is None else f64(gammaf)
+        self.lib.check(self.lib.c.b200_non_orth_correction(self.h, _d(g), _d(f64(vf)), _d(f64(vfb)), _d(out)))
+        return out
 
     # ---- a7/a8
     def flux_limited(self, scheme, bc, faceFlux, vf, vfb):

@@ -40,26 +40,6 @@ static uint64_t addressingHash(int32_t nCells, int32_t nFaces, const int32_t* lo
 
 struct b200_polymesh { PolyMesh pm; };
 
-namespace b200 {
-__global__ void k_sumA(MeshView mv, const double* __restrict__ diag, const double* __restrict__ upS,
-                       const double* __restrict__ loS, const double* __restrict__ bou, double* __restrict__ out) {
-    int row = blockIdx.x * blockDim.x + threadIdx.x, s = row >> 5, lane = row & 31;
-    if (row >= mv.N) return;
-    double sA = diag[row];
-    int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5;
-    for (int j = 0; j < nbw; j++) {
-        int pk = mv.loPk[nb0 + (j << 5) + lane];
-        if (pk >= 0) { int l; int pos = facePosOf(mv, pk, l); sA = sA + loS[pos]; }
-    }
-    int so0 = mv.sliceOff[s], ow = (mv.sliceOff[s + 1] - so0) >> 5;
-    for (int k = 0; k < ow; k++) { int pos = so0 + (k << 5) + lane; if (mv.upIdx[pos] >= 0) sA = sA + upS[pos]; }
-    if (bou && ((mv.bMask[s] >> lane) & 1u)) {
-        int i = mv.bBase[s] + __popc(mv.bMask[s] & ((1u << lane) - 1u));
-        for (int q = mv.bRowStart[i]; q < mv.bRowStart[i + 1]; q++) { int bf = mv.bRowFaces[q]; if (mv.bCoupled[bf]) sA = sA - bou[bf]; }
-    }
-    out[row] = sA;
-}
-}  // namespace b200
 
 static DeviceMesh* asMesh(b200_ldu_t* l) { return reinterpret_cast<DeviceMesh*>(l); }
 static DeviceMesh* asMesh(b200_mesh_t* l) { return reinterpret_cast<DeviceMesh*>(l); }
@@ -305,6 +285,61 @@ int b200_pcg_solve(b200_ldu_t* ldu, const double* diag, const double* upper, con
     API_END
 }
 
+// ---------------------------------------------------------------------------------------------- f1: b200PBiCG + DILU
+static const double* stageLower(DeviceMesh& m, PcgWorkspace& w, const double* lower) {
+    w.loS.ensure(m.Fs + 1);
+    m.uploadFaces(lower, w.loS, false);
+    return w.loS.p;
+}
+int b200_dilu_calc_reciprocal_d(b200_ldu_t* ldu, const double* diag, const double* upper, const double* lower, double* rD) {
+    API_BEGIN
+    requireDevice();
+    B200_REQUIRE(ldu && diag && upper && lower && rD, B200_ERR_ARG, "b200_dilu_calc_reciprocal_d: null argument");
+    DeviceMesh& m = *asMesh(ldu);
+    PcgWorkspace& w = pcgWorkspace(m);
+    stageMatrix(m, w, diag, upper, nullptr);
+    const double* lo = stageLower(m, w, lower);
+    diluCalcReciprocalD(m, w.diag, w.upS, lo, w.rD);
+    m.downloadCells(w.rD, rD);
+    API_END
+}
+int b200_dilu_precondition(b200_ldu_t* ldu, const double* rD, const double* upper, const double* lower, const double* rA, double* wA,
+                           int32_t transpose) {
+    API_BEGIN
+    requireDevice();
+    B200_REQUIRE(ldu && rD && upper && lower && rA && wA, B200_ERR_ARG, "b200_dilu_precondition: null argument");
+    DeviceMesh& m = *asMesh(ldu);
+    PcgWorkspace& w = pcgWorkspace(m);
+    w.upS.ensure(m.Fs + 1);
+    m.uploadFaces(upper, w.upS, false);
+    const double* lo = stageLower(m, w, lower);
+    m.uploadCells(rD, w.rD);
+    m.uploadCells(rA, w.rA);
+    diluPrecondition(m, w.rD, w.upS, lo, w.rA, w.wA, transpose != 0);
+    m.downloadCells(w.wA, wA);
+    API_END
+}
+int b200_pbicg_solve(b200_ldu_t* ldu, const double* diag, const double* upper, const double* lower, const double* bouCoeffs,
+                     const double* intCoeffs, double* x, const double* b, const b200_solver_controls* ctl, b200_solver_perf* perf,
+                     double* resHist, int32_t histCap) {
+    API_BEGIN
+    requireDevice();
+    B200_REQUIRE(ldu && diag && upper && ctl && perf && x && b, B200_ERR_ARG, "b200_pbicg_solve: null argument");
+    DeviceMesh& m = *asMesh(ldu);
+    PcgWorkspace& w = pcgWorkspace(m);
+    stageMatrix(m, w, diag, upper, bouCoeffs);
+    const double* lo = (lower && lower != upper) ? stageLower(m, w, lower) : (const double*)w.upS.p;
+    if (intCoeffs && m.B) { w.intc.ensure(m.B); m.uploadBoundary(intCoeffs, w.intc); }
+    w.x.ensure(m.N); w.b.ensure(m.N);
+    m.uploadCells(x, w.x);
+    m.uploadCells(b, w.b);
+    std::vector<double> hist;
+    *perf = pbicgSolveDevice(m, w.diag, w.upS, lo, bouCoeffs ? w.bou.p : nullptr, intCoeffs ? w.intc.p : nullptr, w.x, w.b, *ctl, resHist ? &hist : nullptr);
+    m.downloadCells(w.x, x);
+    if (resHist) for (int i = 0; i < histCap && i < (int)hist.size(); i++) resHist[i] = hist[i];
+    API_END
+}
+
 // ---------------------------------------------------------------------------------------------- mesh
 int b200_mesh_create(const b200_mesh_desc* d, b200_mesh_t** out) {
     API_BEGIN
@@ -349,6 +384,12 @@ int b200_polymesh_jitter(b200_polymesh_t* pm, double frac, double dx, double dy,
     API_BEGIN
     B200_REQUIRE(pm && frac >= 0.0 && frac < 0.5, B200_ERR_ARG, "b200_polymesh_jitter: frac must be in [0, 0.5)");
     jitterPoints(pm->pm, frac, dx, dy, dz, seed);
+    API_END
+}
+int b200_polymesh_shear(b200_polymesh_t* pm, double sxy, double sxz, double syz) {
+    API_BEGIN
+    B200_REQUIRE(pm, B200_ERR_ARG, "b200_polymesh_shear: null mesh");
+    shearPoints(pm->pm, sxy, sxz, syz);
     API_END
 }
 int b200_polymesh_agglomerate(const b200_polymesh_t* pm, const int64_t* group, b200_polymesh_t** out) {
@@ -461,6 +502,30 @@ DeviceMesh& geoMesh(b200_mesh_t* mesh) {
 int nmaxOf(const DeviceMesh& m) { return std::max(std::max(m.N, m.B), 1); }
 }  // namespace
 
+int b200_mesh_non_orthogonality(b200_mesh_t* mesh, double* degrees, int32_t* orthogonal) {
+    API_BEGIN
+    DeviceMesh& m = geoMesh(mesh);
+    if (degrees) *degrees = nonOrthogonalityDegrees(m.nonOrthSum[0], m.nonOrthSum[1]);   // this rank's faces
+    if (orthogonal) *orthogonal = m.orthogonal ? 1 : 0;                                    // global
+    API_END
+}
+int b200_non_orth_correction(b200_mesh_t* mesh, const double* gammaf, const double* vf, const double* vfBoundary, double* out) {
+    API_BEGIN
+    DeviceMesh& m = geoMesh(mesh);
+    B200_REQUIRE(vf && vfBoundary && out, B200_ERR_ARG, "b200_non_orth_correction: null argument");
+    Stage s(m);
+    FvWorkspace& w = s.w;
+    double* d = s.cells(vf); double* db = s.bnd(vfBoundary); double* g = gammaf ? s.faces(gammaf) : nullptr; double* o = s.buf(m.nFaceField());
+    if (m.N) B200_LAUNCH(k_grad_scalar, gridFor(m.N), BLOCK, rt().stream, m.view(), (const double*)d, (const double*)db, w.gx.p, w.gy.p, w.gz.p);
+    if (rt().nRanks > 1 && meshHasProcessorPatches(m)) {
+        const double* src[3] = {w.gx.p, w.gy.p, w.gz.p};
+        for (int k = 0; k < 3; k++) { haloPack(m, src[k], w.haloSend.p); haloExchange(m, w.haloSend.p, w.gb.p + (size_t)k * m.B); }
+    }
+    B200_LAUNCH(k_nonorth_ffc, gridFor(nmaxOf(m)), BLOCK, rt().stream, m.view(), (const double*)g, (const double*)w.gx.p, (const double*)w.gy.p,
+                (const double*)w.gz.p, (const double*)w.gb.p, o);
+    m.downloadFaces(o, out, true);
+    API_END
+}
 int b200_interpolate(b200_mesh_t* mesh, const double* vf, const double* vfBoundary, int32_t nCmpt, double* out) {
     API_BEGIN
     DeviceMesh& m = geoMesh(mesh);
@@ -581,7 +646,7 @@ int b200_laplacian_assemble(b200_mesh_t* mesh, const b200_bc* bc, const double* 
     double* g = s.faces(gammaf); double* pb = s.bnd(psiBoundary); double* dphi = phi ? s.faces(phi) : nullptr;
     double* dd = s.buf(m.N); double* du = s.buf(m.nFaceField()); double* ds = s.buf(m.N); double* dic = s.buf(m.B); double* dbc2 = s.buf(m.B);
     ScopedTimer t(T_ASSEMBLY);
-    if (m.N) B200_LAUNCH(k_lap_row, gridFor(m.N), BLOCK, rt().stream, m.view(), (const double*)g, (const double*)dphi, dd, du, ds);
+    if (m.N) B200_LAUNCH(k_lap_row, gridFor(m.N), BLOCK, rt().stream, m.view(), (const double*)g, (const double*)dphi, dd, du, ds, (const double*)nullptr);
     if (m.B) B200_LAUNCH(k_lap_boundary, gridFor(m.B), BLOCK, rt().stream, m.view(), dbc.view(), (const double*)g, (const double*)pb, dic, dbc2);
     m.downloadCells(dd, diag); m.downloadFaces(du, upper, false); m.downloadCells(ds, source);
     m.downloadBoundary(dic, internalCoeffs); m.downloadBoundary(dbc2, boundaryCoeffs);
@@ -595,7 +660,7 @@ int b200_matrix_flux(b200_mesh_t* mesh, const double* upper, const double* lower
     double* du = s.facesInt(upper); double* dl = (lower && lower != upper) ? s.facesInt(lower) : du;
     double* dic = s.bnd(internalCoeffs); double* dbc2 = s.bnd(boundaryCoeffs); double* dpsi = s.cells(psi); double* o = s.buf(m.nFaceField());
     B200_LAUNCH(k_matrix_flux<false>, gridFor(nmaxOf(m)), BLOCK, rt().stream, m.view(), (const double*)du, (const double*)dl, (const double*)dic,
-                (const double*)dbc2, (const double*)dpsi, (const double*)nullptr, o);
+                (const double*)dbc2, (const double*)dpsi, (const double*)nullptr, o, (const double*)nullptr);
     m.downloadFaces(o, flux, true);
     API_END
 }

@@ -20,7 +20,8 @@ __global__ void k_halo_pack(MeshView mv, const double* __restrict__ cf, double* 
 // processor faces get the geometry of the internal face they were before decomposition (seen from this side):
 // weights = |Sf.(Cn-Cf)| / (|Sf.(Cf-C)| + |Sf.(Cn-Cf)|), deltaCoeffs = 1/|Cn - C|   [UPSTREAM surfaceInterpolation.C]
 __global__ void k_couple_geometry(MeshView mv, const double* __restrict__ Cfx, const double* __restrict__ Cfy,
-                                  const double* __restrict__ Cfz, double* __restrict__ w, double* __restrict__ dc) {
+                                  const double* __restrict__ Cfz, double* __restrict__ w, double* __restrict__ dc,
+                                  double* __restrict__ cvx, double* __restrict__ cvy, double* __restrict__ cvz) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= mv.B || !mv.bCoupled[b]) return;
     int p = mv.Fs + b, c = mv.bFaceRow[b];
@@ -31,6 +32,8 @@ __global__ void k_couple_geometry(MeshView mv, const double* __restrict__ Cfx, c
     w[p] = SfdNei / (SfdOwn + SfdNei);
     double dx = nx - ox, dy = ny - oy, dz = nz - oz;
     dc[p] = 1.0 / sqrt((dx * dx + dy * dy) + dz * dz);
+    const double ms = mv.magSf[p];
+    cvx[p] = sx / ms - dx * dc[p]; cvy[p] = sy / ms - dy * dc[p]; cvz[p] = sz / ms - dz * dc[p];
 }
 
 bool meshHasProcessorPatches(const DeviceMesh& m) {
@@ -38,13 +41,22 @@ bool meshHasProcessorPatches(const DeviceMesh& m) {
     return false;
 }
 void DeviceMesh::coupleGeometry() {
+    if (hasGeometry && rt().nRanks > 1) {   // mesh.orthogonal() is a global property: gSum of both sums (collective: every rank's mesh)
+        DevBuf<double> s2(2);
+        B200_CHECK_CUDA(cudaMemcpyAsync(s2.p, nonOrthSum, 16, cudaMemcpyHostToDevice, rt().stream));
+        allReduce(s2.p, 2, RED_SUM);
+        double h[2];
+        B200_CHECK_CUDA(cudaMemcpyAsync(h, s2.p, 16, cudaMemcpyDeviceToHost, rt().stream));
+        syncStream();
+        orthogonal = nonOrthogonalityDegrees(h[0], h[1]) < 0.1;
+    }
     if (!hasGeometry || !meshHasProcessorPatches(*this)) return;
     DevBuf<double> send(B);
     const double* src[3] = {dCx.p, dCy.p, dCz.p};
     double* dst[3] = {dCnx.p, dCny.p, dCnz.p};
     for (int k = 0; k < 3; k++) { haloPack(*this, src[k], send.p); haloExchange(*this, send.p, dst[k]); }
     B200_LAUNCH(k_couple_geometry, gridFor(B), BLOCK, rt().stream, view(), (const double*)dCfx.p, (const double*)dCfy.p,
-                (const double*)dCfz.p, dW.p, dDc.p);
+                (const double*)dCfz.p, dW.p, dDc.p, dCvx.p, dCvy.p, dCvz.p);
     syncStream();
 }
 void haloPack(const DeviceMesh& m, const double* cellField, double* send) {

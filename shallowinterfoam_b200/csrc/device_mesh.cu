@@ -1,6 +1,8 @@
 // device_mesh.cu -- build the renumbered owner-slot SELL-32 layout on the host, upload it, and convert fields
 // between foam-extend's host layout and the device layout.
 #include "device_mesh.cuh"
+#include <cmath>
+#include <algorithm>
 #include <algorithm>
 
 namespace b200 {
@@ -34,6 +36,11 @@ __global__ void k_copy_vec_b(const double* __restrict__ srcXYZ, double* __restri
                              double* __restrict__ dz, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { dx[i] = srcXYZ[3 * (size_t)i]; dy[i] = srcXYZ[3 * (size_t)i + 1]; dz[i] = srcXYZ[3 * (size_t)i + 2]; }
+}
+
+double nonOrthogonalityDegrees(double sumMagSfCorr, double sumMagSf) {
+    if (!(sumMagSf > 0.0)) return 0.0;
+    return std::asin(std::min(sumMagSfCorr / sumMagSf, 1.0)) * 180.0 / 3.14159265358979323846;
 }
 
 void fillSentinel(double* p, size_t n) {
@@ -205,6 +212,28 @@ void DeviceMesh::setGeometry(const double* Sf, const double* magSf, const double
     uploadFaceVec(Sf, dSfx, dSfy, dSfz); uploadFaceVec(Cf, dCfx, dCfy, dCfz);
     uploadFaces(magSf, dMagSf, true); uploadFaces(w, dW, true); uploadFaces(dc, dDc, true);
     syncStream();
+    // non-orthogonal correction vectors (internal faces; boundary faces zero, processor faces in coupleGeometry) and the
+    // non-orthogonality measure, both in the sequential face order of upstream's makeCorrectionVectors
+    {
+        std::vector<double> cv(3 * ((size_t)F + B), 0.0);
+        double sMC = 0.0, sM = 0.0;
+        for (int f = 0; f < F; f++) {
+            const int o = lower[f], n = upper[f];
+            double c[3];
+            for (int k = 0; k < 3; k++) {
+                const double d = C[3 * (size_t)n + k] - C[3 * (size_t)o + k];
+                c[k] = Sf[3 * (size_t)f + k] / magSf[f] - d * dc[f];
+                cv[3 * (size_t)f + k] = c[k];
+            }
+            sMC += magSf[f] * std::sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+            sM += magSf[f];
+        }
+        nonOrthSum[0] = sMC; nonOrthSum[1] = sM;
+        orthogonal = nonOrthogonalityDegrees(sMC, sM) < 0.1;       // single rank; coupleGeometry() makes it global
+        dCvx.alloc(nf); dCvy.alloc(nf); dCvz.alloc(nf);
+        uploadFaceVec(cv.data(), dCvx, dCvy, dCvz);
+        syncStream();
+    }
     hasGeometry = true;
 }
 
@@ -216,6 +245,7 @@ MeshView DeviceMesh::view() const {
     v.bFaceRow = dBFaceRow; v.bPatch = dBPatch; v.bCoupled = dBCoupled;
     v.V = dV; v.Cx = dCx; v.Cy = dCy; v.Cz = dCz; v.Sfx = dSfx; v.Sfy = dSfy; v.Sfz = dSfz;
     v.magSf = dMagSf; v.w = dW; v.dc = dDc; v.Cnx = dCnx; v.Cny = dCny; v.Cnz = dCnz;
+    v.cvx = dCvx; v.cvy = dCvy; v.cvz = dCvz;
     return v;
 }
 

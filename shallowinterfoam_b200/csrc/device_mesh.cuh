@@ -40,6 +40,9 @@ struct MeshView {  // POD handed to kernels by value
     const double *Sfx, *Sfy, *Sfz;   // [Fs+B]
     const double *magSf, *w, *dc;    // [Fs+B]  (processor faces: internal-face weights / deltaCoeffs, see coupleGeometry)
     const double *Cnx, *Cny, *Cnz;   // [B] neighbour cell centre of processor faces
+    // non-orthogonal correction vectors  corrVec = Sf/magSf - d*deltaCoeffs  (d = C[N] - C[P]; 0 on physical boundary faces; processor
+    // faces as the internal faces they were) [UPSTREAM surfaceInterpolation.C makeCorrectionVectors]
+    const double *cvx, *cvy, *cvz;   // [Fs+B]
 };
 
 // slot of the face a packed neighbour-side reference names; uniform slice widths make it arithmetic (no look-up of the owner's slice)
@@ -98,6 +101,11 @@ struct DeviceMesh {
     DevBuf<unsigned> dBMask;
     DevBuf<int> dSlotFace, dFacePos, dRowCell, dCellRow;
     DevBuf<double> dCnx, dCny, dCnz;
+    DevBuf<double> dCvx, dCvy, dCvz;
+    // mesh.orthogonal() [UPSTREAM surfaceInterpolation::makeCorrectionVectors]: asin(min(sum(magSf*|corrVec|)/sum(magSf), 1)) < 0.1 degrees
+    // over the internal faces of ALL ranks; `corrected` snGrad / laplacian schemes are no-ops on an orthogonal mesh
+    double nonOrthSum[2] = {0.0, 0.0};    // this rank's sum(magSf*|corrVec|), sum(magSf)
+    bool orthogonal = true;
     DevBuf<double> dV, dCx, dCy, dCz, dSfx, dSfy, dSfz, dMagSf, dW, dDc, dCfx, dCfy, dCfz;
     // staging buffers for the host-pointer API
     DevBuf<double> stageA, stageB;
@@ -133,6 +141,7 @@ struct DeviceMesh {
     double* stage(DevBuf<double>& buf, size_t n) { buf.ensure(n); return buf.p; }
 };
 
+double nonOrthogonalityDegrees(double sumMagSfCorr, double sumMagSf);
 void fillSentinel(double* p, size_t n);
 void fillValue(double* p, size_t n, double v);
 

@@ -153,7 +153,7 @@ __device__ __forceinline__ void pollHalo(const SweepTile& t, const TileSmem& s, 
 // current gathers are in flight, and the critical path is
 //   BAR -> D x LDS.64 (sources) -> D x DMUL -> D x DADD -> STS -> BAR.
 // No global access inside the loop: bar.sync would wait for the L2 acknowledge of a gpu-scope store (~400 cycles per step).
-// OP 0: w -= c*v ; OP 1: w -= c*c/v (calcReciprocalD).  DIR +1: steps upwards (forward sweep), -1: downwards (backward).
+// OP 0: w -= c*v ; OP 1: w -= c/v (calcReciprocalD: c = upper*upper for DIC, upper*lower for DILU, formed by k_dic_coeffs).  DIR +1: steps upwards (forward sweep), -1: downwards (backward).
 // out != null: every row is also stored to out[row] (plain write-through store) in the step that computes it, so that when the
 // last step ends only its own rows are still on their way to L2 -- the dependants' polls see the tile ~0.3 us after its last step
 // instead of after a whole-tile publish pass.  Each 8-byte value is its own ready flag, so no ordering between the stores is needed,
@@ -178,7 +178,7 @@ __device__ __forceinline__ void sweepStepsD(const TileSmem& s, const SweepTile& 
         const uint2 npk = PK[nslot];
         const double nw = ldsAt(s.vals, npk.y >> 16);   // the next step's own rows still hold their start values
         if (OP == 0) { w = w - c0 * v0; if (D > 1) w = w - c1 * v1; if (D > 2) w = w - c2 * v2; }
-        else { w = w - c0 * c0 / v0; if (D > 1) w = w - c1 * c1 / v1; if (D > 2) w = w - c2 * c2 / v2; }
+        else { w = w - c0 / v0; if (D > 1) w = w - c1 / v1; if (D > 2) w = w - c2 / v2; }
         stsAt(s.vals, pk.y >> 16, w);
         if (out && (pk.y >> 16) < rowBytes) stWeak((double*)(outB + (pk.y >> 16)), w);   // (deferring it past the barrier is slower)
         __syncthreads();
@@ -256,7 +256,7 @@ __device__ __forceinline__ bool sweepSteps(const TileSmem& s, const SweepTile& t
             double w = s.vals[r];
             for (int j = 0; j < t.d; j++) {
                 double c = s.blk[j * S + slot], v = ldsAt(s.vals, OFF[((j >> 2) * S + slot) * 4 + (j & 3)]);
-                if (OP == 0) w = w - c * v; else w = w - c * c / v;
+                if (OP == 0) w = w - c * v; else w = w - c / v;
             }
             s.vals[r] = w;
         }
@@ -314,7 +314,7 @@ struct PcgFuse {
 };
 
 // MODE 0: forward precondition sweep: y[row] = rD*rA - sum_j cf_j * y[src_j]              (cf = rD[row]*upper, per solve)
-// MODE 1: calcReciprocalD           : Dt[row] = diag - sum_j up_j*up_j / Dt[src_j] ; rD = 1/Dt (operand block = plain upper)
+// MODE 1: calcReciprocalD           : Dt[row] = diag - sum_j (up_j*lo_j) / Dt[src_j] ; rD = 1/Dt (operand block = the products, lo = up for DIC)
 template <int MODE>
 static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, const double* __restrict__ a0,
         const double* a1, const double* __restrict__ coef, const double* __restrict__ blocks, double* y,
@@ -496,11 +496,14 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
     sweepExit(ctl);
 }
 
-// per solve: coefficient columns of the operand blocks: cf = rD[row]*upper (forward), cb = rD[row]*upper (backward).
-// rD == null: the plain upper coefficients (what calcReciprocalD sweeps with; 1.0*upper is exact).
+// per solve: coefficient columns of the operand blocks: cf = rD[row]*srcF (forward), cb = rD[row]*srcB (backward), where
+//   DIC                          : srcF = srcB = upper            [UPSTREAM DICPreconditioner::precondition]
+//   DILU precondition            : srcF = lower, srcB = upper     [UPSTREAM DILUPreconditioner::precondition]
+//   DILU preconditionT           : srcF = upper, srcB = lower     [UPSTREAM DILUPreconditioner::preconditionT]
+// rD == null (calcReciprocalD): cf = srcF*srcB, the face products upper*upper (DIC) / upper*lower (DILU) the sweep divides by Dt.
 // grid = 2*nTiles (forward tiles, then backward tiles) or nTiles (forward only); block = lanes
 static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_coeffs(SweepView sv, const double* __restrict__ rD,
-        const double* __restrict__ upS, double* __restrict__ cf, double* __restrict__ cb, const PcgScalars* gate) {
+        const double* __restrict__ srcF, const double* __restrict__ srcB, double* __restrict__ cf, double* __restrict__ cb, const PcgScalars* gate) {
     if (gate && gate->stop) return;
     const bool bw = (int)blockIdx.x >= sv.nTiles;
     const SweepTile t = bw ? sv.bwd[blockIdx.x - sv.nTiles] : sv.fwd[blockIdx.x];
@@ -509,11 +512,11 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_coeffs(SweepView s
     const int W = blockDim.x, S = t.nSteps * W;
     for (int k = 0; k < t.nSteps; k++) {
         const bool valid = (int)threadIdx.x < sv.stepLen[t.step0 + k];
-        const double rd = !valid ? 0.0 : rD ? rD[sv.stepRow[t.step0 + k] + threadIdx.x] : 1.0;
+        const double rd = (valid && rD) ? rD[sv.stepRow[t.step0 + k] + threadIdx.x] : 0.0;
         for (int j = 0; j < t.d; j++) {
             const int e = t.blk + j * S + k * W + threadIdx.x;
             const int p = valid ? pos[e] : -1;
-            out[e] = p >= 0 ? rd * upS[p] : 0.0;
+            out[e] = p < 0 ? 0.0 : rD ? rd * (bw ? srcB : srcF)[p] : srcF[p] * srcB[p];
         }
     }
 }

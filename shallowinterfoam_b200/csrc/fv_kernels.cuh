@@ -478,19 +478,22 @@ static __global__ void __launch_bounds__(BLOCK) k_mules_update(MeshView mv, cons
 
 // ---- a10/a11/a12: pressure assembly ---------------------------------------------------------------------------
 // upper = dc*(gamma*magSf) ; diag = -sum(upper) ; source = V*(sum(+-phi)/V)  [UPSTREAM fvmLaplacianUncorrected, negSumDiag, ==div]
+// ffc (optional): faceFluxCorrection of the `corrected` laplacian; source -= V*div(ffc) before the == div(phi) term is added
 static __global__ void __launch_bounds__(BLOCK) k_lap_row(MeshView mv, const double* __restrict__ gammaf, const double* __restrict__ phi,
-                                                           double* __restrict__ diag, double* __restrict__ upper, double* __restrict__ source) {
+                                                           double* __restrict__ diag, double* __restrict__ upper, double* __restrict__ source,
+                                                           const double* __restrict__ ffc) {
     ROW_PROLOGUE(mv)
     if (row >= mv.N) return;
     PREFETCH_OWN_FACES(mv, s, lane, gammaf)
     PREFETCH_OWN_FACES(mv, s, lane, mv.dc)
     PREFETCH_OWN_FACES(mv, s, lane, mv.magSf)
     PREFETCH_OWN_FACES(mv, s, lane, phi)
-    double d = 0.0, a = 0.0;
+    double d = 0.0, a = 0.0, cc = 0.0;
     FOR_NBR_FACES(mv, s, lane, pos, l)
         (void)l;
         d = d - mv.dc[pos] * (gammaf[pos] * mv.magSf[pos]);
         if (phi) a = a - phi[pos];
+        if (ffc) cc = cc - ffc[pos];
     END_FACES
     FOR_OWN_FACES(mv, s, lane, pos, u)
         (void)u;
@@ -498,8 +501,14 @@ static __global__ void __launch_bounds__(BLOCK) k_lap_row(MeshView mv, const dou
         upper[pos] = up;
         d = d - up;
         if (phi) a = a + phi[pos];
+        if (ffc) cc = cc + ffc[pos];
     END_FACES
     double src = 0.0;
+    if (ffc) {   // fvm.source() -= mesh.V()*fvc::div(faceFluxCorrection) [UPSTREAM gaussLaplacianScheme::fvmLaplacian]
+        FOR_BND_FACES(mv, s, lane, b) cc = cc + ffc[mv.Fs + b]; END_BND
+        double V = mv.V[row];
+        src = src - V * (cc / V);
+    }
     if (phi) {
         FOR_BND_FACES(mv, s, lane, b) a = a + phi[mv.Fs + b]; END_BND
         double V = mv.V[row];
@@ -539,19 +548,53 @@ template <bool SUB>
 static __global__ void k_matrix_flux(MeshView mv, const double* __restrict__ upper, const double* __restrict__ lower,
                                      const double* __restrict__ ic, const double* __restrict__ bcv, const double* __restrict__ psi,
                                      const double* __restrict__ psib /*patchNeighbourField on processor faces (may be null without them)*/,
-                                     double* __restrict__ out) {
+                                     double* __restrict__ out, const double* __restrict__ ffc /*faceFluxCorrection or null*/) {
     ROW_PROLOGUE(mv)
     if (row < mv.N) {
         double a = psi[row];
         FOR_OWN_FACES(mv, s, lane, pos, u)
             double fl = upper[pos] * psi[u] - lower[pos] * a;
+            if (ffc) fl = fl + ffc[pos];      // fieldFlux += *faceFluxCorrectionPtr_ [UPSTREAM fvMatrix::flux]
             if (SUB) out[pos] = out[pos] - fl; else out[pos] = fl;
         END_FACES
     }
     if (row < mv.B) {
         int b = row, p = mv.Fs + b;
         double fl = ic[b] * psi[mv.bFaceRow[b]] - (mv.bCoupled[b] ? bcv[b] * psib[b] : bcv[b]);
+        if (ffc) fl = fl + ffc[p];
         if (SUB) out[p] = out[p] - fl; else out[p] = fl;
+    }
+}
+
+// ---- non-orthogonal correction [UPSTREAM correctedSnGrad::correction, gaussLaplacianScheme::fvmLaplacian] -------
+// corr_f = corrVec_f & linearInterpolate(grad(vf))_f  (grad = the case's gradScheme: Gauss linear); physical boundary faces: 0;
+// processor faces: the internal-face formula with the neighbour-rank cell's gradient (gbn, halo).
+__device__ __forceinline__ double nonOrthCorr(const MeshView& mv, int pos, double gPx, double gPy, double gPz, double gNx, double gNy, double gNz) {
+    const double w = mv.w[pos];
+    const double fx = w * (gPx - gNx) + gNx, fy = w * (gPy - gNy) + gNy, fz = w * (gPz - gNz) + gNz;
+    return (mv.cvx[pos] * fx + mv.cvy[pos] * fy) + mv.cvz[pos] * fz;
+}
+// out = scale_f * corr_f with scale = gammaf*magSf (faceFluxCorrection of fvm::laplacian(gamma, vf)); gammaf == null: scale = 1
+static __global__ void __launch_bounds__(BLOCK) k_nonorth_ffc(MeshView mv, const double* __restrict__ gammaf, const double* __restrict__ gx,
+                                                               const double* __restrict__ gy, const double* __restrict__ gz,
+                                                               const double* __restrict__ gbn, double* __restrict__ out) {
+    ROW_PROLOGUE(mv)
+    if (row < mv.N) {
+        const double ax = gx[row], ay = gy[row], az = gz[row];
+        FOR_OWN_FACES(mv, s, lane, pos, u)
+            const double c = nonOrthCorr(mv, pos, ax, ay, az, gx[u], gy[u], gz[u]);
+            out[pos] = gammaf ? (gammaf[pos] * mv.magSf[pos]) * c : c;
+        END_FACES
+    }
+    if (row < mv.B) {
+        const int b = row, p = mv.Fs + b;
+        double v = 0.0;
+        if (mv.bCoupled[b]) {
+            const int c0 = mv.bFaceRow[b];
+            const double c = nonOrthCorr(mv, p, gx[c0], gy[c0], gz[c0], gbn[b], gbn[mv.B + b], gbn[2 * mv.B + b]);
+            v = gammaf ? (gammaf[p] * mv.magSf[p]) * c : c;
+        }
+        out[p] = v;
     }
 }
 

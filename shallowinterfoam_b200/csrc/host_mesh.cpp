@@ -188,6 +188,15 @@ void jitterPoints(PolyMesh& m, double frac, double dx, double dy, double dz, uin
     }
 }
 
+void shearPoints(PolyMesh& m, double sxy, double sxz, double syz) {
+    const size_t nP = m.points.size() / 3;
+    for (size_t p = 0; p < nP; p++) {
+        const double y = m.points[3 * p + 1], z = m.points[3 * p + 2];
+        m.points[3 * p + 0] = m.points[3 * p + 0] + (sxy * y + sxz * z);
+        m.points[3 * p + 1] = y + syz * z;
+    }
+}
+
 Geometry computeGeometry(const PolyMesh& m) {
     Geometry g;
     int32_t N = m.nCells, F = m.nInternalFaces(), nF = m.nFaces();

@@ -40,6 +40,9 @@ PolyMesh makeBox(int nx, int ny, int nz, double lx, double ly, double lz);
 PolyMesh subsetMesh(const PolyMesh& m, const std::vector<uint8_t>& keep, const std::string& exposedName);
 PolyMesh agglomerate(const PolyMesh& m, const int64_t* group);
 void jitterPoints(PolyMesh& m, double frac, double dx, double dy, double dz, uint64_t seed);
+// affine shear of every point: x += sxy*y + sxz*z ; y += syz*z.  Faces stay planar and face centres stay on the line between the
+// cell centres (no skewness), but Sf is no longer parallel to d: a purely NON-ORTHOGONAL mesh
+void shearPoints(PolyMesh& m, double sxy, double sxz, double syz);
 std::vector<uint8_t> weirKeepMask(int nx, int ny, int nz, double x0, double x1, double zfrac);
 
 // [UPSTREAM primitiveMeshFaceCentresAndAreas.C, primitiveMeshCellCentresAndVols.C, surfaceInterpolation.C]

@@ -284,6 +284,26 @@ inline int persistentGrid(int nRows, K kernel) {
         else B200_LAUNCH_PDL(pdl, (k_amul<MODE, false>), persistentGrid((mv).N, k_amul<MODE, false>), BLOCK, 0, rt().stream, mv, __VA_ARGS__);               \
     } while (0)
 
+// [UPSTREAM lduMatrixATmul.C sumA]
+static __global__ void k_sumA(MeshView mv, const double* __restrict__ diag, const double* __restrict__ upS,
+                       const double* __restrict__ loS, const double* __restrict__ bou, double* __restrict__ out) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x, s = row >> 5, lane = row & 31;
+    if (row >= mv.N) return;
+    double sA = diag[row];
+    int nb0 = mv.nbrOff[s], nbw = (mv.nbrOff[s + 1] - nb0) >> 5;
+    for (int j = 0; j < nbw; j++) {
+        int pk = mv.loPk[nb0 + (j << 5) + lane];
+        if (pk >= 0) { int l; int pos = facePosOf(mv, pk, l); sA = sA + loS[pos]; }
+    }
+    int so0 = mv.sliceOff[s], ow = (mv.sliceOff[s + 1] - so0) >> 5;
+    for (int k = 0; k < ow; k++) { int pos = so0 + (k << 5) + lane; if (mv.upIdx[pos] >= 0) sA = sA + upS[pos]; }
+    if (bou && ((mv.bMask[s] >> lane) & 1u)) {
+        int i = mv.bBase[s] + __popc(mv.bMask[s] & ((1u << lane) - 1u));
+        for (int q = mv.bRowStart[i]; q < mv.bRowStart[i + 1]; q++) { int bf = mv.bRowFaces[q]; if (mv.bCoupled[bf]) sA = sA - bou[bf]; }
+    }
+    out[row] = sA;
+}
+
 // processor-interface update  Apsi[faceCells] -= bouCoeffs*psiNbr, per boundary row in patch order
 static __global__ void k_interface_update(MeshView mv, const double* __restrict__ bou, const double* __restrict__ psiNbr,
                                    double* __restrict__ Apsi, int nBRows, const int* __restrict__ bRowOfSlot) {

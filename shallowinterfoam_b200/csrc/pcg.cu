@@ -68,15 +68,20 @@ static int sweepGridOf(const DeviceMesh& m, const PcgWorkspace&) {
 }
 static int sweepThreads(const DeviceMesh& m) { return m.plan.lanes; }   // one row per thread per step
 // gate (optional): device flag of the DIC reuse; when it says "unchanged" the kernels return at once and rD / cf / cb stay as they are
-static void launchCalcRD(DeviceMesh& m, PcgWorkspace& w, const double* diag, const double* upS, double* rD, const PcgScalars* gate = nullptr) {
+// loS == upS: DIC (rD[u] -= upper*upper/rD[l]); loS != upS: DILU (rD[u] -= upper*lower/rD[l]).  cf is used as scratch for the products.
+static void launchCalcRD(DeviceMesh& m, PcgWorkspace& w, const double* diag, const double* upS, const double* loS, double* rD, double* cf,
+                         const PcgScalars* gate = nullptr) {
     fillSentinel(w.Dt, m.N);
-    // forward operand blocks <- plain upper coefficients (fully parallel), so that the sweep stages them with one TMA copy per tile
-    B200_LAUNCH(k_dic_coeffs, m.nTiles, sweepThreads(m), rt().stream, m.sweep(), (const double*)nullptr, upS, w.cf.p, w.cb.p, gate);
+    // forward operand blocks <- face products (fully parallel), so that the sweep stages them with one TMA copy per tile
+    B200_LAUNCH(k_dic_coeffs, m.nTiles, sweepThreads(m), rt().stream, m.sweep(), (const double*)nullptr, upS, loS, cf, (double*)nullptr, gate);
     B200_LAUNCH_SMEM(k_dic_fwd<1>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), diag, (const double*)nullptr, upS,
-                     (const double*)w.cf.p, w.Dt.p, rD, sweepCtl(w), gate, PcgFuse{});
+                     (const double*)cf, w.Dt.p, rD, sweepCtl(w), gate, PcgFuse{});
 }
-static void launchCoeffs(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* upS, const PcgScalars* gate = nullptr) {
-    B200_LAUNCH(k_dic_coeffs, 2 * m.nTiles, sweepThreads(m), rt().stream, m.sweep(), rD, upS, w.cf.p, w.cb.p, gate);
+// forward operand blocks <- rD[row]*srcF, backward <- rD[row]*srcB (DIC: both upper; DILU: lower/upper, transposed: upper/lower)
+static void launchCoeffs(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* srcF, const double* srcB, double* cf, double* cb,
+                         const PcgScalars* gate = nullptr) {
+    (void)w;
+    B200_LAUNCH(k_dic_coeffs, 2 * m.nTiles, sweepThreads(m), rt().stream, m.sweep(), rD, srcF, srcB, cf, cb, gate);
 }
 // DIC reuse: closes the gate, then re-opens it if diag / upper differ from the kept copies (refreshed in the same pass)
 static const PcgScalars* launchMatrixGate(DeviceMesh& m, PcgWorkspace& w, const double* diag, const double* upS) {
@@ -93,12 +98,14 @@ static const PcgScalars* launchMatrixGate(DeviceMesh& m, PcgWorkspace& w, const 
     return w.gate.p;
 }
 // pdl: the kernel may start (ticket, descriptor, operand-block staging) while its predecessor in the stream is still running
-static void launchFwd(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* rA, const PcgScalars* sc, PcgFuse fz = PcgFuse{}, bool pdl = false) {
+static void launchFwd(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* rA, const PcgScalars* sc, PcgFuse fz = PcgFuse{}, bool pdl = false,
+                      const double* cf = nullptr) {
     B200_LAUNCH_PDL(pdl, k_dic_fwd<0>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), rD, rA, (const double*)nullptr,
-                    (const double*)w.cf.p, w.y.p, (double*)nullptr, sweepCtl(w), sc, fz);
+                    cf ? cf : (const double*)w.cf.p, w.y.p, (double*)nullptr, sweepCtl(w), sc, fz);
 }
-static void launchBwd(DeviceMesh& m, PcgWorkspace& w, const double* rA, PcgScalars* sc, double* part, unsigned* cnt, double* dotOut = nullptr, bool pdl = false) {
-    B200_LAUNCH_PDL(pdl, k_dic_bwd, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), (const double*)w.cb.p, (const double*)rA, w.y.p, w.z.p,
+static void launchBwd(DeviceMesh& m, PcgWorkspace& w, const double* rA, PcgScalars* sc, double* part, unsigned* cnt, double* dotOut = nullptr, bool pdl = false,
+                      const double* cb = nullptr) {
+    B200_LAUNCH_PDL(pdl, k_dic_bwd, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), cb ? cb : (const double*)w.cb.p, (const double*)rA, w.y.p, w.z.p,
                     sweepCtl(w, true), sc, part, cnt, dotOut ? dotOut : (sc ? &sc->wArA : nullptr));
 }
 
@@ -121,7 +128,7 @@ void dicCalcReciprocalD(DeviceMesh& m, const double* diag, const double* upS, do
     ScopedTimer t(T_DIC_RD);
     if (!m.N) return;
     w.keptValid = false;   // the operand blocks no longer belong to the kept matrix
-    launchCalcRD(m, w, diag, upS, rD);
+    launchCalcRD(m, w, diag, upS, upS, rD, w.cf.p);
 }
 
 void dicPrecondition(DeviceMesh& m, const double* rD, const double* upS, const double* rA, double* wA) {
@@ -131,7 +138,7 @@ void dicPrecondition(DeviceMesh& m, const double* rD, const double* upS, const d
     // y / z double as ready flags (NaN sentinel = not yet published).  A PCG solve that stopped leaves whichever sweep ran last fully
     // populated (the kernels after the stop flag return at once and never re-arm it), so every entry point re-arms both first.
     fillSentinel(w.y, m.N); fillSentinel(w.z, m.N);
-    { ScopedTimer t(T_DIC_RD); launchCoeffs(m, w, rD, upS); }
+    { ScopedTimer t(T_DIC_RD); launchCoeffs(m, w, rD, upS, upS, w.cf.p, w.cb.p); }
     { ScopedTimer t(T_DIC_FWD); launchFwd(m, w, rD, rA, nullptr); }
     { ScopedTimer t(T_DIC_BWD); launchBwd(m, w, rA, nullptr, nullptr, nullptr); }
     B200_CHECK_CUDA(cudaMemcpyAsync(wA, w.z.p, 8 * (size_t)m.N, cudaMemcpyDeviceToDevice, rt().stream));
@@ -178,7 +185,7 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
     if (N) {
         ScopedTimer t(T_DIC_RD);
         const PcgScalars* gate = launchMatrixGate(m, w, diag, upS);
-        launchCalcRD(m, w, diag, upS, w.rD.p, gate); launchCoeffs(m, w, w.rD.p, upS, gate);
+        launchCalcRD(m, w, diag, upS, upS, w.rD.p, w.cf.p, gate); launchCoeffs(m, w, w.rD.p, upS, upS, w.cf.p, w.cb.p, gate);
         fillSentinel(w.y, N); fillSentinel(w.z, N);   // re-arm both ready-flag vectors (see dicPrecondition): the previous solve's stop path left one dirty
     }
     B200_CHECK_CUDA(cudaEventSynchronize(w.ev[0]));
@@ -252,6 +259,157 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
         B200_CHECK_CUDA(cudaMemcpyAsync(resHist->data(), w.hist.p, 8 * (size_t)(h.nIter + 1), cudaMemcpyDeviceToHost, st));
         syncStream();
     }
+    return perf;
+}
+
+// ================================================================================================ b200PBiCG + DILU
+// [UPSTREAM DILUPreconditioner.C]  calcReciprocalD: rD[u] -= upper*lower/rD[l] (faces ascending), rD = 1/rD
+//   precondition  : wA = rD*rA; forward (losort order)  wA[u] -= rD[u]*lower*wA[l]; backward (faces descending) wA[l] -= rD[l]*upper*wA[u]
+//   preconditionT : wT = rD*rT; forward (faces asc)     wT[u] -= rD[u]*upper*wT[l]; backward (losort desc)      wT[l] -= rD[l]*lower*wT[u]
+// Per row the updates arrive in the same order as in DIC (faces with u == row ascending; faces with l == row descending), so the
+// closed-tile sweeps of dic_kernels.cuh apply unchanged with other coefficient columns: bitwise the sequential loops.
+static void diluEnsure(DeviceMesh& m, PcgWorkspace& w) {
+    if (w.pT.n >= (size_t)std::max(m.N, 1)) return;
+    w.pT.alloc(m.N); w.wT.alloc(m.N); w.rT.alloc(m.N); w.cfT.alloc(m.fwdBlkSize); w.cbT.alloc(m.bwdBlkSize); w.dotScal.alloc(8);
+    if (m.fwdBlkSize) B200_CHECK_CUDA(cudaMemcpyAsync(w.cfT.p, m.dFwdBlk0.p, 8 * m.fwdBlkSize, cudaMemcpyDeviceToDevice, rt().stream));
+    if (m.bwdBlkSize) B200_CHECK_CUDA(cudaMemcpyAsync(w.cbT.p, m.dBwdBlk0.p, 8 * m.bwdBlkSize, cudaMemcpyDeviceToDevice, rt().stream));
+}
+void diluCalcReciprocalD(DeviceMesh& m, const double* diag, const double* upS, const double* loS, double* rD) {
+    PcgWorkspace& w = pcgWorkspace(m);
+    ScopedTimer t(T_DIC_RD);
+    if (!m.N) return;
+    w.keptValid = false;
+    launchCalcRD(m, w, diag, upS, loS, rD, w.cf.p);
+}
+// one application of the preconditioner with the operand blocks cf / cb (already filled): out = M^-1 rA
+static void sweepApply(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* rA, const double* cf, const double* cb, double* out) {
+    fillSentinel(w.y, m.N); fillSentinel(w.z, m.N);
+    { ScopedTimer t(T_DIC_FWD); launchFwd(m, w, rD, rA, nullptr, PcgFuse{}, false, cf); }
+    { ScopedTimer t(T_DIC_BWD); launchBwd(m, w, rA, nullptr, nullptr, nullptr, nullptr, false, cb); }
+    B200_CHECK_CUDA(cudaMemcpyAsync(out, w.z.p, 8 * (size_t)m.N, cudaMemcpyDeviceToDevice, rt().stream));
+}
+void diluPrecondition(DeviceMesh& m, const double* rD, const double* upS, const double* loS, const double* rA, double* wA, bool transpose) {
+    PcgWorkspace& w = pcgWorkspace(m);
+    if (!m.N) return;
+    w.keptValid = false;
+    { ScopedTimer t(T_DIC_RD); launchCoeffs(m, w, rD, transpose ? upS : loS, transpose ? loS : upS, w.cf.p, w.cb.p); }
+    sweepApply(m, w, rD, rA, w.cf.p, w.cb.p, wA);
+}
+
+// rA = b - wA ; rT = rA ; partial sums of x and |rA|
+static __global__ void k_pbicg_resid(int N, const double* __restrict__ b, const double* __restrict__ wA, const double* __restrict__ x,
+                                     double* __restrict__ rA, double* __restrict__ rT, PcgScalars* sc, double* partials, unsigned* counter) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[2] = {0.0, 0.0};
+    if (row < N) { double r = b[row] - wA[row]; rA[row] = r; rT[row] = r; v[0] = x[row]; v[1] = fabs(r); }
+    gridReduce<2, OpSum>(v, blockIdx.x, gridDim.x, partials, counter, nullptr);
+    gridFinalize<2, OpSum>(gridDim.x, partials, counter, &sc->sumX, &sc->sumMagR);
+}
+// pA = wA + beta*pA ; pT = wT + beta*pT  (first iteration: copies)
+static __global__ void k_pbicg_p(int N, const double* __restrict__ wA, const double* __restrict__ wT, double* __restrict__ pA, double* __restrict__ pT,
+                                 int first, double beta) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= N) return;
+    if (first) { pA[row] = wA[row]; pT[row] = wT[row]; }
+    else { pA[row] = wA[row] + beta * pA[row]; pT[row] = wT[row] + beta * pT[row]; }
+}
+// psi += alpha*pA ; rA -= alpha*wA ; rT -= alpha*wT ; sum|rA|
+static __global__ void k_pbicg_update(int N, double alpha, const double* __restrict__ pA, const double* __restrict__ wA, const double* __restrict__ wT,
+                                      double* __restrict__ x, double* __restrict__ rA, double* __restrict__ rT, double* out, double* partials,
+                                      unsigned* counter) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[1] = {0.0};
+    if (row < N) {
+        x[row] = x[row] + alpha * pA[row];
+        double r = rA[row] - alpha * wA[row];
+        rA[row] = r; rT[row] = rT[row] - alpha * wT[row];
+        v[0] = fabs(r);
+    }
+    gridReduce<1, OpSum>(v, blockIdx.x, gridDim.x, partials, counter, nullptr);
+    gridFinalize<1, OpSum>(gridDim.x, partials, counter, out);
+}
+
+// [UPSTREAM PBiCG.C solve]  The momentum predictor converges in a handful of iterations, so the scalars (wArT, wApT, alpha, beta, residual)
+// are read back every iteration and the loop is upstream's, line by line; vectors, sweeps and products stay on the device.
+b200_solver_perf pbicgSolveDevice(DeviceMesh& m, const double* diag, const double* upS, const double* loS, const double* bou, const double* intc,
+                                  double* x, const double* b, const b200_solver_controls& ctl, std::vector<double>* resHist) {
+    PcgWorkspace& w = pcgWorkspace(m);
+    ScopedTimer tt(T_PCG_SOLVE);
+    diluEnsure(m, w);
+    cudaStream_t st = rt().stream;
+    const int N = m.N, grid = std::max(1, gridFor(N));
+    const bool multi = rt().nRanks > 1;
+    MeshView mv = m.view();
+    PcgScalars* sc = w.sc.p;
+    double* part = w.partials.p; unsigned* cnt = w.counters.p;
+    double* ds = w.dotScal.p;
+    auto readScal = [&](const double* p, int n, double* h) {
+        B200_CHECK_CUDA(cudaMemcpyAsync(h, p, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+        syncStream();
+    };
+    auto gsumDev = [&](double* p, int n) { if (multi) allReduce(p, n, RED_SUM); };
+    auto dot = [&](const double* a, const double* c) {
+        B200_LAUNCH(k_dot, grid, BLOCK, st, N, a, c, ds, part, cnt, (const PcgScalars*)nullptr);
+        gsumDev(ds, 1);
+        double h; readScal(ds, 1, &h); return h;
+    };
+    // wA = A psi ; wT = A^T psi (only its interface part differs from what the iteration needs: upstream computes it and so do we)
+    amulDevice(m, diag, upS, loS, x, w.wA, bou);
+    B200_LAUNCH(k_pbicg_resid, grid, BLOCK, st, N, b, (const double*)w.wA.p, (const double*)x, w.rA.p, w.rT.p, sc, part, cnt);
+    gsumDev(&sc->sumX, 2);
+    // normFactor [UPSTREAM lduMatrix::solver::normFactor]: sumA -> pA (scratch), xRef = gAverage(psi)
+    double hN = (double)N;
+    B200_CHECK_CUDA(cudaMemcpyAsync(&sc->nGlobal, &hN, 8, cudaMemcpyHostToDevice, st));
+    gsumDev(&sc->nGlobal, 1);
+    if (N) B200_LAUNCH(k_sumA, grid, BLOCK, st, mv, diag, upS, loS, (multi && bou && meshHasProcessorPatches(m)) ? bou : (const double*)nullptr, w.pA.p);
+    B200_LAUNCH(k_pcg_init2, grid, BLOCK, st, N, (const double*)w.wA.p, b, (const double*)w.pA.p, sc, part, cnt);
+    gsumDev(&sc->nfSum, 1);
+    double h2[2];   // {sumMagR, nfSum}: sumMagR sits at offset 1, nfSum at offset 3 of PcgScalars
+    PcgScalars hs;
+    B200_CHECK_CUDA(cudaMemcpyAsync(&hs, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
+    syncStream();
+    (void)h2;
+    const double normFactor = hs.nfSum + 1.0e-20;
+    b200_solver_perf perf;
+    perf.initialResidual = perf.finalResidual = hs.sumMagR / normFactor;
+    perf.nIterations = 0; perf.singular = 0; perf.converged = 0;
+    if (resHist) { resHist->clear(); resHist->push_back(perf.initialResidual); }
+    auto converged = [&]() { return perf.finalResidual < ctl.tolerance || (ctl.relTol > 0 && perf.finalResidual < ctl.relTol * perf.initialResidual); };
+    auto stop = [&]() { return perf.nIterations >= ctl.minIter && (perf.nIterations >= ctl.maxIter || converged()); };
+    if (!stop()) {
+        // DILU: rD once, then the operand blocks of M^-1 (cf, cb) and of M^-T (cfT, cbT)
+        w.keptValid = false;
+        if (N) {
+            ScopedTimer t(T_DIC_RD);
+            launchCalcRD(m, w, diag, upS, loS, w.rD.p, w.cf.p);
+            launchCoeffs(m, w, w.rD.p, loS, upS, w.cf.p, w.cb.p);
+            launchCoeffs(m, w, w.rD.p, upS, loS, w.cfT.p, w.cbT.p);
+        }
+        double wArT = 1.0e20, wArTold;
+        do {
+            wArTold = wArT;
+            sweepApply(m, w, w.rD.p, w.rA.p, w.cf.p, w.cb.p, w.wA.p);
+            sweepApply(m, w, w.rD.p, w.rT.p, w.cfT.p, w.cbT.p, w.wT.p);
+            wArT = dot(w.wA.p, w.rT.p);
+            { ScopedTimer t(T_PCG_VEC);
+              B200_LAUNCH(k_pbicg_p, grid, BLOCK, st, N, (const double*)w.wA.p, (const double*)w.wT.p, w.pA.p, w.pT.p, perf.nIterations == 0 ? 1 : 0,
+                          perf.nIterations == 0 ? 0.0 : wArT / wArTold); }
+            amulDevice(m, diag, upS, loS, w.pA, w.wA, bou);
+            amulDevice(m, diag, loS, upS, w.pT, w.wT, intc);       // Tmul: lower and upper swap roles, interfaces use interfaceIntCoeffs
+            const double wApT = dot(w.wA.p, w.pT.p);
+            if (fabs(wApT) / normFactor <= 1.0e-300) { perf.singular = 1; break; }   // checkSingularity
+            const double alpha = wArT / wApT;
+            { ScopedTimer t(T_PCG_VEC);
+              B200_LAUNCH(k_pbicg_update, grid, BLOCK, st, N, alpha, (const double*)w.pA.p, (const double*)w.wA.p, (const double*)w.wT.p, x, w.rA.p, w.rT.p,
+                          ds, part, cnt); }
+            gsumDev(ds, 1);
+            double s; readScal(ds, 1, &s);
+            perf.finalResidual = s / normFactor;
+            perf.nIterations++;
+            if (resHist) resHist->push_back(perf.finalResidual);
+        } while (!stop());
+    }
+    perf.converged = converged() ? 1 : 0;
     return perf;
 }
 

@@ -10,6 +10,8 @@ namespace b200 {
 struct PcgWorkspace {
     DevBuf<double> pA, wA, rA, y, z, rD, Dt, partials, hist;
     DevBuf<double> cf, cb;                     // per-solve DIC coefficients rD[row]*upper in the sweep tiles' ELL layout
+    // b200PBiCG + DILU (momentum predictor): the transposed system's vectors and sweep operand blocks (allocated on first use)
+    DevBuf<double> pT, wT, rT, cfT, cbT, loS, intc, dotScal;
     DevBuf<double> diag, upS, x, b, bou;       // staging for the host-pointer API
     DevBuf<double> sendBuf, recvBuf;           // processor-patch halo
     DevBuf<PcgScalars> sc;
@@ -41,5 +43,11 @@ void dicPrecondition(DeviceMesh& m, const double* rD, const double* upS, const d
 // x in/out (rows); bou = interface coefficients of processor patches ([B], may be null)
 b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double* upS, const double* bou, double* x,
                                 const double* b, const b200_solver_controls& ctl, std::vector<double>* resHist);
+// b200PBiCG + DILU [UPSTREAM PBiCG.C solve; DILUPreconditioner.C]: asymmetric systems (momentum predictor, [REF region3d/UEqn.H:19-34]).
+// bou / intc: interfaceBouCoeffs (Amul) and interfaceIntCoeffs (Tmul) of processor patches ([B], may be null)
+void diluCalcReciprocalD(DeviceMesh& m, const double* diag, const double* upS, const double* loS, double* rD);
+void diluPrecondition(DeviceMesh& m, const double* rD, const double* upS, const double* loS, const double* rA, double* wA, bool transpose);
+b200_solver_perf pbicgSolveDevice(DeviceMesh& m, const double* diag, const double* upS, const double* loS, const double* bou, const double* intc,
+                                  double* x, const double* b, const b200_solver_controls& ctl, std::vector<double>* resHist);
 
 }  // namespace b200

@@ -306,6 +306,48 @@ static __global__ void k_ueqn_boundary(MeshView mv, BCView bc, int upwind, const
         uBC[idx] = dBC - lBC;
     }
 }
+// momentum predictor [REF region3d/UEqn.H:23-31]: out = (interpolate(sigmaK)*snGrad(alpha1) - ghf*snGrad(rho) - snGrad(pd))*magSf
+static __global__ void __launch_bounds__(BLOCK) k_mom_flux(MeshView mv, BCView bcA, BCView bcP, double sigma, const double* __restrict__ K,
+        const double* __restrict__ Kb, const double* __restrict__ alpha, const double* __restrict__ alphab, const double* __restrict__ rho,
+        const double* __restrict__ rhob, const double* __restrict__ pd, const double* __restrict__ pdb, const double* __restrict__ ghf,
+        const double* __restrict__ corrA, const double* __restrict__ corrR, const double* __restrict__ corrP, double* __restrict__ out) {
+    ROW_PROLOGUE(mv)
+    if (row < mv.N) {
+        double sKl = sigma * K[row], al = alpha[row], rl = rho[row], pl = pd[row];
+        FOR_OWN_FACES(mv, s, lane, pos, u)
+            double sKu = sigma * K[u], dc = mv.dc[pos];
+            double sKf = mv.w[pos] * (sKl - sKu) + sKu;
+            double sga = dc * (alpha[u] - al), sgr = dc * (rho[u] - rl), sgp = dc * (pd[u] - pl);
+            if (corrA) { sga = sga + corrA[pos]; sgr = sgr + corrR[pos]; sgp = sgp + corrP[pos]; }
+            out[pos] = ((sKf * sga - ghf[pos] * sgr) - sgp) * mv.magSf[pos];
+        END_FACES
+    }
+    if (row < mv.B) {
+        int b = row, p = mv.Fs + b, c = mv.bFaceRow[b], t = bcA.type[mv.bPatch[b]], tp = bcP.type[mv.bPatch[b]];
+        double dc = mv.dc[p];
+        double sKf = sigma * K[c];
+        if (mv.bCoupled[b]) { double sKn = sigma * Kb[b]; sKf = mv.w[p] * (sKf - sKn) + sKn; }
+        double sga = bcSnGrad(bcA, t, b, b, dc, alpha[c], alphab[b]);
+        double sgr = bcSnGrad(bcA, t, b, b, dc, rho[c], rhob[b]);
+        double sgp = bcSnGrad(bcP, tp, b, b, dc, pd[c], pdb[b]);
+        if (corrA) { sga = sga + corrA[p]; sgr = sgr + corrR[p]; sgp = sgp + corrP[p]; }
+        out[p] = ((sKf * sga - ghf[p] * sgr) - sgp) * mv.magSf[p];
+    }
+}
+// component k of the system fvMatrix<vector>::solve hands to the solver [UPSTREAM fvMatrixSolve.C]:
+//   diag = UEqn.diag + internalCoeffs.component(k) (addBoundaryDiag) ; source = (UEqn.source + V*R).component(k) + boundaryCoeffs (non-coupled)
+static __global__ void __launch_bounds__(BLOCK) k_mom_system(MeshView mv, int k, const double* __restrict__ uDiag, const double* __restrict__ uS,
+        const double* __restrict__ Rk, const double* __restrict__ uIC, const double* __restrict__ uBC, double* __restrict__ diagK, double* __restrict__ srcK) {
+    ROW_PROLOGUE(mv)
+    if (row >= mv.N) return;
+    int B = mv.B;
+    double d = uDiag[row], sc = uS[row] + mv.V[row] * Rk[row];
+    FOR_BND_FACES(mv, s, lane, b)
+        d = d + uIC[k * B + b];
+        if (!mv.bCoupled[b]) sc = sc + uBC[k * B + b];
+    END_BND
+    diagK[row] = d; srcK[row] = sc;
+}
 // rUA = 1/UEqn.A() ; Unew = rUA*UEqn.H()  [REF region3d/pEqn.H:2,5] [UPSTREAM fvMatrix::A(), H(); lduMatrix::H]
 static __global__ void __launch_bounds__(BLOCK) k_ua_h(MeshView mv, const double* __restrict__ uDiag, const double* __restrict__ uLower,
         const double* __restrict__ uUpper, const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ sz,
@@ -450,7 +492,8 @@ static __global__ void k_adjust_scale(MeshView mv, BCView bcU, const double* __r
 // phi = phiU + (interpolate(sigmaK)*snGrad(alpha1) - ghf*snGrad(rho))*rUAf*magSf  [REF region3d/pEqn.H:16-20]
 static __global__ void __launch_bounds__(BLOCK) k_phi(MeshView mv, BCView bcA, double sigma, const double* __restrict__ K, const double* __restrict__ Kb,
         const double* __restrict__ alpha, const double* __restrict__ alphab, const double* __restrict__ rho, const double* __restrict__ rhob,
-        const double* __restrict__ ghf, const double* __restrict__ rUAf, const double* __restrict__ phiU, double* __restrict__ phi) {
+        const double* __restrict__ ghf, const double* __restrict__ rUAf, const double* __restrict__ phiU, double* __restrict__ phi,
+        const double* __restrict__ corrA, const double* __restrict__ corrR /*corrected snGrad: explicit non-orthogonal parts, or null*/) {
     ROW_PROLOGUE(mv)
     if (row < mv.N) {
         double sKl = sigma * K[row], al = alpha[row], rl = rho[row];
@@ -458,6 +501,7 @@ static __global__ void __launch_bounds__(BLOCK) k_phi(MeshView mv, BCView bcA, d
             double sKu = sigma * K[u], dc = mv.dc[pos];
             double sKf = mv.w[pos] * (sKl - sKu) + sKu;
             double sga = dc * (alpha[u] - al), sgr = dc * (rho[u] - rl);
+            if (corrA) { sga = sga + corrA[pos]; sgr = sgr + corrR[pos]; }
             phi[pos] = phiU[pos] + (sKf * sga - ghf[pos] * sgr) * rUAf[pos] * mv.magSf[pos];
         END_FACES
     }
@@ -468,6 +512,7 @@ static __global__ void __launch_bounds__(BLOCK) k_phi(MeshView mv, BCView bcA, d
         if (mv.bCoupled[b]) { double sKn = sigma * Kb[b]; sKf = mv.w[p] * (sKf - sKn) + sKn; }
         double sga = bcSnGrad(bcA, t, b, b, dc, alpha[c], alphab[b]);
         double sgr = bcSnGrad(bcA, t, b, b, dc, rho[c], rhob[b]);
+        if (corrA) { sga = sga + corrA[p]; sgr = sgr + corrR[p]; }
         phi[p] = phiU[p] + (sKf * sga - ghf[p] * sgr) * rUAf[p] * mv.magSf[p];
     }
 }
@@ -532,6 +577,7 @@ void Region3D::create(DeviceMesh* mesh, const b200_region3d_controls& c, const b
     for (DevBuf<double>* b : {&alphab, &pdb, &rhob, &rho0b, &ic, &bcv, &pcorrb, &Kb, &rUAb, &haloSend}) { b->alloc(B); b->zero(); }
     for (DevBuf<double>* b : {&Ub, &U0b, &uIC, &uBC}) { b->alloc(3 * B); b->zero(); }
     for (DevBuf<double>* b : {&phi, &phi0, &rhoPhi, &rhoPhiSum, &nHatf, &ghf, &phiAlpha, &phiU, &rUAf, &muf, &uLower, &uUpper, &pdUpper, &oneF}) { b->alloc(nf); b->zero(); }
+    if (nonOrth()) for (DevBuf<double>* b : {&ffc, &corrA, &corrR}) { b->alloc(nf); b->zero(); }
     scal.alloc(64); scal.zero();
     B200_CHECK_CUDA(cudaMallocHost((void**)&hscal, 64 * sizeof(double)));
     fillValue(oneF, nf, 1.0);
@@ -652,6 +698,19 @@ void Region3D::assembleUEqn() {
     if (B) B200_LAUNCH(k_ueqn_boundary, gridFor(B), BLOCK, st, mv, bcU.view(), ctl.divUScheme == B200_SCHEME_UPWIND ? 1 : 0, (const double*)rhoPhi.p, (const double*)muf.p, (const double*)Ub.p, uIC.p, uBC.p);
 }
 
+// [UPSTREAM correctedSnGrad::correction]: Gauss-linear gradient of vf (boundary values vfb), interpolated to the faces, dotted with the
+// non-orthogonal correction vectors; processor faces take the neighbour rank's cell gradient through the halo swap
+void Region3D::nonOrthCorrection(const double* vf, const double* vfb, const double* gammaf, double* out) {
+    FvWorkspace& w = fvWorkspace(*m);
+    MeshView mv = m->view();
+    cudaStream_t st = rt().stream;
+    int N = m->N, B = m->B, nmax = std::max(std::max(N, B), 1);
+    B200_LAUNCH(k_grad_scalar, gridFor(N), BLOCK, st, mv, vf, vfb, w.gx.p, w.gy.p, w.gz.p);
+    haloScalar(w.gx, w.gb.p); haloScalar(w.gy, w.gb.p + B); haloScalar(w.gz, w.gb.p + 2 * (size_t)B);
+    B200_LAUNCH(k_nonorth_ffc, gridFor(nmax), BLOCK, st, mv, gammaf, (const double*)w.gx.p, (const double*)w.gy.p, (const double*)w.gz.p,
+                (const double*)w.gb.p, out);
+}
+
 void Region3D::solvePressureLike(const DevBC& bc, const double* gammaf, double* psi, double* psib, double tol, double relTol,
                                  bool subtractFlux) {
     MeshView mv = m->view();
@@ -659,7 +718,9 @@ void Region3D::solvePressureLike(const DevBC& bc, const double* gammaf, double* 
     PcgWorkspace& pw = pcgWorkspace(*m);
     int N = m->N, B = m->B, nmax = std::max(std::max(N, B), 1);
     { ScopedTimer t(T_ASSEMBLY);
-      B200_LAUNCH(k_lap_row, gridFor(N), BLOCK, st, mv, gammaf, (const double*)phi.p, pdDiag.p, pdUpper.p, pdSource.p);
+      const bool corr = nonOrth();   // laplacian `corrected`: explicit faceFluxCorrection from the CURRENT psi (re-assembled per non-orthogonal corrector)
+      if (corr) nonOrthCorrection(psi, psib, gammaf, ffc.p);
+      B200_LAUNCH(k_lap_row, gridFor(N), BLOCK, st, mv, gammaf, (const double*)phi.p, pdDiag.p, pdUpper.p, pdSource.p, corr ? (const double*)ffc.p : (const double*)nullptr);
       // pdEqn.setReference(pdRefCell, pdRefValue) [REF region3d/pEqn.H:30; correctPhi.H:43]
       if (pdNeedRef && refRow >= 0) B200_LAUNCH(k_set_reference, 1, 32, st, refRow, ctl.pdRefValue, pdDiag.p, pdSource.p);
       if (B) {
@@ -684,7 +745,35 @@ void Region3D::solvePressureLike(const DevBC& bc, const double* gammaf, double* 
       evalPdBC(bc, psi, psib);
       if (subtractFlux)
           B200_LAUNCH(k_matrix_flux<true>, gridFor(nmax), BLOCK, st, mv, (const double*)pdUpper.p, (const double*)pdUpper.p, (const double*)ic.p,
-                      (const double*)bcv.p, (const double*)psi, (const double*)psib, phi.p); }
+                      (const double*)bcv.p, (const double*)psi, (const double*)psib, phi.p, nonOrth() ? (const double*)ffc.p : (const double*)nullptr); }
+}
+
+// [REF region3d/UEqn.H:19-34]
+void Region3D::momentumPredictor() {
+    MeshView mv = m->view();
+    cudaStream_t st = rt().stream;
+    int N = m->N, B = m->B, nmax = std::max(std::max(N, B), 1);
+    if (!momFlux.p) { momFlux.alloc(m->nFaceField()); momDiag.alloc(N); momSrc.alloc(N); if (nonOrth()) corrP.alloc(m->nFaceField()); }
+    { ScopedTimer t(T_UEQN);
+      const bool corr = nonOrth();
+      if (corr) { nonOrthCorrection(alpha, alphab, nullptr, corrA.p); nonOrthCorrection(rho, rhob, nullptr, corrR.p); nonOrthCorrection(pd, pdb, nullptr, corrP.p); }
+      B200_LAUNCH(k_mom_flux, gridFor(nmax), BLOCK, st, mv, bcAlpha.view(), bcPd.view(), ctl.sigma, (const double*)K.p, (const double*)Kb.p,
+                  (const double*)alpha.p, (const double*)alphab.p, (const double*)rho.p, (const double*)rhob.p, (const double*)pd.p, (const double*)pdb.p,
+                  (const double*)ghf.p, corr ? (const double*)corrA.p : (const double*)nullptr, corr ? (const double*)corrR.p : (const double*)nullptr,
+                  corr ? (const double*)corrP.p : (const double*)nullptr, momFlux.p);
+      B200_LAUNCH(k_reconstruct<0>, gridFor(N), BLOCK, st, mv, reconTensor(*m), (const double*)momFlux.p, (const double*)nullptr, (const double*)nullptr,
+                  (const double*)nullptr, Hx.p, Hy.p, Hz.p); }
+    b200_solver_controls sc{ctl.UTol, ctl.URelTol, ctl.minIter, ctl.maxIter};
+    double* Uk[3] = {Ux.p, Uy.p, Uz.p}; const double* Rk[3] = {Hx.p, Hy.p, Hz.p}; const double* Sk[3] = {uSx.p, uSy.p, uSz.p};
+    for (int k = 0; k < 3; k++) {
+        { ScopedTimer t(T_UEQN);
+          B200_LAUNCH(k_mom_system, gridFor(N), BLOCK, st, mv, k, (const double*)uDiag.p, Sk[k], Rk[k], (const double*)uIC.p, (const double*)uBC.p, momDiag.p, momSrc.p); }
+        std::vector<double> hist;
+        b200_solver_perf perf = pbicgSolveDevice(*m, momDiag, uUpper, uLower, coupled() ? uBC.p + (size_t)k * B : nullptr, coupled() ? uIC.p + (size_t)k * B : nullptr,
+                                                 Uk[k], momSrc, sc, keepHist ? &hist : nullptr);
+        perfs.push_back(perf);
+        if (keepHist) resHist.insert(resHist.end(), hist.begin(), hist.end());
+    }
 }
 
 // [REF include/CourantNoMultiRegion.H:78-92]
@@ -743,8 +832,11 @@ void Region3D::pEqn(int corr) {
           if (rt().nRanks > 1) allReduce(scal.p + 1, 4, RED_SUM);
           if (B) B200_LAUNCH(k_adjust_scale, gridFor(B), BLOCK, st, mv, bcU.view(), (const double*)(scal.p + 1), phiU.p);
       }
+      const bool corr = nonOrth();   // snGrad `corrected` [REF region3d/pEqn.H:18-19]
+      if (corr) { nonOrthCorrection(alpha, alphab, nullptr, corrA.p); nonOrthCorrection(rho, rhob, nullptr, corrR.p); }
       B200_LAUNCH(k_phi, gridFor(nmax), BLOCK, st, mv, bcAlpha.view(), ctl.sigma, (const double*)K.p, (const double*)Kb.p, (const double*)alpha.p, (const double*)alphab.p,
-                  (const double*)rho.p, (const double*)rhob.p, (const double*)ghf.p, (const double*)rUAf.p, (const double*)phiU.p, phi.p); }
+                  (const double*)rho.p, (const double*)rhob.p, (const double*)ghf.p, (const double*)rUAf.p, (const double*)phiU.p, phi.p,
+                  corr ? (const double*)corrA.p : (const double*)nullptr, corr ? (const double*)corrR.p : (const double*)nullptr); }
     for (int nonOrth = 0; nonOrth <= ctl.nNonOrthCorr; nonOrth++) {
         bool fin = (corr == ctl.nCorr - 1 && nonOrth == ctl.nNonOrthCorr);
         solvePressureLike(bcPd, rUAf, pd, pdb, fin ? ctl.pdFinalTol : ctl.pdTol, fin ? ctl.pdFinalRelTol : ctl.pdRelTol,
@@ -787,6 +879,7 @@ void Region3D::step() {
     calculateK();
     B200_LAUNCH(k_rho, gridFor(nmax), BLOCK, st, (int)N, (int)B, (const double*)alpha.p, (const double*)alphab.p, ctl.rho1, ctl.rho2, rho.p, rhob.p);
     assembleUEqn();
+    if (ctl.momentumPredictor) momentumPredictor();
     evalUBC();
     for (int corr = 0; corr < ctl.nCorr; corr++) pEqn(corr);
     B200_LAUNCH(k_cont_err, gridFor((long long)std::max<size_t>(N, 1)), BLOCK, st, mv, (const double*)phi.p, scal.p + 9, w.partials.p, w.counter.p);

@@ -51,6 +51,8 @@ struct Region3D {
     DevBuf<double> alphab, pdb, rhob, rho0b, Ub, U0b, uIC, uBC, ic, bcv, pcorrb, Kb, rUAb, haloSend;
     // face fields
     DevBuf<double> phi, phi0, rhoPhi, rhoPhiSum, nHatf, ghf, phiAlpha, phiU, rUAf, muf, uLower, uUpper, pdUpper, oneF;
+    DevBuf<double> momFlux, momDiag, momSrc, corrP;   // momentum predictor: face flux of the explicit pressure-gradient terms, per-component system
+    DevBuf<double> ffc, corrA, corrR;   // non-orthogonal correction: faceFluxCorrection of the pd / pcorr laplacian; corrected-snGrad parts of alpha1, rho
     DevBuf<double> scal;  // device scalars: [0] maxPhic, [1..4] adjustPhi sums, [5..8] alpha stats, [9..11] contErr sums
     double* hscal = nullptr;
     double deltaN = 0;
@@ -75,12 +77,16 @@ struct Region3D {
     void calculateK();
     void alphaEqn(double dt);
     void assembleUEqn();
+    void momentumPredictor();                               // [REF region3d/UEqn.H:19-34] solve(UEqn == reconstruct(...)) with b200PBiCG + DILU
     void pEqn(int corr);
     void solvePressureLike(const DevBC& bc, const double* gammaf, double* psi, double* psib, double tol, double relTol,
                            bool subtractFlux);
     void correctPhi();
     void step();
     void resolveStats();
+    bool nonOrth() const { return ctl.nonOrthCorrected != 0 && !m->orthogonal; }   // `corrected` schemes act only on a non-orthogonal mesh
+    // out[f] = (gammaf*magSf)_f * (corrVec & interpolate(grad(vf)))_f   (gammaf null: the bare correction of the corrected snGrad)
+    void nonOrthCorrection(const double* vf, const double* vfb, const double* gammaf, double* out);
     void courant(double* out3);                             // {meanCoNum, CoNum, velMag} [REF include/CourantNoMultiRegion.H:78-92]
     void refreshDerived();                                  // rho and interface.correct() from the current alpha1 (restart)
     bool coupled() const;                                   // nRanks > 1 and the mesh has processor patches

@@ -58,7 +58,8 @@ def main():
 def decomposed_checks(lib, rank, world, dims=(16, 4, 8)):
     """The decomposed hot path of `lib` (already initialised for `world` ranks) against the N-rank / serial oracle on a small
     weir channel: Amul bitwise, two consecutive b200PCG solves (rank-local DIC; iteration counts, residual history 1e-8), two
-    region steps (fields 1e-7 with tight solver tolerances).  Collective: every rank calls it.  Returns the measured errors;
+    region steps vs the SERIAL oracle (fields 1e-7 with tight solver tolerances), and correctPhi + 2 region steps vs the N-RANK oracle
+    at the default tolerances (equal iteration counts, histories 1e-8, fields 1e-10).  Collective: every rank calls it.  Returns the measured errors;
     raises AssertionError on a mismatch.  Also used by bench.py's untimed pre-flight on the real GPUs (N > 1)."""
     res = {}
     L = (5.0, 1.0, 2.0)
@@ -157,6 +158,60 @@ def decomposed_checks(lib, rank, world, dims=(16, 4, 8)):
         check("step%d" % s, 1e-7)
     so, sg = ro.alpha_stats()[-1], rg.alpha_stats()[-1]
     assert np.allclose(so, sg, rtol=1e-8, atol=1e-12)
+    rg.release()
+
+    # ---------------- the decomposed region step vs the N-RANK oracle (one thread per sub-domain, rank-local DIC) at the DEFAULT
+    # solver tolerances: identical PCG iteration counts, residual histories to 1e-8, fields to 1e-10
+    infos = [dict(owner=sb.owner, nInternalFaces=sb.nInternalFaces, geom=sb.geometry(),
+                  patches=[(sb.patchNames[p], int(sb.patchStart[p]), int(sb.patchSize[p]), int(sb.patchNeighbRank[p])) for p in range(sb.nPatches)])
+             for sb in subs]
+    coupled = fo.couple_submeshes(infos)
+    # momentum predictor ON here (the reference's default [REF region3d/readRegion3dPISOControls.H:9-10]): b200PBiCG + DILU with processor
+    # interfaces; all three velocity components made non-trivial so that none of the solves works on round-off noise
+    gC = gpm.geometry()["C"]
+    Uswirl = cs["U"].copy()
+    Uswirl[:, 1] = 0.2 * np.sin(2 * np.pi * gC[:, 0] / L[0]) * np.cos(np.pi * gC[:, 1] / L[1]) * cs["alpha"]
+    Uswirl[:, 2] = 0.1 * np.cos(2 * np.pi * gC[:, 0] / L[0]) * np.sin(np.pi * gC[:, 2] / L[2])
+    def mom(c):
+        c.momentumPredictor = 1; c.UTol = 1e-7; c.URelTol = 0.0
+        return c
+    ranks = []
+    for q, sb in enumerate(subs):
+        nbrRank, nbrCell, Cn, sg = coupled[q]
+        kinds = [1 if r_ >= 0 else 0 for r_ in sb.patchNeighbRank]
+        om = fo.Mesh(sb.owner, sb.neighbour, sb.patches, sg, sb.nCells, kinds, Cn)
+        Fq = sb.nInternalFaces; bm = sb.faceMap[Fq:]
+        ph = np.array([sb.patchNeighbRank[p] < 0 for p in range(sb.nPatches) for _ in range(sb.patchSize[p])])
+        ra = np.zeros(sb.nBoundaryFaces); ru = np.zeros((sb.nBoundaryFaces, 3))
+        ra[ph] = cs["rvA"][bm[ph] - gB0]; ru[ph] = cs["rvU"][bm[ph] - gB0]
+        def ty(t, sb=sb):
+            return [PR if sb.patchNeighbRank[p] >= 0 else t[gpm.patchNames.index(sb.patchNames[p])] for p in range(sb.nPatches)]
+        ranks.append(dict(mesh=om, ctl=mom(default_controls(fo.OrcControls)), bcAlpha=fo.BC(om, ty(cs["tA"]), 1, ra), bcU=fo.BC(om, ty(cs["tU"]), 3, ru),
+                          bcPd=fo.BC(om, ty(cs["tP"]), 1), alpha=cs["alpha"][sb.cellMap], U=Uswirl[sb.cellMap], pd=cs["pd"][sb.cellMap],
+                          nbrRank=nbrRank, nbrCell=nbrCell))
+    wo = fo.World(ranks)
+    rg = dm.region3d(mom(default_controls(capi.Region3dControls)), dm.bc(types(cs["tA"]), 1, rvA), dm.bc(types(cs["tU"]), 3, rvU),
+                     dm.bc(types(cs["tP"]), 1), cs["alpha"][pm.cellMap], Uswirl[pm.cellMap], cs["pd"][pm.cellMap])
+    res["nrank_fields_linf"] = 0.0
+    def check_n(tag, tol=1e-10):
+        fo_, fg = wo.fields(rank), rg.fields()
+        for k in ("alpha1", "U", "pd", "phi", "p", "rho"):
+            err = np.abs(fo_[k] - fg[k]).max() / max(np.abs(fo_[k]).max(), 1e-300)
+            assert err <= tol, (tag, k, err)
+            res["nrank_fields_linf"] = max(res["nrank_fields_linf"], float(err))
+        po, pg_ = wo.perfs(), rg.perfs()
+        assert [p[2] for p in po] == [p[2] for p in pg_], (tag, [p[2] for p in po], [p[2] for p in pg_])
+        ho_, hg_ = wo.res_hist(), rg.res_hist()
+        assert ho_.shape == hg_.shape and np.allclose(ho_, hg_, rtol=1e-8, atol=1e-13), tag
+        assert np.allclose(wo.alpha_stats(), rg.alpha_stats(), rtol=1e-12, atol=1e-25), tag
+    check_n("init")
+    wo.correct_phi(); rg.correct_phi()
+    check_n("correctPhi")
+    for s in range(2):
+        wo.step(); rg.step()
+        check_n("step%d" % s)
+    assert np.allclose(wo.courant(), rg.courant(), rtol=1e-10)
+    res["nrank_pcg_iterations"] = [int(p[2]) for p in rg.perfs()]
     rg.release(); dm.release(); ldu.release()
     return res
 

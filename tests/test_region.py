@@ -14,6 +14,11 @@ def build(lib, oracle, dims, weir, **kw):
     pm = lib.polymesh_box(*dims, *L, weir=weir)
     m = oracle_mesh_of(pm)
     cs = channel_case(pm, *L)
+    if kw.get("momentumPredictor"):
+        # make all three velocity components non-trivial (the plain channel has Uy = 0 up to round-off: a solve of pure noise)
+        C_ = pm.geometry()["C"]
+        cs["U"][:, 1] = 0.2 * np.sin(2 * np.pi * C_[:, 0] / L[0]) * np.cos(np.pi * C_[:, 1] / L[1]) * cs["alpha"]
+        cs["U"][:, 2] = 0.1 * np.cos(2 * np.pi * C_[:, 0] / L[0]) * np.sin(np.pi * C_[:, 2] / L[2])
     dm = pm.device_mesh()
     co = default_controls(oracle.OrcControls); cg = default_controls(capi.Region3dControls)
     for k, v in kw.items():
@@ -44,6 +49,9 @@ def compare(ro, rg):
     ((20, 6, 10), (0.45, 0.55, 0.3), {}, 3),
     ((16, 4, 8), None, dict(nAlphaSubCycles=1, nCorr=2, adjustPhi=0, divUScheme=3), 2),
     ((16, 4, 8), None, dict(nAlphaSubCycles=3, nAlphaCorr=2, nNonOrthCorr=1, mulesIncludeOwn=1), 2),
+    # f1: momentum predictor on (the reference's default), b200PBiCG + DILU per velocity component [REF region3d/UEqn.H:19-34]
+    ((20, 6, 10), (0.45, 0.55, 0.3), dict(momentumPredictor=1, UTol=1e-7, URelTol=0.0), 3),
+    ((16, 4, 8), None, dict(momentumPredictor=1, UTol=1e-6, URelTol=0.1, divUScheme=3, nCorr=2), 2),
 ])
 def test_region_step_matches_oracle(lib, oracle, dims, weir, kw, nsteps):
     pm, m, dm, ro, rg = build(lib, oracle, dims, weir, **kw)
