@@ -1,16 +1,15 @@
 /*---------------------------------------------------------------------------*\
   b200MULES.C -- host adapter: flattens the foam-extend fields into the C-ABI layout ([internal faces][boundary faces patch by
   patch]), keeps the virtual BC dispatch (psi.correctBoundaryConditions(): sifAlpha1 et al.) on the host, and calls
-  b200_mules_explicit_solve.  Compiled only where foam-extend-3.1 exists.
+  b200_mules_explicit_solve.  Compiled with wmake where foam-extend-3.1 exists; in this repository against foam/miniFoam.H (foam/Makefile) and run by tests/test_adapter.py.
 \*---------------------------------------------------------------------------*/
 #include "b200MULES.H"
-#include "b200foam.h"
+#include "b200Runtime.H"
 #ifndef B200_MINIFOAM
 #include "fvMesh.H"
 #include "processorFvPatch.H"
-#include "mixedFvPatchFields.H"
-#include "zeroGradientFvPatchFields.H"
-#include "fixedValueFvPatchFields.H"
+#include "HashTable.H"
+#endif
 
 namespace
 {
@@ -71,7 +70,6 @@ namespace
         forAll(s.boundaryField(), p) { forAll(s.boundaryField()[p], i) out[off + i] = s.boundaryField()[p][i]; off += s.boundaryField()[p].size(); }
     }
 }
-#endif
 
 void Foam::b200::MULES::explicitSolve
 (
@@ -82,7 +80,7 @@ void Foam::b200::MULES::explicitSolve
     const scalar psiMin
 )
 {
-#ifndef B200_MINIFOAM
+    b200::start();                                       // MULES may be reached before any b200PCG solve (stock solver for pd / pcorr)
     const fvMesh& mesh = psi.mesh();
     psi.correctBoundaryConditions();                     // virtual BC dispatch stays on the host (sifAlpha1::updateCoeffs)
 
@@ -119,7 +117,4 @@ void Foam::b200::MULES::explicitSolve
     forAll(phiPsi.boundaryField(), p) { forAll(phiPsi.boundaryField()[p], i) phiPsi.boundaryField()[p][i] = phiPsiFlat[off + i]; off += phiPsi.boundaryField()[p].size(); }
 
     psi.correctBoundaryConditions();
-#else
-    (void)psi; (void)phi; (void)phiPsi; (void)psiMax; (void)psiMin;
-#endif
 }
