@@ -398,6 +398,10 @@ def run_ours(args):
         ldu = dm.ldu
         bcA = dm.bc(cs["tA"], 1, cs["rvA"])
         t_solve, it_solve, t_mul = [], [], []
+        if solves:      # one untimed call of each plug point: first-use allocations of the host-pointer staging buffers
+            s0 = solves[0]; ldu.pcg_solve(s0["diag"], s0["upper"], s0["x0"], s0["source"], tol=s0["tol"], relTol=s0["relTol"], maxIter=ctl.maxIter)
+        if mules:
+            q0 = mules[0]; dm.mules_explicit_solve(bcA, q0["psi"], q0["psib"], q0["psi0"], q0["phi"], q0["phiPsi"], q0["deltaT"])
         for s in solves:
             t0 = time.time()
             x, pf, _ = ldu.pcg_solve(s["diag"], s["upper"], s["x0"], s["source"], tol=s["tol"], relTol=s["relTol"], maxIter=ctl.maxIter)

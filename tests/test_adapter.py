@@ -101,6 +101,7 @@ def test_b200PCG_and_b200PBiCG_through_the_selection_tables(mini, oracle):
     assert rc == 1 and "Unknown asymmetric matrix solver b200PCG" in err          # PCG is registered in the symMatrix table only
     rc, *_, err = solve(mini, "b200PBiCG", "DIC", pm, dg, upper, lower, x0, b)
     assert rc == 1 and "implements DILU only" in err
+    F = pm.nInternalFaces
     fc = pm.owner[F:F + 5]
     rc, *_, err = solve(mini, "b200PCG", "DIC", pm, diag, upper, None, x0, b, ifaces=[(fc, -1, np.zeros(5))])
     assert rc == 1 and "only processor interfaces" in err
