@@ -15,8 +15,21 @@ int main(int argc, char** argv) {
     int band = argc > 4 ? atoi(argv[4]) : 16, maxRows = argc > 5 ? atoi(argv[5]) : 4096, smem = argc > 6 ? atoi(argv[6]) : 225000;
     int lanes = argc > 7 ? atoi(argv[7]) : 256;
     double s = argc > 8 ? atof(argv[8]) : 126.0, o = argc > 9 ? atof(argv[9]) : 450.0;
+    const bool poly = argc > 10 && atoi(argv[10]) != 0;   // 11th argument != 0: the polyhedral box of configs[3] (mesh_oracle.block_groups)
     PolyMesh box = makeBox(nx, ny, nz, 20.0, 5.0, 10.0);
-    PolyMesh m = subsetMesh(box, weirKeepMask(nx, ny, nz, 0.45, 0.5, 0.3), "weir");
+    PolyMesh m;
+    if (!poly) m = subsetMesh(box, weirKeepMask(nx, ny, nz, 0.45, 0.5, 0.3), "weir");
+    else {
+        std::vector<int64_t> key((size_t)nx * ny * nz);
+        for (int k = 0; k < nz; k++) for (int j = 0; j < ny; j++) for (int i = 0; i < nx; i++) {
+            int I = i / 2, J = j / 2, K = k / 2;
+            bool full = 2 * I + 1 < nx && 2 * J + 1 < ny && 2 * K + 1 < nz;
+            bool merged = full && ((I + J + K) % 3 != 0);
+            int64_t cell = i + (int64_t)nx * (j + (int64_t)ny * k);
+            key[cell] = merged ? (int64_t)nx * ny * nz + (I + (int64_t)(nx / 2 + 1) * (J + (int64_t)(ny / 2 + 1) * K)) : cell;
+        }
+        m = agglomerate(box, key.data());
+    }
     int F = m.nInternalFaces();
     SweepPlan P;
     buildSweepPlan(m.nCells, m.owner.data(), m.neighbour.data(), F, band, maxRows, smem, lanes, P);
@@ -44,6 +57,8 @@ int main(int argc, char** argv) {
         crit = std::max(crit, done[t]);
         maxHalo = std::max(maxHalo, P.fwdHalo[t + 1] - P.fwdHalo[t]);
     }
+    int maxD = 0; for (int t = 0; t < nT; t++) maxD = std::max(maxD, std::max(P.fwdD[t], P.bwdD[t]));
+    printf("faces/cell %.2f  max sources per row %d  strides %d %d %d\n", 2.0 * F / m.nCells, maxD, P.stride[0], P.stride[1], P.stride[2]);
     printf("N %d levels %d | band %d maxRows %d lanes %d binJ %d binK %d | tiles %d tileLevels %d | steps/tile mean %.1f max %lld (>16: %lld) lane-util %.2f | smem %zu maxHalo %d | model crit path %.1f us (s=%.0f ns, o=%.0f ns)\n",
            m.nCells, P.nLevels, band, maxRows, lanes, P.binJ, P.binK, nT, P.nTileLevels, (double)totSteps / nT, maxSteps, over16,
            util / ((double)totSteps * lanes), std::max(P.smemFwd, P.smemBwd), maxHalo, crit / 1000.0, s, o);

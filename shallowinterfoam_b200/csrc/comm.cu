@@ -69,8 +69,6 @@ void haloPack(const DeviceMesh& m, const double* cellField, double* send) {
 // (peer stores over NVLink), spins on its own mailbox until all tags of this epoch are in, and combines the values in rank order
 // (same order on every rank => identical result everywhere).  One 32-thread kernel, ~5 us, instead of an NCCL launch (~20 us).
 // Slots are 4-deep: a rank can be at most one all-reduce ahead of its slowest peer.
-constexpr int P2P_MAX_RANKS = 16, P2P_SLOTS = 4, P2P_ENTRY = 8;   // entry = 7 values + tag
-struct P2PView { double* mbox; double* peer[P2P_MAX_RANKS]; int rank, nRanks; };
 struct P2PState { bool ok = false; P2PView v; unsigned long long epoch = 0; void* opened[P2P_MAX_RANKS] = {nullptr}; double* own = nullptr; };
 static P2PState g_p2p;
 
@@ -79,30 +77,9 @@ static P2PState g_p2p;
 __global__ void k_p2p_allreduce(double* data, int count, int op, P2PView pv, unsigned long long epoch, PcgScalars* post, double* hist) {
     pdlTrigger();   // (launched without the PDL attribute: everything before it is complete) lets a PDL successor -- the next forward
                     // sweep -- run its prologue while this warp waits for the peers
-    const int lane = threadIdx.x, slot = (int)(epoch & (P2P_SLOTS - 1));
-    const double tag = (double)epoch;
-    if (lane < pv.nRanks) {
-        volatile double* dst = pv.peer[lane] + ((size_t)slot * pv.nRanks + pv.rank) * P2P_ENTRY;
-        for (int i = 0; i < count; i++) dst[i] = data[i];
-        __threadfence_system();
-        dst[P2P_ENTRY - 1] = tag;
-        volatile double* src = pv.mbox + ((size_t)slot * pv.nRanks + lane) * P2P_ENTRY;
-        while (src[P2P_ENTRY - 1] != tag) {}
-        __threadfence_system();
-    }
-    __syncwarp();
-    if (lane < count) {
-        volatile double* base = pv.mbox + (size_t)slot * pv.nRanks * P2P_ENTRY;
-        double acc = base[lane];
-        for (int r = 1; r < pv.nRanks; r++) {
-            double v = base[(size_t)r * P2P_ENTRY + lane];
-            acc = op == 0 ? acc + v : op == 1 ? (acc > v ? acc : v) : (acc < v ? acc : v);
-        }
-        data[lane] = acc;
-    }
+    p2pAllreduceWarp(data, count, op, pv, epoch);
     if (post) {
-        __syncwarp();
-        if (lane == 0 && !post->stop) {
+        if (threadIdx.x == 0 && !post->stop) {
             if (post->pendingCheck) { post->pendingCheck = 0; pcgEndOfIteration(post, hist); }
             if (!post->stop) post->wArA = post->wArAnew;
         }
@@ -313,6 +290,12 @@ PeerHaloWait peerHaloWait(const PeerHalo* h) {
     return w;
 }
 
+P2PFold p2pFoldNext() {
+    P2PFold f; memset(&f, 0, sizeof(f));
+    if (!p2pAllreduceOn() || rt().opt("p2p_fold", 1) <= 0) return f;
+    f.on = 1; f.v = g_p2p.v; f.epoch = ++g_p2p.epoch;
+    return f;
+}
 bool allReduceSumThenPcgCheck(double* p, int count, PcgScalars* sc, double* hist) {
     if (!(p2pAllreduceOn() && count <= P2P_ENTRY - 1)) return false;
     g_p2p.epoch++;
@@ -346,6 +329,7 @@ bool commUsesPeerMemory() { return false; }
 int commUniqueId(void* out128) { memset(out128, 0, 128); return 128; }
 void allReduce(double* p, int count, ReduceOp op) { if (rt().nRanks > 1) g_emuAllreduce(p, count, (int)op); }
 bool allReduceSumThenPcgCheck(double*, int, PcgScalars*, double*) { return false; }
+P2PFold p2pFoldNext() { P2PFold f; memset(&f, 0, sizeof(f)); return f; }
 struct PeerHalo {};
 PeerHalo* peerHaloGet(DeviceMesh&) { return nullptr; }
 void peerHaloRelease(PeerHalo*) {}
@@ -370,6 +354,7 @@ int commUniqueId(void* out128) { memset(out128, 0, 128); return 128; }
 void allReduce(double*, int, ReduceOp) {}
 void haloExchange(const DeviceMesh&, const double*, double*) {}
 bool allReduceSumThenPcgCheck(double*, int, PcgScalars*, double*) { return false; }
+P2PFold p2pFoldNext() { P2PFold f; memset(&f, 0, sizeof(f)); return f; }
 struct PeerHalo {};
 PeerHalo* peerHaloGet(DeviceMesh&) { return nullptr; }
 void peerHaloRelease(PeerHalo*) {}

@@ -14,6 +14,47 @@ struct PcgScalars;
 // caller does allReduce + k_pcg_check
 bool allReduceSumThenPcgCheck(double* devPtr, int count, PcgScalars* sc, double* hist);
 bool commUsesPeerMemory();   // scalar all-reduces run over NVLink peer memory (mailboxes) instead of NCCL
+
+// ---- scalar all-reduce over NVLink peer memory (gSum / gMax / gMin of PCG and MULES: 1-7 doubles, pure latency).
+// Every rank owns a mailbox; an all-reduce = each rank stores its values + an epoch tag into its slot of EVERY rank's mailbox
+// (peer stores over NVLink), spins on its own mailbox until all tags of this epoch are in, and combines the values in rank order
+// (same order on every rank => identical result everywhere).  Slots are 4-deep: a rank can be at most one all-reduce ahead of its
+// slowest peer.  The exchange is ONE WARP's work, so besides the stand-alone kernel (k_p2p_allreduce) it can ride in the tail of the
+// kernel that produces the values: the last CTA of the backward sweep and of the interface update (P2PFold) -- no launch of its own.
+constexpr int P2P_MAX_RANKS = 16, P2P_SLOTS = 4, P2P_ENTRY = 8;   // entry = 7 values + tag
+struct P2PView { double* mbox; double* peer[P2P_MAX_RANKS]; int rank, nRanks; };
+struct P2PFold { int on; P2PView v; unsigned long long epoch; };   // on = 0: the caller runs the all-reduce as a separate step
+// a new epoch for an all-reduce folded into another kernel; on = 0 when peer memory is unavailable or switched off (p2p_allreduce = 0)
+P2PFold p2pFoldNext();
+#ifndef B200_EMU
+// executed by the 32 threads of ONE warp (lane = threadIdx.x & 31); data[0..count) in place; op: 0 sum, 1 max, 2 min
+__device__ __forceinline__ void p2pAllreduceWarp(double* data, int count, int op, const P2PView& pv, unsigned long long epoch) {
+    const int lane = threadIdx.x & 31, slot = (int)(epoch & (P2P_SLOTS - 1));
+    const double tag = (double)epoch;
+    if (lane < pv.nRanks) {
+        volatile double* dst = pv.peer[lane] + ((size_t)slot * pv.nRanks + pv.rank) * P2P_ENTRY;
+        for (int i = 0; i < count; i++) dst[i] = ((volatile double*)data)[i];
+        __threadfence_system();
+        dst[P2P_ENTRY - 1] = tag;
+        volatile double* src = pv.mbox + ((size_t)slot * pv.nRanks + lane) * P2P_ENTRY;
+        while (src[P2P_ENTRY - 1] != tag) {}
+        __threadfence_system();
+    }
+    __syncwarp();
+    if (lane < count) {
+        volatile double* base = pv.mbox + (size_t)slot * pv.nRanks * P2P_ENTRY;
+        double acc = base[lane];
+        for (int r = 1; r < pv.nRanks; r++) {
+            double v = base[(size_t)r * P2P_ENTRY + lane];
+            acc = op == 0 ? acc + v : op == 1 ? (acc > v ? acc : v) : (acc < v ? acc : v);
+        }
+        data[lane] = acc;
+    }
+    __syncwarp();
+}
+#else
+__device__ __forceinline__ void p2pAllreduceWarp(double*, int, int, const P2PView&, unsigned long long) {}
+#endif
 // exchange per-boundary-face values on processor patches: recv[b] = neighbour rank's send[b'] (same face)
 void haloExchange(const DeviceMesh& m, const double* send, double* recv);
 bool meshHasProcessorPatches(const DeviceMesh& m);

@@ -429,9 +429,12 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
 
 // backward: z[row] = y[row] - sum_{owner faces DESC} cb_j * z[u_j]   (cb = rD[row]*upper) ; y[row] <- sentinel (re-armed) ;
 // per-tile partial of sum(z*rA) (fixed rows per partial, fixed order => deterministic) -> *dotOut (sc->wArA; multi-rank: sc->wArAnew)
+// fold (multi-rank): the last CTA also runs the ONE scalar all-reduce of the iteration's first half -- (sum|rA| left by the forward
+// sweep, sum(wA*rA) of this sweep; adjacent in PcgScalars) -- over NVLink peer memory and then closes the previous iteration
+// (k_pcg_check's body): no stand-alone 32-thread kernel between the sweeps and the p-update
 static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, const double* __restrict__ blocks,
         const double* __restrict__ rA, double* y, double* z, SweepCtl ctl, PcgScalars* sc, double* partials, unsigned* counter,
-        double* dotOut) {
+        double* dotOut, P2PFold fold, double* hist) {
     B200_DYN_SMEM(smem);
     __shared__ int sRow[SWEEP_MAX_STEPS], sLen[SWEEP_MAX_STEPS];
     __shared__ TileBar sBar;
@@ -492,7 +495,17 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
         }
     }
     if (threadIdx.x == 0) bulkStoreWaitAll();
-    if (partials) gridFinalize<1, OpSum>(sv.nTiles, partials, counter, dotOut);
+    if (partials) {
+        const bool last = gridFinalizeLast<OpSum>(sv.nTiles, partials, counter, dotOut);
+        if (last && fold.on) {
+            if (threadIdx.x < 32) p2pAllreduceWarp(&sc->sumMagR, 2, 0, fold.v, fold.epoch);
+            __syncthreads();
+            if (threadIdx.x == 0 && !sc->stop) {
+                if (sc->pendingCheck) { sc->pendingCheck = 0; pcgEndOfIteration(sc, hist); }
+                if (!sc->stop) sc->wArA = sc->wArAnew;
+            }
+        }
+    }
     sweepExit(ctl);
 }
 

@@ -402,7 +402,7 @@ static __global__ void k_pcg_check(PcgScalars* sc, double* hist) {
 static __global__ void __launch_bounds__(BLOCK) k_iface_rows(MeshView mv, const double* __restrict__ bou, const double* psiNbr,
                                                        double* __restrict__ Apsi, const double* __restrict__ psi, int nBRows,
                                                        const int* __restrict__ bRowOfSlot, PcgScalars* sc, double* partials,
-                                                       unsigned* counter, PeerHaloWait hw) {
+                                                       unsigned* counter, PeerHaloWait hw, P2PFold fold) {
     if (sc->stop) return;
     peerHaloWaitDevice(hw);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -422,6 +422,11 @@ static __global__ void __launch_bounds__(BLOCK) k_iface_rows(MeshView mv, const 
     __shared__ double corr;
     const bool last = gridFinalizeLast<OpSum>(gridDim.x, partials, counter, &corr);
     if (last && threadIdx.x == 0) sc->wApA = sc->wApA + corr;
+    // folded gSumProd(wA, pA): the last CTA's first warp exchanges the rank's sum over NVLink peer memory right here (no kernel of its own)
+    if (last && fold.on) {
+        __syncthreads();
+        if (threadIdx.x < 32) p2pAllreduceWarp(&sc->wApA, 1, 0, fold.v, fold.epoch);
+    }
 }
 // pA = z + beta*pA (first iteration: pA = z);  z <- sentinel (re-armed for the next sweep)
 static __global__ void __launch_bounds__(BLOCK) k_pcg_p_update(int N, double* __restrict__ z, double* __restrict__ pA,

@@ -104,9 +104,9 @@ static void launchFwd(DeviceMesh& m, PcgWorkspace& w, const double* rD, const do
                     cf ? cf : (const double*)w.cf.p, w.y.p, (double*)nullptr, sweepCtl(w), sc, fz);
 }
 static void launchBwd(DeviceMesh& m, PcgWorkspace& w, const double* rA, PcgScalars* sc, double* part, unsigned* cnt, double* dotOut = nullptr, bool pdl = false,
-                      const double* cb = nullptr) {
+                      const double* cb = nullptr, P2PFold fold = P2PFold{}, double* hist = nullptr) {
     B200_LAUNCH_PDL(pdl, k_dic_bwd, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), cb ? cb : (const double*)w.cb.p, (const double*)rA, w.y.p, w.z.p,
-                    sweepCtl(w, true), sc, part, cnt, dotOut ? dotOut : (sc ? &sc->wArA : nullptr));
+                    sweepCtl(w, true), sc, part, cnt, dotOut ? dotOut : (sc ? &sc->wArA : nullptr), fold, hist);
 }
 
 void amulDevice(DeviceMesh& m, const double* diag, const double* upS, const double* loS, const double* psi, double* Apsi,
@@ -207,27 +207,32 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
           // (the first sweep of a solve follows k_dic_coeffs, which writes the operand blocks the prologue stages: no early start)
           launchFwd(m, w, w.rD.p, w.rA.p, sc, PcgFuse{x, w.rA.p, w.pA.p, w.wA.p, sc, part, cnt, hist, multi ? 0 : 1}, pdlSweeps && !firstIteration); }
         firstIteration = false;
-        { KT(T_DIC_BWD); launchBwd(m, w, w.rA.p, sc, part, cnt, multi ? &sc->wArAnew : &sc->wArA, pdlSweeps); }
         // multi-rank: ONE all-reduce carries the previous iteration's sum|rA| and this iteration's sum(wA*rA); the convergence
-        // test therefore runs after the backward sweep (one wasted sweep at the end of a solve)
-        if (multi) { KT(T_ALLREDUCE);
+        // test therefore runs after the backward sweep (one wasted sweep at the end of a solve).  Over peer memory it rides in the
+        // tail of the backward sweep (fold1); otherwise a stand-alone kernel / NCCL + k_pcg_check
+        const P2PFold fold1 = (multi && !kt) ? p2pFoldNext() : P2PFold{};
+        { KT(T_DIC_BWD); launchBwd(m, w, w.rA.p, sc, part, cnt, multi ? &sc->wArAnew : &sc->wArA, pdlSweeps, nullptr, fold1, hist); }
+        if (multi && !fold1.on) { KT(T_ALLREDUCE);
           if (!allReduceSumThenPcgCheck(&sc->sumMagR, 2, sc, hist)) { allReduce(&sc->sumMagR, 2, RED_SUM); B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist); } }
         { KT(T_PCG_VEC);
           B200_LAUNCH_PDL(pdl || (pdlSweeps && commUsesPeerMemory()), k_pcg_p_update, grid, BLOCK, 0, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc); }
+        P2PFold fold2 = P2PFold{};
         if (halo) {
             // Amul of the local block with its dot product, then the interface update (+ dot correction) over the boundary rows only.
             // peer: the halo goes over NVLink peer memory -- push -> Amul (overlaps the transfer) -> wait inside k_iface_rows; else NCCL
             { KT(T_HALO); if (peer) peerHaloPush(peer, m, w.pA, pdlSweeps); else haloPack(m, w.pA, w.sendBuf); }
             { KT(T_AMUL); B200_LAUNCH_AMUL(1, pdlSweeps && peer != nullptr, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt); }
+            // ... and gSumProd(wA, pA) rides in the tail of the interface update (fold2)
+            fold2 = !kt ? p2pFoldNext() : P2PFold{};
             { KT(T_HALO);
               if (!peer) haloExchange(m, w.sendBuf, w.recvBuf);
               B200_LAUNCH(k_iface_rows, std::max(1, gridFor(m.nBRows)), BLOCK, st, mv, bou, peer ? peerHaloRecv(peer) : (const double*)w.recvBuf.p, w.wA.p,
-                          (const double*)w.pA.p, m.nBRows, (const int*)w.bRowOfSlot.p, sc, part, cnt, peer ? peerHaloWait(peer) : PeerHaloWait{}); }
+                          (const double*)w.pA.p, m.nBRows, (const int*)w.bRowOfSlot.p, sc, part, cnt, peer ? peerHaloWait(peer) : PeerHaloWait{}, fold2); }
         } else {
             KT(T_AMUL);
             B200_LAUNCH_AMUL(1, pdl, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt);
         }
-        if (multi) { KT(T_ALLREDUCE); allReduce(&sc->wApA, 1, RED_SUM); }
+        if (multi && !fold2.on) { KT(T_ALLREDUCE); allReduce(&sc->wApA, 1, RED_SUM); }
     };
 #undef KT
     // two batches in flight: while the host waits for batch i's flag, batch i+1 is already queued

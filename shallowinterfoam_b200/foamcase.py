@@ -280,11 +280,11 @@ def read_polymesh(mesh_dir):
 
 
 # ------------------------------------------------------------------------------------------------------ command line
-def _bench_case(dims, lengths, weir):
+def _bench_case(dims, lengths, weir, lib=None):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import bench
     from . import capi
-    lib = capi.load()
+    lib = lib or capi.load()
     pm = lib.polymesh_box(*dims, *lengths, weir=weir)
     g = pm.geometry()
     F = pm.nInternalFaces
@@ -294,7 +294,8 @@ def _bench_case(dims, lengths, weir):
     return lib, pm, cs, ctl, bench.DELTA_T
 
 
-def main(argv=None):
+def main(argv=None, lib=None):
+    """lib: an already loaded (and, for `check`, initialised) B200Lib -- the tests pass theirs; the command line loads the product library"""
     import argparse
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     ap.add_argument("cmd", choices=["write", "check"])
@@ -307,7 +308,8 @@ def main(argv=None):
     ap.add_argument("--procs", type=int, nargs=3, default=None, help="also write processor*/ for this `simple` decomposition")
     ap.add_argument("--solver", default="PCG")
     a = ap.parse_args(argv)
-    lib, pm, cs, ctl, dt = _bench_case(tuple(a.dims), tuple(a.lengths), tuple(a.weir) if a.weir else None)
+    given = lib is not None
+    lib, pm, cs, ctl, dt = _bench_case(tuple(a.dims), tuple(a.lengths), tuple(a.weir) if a.weir else None, lib)
     if a.cmd == "write":
         write_case(a.case, pm, cs, ctl, dt, a.steps, a.region, a.solver, ("libb200Foam.so",) if a.solver == "b200PCG" else ())
         if a.procs:
@@ -316,7 +318,8 @@ def main(argv=None):
             a.case, pm.nCells, len(pm.owner), pm.nPatches, a.case, a.case))
         return 0
     # check: our device run of the same case against foam-extend's log and written fields
-    lib.init(0, 0, 1)
+    if not given:
+        lib.init(0, 0, 1)
     dm = pm.device_mesh()
     reg = dm.region3d(ctl, dm.bc(cs["tA"], 1, cs["rvA"]), dm.bc(cs["tU"], 3, cs["rvU"]), dm.bc(cs["tP"], 1), cs["alpha"], cs["U"], cs["pd"])
     reg.correct_phi(); reg.clear_log()

@@ -114,3 +114,54 @@ b200PCG:  Solving for pd, Initial residual = 0.5, Final residual = 0.02, No Iter
     assert fc.parse_log(log, "pcorr")[0][4] == 40
     line = fc.format_log_line("b200PCG", "pd", 0.5, 0.02, 11)
     assert fc.parse_log(line + "\n", "pd")[0][2:] == (0.5, 0.02, 11)
+
+
+def test_check_command_against_a_foam_extend_style_run(lib, oracle, tmp_path, capsys):
+    """f4, the `check` leg: `foamcase check CASE` replays the case through the library and compares it with foam-extend's log and
+    written fields.  No foam-extend exists here, so the stand-in for its output is produced by the CPU ORACLE in foam-extend's own
+    formats (lduSolverPerformance::print lines under `Time = ...` headers; ASCII volScalarField / volVectorField files in the last time
+    directory): what passes here is the whole pinning pipeline -- case writer, log parser, field reader, comparison, verdict -- and a
+    doctored log / field must make it fail."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from cases import oracle_mesh_of
+    dims, lengths, steps = (20, 6, 10), (5.0, 1.0, 2.0), 3
+    case = str(tmp_path / "case")
+    argv = [case, "--dims"] + [str(d) for d in dims] + ["--lengths"] + [str(x) for x in lengths] + ["--steps", str(steps)]
+    assert fc.main(["write"] + argv, lib=lib) == 0
+    # "foam-extend": the oracle, serial, same controls as the case's dictionaries
+    pm = lib.polymesh_box(*dims, *lengths)
+    m = oracle_mesh_of(pm)
+    g = pm.geometry(); F = pm.nInternalFaces
+    cs = bench.channel_fields(pm.patchNames, g["C"], g["Cf"][F:], {n: pm.patch_slice(n) for n in pm.patchNames}, lengths)
+    ro = oracle.Region(m, bench.set_controls(oracle.OrcControls()), oracle.BC(m, cs["tA"], 1, cs["rvA"]), oracle.BC(m, cs["tU"], 3, cs["rvU"]),
+                       oracle.BC(m, cs["tP"], 1), cs["alpha"], cs["U"], cs["pd"])
+    ro.correct_phi()
+    log = "Create time\n\n" + fc.format_log_line("DICPCG", "pcorr", *ro.perfs()[0][:3]) + "\n"
+    ro.clear_log()
+    dt = bench.DELTA_T
+    for s_ in range(steps):
+        ro.step()
+        log += "\nTime = %s\n\nMULES: Solving for alpha1\n" % fc._fmt(dt * (s_ + 1))
+        for p in ro.perfs()[-3:]:
+            log += fc.format_log_line("DICPCG", "pd", p[0], p[1], p[2]) + "\n"
+        log += "ExecutionTime = 0 s\n"
+    open(os.path.join(case, "log"), "w").write(log)
+    fo_ = ro.fields()
+    tdir = os.path.join(case, fc._fmt(dt * steps).rstrip("0").rstrip("."), "region3d")
+    patches = pm.patches
+    zg = [fc.ZG] * pm.nPatches
+    for name, arr in (("alpha1", fo_["alpha1"]), ("pd", fo_["pd"]), ("U", fo_["U"])):
+        fc.write_field(os.path.join(tdir, name), name, arr, patches, F, zg, None, os.path.basename(os.path.dirname(tdir)) + "/region3d")
+    capsys.readouterr()
+    assert fc.main(["check"] + argv, lib=lib) == 0
+    out = capsys.readouterr().out
+    assert "PARITY PINNED" in out and out.count(" ok") >= 3 * steps + 3 and "DIFFERS" not in out
+    # a log whose iteration count is off by one, and a field that is off in the 6th digit, must both be caught
+    bad = log.replace("No Iterations %d" % ro.perfs()[-1][2], "No Iterations %d" % (ro.perfs()[-1][2] + 1), 1)
+    open(os.path.join(case, "log"), "w").write(bad)
+    assert fc.main(["check"] + argv, lib=lib) == 1 and "DIFFERS" in capsys.readouterr().out
+    open(os.path.join(case, "log"), "w").write(log)
+    fc.write_field(os.path.join(tdir, "pd"), "pd", fo_["pd"] * (1 + 1e-6), patches, F, zg, None, "x/region3d")
+    assert fc.main(["check"] + argv, lib=lib) == 1 and "parity NOT pinned" in capsys.readouterr().out
