@@ -398,18 +398,35 @@ def run_ours(args):
         ldu = dm.ldu
         bcA = dm.bc(cs["tA"], 1, cs["rvA"])
         t_solve, it_solve, t_mul = [], [], []
+        import ctypes as C
+        dpt = C.POINTER(C.c_double)
+
+        def ptr(a):
+            return a.ctypes.data_as(dpt)
+
+        def plug_pcg(s, timed=True):
+            # exactly the adapter's call: b200_pcg_solve(ldu, diag, upper, NULL, NULL, x, b, ctl, perf, NULL, 0) on pageable arrays
+            x = s["x0"].copy(); ctl_ = capi.SolverControls(s["tol"], s["relTol"], ctl.minIter, ctl.maxIter); perf = capi.SolverPerf()
+            t0 = time.time()
+            lib.check(lib.c.b200_pcg_solve(ldu.h, ptr(s["diag"]), ptr(s["upper"]), None, None, ptr(x), ptr(s["source"]), C.byref(ctl_), C.byref(perf), None, C.c_int32(0)))
+            return time.time() - t0, int(perf.nIterations)
+
+        def plug_mules(q):
+            psi = q["psi"].copy(); phiPsi = q["phiPsi"].copy()
+            t0 = time.time()
+            lib.check(lib.c.b200_mules_explicit_solve(dm.h, bcA.ref, ptr(psi), ptr(q["psib"]), ptr(q["psi0"]), ptr(q["phi"]), ptr(phiPsi),
+                                                      C.c_double(q["deltaT"]), C.c_double(1.0), C.c_double(0.0), None))
+            return time.time() - t0
+
         if solves:      # one untimed call of each plug point: first-use allocations of the host-pointer staging buffers
-            s0 = solves[0]; ldu.pcg_solve(s0["diag"], s0["upper"], s0["x0"], s0["source"], tol=s0["tol"], relTol=s0["relTol"], maxIter=ctl.maxIter)
+            plug_pcg(solves[0])
         if mules:
-            q0 = mules[0]; dm.mules_explicit_solve(bcA, q0["psi"], q0["psib"], q0["psi0"], q0["phi"], q0["phiPsi"], q0["deltaT"])
+            plug_mules(mules[0])
         for s in solves:
-            t0 = time.time()
-            x, pf, _ = ldu.pcg_solve(s["diag"], s["upper"], s["x0"], s["source"], tol=s["tol"], relTol=s["relTol"], maxIter=ctl.maxIter)
-            t_solve.append(time.time() - t0); it_solve.append(int(pf.nIterations))
+            dt_, it_ = plug_pcg(s)
+            t_solve.append(dt_); it_solve.append(it_)
         for q in mules:
-            t0 = time.time()
-            dm.mules_explicit_solve(bcA, q["psi"], q["psib"], q["psi0"], q["phi"], q["phiPsi"], q["deltaT"])
-            t_mul.append(time.time() - t0)
+            t_mul.append(plug_mules(q))
         plug_s = sum(t_solve) + sum(t_mul)
         resident_ms = tk["pcg_solve"][0] + tk["mules"][0]
         e2e_plugin = {"ms_per_step_in_plugin_calls": 1e3 * plug_s, "pcg_solve_ms": [1e3 * t for t in t_solve], "pcg_iterations": it_solve,
