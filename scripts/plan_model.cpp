@@ -50,9 +50,19 @@ int main(int argc, char** argv) {
         if (a != b) preds[b].push_back(a);
     }
     double crit = 0; int maxHalo = 0;
+    // streamed lateral halo (what-if, argv[11] = look-ahead steps, 0 = closed tiles): a consumer may run `la` steps + o behind a producer of
+    // the SAME band instead of after it; producers of earlier bands still have to finish (their last level feeds the consumer's first step)
+    const int la = argc > 11 ? atoi(argv[11]) : 0;
+    std::vector<double> startT(nT, 0.0);
+    std::vector<int> bandOf(nT);
+    for (int t = 0; t < nT; t++) bandOf[t] = P.level[P.rowCell[P.tileStart[t]]] / band;
     for (int t = 0; t < nT; t++) {
         double start = 0;
-        for (int a : preds[t]) start = std::max(start, done[a]);
+        for (int a : preds[t]) {
+            if (la > 0 && bandOf[a] == bandOf[t]) start = std::max(start, std::max(startT[a] + la * s + o, done[a] - cost[t] + la * s + o));
+            else start = std::max(start, done[a]);
+        }
+        startT[t] = start;
         done[t] = start + cost[t];
         crit = std::max(crit, done[t]);
         maxHalo = std::max(maxHalo, P.fwdHalo[t + 1] - P.fwdHalo[t]);
