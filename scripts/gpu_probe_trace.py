@@ -4,8 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from shallowinterfoam_b200 import capi
 lib = capi.load(); lib.init(0, 0, 1)
-dims = (200, 50, 100)
-pm = lib.polymesh_box(*dims, 20.0, 5.0, 10.0, weir=(0.45, 0.5, 0.3))
+dims = tuple(int(v) for v in sys.argv[2:5]) if len(sys.argv) > 4 else (200, 50, 100)
+pm = lib.polymesh_box(*dims, dims[0] / 10.0, dims[1] / 10.0, dims[2] / 10.0, weir=(0.45, 0.5, 0.3))
 ldu = pm.ldu(); N, F = pm.nCells, pm.nInternalFaces
 rng = np.random.default_rng(0)
 upper = -rng.uniform(0.5, 1.5, F)
@@ -13,15 +13,15 @@ diag = np.zeros(N); np.add.at(diag, pm.owner[:F], -upper); np.add.at(diag, pm.ne
 b = rng.uniform(-1, 1, N)
 rD = ldu.dic_calc_rd(diag, upper)
 ref = ldu.dic_precondition(rD, upper, b)
-for ro in (0, 1):     # operands through shared memory (round 1) / register-resident (round 2)
-    lib.set_option("sweep_reg_ops", ro)
+for ro, pub in ((0, 1), (1, 1), (1, 2)):     # operands in shared memory (round 1) / registers (round 2) / registers + hybrid publish
+    lib.set_option("sweep_reg_ops", ro); lib.set_option("sweep_publish", pub)
     assert np.array_equal(ldu.dic_precondition(rD, upper, b), ref)
     lib.timers_reset()
     for i in range(10):
         ldu.dic_precondition(rD, upper, b)
     tm = lib.timers()
-    print("sweep_reg_ops %d: fwd %6.1f bwd %6.1f us" % (ro, 1e3 * tm["dic_fwd"][0] / tm["dic_fwd"][1], 1e3 * tm["dic_bwd"][0] / tm["dic_bwd"][1]), flush=True)
-lib.set_option("sweep_reg_ops", int(sys.argv[1]) if len(sys.argv) > 1 else 1)
+    print("sweep_reg_ops %d publish %d: fwd %6.1f bwd %6.1f us" % (ro, pub, 1e3 * tm["dic_fwd"][0] / tm["dic_fwd"][1], 1e3 * tm["dic_bwd"][0] / tm["dic_bwd"][1]), flush=True)
+lib.set_option("sweep_reg_ops", 1); lib.set_option("sweep_publish", int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 lib.set_option("sweep_trace", 1)
 ldu.dic_precondition(rD, upper, b)
 tr, tl, ts = ldu.sweep_trace()

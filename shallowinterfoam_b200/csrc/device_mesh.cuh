@@ -72,7 +72,8 @@ struct SweepView {
     const int *fwdHaloRow, *bwdHaloRow;      // device rows a tile polls
     int pollNs;                              // back-off between polls of a not-yet-published halo value
     int regOps;                              // 1 (default): tiles with <= 3 sources per row and <= 16 steps keep their operands in registers (dic_kernels.cuh)
-    int publishMode;                         // 0: one TMA bulk store per tile after its last step; 1 (default): rows are stored in the step that computes them
+    int bulkTail;                            // publishMode 2: the last `bulkTail` steps of a tile store their rows in the loop, the earlier ones leave by one TMA bulk store
+    int publishMode;                         // 2: hybrid (see bulkTail); 0: one TMA bulk store per tile after its last step; 1 (default): rows are stored in the step that computes them
     unsigned long long* trace;               // debug: [8*nTiles] globaltimer stamps per tile (ticket, staged, halo ready, steps done, published) or null
 };
 
@@ -122,8 +123,15 @@ struct DeviceMesh {
                      const double* w, const double* dc);
     MeshView view() const;
     SweepView sweep() const {
-        return SweepView{nTiles, dTilesF.p, dTilesB.p, dStepRow.p, dStepLen.p, plan.lanes, dFwdPos.p, dBwdPos.p, dFwdHaloRow.p, dBwdHaloRow.p, (int)rt().opt("sweep_poll_ns", 0), (int)rt().opt("sweep_reg_ops", 1), (int)rt().opt("sweep_publish", 1),
+        return SweepView{nTiles, dTilesF.p, dTilesB.p, dStepRow.p, dStepLen.p, plan.lanes, dFwdPos.p, dBwdPos.p, dFwdHaloRow.p, dBwdHaloRow.p, (int)rt().opt("sweep_poll_ns", 0), (int)rt().opt("sweep_reg_ops", 1), (int)rt().opt("sweep_bulk_tail", 4), publishModeOf(),
                          rt().opt("sweep_trace", 0) > 0 ? dTrace.p : nullptr};
+    }
+    // how a tile's rows reach global memory: option sweep_publish (0 bulk store per tile, 1 in the step loop, 2 hybrid); default: hybrid
+    // once the sweep is throughput-bound (more than 8 tiles per SM: 7.88 M cells 592 vs 630 us per precondition), in-loop below that
+    // (985k cells: 162.6 vs 167.5 us) -- profiles/r2_ncu_summary.md
+    int publishModeOf() const {
+        const int o = (int)rt().opt("sweep_publish", -1);
+        return o >= 0 ? o : (nTiles > 8 * rt().numSMs ? 2 : 1);
     }
     void coupleGeometry();   // collective: processor-face weights/deltaCoeffs/neighbour centres from a halo swap of C
     size_t nFaceField() const { return (size_t)Fs + B; }

@@ -216,8 +216,24 @@ __device__ __forceinline__ void loadRegOps(RegOps& o, const double* __restrict__
         o.pk[it] = on ? ldgStream(PK + slot) : make_uint2(0u, 0u);
     }
 }
-template <int DIR>
-__device__ __forceinline__ void sweepStepsReg(const TileSmem& s, const SweepTile& t, const RegOps& o, double* out) {
+// local rows [lo, hi) of the tile -> out by one TMA bulk store (16-byte aligned middle) + scalar gpu-scope stores for odd ends; one thread,
+// after the barrier that follows the writers' fence.proxy.async
+__device__ __forceinline__ void publishRange(const TileSmem& s, const SweepTile& t, double* out, int lo, int hi) {
+    if (hi <= lo) return;
+    const int a = lo + ((t.row0 + lo) & 1), e = hi - ((t.row0 + hi) & 1);
+    if (e > a) {
+        for (int q = a; q < e; q += (int)(BULK_MAX / 8)) bulkStore(out + t.row0 + q, s.vals + q, (unsigned)((e - q < (int)(BULK_MAX / 8) ? e - q : (int)(BULK_MAX / 8)) * 8));
+        bulkStoreCommit();
+    }
+    if (a > lo) stPublish(out + t.row0 + lo, s.vals[lo]);
+    if (e < hi && e >= a) stPublish(out + t.row0 + hi - 1, s.vals[hi - 1]);
+}
+// BULK > 0 (hybrid publish): the rows of the first BULK processing steps leave by ONE asynchronous TMA bulk store issued when
+// they are complete -- it lands while the remaining steps run -- and only the last steps store their rows in the loop (their rows are the
+// ones the dependants wait for).  A store in the step loop costs every step ~28 ns (the following bar.sync waits for it).
+// (BULK is a compile-time constant: the step loop is so short that two run-time tests per step cost a quarter of it)
+template <int DIR, int BULK>
+__device__ __forceinline__ void sweepStepsReg(const TileSmem& s, const SweepTile& t, const RegOps& o, double* out, int bulkLo = 0, int bulkHi = 0) {
     const unsigned rowBytes = 8u * (unsigned)t.nRows;
     char* outB = (char*)(out + t.row0);
     double w = ldsAt(s.vals, o.pk[0].y >> 16);
@@ -233,11 +249,22 @@ __device__ __forceinline__ void sweepStepsReg(const TileSmem& s, const SweepTile
             const double nw = (nit != it && nit < t.nSteps) ? ldsAt(s.vals, o.pk[nit].y >> 16) : 0.0;
             w = w - o.c[it][0] * v0; w = w - o.c[it][1] * v1; w = w - o.c[it][2] * v2;
             stsAt(s.vals, pk.y >> 16, w);
-            if (out && (pk.y >> 16) < rowBytes) stWeak((double*)(outB + (pk.y >> 16)), w);
+            if (it >= BULK) { if (out && (pk.y >> 16) < rowBytes) stWeak((double*)(outB + (pk.y >> 16)), w); }
+            if (it + 1 == BULK) fenceAsyncProxy();      // this thread's results of the bulk steps, for the TMA store below
             __syncthreads();
+            if (it + 1 == BULK) { if (threadIdx.x == 0) publishRange(s, t, out, bulkLo, bulkHi); }
             w = nw;
         }
     }
+}
+// hybrid publish of a register-path tile: how many leading processing steps go by bulk store, and which local rows they cover
+constexpr int SWEEP_BULK_STEPS = 12;      // full tiles (16 steps): steps 0..11 by bulk store, 12..15 in the loop
+__device__ __forceinline__ bool bulkPlan(const SweepView& sv, const SweepTile& t, const int* sRow, int dir, int& lo, int& hi) {
+    lo = hi = 0;
+    if (sv.publishMode != 2 || t.nSteps != SWEEP_REG_STEPS) return false;
+    if (dir > 0) { lo = 0; hi = sRow[SWEEP_BULK_STEPS] - t.row0; }                              // forward: the first rows
+    else { lo = sRow[t.nSteps - SWEEP_BULK_STEPS] - t.row0; hi = t.nRows; }                      // backward: the last rows
+    return true;
 }
 __device__ __forceinline__ bool tileUsesRegOps(const SweepView& sv, const SweepTile& t) {
     return sv.regOps && t.d >= 1 && t.d <= 3 && t.nSteps >= 1 && t.nSteps <= SWEEP_REG_STEPS;
@@ -395,8 +422,15 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
         SWEEP_TRACE(2);
         // 3. the steps, then publish
         bool inLoop;
-        if (viaReg) { sweepStepsReg<1>(s, t, ro, sv.publishMode == 1 ? y : nullptr); inLoop = sv.publishMode == 1; }
-        else inLoop = sweepSteps<MODE, 1>(s, t, sRow, sLen, sv.publishMode == 1 ? y : nullptr);
+        if (viaReg) {
+            int blo, bhi;
+            if (bulkPlan(sv, t, sRow, 1, blo, bhi)) {
+                sweepStepsReg<1, SWEEP_BULK_STEPS>(s, t, ro, y, blo, bhi);
+                if (tid == 0) bulkStoreWaitRead();          // (the value array is reused by the next tile)
+            } else sweepStepsReg<1, 0>(s, t, ro, sv.publishMode >= 1 ? y : nullptr);
+            inLoop = sv.publishMode >= 1;
+        }
+        else inLoop = sweepSteps<MODE, 1>(s, t, sRow, sLen, sv.publishMode >= 1 ? y : nullptr);
         if (sv.publishMode == 0) {
             fenceAsyncProxy();    // this thread's results, for the TMA store below (writers fence, barrier, one thread stores)
             __syncthreads();
@@ -473,8 +507,15 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
         if (!viaReg) { barWait(&sBar, phase); phase ^= 1u; }
         __syncthreads();
         bool inLoop;
-        if (viaReg) { sweepStepsReg<-1>(s, t, ro, sv.publishMode == 1 ? z : nullptr); inLoop = sv.publishMode == 1; }
-        else inLoop = sweepSteps<0, -1>(s, t, sRow, sLen, sv.publishMode == 1 ? z : nullptr);
+        if (viaReg) {
+            int blo, bhi;
+            if (bulkPlan(sv, t, sRow, -1, blo, bhi)) {
+                sweepStepsReg<-1, SWEEP_BULK_STEPS>(s, t, ro, z, blo, bhi);
+                if (tid == 0) bulkStoreWaitRead();
+            } else sweepStepsReg<-1, 0>(s, t, ro, sv.publishMode >= 1 ? z : nullptr);
+            inLoop = sv.publishMode >= 1;
+        }
+        else inLoop = sweepSteps<0, -1>(s, t, sRow, sLen, sv.publishMode >= 1 ? z : nullptr);
         if (sv.publishMode == 0) {
             fenceAsyncProxy();
             __syncthreads();

@@ -199,3 +199,26 @@ def test_registry_key_reuse_with_new_addressing_rebuilds(lib, oracle):
     l3 = pm2.ldu(key=key)
     assert np.array_equal(oracle.amul(m2, diag, upper, upper, psi), l3.amul(diag, upper, psi))
     l3.release()
+
+
+@pytest.mark.parametrize("publish,tail", [(0, 4), (1, 4), (2, 4)])
+def test_dic_publish_modes_bitwise(lib, oracle, publish, tail):
+    """how a sweep tile's rows reach global memory (one TMA bulk store per tile / a store in the step that computes the row / hybrid:
+    early steps by one asynchronous bulk store, the last `tail` steps in the loop) never changes a bit of the result"""
+    lib.set_option("sweep_publish", publish); lib.set_option("sweep_bulk_tail", tail)
+    try:
+        pm, ldu = make(lib, (18, 9, 11), (0.45, 0.6, 0.3))
+        m = oracle_mesh_of(pm)
+        diag, upper = random_spd(m, seed=31)
+        rng = np.random.default_rng(32)
+        rA = rng.uniform(-1, 1, m.N); b = rng.uniform(-1, 1, m.N)
+        rD = oracle.dic_calc_rd(m, diag, upper)
+        w = oracle.dic_precondition(m, rD, upper, rA)
+        for _ in range(2):
+            assert np.array_equal(w, ldu.dic_precondition(rD, upper, rA))
+        xo, po, ho = oracle.pcg_solve(m, diag, upper, np.zeros(m.N), b, tol=1e-9, maxIter=300)
+        xg, pg, hg = ldu.pcg_solve(diag, upper, np.zeros(m.N), b, tol=1e-9, maxIter=300)
+        assert pg.nIterations == po.nIterations and np.allclose(hg, ho, rtol=1e-8, atol=1e-13 * ho[0])
+        ldu.release()
+    finally:
+        lib.set_option("sweep_publish", -1); lib.set_option("sweep_bulk_tail", 4)
