@@ -91,6 +91,29 @@ def problem(args, world):
     return dims, lengths, weir, desc
 
 
+def decomposition(args, dims, world):
+    """`simple` decomposition (n_x n_y n_z) of decomposeParDict.  Weak scaling: x-slabs (each rank keeps the 200x50x100 block).  Strong scaling:
+    the split whose sub-domains have the shortest DIC wavefront chain, nx/px + ny/py + nz/pz (a rank's sweep is as long as its chain, not as
+    its cell count), ties broken by the smaller processor-patch area -- 400x100x200 over 8 ranks: (4,1,2) = 100^3 blocks, 298 wavefronts
+    instead of the 348 of x-slabs."""
+    if args.scaling != "strong":
+        return (world, 1, 1)
+    best = None
+    for a in range(1, world + 1):
+        if world % a:
+            continue
+        for b in range(1, world // a + 1):
+            if (world // a) % b:
+                continue
+            c = world // a // b
+            chain = dims[0] / a + dims[1] / b + dims[2] / c
+            area = (a > 1) * dims[1] * dims[2] / (b * c) + (b > 1) * dims[0] * dims[2] / (a * c) + (c > 1) * dims[0] * dims[1] / (a * b)
+            key = (chain, area)
+            if best is None or key < best[0]:
+                best = (key, (a, b, c))
+    return best[1]
+
+
 def workload(args, desc):
     return {"workload": desc, "deltaT": args.delta_t, "Co_target": "max Co ~0.2-0.35 (see `courant`)", "nCorrectors": 3, "nAlphaSubCycles": 2, "nAlphaCorr": 1,
             "pd_solver": "b200PCG+DIC tol 1e-7 relTol 0.05 (pdFinal relTol 0)", "momentumPredictor": "no", "turbulence": "laminar",
@@ -221,6 +244,30 @@ def preflight(lib, rank, world, dist):
     return summary
 
 
+def build_case(lib, args, world, rank, mixed_alpha_patch=None):
+    """this rank's sub-mesh of the global channel on the device + the 3D region with the synthetic fields.  mixed_alpha_patch: name of a
+    patch whose alpha1 condition becomes `mixed` (the sif* coupling conditions are mixed BCs evaluated by the host)"""
+    from shallowinterfoam_b200 import capi
+    dims, lengths, weir, desc = problem(args, world)
+    gpm = lib.polymesh_box(*dims, *lengths, weir=weir)
+    if world > 1:
+        proc = gpm.decompose_simple(decomposition(args, dims, world))
+        pm = gpm.submesh(proc, world, rank)
+        gpm.release()
+    else:
+        pm = gpm
+    g = pm.geometry()
+    F = pm.nInternalFaces
+    slices = {n: pm.patch_slice(n) for n in pm.patchNames}
+    cs = channel_fields(pm.patchNames, g["C"], g["Cf"][F:], slices, lengths)
+    if mixed_alpha_patch in pm.patchNames:
+        cs["tA"][pm.patchNames.index(mixed_alpha_patch)] = 2
+    dm = pm.device_mesh()
+    ctl = set_controls(capi.Region3dControls(), args.delta_t)
+    reg = dm.region3d(ctl, dm.bc(cs["tA"], 1, cs["rvA"]), dm.bc(cs["tU"], 3, cs["rvU"]), dm.bc(cs["tP"], 1), cs["alpha"], cs["U"], cs["pd"])
+    return pm, dm, reg, cs, ctl, dims, lengths, desc
+
+
 def run_ours(args):
     try:
         import torch  # noqa: F401  (first, so libb200foam.so binds to the NCCL torch bundles; pinned host buffers; torch.distributed plumbing)
@@ -262,22 +309,9 @@ def run_ours(args):
                 emit({"metric": METRIC, "error": "multi-GPU parity pre-flight failed", "parity_check": parity})
             sys.exit(3)
 
-    # ---- mesh: this rank's part of the global channel
-    dims, lengths, weir, desc = problem(args, world)
-    gpm = lib.polymesh_box(*dims, *lengths, weir=weir)
-    if world > 1:
-        proc = gpm.decompose_simple((world, 1, 1))
-        pm = gpm.submesh(proc, world, rank)
-        gpm.release()
-    else:
-        pm = gpm
-    g = pm.geometry()
+    # ---- mesh + region: this rank's part of the global channel
+    pm, dm, reg, cs, ctl, dims, lengths, desc = build_case(lib, args, world, rank)
     F = pm.nInternalFaces
-    slices = {n: pm.patch_slice(n) for n in pm.patchNames}
-    cs = channel_fields(pm.patchNames, g["C"], g["Cf"][F:], slices, lengths)
-    dm = pm.device_mesh()
-    ctl = set_controls(capi.Region3dControls(), args.delta_t)
-    reg = dm.region3d(ctl, dm.bc(cs["tA"], 1, cs["rvA"]), dm.bc(cs["tU"], 3, cs["rvU"]), dm.bc(cs["tP"], 1), cs["alpha"], cs["U"], cs["pd"])
     reg.correct_phi(); reg.clear_log()
     N = pm.nCells
     total_cells = N
@@ -439,17 +473,75 @@ def run_ours(args):
                              "(what foam/b200PCG + foam/b200MULES call); the rest of the step stays in foam-extend on the host and is not timed"
                              % (len(solves), len(mules))}
 
+    # ---- e2e_coupled: the same K steps with a HOST boundary-condition callback every step, the way the sif* coupling conditions work
+    #      [REF shallowInterFoam.C:109-128; sifAlpha1FvPatchScalarField.C:431-435]: alpha1 on the outlet patch is a `mixed` condition
+    #      whose refValue / refGrad / valueFraction the host evaluates from the patch-internal alpha1 and U it reads back (KBs, not fields).
+    #      valueFraction = 0 and refGrad = 0 keep the physics of the zeroGradient outlet, so the iteration counts stay comparable.
+    reg2 = dm.region3d(ctl, dm.bc([2 if n == "outlet" else t for n, t in zip(pm.patchNames, cs["tA"])], 1, cs["rvA"]), dm.bc(cs["tU"], 3, cs["rvU"]),
+                       dm.bc(cs["tP"], 1), cs["alpha"], cs["U"], cs["pd"])
+    reg2.restore(ck["alpha1"], ck["U"], ck["pd"], ck["phi"])
+    p_out = pm.patchNames.index("outlet"); n_out = int(pm.patchSize[p_out])
+    reg2.clear_log()
+    barrier(); t0 = time.time(); t_bc = 0.0
+    for _ in range(K):
+        tb = time.time()
+        if n_out:
+            a_int = reg2.patch_internal(0, p_out); u_int = reg2.patch_internal(1, p_out).reshape(-1, 3)
+            ref_val = np.clip(a_int, 0.0, 1.0) * (u_int[:, 0] >= 0)                  # (a stand-in for the sif formulae: any host function of them)
+            reg2.set_patch_mixed(0, p_out, ref_val, np.zeros(n_out), np.zeros(n_out))
+        t_bc += time.time() - tb
+        reg2.step(1)
+    cpl_s = time.time() - t0
+    iters_cpl = [p[2] for p in reg2.perfs()]
+    barrier()
+    cpl_s, t_bc = reduce_max([cpl_s, t_bc])
+    e2e_coupled = {"value": total_cells * K / cpl_s, "unit": UNIT, "steps": K, "host_bc_ms_per_step": 1e3 * t_bc / K,
+                   "d2h_bytes_per_step": 8 * 4 * n_out, "h2d_bytes_per_step": 8 * 3 * n_out, "pcg_iterations_per_step": sum(iters_cpl) / K,
+                   "same_iterations_as_value_leg": iters_cpl == iters_value,
+                   "api": "b200_region3d_get_patch_internal + b200_region3d_set_patch_mixed on the outlet patch every step, then b200_region3d_step(1)"}
+    reg2.release()
+
+    # ---- strong-scaling leg (default run only): BASELINE configs[2], ONE 7.88 M-cell channel decomposed over the same N GPUs
+    strong = None
+    if args.scaling == "weak" and not args.no_strong_leg:
+        reg.release(); dm.release(); pm.release()
+        sargs = argparse.Namespace(**vars(args)); sargs.scaling = "strong"
+        spm, sdm, sreg, scs, sctl, sdims, slengths, sdesc = build_case(lib, sargs, world, rank)
+        sreg.correct_phi()
+        for _ in range(2):
+            sreg.step()
+        sreg.clear_log()
+        barrier(); lib.timers_reset()
+        sreg.step(3)
+        stm = lib.timers(); barrier()
+        s_dev, = reduce_max([stm["step"][0] * 1e-3])
+        s_iters = sum(p[2] for p in sreg.perfs())
+        s_cells = spm.nCells
+        if dist:
+            import torch
+            t = torch.tensor([s_cells], dtype=torch.int64); dist.all_reduce(t); s_cells = int(t.item())
+        strong = {"workload": sdesc, "cells_total": s_cells, "value": s_cells * 3 / s_dev, "unit": UNIT, "steps": 3, "warmup": 2,
+                  "ms_per_step": 1e3 * s_dev / 3, "pcg_iterations_per_step": s_iters / 3, "us_per_pcg_iteration": 1e6 * s_dev / max(s_iters, 1),
+                  "scaling": "strong", "decomposition": "simple %s" % (decomposition(sargs, sdims, world),) if world > 1 else "none"}
+        sreg.release(); sdm.release(); spm.release()
+
     if rank != 0:
         return
     its = sum(iters_value)
+    desc_cfg = dict(workload(args, desc), cells_total=total_cells, l2="inputs (~1 GB of fields+mesh per GPU) exceed the 126 MB L2")
+    if world > 1:
+        desc_cfg["decomposition"] = "simple %s" % (decomposition(args, dims, world),)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": dict(workload(args, desc), cells_total=total_cells, l2="inputs (~1 GB of fields+mesh per GPU) exceed the 126 MB L2"),
+            "data": "synthetic", "config": desc_cfg,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "pcg_iterations_per_step": its / max(K, 1), "us_per_pcg_iteration": 1e6 * dev_s / max(its, 1),
             "wall_ms_per_step": 1e3 * wall / K,
             "courant": {"mean_start": courant0[0], "max_start": courant0[1], "mean_end": courant1[0], "max_end": courant1[1],
                         "api": "b200_region3d_get_courant (device reduction)"}}
+    line["e2e_coupled"] = e2e_coupled
+    if strong:
+        line["strong_scaling_leg"] = strong
     if e2e_plugin:
         line["e2e_plugin"] = e2e_plugin
     if parity:
@@ -492,6 +584,7 @@ def main():
     ap.add_argument("--delta-t", dest="delta_t", type=float, default=DELTA_T)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-preflight", action="store_true")
+    ap.add_argument("--no-strong-leg", action="store_true", help="skip the configs[2] strong-scaling leg of the default (weak) run")
     ap.add_argument("--cpu-procs", type=int, default=0, help="sub-domains (threads) of the CPU arm; default = host cores")
     ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of timed CPU work before the CPU arm stops early")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (repeatable)")
