@@ -92,26 +92,16 @@ def problem(args, world):
 
 
 def decomposition(args, dims, world):
-    """`simple` decomposition (n_x n_y n_z) of decomposeParDict.  Weak scaling: x-slabs (each rank keeps the 200x50x100 block).  Strong scaling:
-    the split whose sub-domains have the shortest DIC wavefront chain, nx/px + ny/py + nz/pz (a rank's sweep is as long as its chain, not as
-    its cell count), ties broken by the smaller processor-patch area -- 400x100x200 over 8 ranks: (4,1,2) = 100^3 blocks, 298 wavefronts
-    instead of the 348 of x-slabs."""
-    if args.scaling != "strong":
-        return (world, 1, 1)
-    best = None
-    for a in range(1, world + 1):
-        if world % a:
-            continue
-        for b in range(1, world // a + 1):
-            if (world // a) % b:
-                continue
-            c = world // a // b
-            chain = dims[0] / a + dims[1] / b + dims[2] / c
-            area = (a > 1) * dims[1] * dims[2] / (b * c) + (b > 1) * dims[0] * dims[2] / (a * c) + (c > 1) * dims[0] * dims[1] / (a * b)
-            key = (chain, area)
-            if best is None or key < best[0]:
-                best = (key, (a, b, c))
-    return best[1]
+    """`simple` decomposition (n_x n_y n_z) of decomposeParDict: x-slabs unless `--decomp a,b,c` says otherwise.  Weak scaling: each rank keeps
+    the 200x50x100 block.  Strong scaling: x-slabs too -- measured at N=8 on 400x100x200 (profiles/bench_r2c_n8.json against
+    bench_r2b_strong_n8.json): (4,1,2) = 100^3 blocks has the shorter wavefront chain (298 against 348) and a 7% shorter iteration (280 us
+    against 299 us), but the rank-local DIC of the extra z cut costs ~9% more iterations, so the step is no faster."""
+    if args.decomp:
+        d = tuple(int(v) for v in args.decomp.split(","))
+        if len(d) != 3 or d[0] * d[1] * d[2] != world:
+            raise SystemExit("--decomp %s does not multiply to %d ranks" % (args.decomp, world))
+        return d
+    return (world, 1, 1)
 
 
 def workload(args, desc):
@@ -581,6 +571,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--decomp", default="", help="`simple` decomposition a,b,c (default: x-slabs)")
     ap.add_argument("--delta-t", dest="delta_t", type=float, default=DELTA_T)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-preflight", action="store_true")
