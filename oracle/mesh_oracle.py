@@ -402,12 +402,19 @@ def sweep_plan(lower, upper, N, band_levels=16, max_rows=4096, smem_budget=22500
     Three potentials that never decrease along a dependency l -> u: level, potJ / potK = most faces of stride class 1 / 2 on any
     path (stride classes = the three dominant magnitudes of upper - lower).  Tile class = (level // band, potK // binK, potJ // binJ);
     oversized classes are cut into consecutive pieces of their (level, index) order; tiles are ordered by their longest-path level
-    in the tile graph; device row order = (tile, level, original index)."""
+    in the tile graph; device row order = (tile, level, original index).  Where the stride classes shred the mesh (more than three
+    times the ideal number of tiles) the lateral potential becomes the cell index itself (potK = index // indexBins, potJ = 0).
+    CHUNKED plans (a row with more than 3 lower or upper neighbours: the rows are applied as chains of <= 3-source chunks whose list
+    schedule decides the budget cuts) are not restated: the result then only carries level / chunked, and the tests check the library's
+    plan through its properties (permutation, topological tile order) and the arithmetic."""
     lower = np.asarray(lower, dtype=np.int64); upper = np.asarray(upper, dtype=np.int64)
     F = lower.size
     band_levels = max(1, band_levels); max_rows = max(8, min(max_rows, 32768)); lanes = max(32, min(lanes, 1024)) // 32 * 32
     lev = forward_levels(lower.astype(np.int32), upper.astype(np.int32), N).astype(np.int64)
-    out = dict(level=lev.astype(np.int32), bandLevels=band_levels, maxRows=max_rows)
+    out = dict(level=lev.astype(np.int32), bandLevels=band_levels, maxRows=max_rows, chunked=False, indexBins=0)
+    if F and (np.bincount(lower, minlength=N).max() > 3 or np.bincount(upper, minlength=N).max() > 3):
+        out["chunked"] = True
+        return out
     if N == 0:
         out.update(rowCell=np.zeros(0, np.int32), cellRow=np.zeros(0, np.int32), tileStart=np.zeros(1, np.int32),
                    tileLevel=np.zeros(0, np.int32), potJ=np.zeros(0, np.int32), potK=np.zeros(0, np.int32), binJ=1, binK=1)
@@ -451,28 +458,46 @@ def sweep_plan(lower, upper, N, band_levels=16, max_rows=4096, smem_budget=22500
         if best is None or cost < best[0] or (cost == best[0] and prod > best[1]):
             best = (cost, prod, bj, bk)
     binJ, binK = best[2], best[3]
-    nJb, nKb = -(-extJ // binJ), -(-extK // binK)
+
     # 4. classes split into connected components (root = smallest cell), sort, pieces
-    cls_key = ((lev // band_levels) * nKb + potK // binK) * nJb + potJ // binJ
-    same = cls_key[lower] == cls_key[upper]
-    if same.any():
-        from scipy.sparse import coo_matrix
-        from scipy.sparse.csgraph import connected_components
-        g = coo_matrix((np.ones(int(same.sum()), dtype=np.int8), (lower[same], upper[same])), shape=(N, N))
-        _, lab = connected_components(g, directed=False)
-    else:
-        lab = np.arange(N)
-    root = np.full(lab.max() + 1, N, dtype=np.int64)
-    np.minimum.at(root, lab, np.arange(N))
-    root = root[lab]
-    order = np.lexsort((np.arange(N), lev, root, cls_key))
-    ck = cls_key[order] * (N + 1) + root[order]
-    bounds = np.concatenate([[0], np.nonzero(np.diff(ck))[0] + 1, [N]])
-    pieces = []
-    for b0, e0 in zip(bounds[:-1], bounds[1:]):
-        n = int(e0 - b0); npc = -(-n // max_rows); base, rem = divmod(n, npc); at = int(b0)
-        for q in range(npc):
-            sz = base + (1 if q < rem else 0); pieces.append((at, at + sz)); at += sz
+    def make_pieces(potJ, potK, binJ, binK, extJ, extK):
+        nJb, nKb = -(-extJ // binJ), -(-extK // binK)
+        cls_key = ((lev // band_levels) * nKb + potK // binK) * nJb + potJ // binJ
+        same = cls_key[lower] == cls_key[upper]
+        if same.any():
+            from scipy.sparse import coo_matrix
+            from scipy.sparse.csgraph import connected_components
+            g = coo_matrix((np.ones(int(same.sum()), dtype=np.int8), (lower[same], upper[same])), shape=(N, N))
+            _, lab = connected_components(g, directed=False)
+        else:
+            lab = np.arange(N)
+        root = np.full(lab.max() + 1, N, dtype=np.int64)
+        np.minimum.at(root, lab, np.arange(N))
+        root = root[lab]
+        order = np.lexsort((np.arange(N), lev, root, cls_key))
+        ck = cls_key[order] * (N + 1) + root[order]
+        bounds = np.concatenate([[0], np.nonzero(np.diff(ck))[0] + 1, [N]])
+        pieces = []
+        for b0, e0 in zip(bounds[:-1], bounds[1:]):
+            n = int(e0 - b0); npc = -(-n // max_rows); base, rem = divmod(n, npc); at = int(b0)
+            for q in range(npc):
+                sz = base + (1 if q < rem else 0); pieces.append((at, at + sz)); at += sz
+        return order, pieces
+
+    order, pieces = make_pieces(potJ, potK, binJ, binK, extJ, extK)
+    # 4b. fall back to the cell index as the lateral potential where the stride classes shred the mesh
+    n_bands = -(-n_levels // band_levels)
+    ideal = -(-N // max_rows) + n_bands
+    index_bins = 0
+    if len(pieces) > 3 * ideal:
+        rows_per_band = max(1, N // n_bands)
+        Q = max(1, -(-rows_per_band // max_rows))
+        ib = max(1, -(-N // Q))
+        potK2 = np.arange(N, dtype=np.int64) // ib
+        order2, pieces2 = make_pieces(np.zeros(N, dtype=np.int64), potK2, 1, 1, 1, -(-N // ib))
+        if len(pieces2) < len(pieces):
+            order, pieces, index_bins = order2, pieces2, ib
+            potJ, potK, binJ, binK = np.zeros(N, dtype=np.int64), potK2, 1, 1
     owner_start, losort, losort_start = ldu_addressing(lower.astype(np.int32), upper.astype(np.int32), N)
     # 5. budget
     while True:
@@ -518,7 +543,7 @@ def sweep_plan(lower, upper, N, band_levels=16, max_rows=4096, smem_budget=22500
     cell_row = np.empty(N, dtype=np.int32); cell_row[row_cell] = np.arange(N, dtype=np.int32)
     tile_start = np.concatenate([[0], np.cumsum([pieces[t][1] - pieces[t][0] for t in ticket])]).astype(np.int32)
     out.update(rowCell=row_cell, cellRow=cell_row, tileStart=tile_start, tileLevel=np.asarray(tl, np.int32)[ticket],
-               potJ=potJ.astype(np.int32), potK=potK.astype(np.int32), binJ=binJ, binK=binK)
+               potJ=potJ.astype(np.int32), potK=potK.astype(np.int32), binJ=binJ, binK=binK, indexBins=index_bins)
     return out
 
 

@@ -39,8 +39,8 @@ int main(int argc, char** argv) {
     std::vector<double> cost(nT), done(nT, 0.0);
     long long totSteps = 0, maxSteps = 0, over16 = 0; double util = 0;
     for (int t = 0; t < nT; t++) {
-        int ns = P.tileStepStart[t + 1] - P.tileStepStart[t];
-        cost[t] = ns * s + o; totSteps += ns; maxSteps = std::max<long long>(maxSteps, ns); if (ns > 16) over16++;
+        int ns = P.fwdStepStart[t + 1] - P.fwdStepStart[t];
+        cost[t] = ns * (ns <= 16 ? s : 1.26 * s) + o; totSteps += ns; maxSteps = std::max<long long>(maxSteps, ns); if (ns > 16) over16++;
         util += (double)(P.tileStart[t + 1] - P.tileStart[t]);
     }
     // tiles are in ticket (topological) order: one forward pass gives the longest path
@@ -55,7 +55,7 @@ int main(int argc, char** argv) {
     const int la = argc > 11 ? atoi(argv[11]) : 0;
     std::vector<double> startT(nT, 0.0);
     std::vector<int> bandOf(nT);
-    for (int t = 0; t < nT; t++) bandOf[t] = P.level[P.rowCell[P.tileStart[t]]] / band;
+    for (int t = 0; t < nT; t++) bandOf[t] = P.xlevel[P.rowCell[P.tileStart[t]]] / band;
     for (int t = 0; t < nT; t++) {
         double start = 0;
         for (int a : preds[t]) {
@@ -68,6 +68,19 @@ int main(int argc, char** argv) {
         maxHalo = std::max(maxHalo, P.fwdHalo[t + 1] - P.fwdHalo[t]);
     }
     int maxD = 0; for (int t = 0; t < nT; t++) maxD = std::max(maxD, std::max(P.fwdD[t], P.bwdD[t]));
+    // backward sweep: its own step counts (chunked plans), the tile graph reversed
+    double critB = 0; long long totB = 0, maxB = 0;
+    {
+        std::vector<std::vector<int>> succs(nT);
+        for (int t = 0; t < nT; t++) for (int a : preds[t]) succs[a].push_back(t);
+        std::vector<double> doneB(nT, 0.0);
+        for (int t = nT - 1; t >= 0; t--) {
+            int nb = P.bwdStepStart[t + 1] - P.bwdStepStart[t]; totB += nb; maxB = std::max<long long>(maxB, nb);
+            double st = 0; for (int a : succs[t]) st = std::max(st, doneB[a]);
+            doneB[t] = st + nb * (nb <= 16 ? s : 1.26 * s) + o; critB = std::max(critB, doneB[t]);
+        }
+    }
+    printf("chunked %d indexBins %d xlevels %d | bwd steps/tile mean %.1f max %lld | model crit path bwd %.1f us\n", (int)P.chunked, P.indexBins, P.nXLevels, (double)totB / nT, maxB, critB / 1000.0);
     printf("faces/cell %.2f  max sources per row %d  strides %d %d %d\n", 2.0 * F / m.nCells, maxD, P.stride[0], P.stride[1], P.stride[2]);
     printf("N %d levels %d | band %d maxRows %d lanes %d binJ %d binK %d | tiles %d tileLevels %d | steps/tile mean %.1f max %lld (>16: %lld) lane-util %.2f | smem %zu maxHalo %d | model crit path %.1f us (s=%.0f ns, o=%.0f ns)\n",
            m.nCells, P.nLevels, band, maxRows, lanes, P.binJ, P.binK, nT, P.nTileLevels, (double)totSteps / nT, maxSteps, over16,

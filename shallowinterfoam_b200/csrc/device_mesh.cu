@@ -120,60 +120,74 @@ void DeviceMesh::build(int32_t nCells, int32_t nFaces, const int32_t* lo, const 
             loPk[q] = (cellRow[l] << KB) | (f - ownerStart[l]);
         }
     }
-    {   // sweep-plan upload: descriptors, level segments, operand-block templates (source offsets) and face slots, halo rows
+    {   // sweep-plan upload: descriptors, operand-block templates (source / own-row offsets), face slots, slot rows, halo rows
         std::vector<SweepTile> tf(nTiles), tb(nTiles);
         size_t blkF = 0, blkB = 0;
+        const int W = plan.lanes;
         for (int t = 0; t < nTiles; t++) {
             SweepTile d; memset(&d, 0, sizeof(d));
             d.row0 = plan.tileStart[t]; d.nRows = plan.tileStart[t + 1] - d.row0;
-            d.step0 = plan.tileStepStart[t]; d.nSteps = plan.tileStepStart[t + 1] - d.step0;
-            const size_t S = (size_t)d.nSteps * plan.lanes;
+            d.virt = plan.chunked ? 1 : 0;
             tf[t] = d; tb[t] = d;
+            tf[t].slot0 = plan.fwdStepStart[t] * W; tf[t].nSteps = plan.fwdStepStart[t + 1] - plan.fwdStepStart[t];
+            tb[t].slot0 = plan.bwdStepStart[t] * W; tb[t].nSteps = plan.bwdStepStart[t + 1] - plan.bwdStepStart[t];
             tf[t].d = plan.fwdD[t]; tf[t].halo = plan.fwdHalo[t]; tf[t].nHalo = plan.fwdHalo[t + 1] - plan.fwdHalo[t];
             tb[t].d = plan.bwdD[t]; tb[t].halo = plan.bwdHalo[t]; tb[t].nHalo = plan.bwdHalo[t + 1] - plan.bwdHalo[t];
+            B200_REQUIRE(tf[t].d <= 3 && tb[t].d <= 3, B200_ERR_UNSUPPORTED, "sweep plan entry with more than 3 sources (internal error)");
             tf[t].blk = (int)blkF; tb[t].blk = (int)blkB;
-            blkF += (size_t)(tf[t].d + (tf[t].d + 3) / 4) * S; blkB += (size_t)(tb[t].d + (tb[t].d + 3) / 4) * S;
+            blkF += (size_t)(tf[t].d + (tf[t].d ? 1 : 0)) * tf[t].nSteps * W; blkB += (size_t)(tb[t].d + (tb[t].d ? 1 : 0)) * tb[t].nSteps * W;
             B200_REQUIRE(blkF < ((size_t)1 << 31) && blkB < ((size_t)1 << 31), B200_ERR_UNSUPPORTED, "mesh too large for 32-bit sweep block offsets");
         }
         fwdBlkSize = blkF; bwdBlkSize = blkB;
         for (int dir = 0; dir < 2; dir++) {
-            const std::vector<SweepTile>& tl = dir == 0 ? tf : tb;
+            std::vector<SweepTile>& tl = dir == 0 ? tf : tb;
             const std::vector<uint16_t>& idx = dir == 0 ? plan.fwdIdx : plan.bwdIdx;
+            const std::vector<uint16_t>& own = dir == 0 ? plan.fwdOwn : plan.bwdOwn;
             const std::vector<int32_t>& face = dir == 0 ? plan.fwdFace : plan.bwdFace;
             const std::vector<int32_t>& ell = dir == 0 ? plan.fwdEll : plan.bwdEll;
             size_t total = dir == 0 ? blkF : blkB;
             std::vector<double> blk0(total, 0.0);
-            std::vector<int> pos(total, -1);
+            std::vector<int> pos(total, -1), slotRow(own.size(), -1);
             for (int t = 0; t < nTiles; t++) {
-                const SweepTile& d = tl[t];
-                const size_t S = (size_t)d.nSteps * plan.lanes;
+                SweepTile& d = tl[t];
+                const size_t S = (size_t)d.nSteps * W;
+                for (size_t sl = 0; sl < S; sl++) {
+                    const uint16_t o = own[d.slot0 + sl];
+                    if (o != SWEEP_OWN_NONE) slotRow[d.slot0 + sl] = d.row0 + (o & SWEEP_OWN_ROW);
+                }
+                if (!d.virt && d.nSteps == 16) {   // hybrid publish (dic_kernels.cuh bulkPlan): rows of an unchunked tile are contiguous in step order
+                    int first4 = 0, first12 = 0;
+                    for (size_t sl = 0; sl < S; sl++) if (own[d.slot0 + sl] != SWEEP_OWN_NONE) { if (sl < (size_t)4 * W) first4++; if (sl < (size_t)12 * W) first12++; }
+                    if (dir == 0) { d.bulkLo = 0; d.bulkHi = first12; } else { d.bulkLo = first4; d.bulkHi = d.nRows; }
+                }
+                if (d.d == 0) continue;
                 uint16_t* offs = reinterpret_cast<uint16_t*>(blk0.data() + d.blk + (size_t)d.d * S);
-                const int nq = (d.d + 3) / 4;
                 const uint16_t padOff = (uint16_t)(8 * (d.nRows + d.nHalo)), trashOff = (uint16_t)(8 * (d.nRows + d.nHalo + 1));
-                for (size_t e = 0; e < (size_t)nq * S * 4; e++) offs[e] = padOff;
+                for (size_t e = 0; e < S * 4; e++) offs[e] = padOff;
                 for (int j = 0; j < d.d; j++)
                     for (size_t sl = 0; sl < S; sl++) {
                         size_t e = (size_t)ell[t] + (size_t)j * S + sl;
-                        offs[((size_t)(j / 4) * S + sl) * 4 + (j % 4)] = (uint16_t)(8 * idx[e]);
+                        offs[sl * 4 + j] = (uint16_t)(8 * idx[e]);
                         pos[d.blk + (size_t)j * S + sl] = face[e] >= 0 ? facePosHost[face[e]] : -1;
                     }
-                if (d.d >= 1 && d.d <= 3)   // lane 3 of the offset word: where the slot's own row lives in the value array
-                    for (int k = 0; k < d.nSteps; k++)
-                        for (int i = 0; i < plan.lanes; i++) {
-                            int len = plan.stepLen[d.step0 + k], rl = plan.stepRow[d.step0 + k] - d.row0 + i;
-                            offs[((size_t)k * plan.lanes + i) * 4 + 3] = i < len ? (uint16_t)(8 * rl) : trashOff;
-                        }
+                for (size_t sl = 0; sl < S; sl++) {   // lane 3 of the offset word: where the entry's own row lives in the value array (+ chunk flags)
+                    const uint16_t o = own[d.slot0 + sl];
+                    offs[sl * 4 + 3] = o == SWEEP_OWN_NONE ? trashOff
+                        : (uint16_t)(8 * (o & SWEEP_OWN_ROW) + ((o & SWEEP_OWN_PARTIAL) ? OWN_PARTIAL : 0u) + ((o & SWEEP_OWN_CARRY) ? OWN_CARRY : 0u));
+                }
             }
             (dir == 0 ? dFwdBlk0 : dBwdBlk0).upload(blk0);
             (dir == 0 ? dFwdPos : dBwdPos).upload(pos);
+            (dir == 0 ? dFwdSlotRow : dBwdSlotRow).upload(slotRow);
             syncStream();
         }
-        dTilesF.upload(tf); dTilesB.upload(tb); dStepRow.upload(plan.stepRow); dStepLen.upload(plan.stepLen);
+        dTilesF.upload(tf); dTilesB.upload(tb);
         dFwdHaloRow.upload(plan.fwdHaloRow); dBwdHaloRow.upload(plan.bwdHaloRow);
         dTrace.alloc(8 * (size_t)nTiles + 8); dTrace.zero();
         syncStream();   // the host vectors above go out of scope
         plan.fwdFace.clear(); plan.fwdFace.shrink_to_fit(); plan.bwdFace.clear(); plan.bwdFace.shrink_to_fit();
         plan.fwdIdx.clear(); plan.fwdIdx.shrink_to_fit(); plan.bwdIdx.clear(); plan.bwdIdx.shrink_to_fit();
+        plan.fwdOwn.clear(); plan.fwdOwn.shrink_to_fit(); plan.bwdOwn.clear(); plan.bwdOwn.shrink_to_fit();
     }
     // boundary CSR by row
     std::vector<int> cnt(N, 0);

@@ -57,16 +57,21 @@ constexpr int SWEEP_THREADS = 256;    // most threads (= lanes) of a sweep CTA
 // DIC sweep tiles (host_mesh.h SweepPlan, uploaded).  One descriptor per tile and sweep direction.
 struct SweepTile {
     int row0, nRows;       // device rows [row0, row0+nRows)
-    int step0, nSteps;     // steps: stepRow/stepLen[step0 .. step0+nSteps); S = nSteps*lanes value slots
-    int blk, d;            // operand block offset (doubles) and ELL width; block = d coefficient columns [S] followed by
-                           // ceil(d/4) columns of packed 16-bit BYTE offsets of the sources in the tile's value array
+    int slot0, nSteps;     // first slot of the tile in fwdSlotRow / bwdSlotRow; steps of this direction: S = nSteps*lanes slots
+    int blk, d;            // operand block offset (doubles) and ELL width (0..3); block = d coefficient columns [S] followed by
+                           // one column of 4 packed 16-bit BYTE offsets into the tile's value array: 3 sources + the entry's own row
     int halo, nHalo;       // halo list offset and length
-    int pad[4];
+    int virt;              // chunked plan (host_mesh.h): an entry may be one CHUNK of a row; its own-row offset carries OWN_PARTIAL / OWN_CARRY
+    int bulkLo, bulkHi;    // hybrid publish: local rows of the first SWEEP_BULK_STEPS processing steps (bulkHi == 0: not eligible)
+    int pad;
 };
+// flag bits in an entry's own-row byte offset (rows are 8 bytes apart, so the low three bits are free)
+constexpr unsigned OWN_PARTIAL = 1u;   // not the last chunk of its row: the result stays in the tile
+constexpr unsigned OWN_CARRY = 2u;     // continues the chunk this thread computed in the previous step: start value = that result
 struct SweepView {
     int nTiles;
     const SweepTile *fwd, *bwd;              // [nTiles] in ticket order
-    const int *stepRow, *stepLen;            // first device row / rows of each step
+    const int *fwdSlotRow, *bwdSlotRow;      // device row of each slot's entry (-1 = inert lane)
     int lanes;                               // rows per step = threads of a sweep CTA
     const int *fwdPos, *bwdPos;              // face slot of each coefficient entry of the operand blocks (-1 = padding)
     const int *fwdHaloRow, *bwdHaloRow;      // device rows a tile polls
@@ -94,7 +99,7 @@ struct DeviceMesh {
     int nTiles = 0;
     size_t sweepSmem = 0;                  // dynamic shared memory of the sweep kernels (bytes)
     DevBuf<SweepTile> dTilesF, dTilesB;
-    DevBuf<int> dStepRow, dStepLen, dFwdPos, dBwdPos, dFwdHaloRow, dBwdHaloRow;
+    DevBuf<int> dFwdSlotRow, dBwdSlotRow, dFwdPos, dBwdPos, dFwdHaloRow, dBwdHaloRow;
     DevBuf<double> dFwdBlk0, dBwdBlk0;     // operand-block templates: coefficient columns 0, source-offset columns filled
     size_t fwdBlkSize = 0, bwdBlkSize = 0; // doubles
     DevBuf<unsigned long long> dTrace;     // debug trace of the last sweep (option sweep_trace)
@@ -123,7 +128,7 @@ struct DeviceMesh {
                      const double* w, const double* dc);
     MeshView view() const;
     SweepView sweep() const {
-        return SweepView{nTiles, dTilesF.p, dTilesB.p, dStepRow.p, dStepLen.p, plan.lanes, dFwdPos.p, dBwdPos.p, dFwdHaloRow.p, dBwdHaloRow.p, (int)rt().opt("sweep_poll_ns", 0), (int)rt().opt("sweep_reg_ops", 1), (int)rt().opt("sweep_bulk_tail", 4), publishModeOf(),
+        return SweepView{nTiles, dTilesF.p, dTilesB.p, dFwdSlotRow.p, dBwdSlotRow.p, plan.lanes, dFwdPos.p, dBwdPos.p, dFwdHaloRow.p, dBwdHaloRow.p, (int)rt().opt("sweep_poll_ns", 0), (int)rt().opt("sweep_reg_ops", 1), (int)rt().opt("sweep_bulk_tail", 4), publishModeOf(),
                          rt().opt("sweep_trace", 0) > 0 ? dTrace.p : nullptr};
     }
     // how a tile's rows reach global memory: option sweep_publish (0 bulk store per tile, 1 in the step loop, 2 hybrid); default: hybrid

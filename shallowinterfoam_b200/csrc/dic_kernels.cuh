@@ -158,7 +158,12 @@ __device__ __forceinline__ void pollHalo(const SweepTile& t, const TileSmem& s, 
 // last step ends only its own rows are still on their way to L2 -- the dependants' polls see the tile ~0.3 us after its last step
 // instead of after a whole-tile publish pass.  Each 8-byte value is its own ready flag, so no ordering between the stores is needed,
 // and a plain store (unlike a gpu-scope one) does not make the following bar.sync wait for the L2 acknowledge.
-template <int OP, int DIR, int D>
+// VIRT (chunked plans, host_mesh.h): an entry may be one CHUNK (<= 3 consecutive sources) of a row with more sources.  Its own-row offset
+// carries two flags: OWN_PARTIAL -- not the row's last chunk, the partial result stays in the tile (published values are ready flags);
+// OWN_CARRY -- it continues the chunk this thread computed in the previous step, whose result is still in `w` (the own-row slot was
+// prefetched before that result was stored).  A later chunk that runs two or more steps after its predecessor reads the partial result from
+// the row's slot like a start value.
+template <int OP, int DIR, int D, bool VIRT>
 __device__ __forceinline__ void sweepStepsD(const TileSmem& s, const SweepTile& t, double* out) {
     const int W = blockDim.x, S = s.S;
     const unsigned rowBytes = 8u * (unsigned)t.nRows;
@@ -168,7 +173,7 @@ __device__ __forceinline__ void sweepStepsD(const TileSmem& s, const SweepTile& 
     const uint2* PK = (const uint2*)(s.blk + D * S);
     double c0 = C[slot], c1 = D > 1 ? C[S + slot] : 0.0, c2 = D > 2 ? C[2 * S + slot] : 0.0;
     uint2 pk = PK[slot];
-    double w = ldsAt(s.vals, pk.y >> 16);
+    double w = ldsAt(s.vals, VIRT ? (pk.y >> 16) & ~7u : pk.y >> 16);
     for (int it = 0; it < t.nSteps; it++) {
         const double v0 = ldsAt(s.vals, pk.x & 0xffffu);
         const double v1 = D > 1 ? ldsAt(s.vals, pk.x >> 16) : 0.0;
@@ -176,13 +181,15 @@ __device__ __forceinline__ void sweepStepsD(const TileSmem& s, const SweepTile& 
         const int nslot = it + 1 < t.nSteps ? slot + DIR * W : slot;
         const double n0 = C[nslot], n1 = D > 1 ? C[S + nslot] : 0.0, n2 = D > 2 ? C[2 * S + nslot] : 0.0;
         const uint2 npk = PK[nslot];
-        const double nw = ldsAt(s.vals, npk.y >> 16);   // the next step's own rows still hold their start values
+        const unsigned own = VIRT ? (pk.y >> 16) & ~7u : pk.y >> 16;
+        const double nw = ldsAt(s.vals, VIRT ? (npk.y >> 16) & ~7u : npk.y >> 16);   // the next step's own rows still hold their start values
         if (OP == 0) { w = w - c0 * v0; if (D > 1) w = w - c1 * v1; if (D > 2) w = w - c2 * v2; }
         else { w = w - c0 / v0; if (D > 1) w = w - c1 / v1; if (D > 2) w = w - c2 / v2; }
-        stsAt(s.vals, pk.y >> 16, w);
-        if (out && (pk.y >> 16) < rowBytes) stWeak((double*)(outB + (pk.y >> 16)), w);   // (deferring it past the barrier is slower)
+        stsAt(s.vals, own, w);
+        if (out && own < rowBytes && !(VIRT && ((pk.y >> 16) & OWN_PARTIAL))) stWeak((double*)(outB + own), w);   // (deferring it past the barrier is slower)
         __syncthreads();
-        c0 = n0; c1 = n1; c2 = n2; w = nw; pk = npk; slot = nslot;
+        c0 = n0; c1 = n1; c2 = n2; pk = npk; slot = nslot;
+        w = (VIRT && ((npk.y >> 16) & OWN_CARRY)) ? w : nw;
     }
 }
 // ---- register-resident operands (the default for tiles with 1..3 sources per row and at most SWEEP_REG_STEPS steps: every hex mesh).
@@ -232,11 +239,11 @@ __device__ __forceinline__ void publishRange(const TileSmem& s, const SweepTile&
 // they are complete -- it lands while the remaining steps run -- and only the last steps store their rows in the loop (their rows are the
 // ones the dependants wait for).  A store in the step loop costs every step ~28 ns (the following bar.sync waits for it).
 // (BULK is a compile-time constant: the step loop is so short that two run-time tests per step cost a quarter of it)
-template <int DIR, int BULK>
+template <int DIR, int BULK, bool VIRT>
 __device__ __forceinline__ void sweepStepsReg(const TileSmem& s, const SweepTile& t, const RegOps& o, double* out, int bulkLo = 0, int bulkHi = 0) {
     const unsigned rowBytes = 8u * (unsigned)t.nRows;
     char* outB = (char*)(out + t.row0);
-    double w = ldsAt(s.vals, o.pk[0].y >> 16);
+    double w = ldsAt(s.vals, VIRT ? (o.pk[0].y >> 16) & ~7u : o.pk[0].y >> 16);
 #pragma unroll
     for (int it = 0; it < SWEEP_REG_STEPS; it++) {
         if (it < t.nSteps) {   // (uniform: no divergence; the unrolled body indexes the register arrays statically)
@@ -246,43 +253,51 @@ __device__ __forceinline__ void sweepStepsReg(const TileSmem& s, const SweepTile
             const double v2 = ldsAt(s.vals, pk.y & 0xffffu);
             // the next step's own rows still hold their start values
             const int nit = it + 1 < SWEEP_REG_STEPS ? it + 1 : it;   // (compile-time after unrolling)
-            const double nw = (nit != it && nit < t.nSteps) ? ldsAt(s.vals, o.pk[nit].y >> 16) : 0.0;
+            const unsigned nownRaw = o.pk[nit].y >> 16, own = VIRT ? (pk.y >> 16) & ~7u : pk.y >> 16;
+            const double nw = (nit != it && nit < t.nSteps) ? ldsAt(s.vals, VIRT ? nownRaw & ~7u : nownRaw) : 0.0;
             w = w - o.c[it][0] * v0; w = w - o.c[it][1] * v1; w = w - o.c[it][2] * v2;
-            stsAt(s.vals, pk.y >> 16, w);
-            if (it >= BULK) { if (out && (pk.y >> 16) < rowBytes) stWeak((double*)(outB + (pk.y >> 16)), w); }
+            stsAt(s.vals, own, w);
+            if (it >= BULK) { if (out && own < rowBytes && !(VIRT && ((pk.y >> 16) & OWN_PARTIAL))) stWeak((double*)(outB + own), w); }
             if (it + 1 == BULK) fenceAsyncProxy();      // this thread's results of the bulk steps, for the TMA store below
             __syncthreads();
             if (it + 1 == BULK) { if (threadIdx.x == 0) publishRange(s, t, out, bulkLo, bulkHi); }
-            w = nw;
+            w = (VIRT && nit != it && (nownRaw & OWN_CARRY)) ? w : nw;
         }
     }
 }
 // hybrid publish of a register-path tile: how many leading processing steps go by bulk store, and which local rows they cover
 constexpr int SWEEP_BULK_STEPS = 12;      // full tiles (16 steps): steps 0..11 by bulk store, 12..15 in the loop
-__device__ __forceinline__ bool bulkPlan(const SweepView& sv, const SweepTile& t, const int* sRow, int dir, int& lo, int& hi) {
+// (unchunked full tiles only; the row range was counted on the host: forward = the first rows, backward = the last rows, device_mesh.cu)
+__device__ __forceinline__ bool bulkPlan(const SweepView& sv, const SweepTile& t, int& lo, int& hi) {
     lo = hi = 0;
-    if (sv.publishMode != 2 || t.nSteps != SWEEP_REG_STEPS) return false;
-    if (dir > 0) { lo = 0; hi = sRow[SWEEP_BULK_STEPS] - t.row0; }                              // forward: the first rows
-    else { lo = sRow[t.nSteps - SWEEP_BULK_STEPS] - t.row0; hi = t.nRows; }                      // backward: the last rows
+    if (sv.publishMode != 2 || t.bulkHi == 0 || t.nSteps != SWEEP_REG_STEPS) return false;
+    lo = t.bulkLo; hi = t.bulkHi;
     return true;
 }
 __device__ __forceinline__ bool tileUsesRegOps(const SweepView& sv, const SweepTile& t) {
     return sv.regOps && t.d >= 1 && t.d <= 3 && t.nSteps >= 1 && t.nSteps <= SWEEP_REG_STEPS;
 }
-template <int OP, int DIR>
-__device__ __forceinline__ bool sweepSteps(const TileSmem& s, const SweepTile& t, const int* sRow, const int* sLen, double* out) {
+// shared-memory operand path (calcReciprocalD; tiles with more than SWEEP_REG_STEPS steps).  Returns whether the rows were published in the loop.
+// shared-memory operand path (calcReciprocalD; tiles with more than SWEEP_REG_STEPS steps).  Returns whether the rows were published in the loop.
+// The last branch is the plain reference walk of a tile (any width, one entry per thread and step, straight from the slot table); it runs the
+// tiles of isolated rows (d = 0), whose start values already are the results.
+// (Keep it: without this loop in the function ptxas lays the unrolled register path of k_dic_bwd out 4 % slower -- measured A/B on one box,
+// profiles/r2_ncu_summary.md.)
+template <int OP, int DIR, bool VIRT>
+__device__ __forceinline__ bool sweepSteps(const TileSmem& s, const SweepTile& t, double* out, const int* __restrict__ slotRow) {
     if (t.nSteps == 0) return false;
-    if (t.d == 3) { sweepStepsD<OP, DIR, 3>(s, t, out); return out != nullptr; }
-    if (t.d == 2) { sweepStepsD<OP, DIR, 2>(s, t, out); return out != nullptr; }
-    if (t.d == 1) { sweepStepsD<OP, DIR, 1>(s, t, out); return out != nullptr; }
+    if (t.d == 3) { sweepStepsD<OP, DIR, 3, VIRT>(s, t, out); return out != nullptr; }
+    if (t.d == 2) { sweepStepsD<OP, DIR, 2, VIRT>(s, t, out); return out != nullptr; }
+    if (t.d == 1) { sweepStepsD<OP, DIR, 1, VIRT>(s, t, out); return out != nullptr; }
     const int W = blockDim.x, S = s.S;
-    const unsigned short* OFF = (const unsigned short*)(s.blk + t.d * S);   // [ceil(d/4)][S][4]
-    for (int k = DIR > 0 ? 0 : t.nSteps - 1; k >= 0 && k < t.nSteps; k += DIR) {   // polyhedral rows (d > 3), isolated rows (d = 0)
-        if ((int)threadIdx.x < sLen[k]) {
-            const int slot = k * W + threadIdx.x, r = sRow[k] - t.row0 + threadIdx.x;
+    const unsigned short* OFF = (const unsigned short*)(s.blk + t.d * S);   // [S][4]
+    for (int k = DIR > 0 ? 0 : t.nSteps - 1; k >= 0 && k < t.nSteps; k += DIR) {
+        const int slot = k * W + threadIdx.x, row = slotRow[t.slot0 + slot];
+        if (row >= 0) {
+            const int r = row - t.row0;
             double w = s.vals[r];
             for (int j = 0; j < t.d; j++) {
-                double c = s.blk[j * S + slot], v = ldsAt(s.vals, OFF[((j >> 2) * S + slot) * 4 + (j & 3)]);
+                double c = s.blk[j * S + slot], v = ldsAt(s.vals, OFF[slot * 4 + j]);
                 if (OP == 0) w = w - c * v; else w = w - c / v;
             }
             s.vals[r] = w;
@@ -292,7 +307,7 @@ __device__ __forceinline__ bool sweepSteps(const TileSmem& s, const SweepTile& t
     return false;
 }
 // publish of a whole tile by all threads (consecutive threads -> consecutive rows); call after the barrier that ends the steps.
-// Only the variable-width tiles (polyhedral rows) leave this way.  Measured on the 985k-cell channel: a whole-tile publish after the
+// Only tiles of isolated rows (no sources) leave this way.  Measured on the 985k-cell channel: a whole-tile publish after the
 // last step, by TMA bulk store or by these stores, is seen by the dependants ~1.0 us after the last step; step-by-step stores ~0.45 us.
 __device__ __forceinline__ void publishTileDirect(const TileSmem& s, const SweepTile& t, double* out) {
     for (int r = threadIdx.x; r < t.nRows; r += blockDim.x) stWeak(out + t.row0 + r, s.vals[r]);
@@ -308,10 +323,6 @@ __device__ __forceinline__ void stageBlock(const TileSmem& s, const SweepTile& t
         barExpect(bar, (unsigned)bytes);
         bulkLoadChunks(s.blk + skip, blocks + t.blk + skip, bytes, bar);
     }
-}
-// step table of the tile -> shared memory (global first row, length)
-__device__ __forceinline__ void stageSteps(const SweepView& sv, const SweepTile& t, int* sRow, int* sLen) {
-    for (int k = threadIdx.x; k < t.nSteps; k += blockDim.x) { sRow[k] = sv.stepRow[t.step0 + k]; sLen[k] = sv.stepLen[t.step0 + k]; }
 }
 // publish the tile's rows: the results sit contiguously in vals[0..nRows) = device rows [row0, row0+nRows): one TMA bulk
 // store for the 16-byte aligned middle, scalar gpu-scope stores for an odd first / last row.  Called by one thread after the
@@ -342,12 +353,12 @@ struct PcgFuse {
 
 // MODE 0: forward precondition sweep: y[row] = rD*rA - sum_j cf_j * y[src_j]              (cf = rD[row]*upper, per solve)
 // MODE 1: calcReciprocalD           : Dt[row] = diag - sum_j (up_j*lo_j) / Dt[src_j] ; rD = 1/Dt (operand block = the products, lo = up for DIC)
-template <int MODE>
+// VIRT: the kernels of a chunked plan (every tile of a mesh is, or none: chosen at launch -- the unchunked kernels carry none of it)
+template <int MODE, bool VIRT>
 static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, const double* __restrict__ a0,
         const double* a1, const double* __restrict__ coef, const double* __restrict__ blocks, double* y,
         double* __restrict__ rDout, SweepCtl ctl, const PcgScalars* sc, PcgFuse fz) {
     B200_DYN_SMEM(smem);
-    __shared__ int sRow[SWEEP_MAX_STEPS], sLen[SWEEP_MAX_STEPS];
     __shared__ TileBar sBar;
     if (threadIdx.x == 0) barInit(&sBar);
     unsigned phase = 0;
@@ -412,7 +423,6 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
             }
         }
         if (fused) { double v[1] = {mag}; gridReduce<1, OpSum>(v, ti, sv.nTiles, fz.partials, fz.counter, nullptr); }
-        stageSteps(sv, t, sRow, sLen);
         if (tid == 0) { s.vals[n + t.nHalo] = 1.0; s.vals[n + t.nHalo + 1] = 0.0; }
         // 2. external inputs
         if (sv.trace) { __syncthreads(); SWEEP_TRACE(1); }
@@ -424,13 +434,14 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
         bool inLoop;
         if (viaReg) {
             int blo, bhi;
-            if (bulkPlan(sv, t, sRow, 1, blo, bhi)) {
-                sweepStepsReg<1, SWEEP_BULK_STEPS>(s, t, ro, y, blo, bhi);
+            if (VIRT) sweepStepsReg<1, 0, true>(s, t, ro, sv.publishMode >= 1 ? y : nullptr);
+            else if (bulkPlan(sv, t, blo, bhi)) {
+                sweepStepsReg<1, SWEEP_BULK_STEPS, false>(s, t, ro, y, blo, bhi);
                 if (tid == 0) bulkStoreWaitRead();          // (the value array is reused by the next tile)
-            } else sweepStepsReg<1, 0>(s, t, ro, sv.publishMode >= 1 ? y : nullptr);
+            } else sweepStepsReg<1, 0, false>(s, t, ro, sv.publishMode >= 1 ? y : nullptr);
             inLoop = sv.publishMode >= 1;
         }
-        else inLoop = sweepSteps<MODE, 1>(s, t, sRow, sLen, sv.publishMode >= 1 ? y : nullptr);
+        else inLoop = sweepSteps<MODE, 1, VIRT>(s, t, sv.publishMode >= 1 ? y : nullptr, sv.fwdSlotRow);
         if (sv.publishMode == 0) {
             fenceAsyncProxy();    // this thread's results, for the TMA store below (writers fence, barrier, one thread stores)
             __syncthreads();
@@ -466,11 +477,11 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_fwd(SweepView sv, 
 // fold (multi-rank): the last CTA also runs the ONE scalar all-reduce of the iteration's first half -- (sum|rA| left by the forward
 // sweep, sum(wA*rA) of this sweep; adjacent in PcgScalars) -- over NVLink peer memory and then closes the previous iteration
 // (k_pcg_check's body): no stand-alone 32-thread kernel between the sweeps and the p-update
+template <bool VIRT>
 static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, const double* __restrict__ blocks,
         const double* __restrict__ rA, double* y, double* z, SweepCtl ctl, PcgScalars* sc, double* partials, unsigned* counter,
         double* dotOut, P2PFold fold, double* hist) {
     B200_DYN_SMEM(smem);
-    __shared__ int sRow[SWEEP_MAX_STEPS], sLen[SWEEP_MAX_STEPS];
     __shared__ TileBar sBar;
     if (threadIdx.x == 0) barInit(&sBar);
     unsigned phase = 0;
@@ -501,7 +512,6 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
 #pragma unroll
             for (int k = 0; k < 8; k++) { int r = r0 + k * W; if (r < n) { s.vals[r] = a[k]; y[t.row0 + r] = sentinel(); } }
         }
-        stageSteps(sv, t, sRow, sLen);
         if (tid == 0) { s.vals[n + t.nHalo] = 1.0; s.vals[n + t.nHalo + 1] = 0.0; }
         pollHalo(t, s, sv.bwdHaloRow, z, sv.pollNs);
         if (!viaReg) { barWait(&sBar, phase); phase ^= 1u; }
@@ -509,13 +519,14 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_bwd(SweepView sv, 
         bool inLoop;
         if (viaReg) {
             int blo, bhi;
-            if (bulkPlan(sv, t, sRow, -1, blo, bhi)) {
-                sweepStepsReg<-1, SWEEP_BULK_STEPS>(s, t, ro, z, blo, bhi);
+            if (VIRT) sweepStepsReg<-1, 0, true>(s, t, ro, sv.publishMode >= 1 ? z : nullptr);
+            else if (bulkPlan(sv, t, blo, bhi)) {
+                sweepStepsReg<-1, SWEEP_BULK_STEPS, false>(s, t, ro, z, blo, bhi);
                 if (tid == 0) bulkStoreWaitRead();
-            } else sweepStepsReg<-1, 0>(s, t, ro, sv.publishMode >= 1 ? z : nullptr);
+            } else sweepStepsReg<-1, 0, false>(s, t, ro, sv.publishMode >= 1 ? z : nullptr);
             inLoop = sv.publishMode >= 1;
         }
-        else inLoop = sweepSteps<0, -1>(s, t, sRow, sLen, sv.publishMode >= 1 ? z : nullptr);
+        else inLoop = sweepSteps<0, -1, VIRT>(s, t, sv.publishMode >= 1 ? z : nullptr, sv.bwdSlotRow);
         if (sv.publishMode == 0) {
             fenceAsyncProxy();
             __syncthreads();
@@ -562,11 +573,13 @@ static __global__ void __launch_bounds__(SWEEP_THREADS) k_dic_coeffs(SweepView s
     const bool bw = (int)blockIdx.x >= sv.nTiles;
     const SweepTile t = bw ? sv.bwd[blockIdx.x - sv.nTiles] : sv.fwd[blockIdx.x];
     const int* pos = bw ? sv.bwdPos : sv.fwdPos;
+    const int* slotRow = bw ? sv.bwdSlotRow : sv.fwdSlotRow;
     double* out = bw ? cb : cf;
     const int W = blockDim.x, S = t.nSteps * W;
     for (int k = 0; k < t.nSteps; k++) {
-        const bool valid = (int)threadIdx.x < sv.stepLen[t.step0 + k];
-        const double rd = (valid && rD) ? rD[sv.stepRow[t.step0 + k] + threadIdx.x] : 0.0;
+        const int row = slotRow[t.slot0 + k * W + threadIdx.x];
+        const bool valid = row >= 0;
+        const double rd = (valid && rD) ? rD[row] : 0.0;
         for (int j = 0; j < t.d; j++) {
             const int e = t.blk + j * S + k * W + threadIdx.x;
             const int p = valid ? pos[e] : -1;

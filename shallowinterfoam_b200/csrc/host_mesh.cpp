@@ -359,7 +359,35 @@ void levelRenumbering(int32_t N, const int32_t* lower, const int32_t* upper, int
 // --------------------------------------------------------------------------------------------- sweep plan
 namespace {
 struct Piece { int32_t b, e; };   // range in the (class, level, index)-sorted cell order
+
+// chunk boundaries of one row: lv = the (estimated) levels of its sources in application order, -1 = no constraint (halo).  Chunks of at
+// most 3 consecutive sources; minimises the level of the last chunk, then the number of chunks.  Returns that level; cuts (optional)
+// receives the chunk ends (exclusive source positions, ascending).
+int chunkRow(const int* lv, int m, std::vector<int>* cuts, std::vector<int>& f, std::vector<int>& g, std::vector<int>& from) {
+    if (cuts) cuts->clear();
+    if (m == 0) return 0;
+    f.resize(m + 1); g.resize(m + 1); from.resize(m + 1);
+    f[0] = -1; g[0] = 0;
+    for (int i = 1; i <= m; i++) {
+        int bestF = 1 << 30, bestG = 1 << 30, bestK = 1, mx = -1;
+        for (int k = 1; k <= 3 && k <= i; k++) {
+            mx = std::max(mx, lv[i - k]);
+            int v = std::max(f[i - k], mx) + 1, c = g[i - k] + 1;
+            if (v < bestF || (v == bestF && c < bestG)) { bestF = v; bestG = c; bestK = k; }
+        }
+        f[i] = bestF; g[i] = bestG; from[i] = bestK;
+    }
+    if (cuts) {
+        for (int i = m; i > 0; i -= from[i]) cuts->push_back(i);
+        std::reverse(cuts->begin(), cuts->end());
+    }
+    return f[m];
 }
+
+// one (step, lane) entry of a tile's sweep
+struct Entry { int row; int j0, j1; bool partial, carry; };   // tile-local row, source range [j0, j1) in application order
+struct TileSchedule { int nSteps = 0; std::vector<Entry> slot; };   // slot[k*W + lane]; row < 0 = inert
+}  // namespace
 
 void buildSweepPlan(int32_t N, const int32_t* lower, const int32_t* upper, int32_t F, int bandLevels, int maxRows, int smemBudget,
                     int lanes, SweepPlan& P) {
@@ -371,11 +399,49 @@ void buildSweepPlan(int32_t N, const int32_t* lower, const int32_t* upper, int32
     P.smemBudget = smemBudget;
     std::vector<int32_t> lvRow, lvCell;
     levelRenumbering(N, lower, upper, F, P.level, lvRow, lvCell, P.nLevels);   // level[] + validity checks
-    P.tileStart.assign(1, 0); P.tileStepStart.assign(1, 0);
+    P.tileStart.assign(1, 0); P.fwdStepStart.assign(1, 0); P.bwdStepStart.assign(1, 0);
     P.fwdEll.assign(1, 0); P.bwdEll.assign(1, 0); P.fwdHalo.assign(1, 0); P.bwdHalo.assign(1, 0);
     P.potJ.assign(N, 0); P.potK.assign(N, 0); P.rowCell.resize(N); P.cellRow.resize(N);
+    P.xlevel = P.level; P.nXLevels = P.nLevels;
     if (N == 0) return;
+    std::vector<int32_t> ownerStart, losort, losortStart;
+    {
+        std::vector<int32_t> lo(lower, lower + F), up(upper, upper + F);
+        lduDerived(N, lo, up, ownerStart, losort, losortStart);
+    }
+    // sources of a cell in the order the sweep applies them: forward = faces with upper == c ascending, backward = faces with lower == c descending
+    auto nSrc = [&](int32_t c, int dir) { return dir == 0 ? losortStart[c + 1] - losortStart[c] : ownerStart[c + 1] - ownerStart[c]; };
+    auto srcFace = [&](int32_t c, int dir, int j) { return dir == 0 ? losort[losortStart[c] + j] : ownerStart[c + 1] - 1 - j; };
+    auto srcCell = [&](int32_t c, int dir, int j) { int32_t f = srcFace(c, dir, j); return dir == 0 ? lower[f] : upper[f]; };
+    std::vector<int> dpF, dpG, dpFrom, lvBuf;
+    // ---- 0. chunked?  expanded forward levels (cells in ascending index = a topological order)
+    long long nChunks[2] = {0, 0};
+    for (int32_t c = 0; c < N; c++) {
+        if (nSrc(c, 0) > 3 || nSrc(c, 1) > 3) P.chunked = true;
+        for (int dir = 0; dir < 2; dir++) nChunks[dir] += std::max(1, (nSrc(c, dir) + 2) / 3);
+    }
+    if (P.chunked) {
+        P.nXLevels = 0;
+        for (int32_t c = 0; c < N; c++) {
+            const int m = nSrc(c, 0);
+            lvBuf.resize(m);
+            for (int j = 0; j < m; j++) lvBuf[j] = P.xlevel[srcCell(c, 0, j)];
+            P.xlevel[c] = chunkRow(lvBuf.data(), m, nullptr, dpF, dpG, dpFrom);
+            P.nXLevels = std::max(P.nXLevels, P.xlevel[c] + 1);
+        }
+    }
+    // chunked plans: half the band height -- the chunk chains roughly double the steps a band of levels needs (most of all in the backward
+    // sweep, whose rows have the most sources), and tiles of at most SWEEP_REG_STEPS steps keep the register-resident operands
+    if (P.chunked) P.bandLevels = std::max(1, P.bandLevels / 2);
     const int B = P.bandLevels;
+    const std::vector<int32_t>& LV = P.xlevel;     // the level the tiling works with
+    const int32_t nLV = P.nXLevels;
+    // rows of one tile: unchunked = the classic budget; chunked = what fills `lanes` entries per level of a band
+    int rowsCap = P.maxRows;
+    if (P.chunked) {
+        double perRow = (double)std::max(nChunks[0], nChunks[1]) / N;
+        rowsCap = std::max(8, std::min(P.maxRows, (int)((double)W * B / perRow)));
+    }
 
     // ---- 1. stride classes of (upper - lower): up to three dominant magnitudes
     int nc = 0; long long cen[3] = {0, 0, 0};
@@ -399,6 +465,58 @@ void buildSweepPlan(int32_t N, const int32_t* lower, const int32_t* upper, int32
         for (int k = 0; k < nc; k++) P.stride[k] = (int)cen[k];
     }
     auto classOf = [&](long long d) { int c = 0; if (nc > 1 && d * d >= cen[0] * cen[1]) c = 1; if (nc > 2 && d * d >= cen[1] * cen[2]) c = 2; return c; };
+
+    std::vector<int32_t> order(N), root(N);
+    std::vector<long long> ckey(N);
+    std::vector<Piece> pieces;
+    // pieces of the tile classes (band, potK / binK, potJ / binJ): split into connected components (a weir makes two disjoint sets of
+    // cells share a class: before and behind it; together they would need two steps per level); cells sorted by (class, component,
+    // level, index); components -> pieces of at most rowsCap cells.  Components of one class have no path between them (any connecting
+    // tile would have the same key), so the tile graph stays acyclic.
+    // lateralCuts: oversized classes (and, in the budget loop, oversized pieces) are cut into consecutive CELL-INDEX ranges instead of level
+    // ranges: index ranges of one class are ordered like the index itself (l < u), so the tile graph stays acyclic, and the pieces of a
+    // class run side by side (pipelined along the index) instead of one after the other.  Used with the index potential / chunked plans;
+    // the stride-class plans of structured meshes keep their level cuts.
+    bool lateralCuts = P.chunked;
+    auto makePieces = [&](long long extJ, long long extK) {
+        const long long nJb = (extJ + P.binJ - 1) / P.binJ, nKb = (extK + P.binK - 1) / P.binK;
+        for (int32_t c = 0; c < N; c++)
+            ckey[c] = ((((long long)(LV[c] / B) * nKb + P.potK[c] / P.binK) * nJb + P.potJ[c] / P.binJ) * nLV) + LV[c];
+        std::iota(root.begin(), root.end(), 0);
+        auto find = [&](int32_t x) { while (root[x] != x) { root[x] = root[root[x]]; x = root[x]; } return x; };
+        // (chunked plans are list-scheduled, a class of several components costs them nothing: no split, fewer and fuller tiles)
+        for (int32_t f = 0; f < F && !P.chunked; f++)
+            if (ckey[lower[f]] / nLV == ckey[upper[f]] / nLV) {
+                int32_t a = find(lower[f]), b = find(upper[f]);
+                if (a != b) { if (a < b) root[b] = a; else root[a] = b; }   // the root is the smallest cell of the component
+            }
+        for (int32_t c = 0; c < N; c++) root[c] = P.chunked ? 0 : find(c);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+            long long ca = ckey[a] / nLV, cb = ckey[b] / nLV;
+            if (ca != cb) return ca < cb;
+            if (root[a] != root[b]) return root[a] < root[b];
+            return LV[a] < LV[b];
+        });
+        pieces.clear();
+        for (int32_t b0 = 0; b0 < N;) {
+            long long cls = ckey[order[b0]] / nLV;
+            int32_t rt0 = root[order[b0]];
+            int32_t e0 = b0;
+            while (e0 < N && ckey[order[e0]] / nLV == cls && root[order[e0]] == rt0) e0++;
+            int32_t n = e0 - b0, np = (n + rowsCap - 1) / rowsCap, base = n / np, rem = n % np, at = b0;
+            if (lateralCuts && np > 1) {   // cut by cell index (lateral), each piece in (level, index) order
+                std::sort(order.begin() + b0, order.begin() + e0);
+                for (int q = 0; q < np; q++) {
+                    int32_t sz = base + (q < rem ? 1 : 0);
+                    std::stable_sort(order.begin() + at, order.begin() + at + sz, [&](int32_t a, int32_t b) { return LV[a] < LV[b]; });
+                    pieces.push_back({at, at + sz}); at += sz;
+                }
+            } else
+                for (int q = 0; q < np; q++) { int32_t sz = base + (q < rem ? 1 : 0); pieces.push_back({at, at + sz}); at += sz; }
+            b0 = e0;
+        }
+    };
     // ---- 2. potentials: most class-1 / class-2 faces on any path (faces are sorted by lower => one ascending pass)
     for (int32_t f = 0; f < F; f++) {
         int32_t l = lower[f], u = upper[f];
@@ -407,18 +525,18 @@ void buildSweepPlan(int32_t N, const int32_t* lower, const int32_t* upper, int32
         if (a > P.potJ[u]) P.potJ[u] = a;
         if (b > P.potK[u]) P.potK[u] = b;
     }
-    long long extJ = 0, extK = 0;
-    for (int32_t c = 0; c < N; c++) { extJ = std::max<long long>(extJ, P.potJ[c] + 1); extK = std::max<long long>(extK, P.potK[c] + 1); }
-    // ---- 3. bin sizes: A = target cells of one (potJ, potK) bin column per level; minimise the number of bins crossed
-    long long nTriples = 0;
-    {
-        std::vector<long long> key(N);
-        for (int32_t c = 0; c < N; c++) key[c] = ((long long)P.level[c] * extJ + P.potJ[c]) * extK + P.potK[c];
-        std::sort(key.begin(), key.end());
-        for (int32_t c = 0; c < N; c++) if (c == 0 || key[c] != key[c - 1]) nTriples++;
-    }
-    long long A = std::max<long long>(1, (long long)P.maxRows * nTriples / ((long long)B * N));
-    {
+    auto binsAndPieces = [&]() {
+        long long extJ = 0, extK = 0;
+        for (int32_t c = 0; c < N; c++) { extJ = std::max<long long>(extJ, P.potJ[c] + 1); extK = std::max<long long>(extK, P.potK[c] + 1); }
+        // ---- 3. bin sizes: A = target cells of one (potJ, potK) bin column per level; minimise the number of bins crossed
+        long long nTriples = 0;
+        {
+            std::vector<long long> key(N);
+            for (int32_t c = 0; c < N; c++) key[c] = ((long long)LV[c] * extJ + P.potJ[c]) * extK + P.potK[c];
+            std::sort(key.begin(), key.end());
+            for (int32_t c = 0; c < N; c++) if (c == 0 || key[c] != key[c - 1]) nTriples++;
+        }
+        long long A = std::max<long long>(1, (long long)rowsCap * nTriples / ((long long)B * N));
         long long bestBj = 1, bestBk = 1, bestCost = -1, bestProd = 0;
         for (long long bj = 1; bj <= std::min(extJ, A); bj++) {
             long long bk = std::min(extK, std::max<long long>(1, A / bj));
@@ -426,71 +544,164 @@ void buildSweepPlan(int32_t N, const int32_t* lower, const int32_t* upper, int32
             if (bestCost < 0 || cost < bestCost || (cost == bestCost && prod > bestProd)) { bestCost = cost; bestProd = prod; bestBj = bj; bestBk = bk; }
         }
         P.binJ = (int)bestBj; P.binK = (int)bestBk;
-    }
-    const long long nJb = (extJ + P.binJ - 1) / P.binJ, nKb = (extK + P.binK - 1) / P.binK;
-    // ---- 4. classes (band, binK, binJ) are split into their connected components (a weir makes two disjoint sets of cells share
-    //         a class: before and behind it; together they would need two steps per level); cells sorted by (class, component,
-    //         level, index); components -> pieces of at most maxRows cells.  Components of one class have no path between them
-    //         (any connecting tile would have the same key), so the tile graph stays acyclic.
-    std::vector<long long> ckey(N);
-    for (int32_t c = 0; c < N; c++)
-        ckey[c] = ((((long long)(P.level[c] / B) * nKb + P.potK[c] / P.binK) * nJb + P.potJ[c] / P.binJ) * P.nLevels) + P.level[c];
-    std::vector<int32_t> root(N);
-    std::iota(root.begin(), root.end(), 0);
-    auto find = [&](int32_t x) { while (root[x] != x) { root[x] = root[root[x]]; x = root[x]; } return x; };
-    for (int32_t f = 0; f < F; f++)
-        if (ckey[lower[f]] / P.nLevels == ckey[upper[f]] / P.nLevels) {
-            int32_t a = find(lower[f]), b = find(upper[f]);
-            if (a != b) { if (a < b) root[b] = a; else root[a] = b; }   // the root is the smallest cell of the component
-        }
-    for (int32_t c = 0; c < N; c++) root[c] = find(c);
-    std::vector<int32_t> order(N);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-        long long ca = ckey[a] / P.nLevels, cb = ckey[b] / P.nLevels;
-        if (ca != cb) return ca < cb;
-        if (root[a] != root[b]) return root[a] < root[b];
-        return P.level[a] < P.level[b];
-    });
-    std::vector<Piece> pieces;
-    for (int32_t b0 = 0; b0 < N;) {
-        long long cls = ckey[order[b0]] / P.nLevels;
-        int32_t rt0 = root[order[b0]];
-        int32_t e0 = b0;
-        while (e0 < N && ckey[order[e0]] / P.nLevels == cls && root[order[e0]] == rt0) e0++;
-        int32_t n = e0 - b0, np = (n + P.maxRows - 1) / P.maxRows, base = n / np, rem = n % np, at = b0;
-        for (int q = 0; q < np; q++) { int32_t sz = base + (q < rem ? 1 : 0); pieces.push_back({at, at + sz}); at += sz; }
-        b0 = e0;
-    }
-    std::vector<int32_t> ownerStart, losort, losortStart;
+        // ---- 4. classes -> connected components -> pieces
+        makePieces(extJ, extK);
+    };
+    binsAndPieces();
+    // ---- 4b. the stride-class potentials only describe (deformed) structured numberings; where they shred the mesh (polyhedral cells
+    //          renumbered in between), fall back to the one lateral potential every LDU addressing has: the cell index itself (l < u on
+    //          every face).  Class = (band, index / indexBins): aligned index ranges, so a tile depends only on tiles with a smaller or equal
+    //          band and range, and the tile graph's depth is bands + ranges.
     {
-        std::vector<int32_t> lo(lower, lower + F), up(upper, upper + F);
-        lduDerived(N, lo, up, ownerStart, losort, losortStart);
+        const long long nBands = (nLV + B - 1) / B;
+        const long long ideal = (N + rowsCap - 1) / rowsCap + nBands;
+        if ((long long)pieces.size() > 3 * ideal) {
+            const size_t before = pieces.size();
+            const std::vector<int32_t> keepJ = P.potJ, keepK = P.potK;
+            const int keepBj = P.binJ, keepBk = P.binK;
+            // ALIGNED ranges (the same cuts in every band: a tile then depends only on tiles with a smaller or equal band AND range, depth =
+            // bands + ranges; cuts that differ from band to band add a diagonal dependency per band and double the depth), fine enough that
+            // the fullest (band, range) class fits one tile -- the sparse classes become small tiles, which costs SMs, not critical path
+            const long long rowsPerBand = std::max<long long>(1, N / nBands);
+            long long Q = std::max<long long>(1, (rowsPerBand + rowsCap - 1) / rowsCap);
+            std::vector<int32_t> pop;
+            for (;;) {
+                const long long ib = std::max<long long>(1, (N + Q - 1) / Q);
+                pop.assign((size_t)(nBands * ((N + ib - 1) / ib)), 0);
+                int32_t mx = 0;
+                for (int32_t c = 0; c < N; c++) mx = std::max(mx, ++pop[(size_t)(LV[c] / B) * ((N + ib - 1) / ib) + c / ib]);
+                if (mx <= rowsCap || ib <= 64) break;
+                Q += std::max<long long>(1, Q / 4);
+            }
+            P.indexBins = (int)std::max<long long>(1, (N + Q - 1) / Q);
+            for (int32_t c = 0; c < N; c++) { P.potJ[c] = 0; P.potK[c] = c / P.indexBins; }
+            P.binJ = 1; P.binK = 1;
+            const bool keepLat = lateralCuts;
+            lateralCuts = true;
+            makePieces(1, (N + P.indexBins - 1) / P.indexBins);
+            if (pieces.size() >= before) {   // no better: keep the stride classes
+                lateralCuts = keepLat;
+                P.potJ = keepJ; P.potK = keepK; P.binJ = keepBj; P.binK = keepBk; P.indexBins = 0;
+                long long extJ = 0, extK = 0;
+                for (int32_t c = 0; c < N; c++) { extJ = std::max<long long>(extJ, P.potJ[c] + 1); extK = std::max<long long>(extK, P.potK[c] + 1); }
+                makePieces(extJ, extK);
+            }
+        }
     }
-    // ---- 5. shared-memory / index-width budget: offending pieces are halved until they fit
-    std::vector<int32_t> pieceOf(N), stamp(N, -1), stampB(N, -1);
+
+    // ---- 5. schedule of one piece and one direction -> steps of <= W entries
+    std::vector<int32_t> pieceOf(N), localOf(N, -1);
+    // unchunked: step = up to W rows of one level (the rows of a piece are sorted by level), the same steps for both directions
+    auto scheduleLevels = [&](const Piece& pc, TileSchedule& ts) {
+        ts.slot.clear(); ts.nSteps = 0;
+        int used = W;   // entries in the current step
+        for (int32_t i = pc.b; i < pc.e; i++) {
+            bool newLevel = i == pc.b || LV[order[i]] != LV[order[i - 1]];
+            if (newLevel || used == W) { ts.slot.resize((size_t)(ts.nSteps + 1) * W, Entry{-1, 0, 0, false, false}); ts.nSteps++; used = 0; }
+            ts.slot[(size_t)(ts.nSteps - 1) * W + used++] = Entry{i - pc.b, 0, 0, false, false};
+        }
+        for (Entry& e : ts.slot) if (e.row >= 0) e.j1 = 0;   // (source ranges are filled by the ELL builder: all sources)
+    };
+    // chunked: list scheduling of the chunks on W lanes, longest remaining chain first
+    struct Node { int row, j0, j1, prev, height, waiting, step, lane; };
+    std::vector<Node> nodes; std::vector<int> lastNode, est, cuts, succStart, succ, ready, nextReady;
+    auto scheduleChunks = [&](const Piece& pc, int p, int dir, TileSchedule& ts) {
+        const int n = pc.e - pc.b;
+        nodes.clear(); lastNode.assign(n, -1); est.assign(n, 0);
+        // chunk boundaries from in-tile level estimates (topological order: forward = piece order, backward = reversed)
+        for (int q = 0; q < n; q++) {
+            const int r = dir == 0 ? q : n - 1 - q;
+            const int32_t c = order[pc.b + r];
+            const int m = nSrc(c, dir);
+            lvBuf.resize(m);
+            for (int j = 0; j < m; j++) { int32_t o = srcCell(c, dir, j); lvBuf[j] = pieceOf[o] == p ? est[localOf[o]] : -1; }
+            est[r] = chunkRow(lvBuf.data(), m, &cuts, dpF, dpG, dpFrom);
+            if (m == 0) { nodes.push_back(Node{r, 0, 0, -1, 0, 0, -1, -1}); lastNode[r] = (int)nodes.size() - 1; continue; }
+            int j0 = 0, prev = -1;
+            for (int e : cuts) { nodes.push_back(Node{r, j0, e, prev, 0, 0, -1, -1}); prev = (int)nodes.size() - 1; j0 = e; }
+            lastNode[r] = prev;
+        }
+        // dependants (CSR): node -> nodes waiting for it (in-tile sources' last chunks, and the previous chunk of the same row)
+        const int nn = (int)nodes.size();
+        succStart.assign(nn + 1, 0);
+        auto forDeps = [&](int v, auto&& fn) {
+            const Node& nd = nodes[v];
+            if (nd.prev >= 0) fn(nd.prev);
+            const int32_t c = order[pc.b + nd.row];
+            for (int j = nd.j0; j < nd.j1; j++) { int32_t o = srcCell(c, dir, j); if (pieceOf[o] == p) fn(lastNode[localOf[o]]); }
+        };
+        for (int v = 0; v < nn; v++) forDeps(v, [&](int d) { succStart[d + 1]++; nodes[v].waiting++; });
+        for (int v = 0; v < nn; v++) succStart[v + 1] += succStart[v];
+        succ.assign(succStart[nn], 0);
+        { std::vector<int> at(succStart.begin(), succStart.end() - 1); for (int v = 0; v < nn; v++) forDeps(v, [&](int d) { succ[at[d]++] = v; }); }
+        for (int v = nn - 1; v >= 0; v--)   // nodes were created in topological order
+            for (int q = succStart[v]; q < succStart[v + 1]; q++) nodes[v].height = std::max(nodes[v].height, nodes[succ[q]].height + 1);
+        auto prio = [&](int a, int b) { return nodes[a].height != nodes[b].height ? nodes[a].height < nodes[b].height : a > b; };   // heap: top = highest, then first created
+        ready.clear();
+        for (int v = 0; v < nn; v++) if (nodes[v].waiting == 0) ready.push_back(v);
+        std::make_heap(ready.begin(), ready.end(), prio);
+        ts.slot.clear(); ts.nSteps = 0;
+        int done = 0;
+        std::vector<int> picked;
+        while (done < nn) {
+            const int k = ts.nSteps++;
+            ts.slot.resize((size_t)ts.nSteps * W, Entry{-1, 0, 0, false, false});
+            picked.clear();
+            while ((int)picked.size() < W && !ready.empty()) { std::pop_heap(ready.begin(), ready.end(), prio); picked.push_back(ready.back()); ready.pop_back(); }
+            Entry* st = &ts.slot[(size_t)k * W];
+            // continuations of the previous step keep their lane (the partial result stays in the thread's register)
+            for (int v : picked) {
+                Node& nd = nodes[v];
+                if (nd.prev >= 0 && nodes[nd.prev].step == k - 1) { nd.lane = nodes[nd.prev].lane; st[nd.lane] = Entry{nd.row, nd.j0, nd.j1, false, true}; }
+            }
+            int free = 0;
+            for (int v : picked) {
+                Node& nd = nodes[v];
+                if (nd.lane < 0) { while (st[free].row >= 0) free++; nd.lane = free; st[free] = Entry{nd.row, nd.j0, nd.j1, false, false}; }
+                nd.step = k;
+                st[nd.lane].partial = lastNode[nd.row] != v;
+            }
+            nextReady.clear();
+            for (int v : picked) for (int q = succStart[v]; q < succStart[v + 1]; q++) if (--nodes[succ[q]].waiting == 0) nextReady.push_back(succ[q]);
+            for (int v : nextReady) { ready.push_back(v); std::push_heap(ready.begin(), ready.end(), prio); }
+            done += (int)picked.size();
+            if (picked.empty()) throw std::runtime_error("DIC sweep plan: chunk schedule stalled (internal error)");
+        }
+        if (dir == 1)   // the backward sweep walks a tile's steps downwards: store the schedule last step first
+            for (int k = 0; k < ts.nSteps / 2; k++) std::swap_ranges(ts.slot.begin() + (size_t)k * W, ts.slot.begin() + (size_t)(k + 1) * W, ts.slot.begin() + (size_t)(ts.nSteps - 1 - k) * W);
+    };
+    auto setPieceMaps = [&]() {
+        for (size_t p = 0; p < pieces.size(); p++)
+            for (int32_t i = pieces[p].b; i < pieces[p].e; i++) { pieceOf[order[i]] = (int32_t)p; localOf[order[i]] = i - pieces[p].b; }
+    };
+    // ---- 6. shared-memory / index-width budget: offending pieces are halved until they fit
+    std::vector<int32_t> stamp(N, -1), stampB(N, -1);
+    TileSchedule tsF, tsB;
     for (;;) {
-        for (size_t p = 0; p < pieces.size(); p++) for (int32_t i = pieces[p].b; i < pieces[p].e; i++) pieceOf[order[i]] = (int32_t)p;
+        setPieceMaps();
         std::fill(stamp.begin(), stamp.end(), -1); std::fill(stampB.begin(), stampB.end(), -1);
         std::vector<Piece> next; next.reserve(pieces.size());
         bool changed = false;
         for (size_t p = 0; p < pieces.size(); p++) {
-            int n = pieces[p].e - pieces[p].b, dF = 0, dB = 0, hF = 0, hB = 0, nSteps = 0, run = 0;
+            int n = pieces[p].e - pieces[p].b, dF = 0, dB = 0, hF = 0, hB = 0;
             for (int32_t i = pieces[p].b; i < pieces[p].e; i++) {
                 int32_t c = order[i];
-                if (i > pieces[p].b && P.level[c] != P.level[order[i - 1]]) { nSteps += (run + W - 1) / W; run = 0; }
-                run++;
-                dF = std::max(dF, losortStart[c + 1] - losortStart[c]);
-                dB = std::max(dB, ownerStart[c + 1] - ownerStart[c]);
+                dF = std::max(dF, nSrc(c, 0)); dB = std::max(dB, nSrc(c, 1));
                 for (int32_t q = losortStart[c]; q < losortStart[c + 1]; q++) { int32_t l = lower[losort[q]]; if (pieceOf[l] != (int32_t)p && stamp[l] != (int32_t)p) { stamp[l] = (int32_t)p; hF++; } }
                 for (int32_t f = ownerStart[c]; f < ownerStart[c + 1]; f++) { int32_t u = upper[f]; if (pieceOf[u] != (int32_t)p && stampB[u] != (int32_t)p) { stampB[u] = (int32_t)p; hB++; } }
             }
-            nSteps += (run + W - 1) / W;
-            const int S = nSteps * W;
-            size_t need = std::max(sweepSmemBytes(n, S, hF, dF), sweepSmemBytes(n, S, hB, dB));
-            bool tooBig = need > (size_t)smemBudget || n + std::max(hF, hB) + 2 > SWEEP_MAX_SLOTS || nSteps > SWEEP_MAX_STEPS;
+            int stepsF, stepsB;
+            if (P.chunked) { scheduleChunks(pieces[p], (int)p, 0, tsF); scheduleChunks(pieces[p], (int)p, 1, tsB); stepsF = tsF.nSteps; stepsB = tsB.nSteps; dF = std::min(dF, 3); dB = std::min(dB, 3); }
+            else { scheduleLevels(pieces[p], tsF); stepsF = stepsB = tsF.nSteps; }
+            size_t need = std::max(sweepSmemBytes(n, stepsF * W, hF, dF), sweepSmemBytes(n, stepsB * W, hB, dB));
+            bool tooBig = need > (size_t)smemBudget || n + std::max(hF, hB) + 2 > SWEEP_MAX_SLOTS || std::max(stepsF, stepsB) > SWEEP_MAX_STEPS;
             if (tooBig && n > 1) {
                 int32_t mid = pieces[p].b + n / 2;
+                if (lateralCuts) {
+                    std::sort(order.begin() + pieces[p].b, order.begin() + pieces[p].e);
+                    std::stable_sort(order.begin() + pieces[p].b, order.begin() + mid, [&](int32_t a, int32_t b) { return LV[a] < LV[b]; });
+                    std::stable_sort(order.begin() + mid, order.begin() + pieces[p].e, [&](int32_t a, int32_t b) { return LV[a] < LV[b]; });
+                }
                 next.push_back({pieces[p].b, mid}); next.push_back({mid, pieces[p].e});
                 changed = true;
             } else {
@@ -502,7 +713,8 @@ void buildSweepPlan(int32_t N, const int32_t* lower, const int32_t* upper, int32
         if (!changed) break;
     }
     const int nT = (int)pieces.size();
-    // ---- 6. tile graph, longest-path levels (Kahn), ticket order = (tile level, class order)
+    setPieceMaps();
+    // ---- 7. tile graph, longest-path levels (Kahn), ticket order = (tile level, class order)
     std::vector<long long> edges;
     for (int32_t f = 0; f < F; f++) { int32_t a = pieceOf[lower[f]], b = pieceOf[upper[f]]; if (a != b) edges.push_back(((long long)a << 32) | (unsigned)b); }
     std::sort(edges.begin(), edges.end());
@@ -524,67 +736,64 @@ void buildSweepPlan(int32_t N, const int32_t* lower, const int32_t* upper, int32
     std::vector<int32_t> ticket(nT);
     std::iota(ticket.begin(), ticket.end(), 0);
     std::stable_sort(ticket.begin(), ticket.end(), [&](int32_t a, int32_t b) { return tl[a] < tl[b]; });
-    // ---- 7. rows and steps
+    // ---- 8. rows: device row order = (tile in ticket order, level, original index)
     P.nTiles = nT; P.tileLevel.resize(nT);
-    std::vector<int32_t> tileOfCell(N);
     int32_t row = 0;
     for (int t = 0; t < nT; t++) {
         const Piece& pc = pieces[ticket[t]];
         P.tileLevel[t] = tl[ticket[t]];
         P.nTileLevels = std::max(P.nTileLevels, tl[ticket[t]] + 1);
-        for (int32_t i = pc.b; i < pc.e; i++) {
-            int32_t c = order[i];
-            bool newLevel = i == pc.b || P.level[c] != P.level[order[i - 1]];
-            if (newLevel || P.stepLen.back() == W) { P.stepRow.push_back(row); P.stepLen.push_back(0); }
-            P.stepLen.back()++;
-            P.rowCell[row] = c; P.cellRow[c] = row; tileOfCell[c] = t; row++;
-        }
+        for (int32_t i = pc.b; i < pc.e; i++) { int32_t c = order[i]; P.rowCell[row] = c; P.cellRow[c] = row; row++; }
         P.tileStart.push_back(row);
-        P.tileStepStart.push_back((int32_t)P.stepRow.size());
     }
-    // ---- 8. per-tile ELL (slot layout) + halo lists of the two sweeps
+    // ---- 9. per-tile steps and ELL (slot layout) + halo lists of the two sweeps
     P.fwdD.resize(nT); P.bwdD.resize(nT);
-    std::vector<int32_t> slot(N, -1), slotOfRow(N);
-    for (int t = 0; t < nT; t++)
-        for (int32_t k = P.tileStepStart[t]; k < P.tileStepStart[t + 1]; k++)
-            for (int32_t i = 0; i < P.stepLen[k]; i++) slotOfRow[P.stepRow[k] + i] = (k - P.tileStepStart[t]) * W + i;
+    std::vector<int32_t> slot(N, -1);
     std::fill(stamp.begin(), stamp.end(), -1);
     for (int t = 0; t < nT; t++) {
-        const int32_t r0 = P.tileStart[t], n = P.tileStart[t + 1] - r0;
-        const int S = (P.tileStepStart[t + 1] - P.tileStepStart[t]) * W;
+        const int p = ticket[t];
+        const Piece& pc = pieces[p];
+        const int32_t n = pc.e - pc.b;
         for (int dir = 0; dir < 2; dir++) {
+            TileSchedule& ts = dir == 0 ? tsF : tsB;
+            if (P.chunked) scheduleChunks(pc, p, dir, ts); else if (dir == 0) scheduleLevels(pc, ts);
+            const TileSchedule& sc = P.chunked ? ts : tsF;
             std::vector<uint16_t>& idx = dir == 0 ? P.fwdIdx : P.bwdIdx;
             std::vector<int32_t>& face = dir == 0 ? P.fwdFace : P.bwdFace;
             std::vector<int32_t>& haloRow = dir == 0 ? P.fwdHaloRow : P.bwdHaloRow;
             std::vector<int32_t>& ell = dir == 0 ? P.fwdEll : P.bwdEll;
             std::vector<int32_t>& halo = dir == 0 ? P.fwdHalo : P.bwdHalo;
+            std::vector<uint16_t>& own = dir == 0 ? P.fwdOwn : P.bwdOwn;
+            std::vector<int32_t>& stepStart = dir == 0 ? P.fwdStepStart : P.bwdStepStart;
+            const int S = sc.nSteps * W;
             int D = 0;
-            for (int32_t r = 0; r < n; r++) {
-                int32_t c = P.rowCell[r0 + r];
-                D = std::max(D, dir == 0 ? losortStart[c + 1] - losortStart[c] : ownerStart[c + 1] - ownerStart[c]);
-            }
+            for (const Entry& e : sc.slot) if (e.row >= 0) D = std::max(D, P.chunked ? e.j1 - e.j0 : nSrc(order[pc.b + e.row], dir));
             (dir == 0 ? P.fwdD : P.bwdD)[t] = D;
-            size_t e0 = idx.size();
+            size_t e0 = idx.size(), o0 = own.size();
             idx.resize(e0 + (size_t)D * S, 0xffff); face.resize(e0 + (size_t)D * S, -1);
+            own.resize(o0 + (size_t)S, SWEEP_OWN_NONE);
             int nHalo = 0;
-            int32_t st = 2 * t + dir;
-            for (int32_t r = 0; r < n; r++) {
-                int32_t c = P.rowCell[r0 + r], sl = slotOfRow[r0 + r];
-                int cnt = dir == 0 ? losortStart[c + 1] - losortStart[c] : ownerStart[c + 1] - ownerStart[c];
-                for (int j = 0; j < cnt; j++) {
-                    int32_t f = dir == 0 ? losort[losortStart[c] + j] : ownerStart[c + 1] - 1 - j;
-                    int32_t o = dir == 0 ? lower[f] : upper[f];
+            const int32_t st = 2 * t + dir;
+            for (int sl = 0; sl < S; sl++) {
+                const Entry& e = sc.slot[sl];
+                if (e.row < 0) continue;
+                const int32_t c = order[pc.b + e.row];
+                own[o0 + sl] = (uint16_t)(e.row | (e.partial ? SWEEP_OWN_PARTIAL : 0) | (e.carry ? SWEEP_OWN_CARRY : 0));
+                const int j0 = P.chunked ? e.j0 : 0, j1 = P.chunked ? e.j1 : nSrc(c, dir);
+                for (int j = j0; j < j1; j++) {
+                    const int32_t f = srcFace(c, dir, j), o = dir == 0 ? lower[f] : upper[f];
                     int32_t id;
-                    if (tileOfCell[o] == t) id = P.cellRow[o] - r0;
+                    if (pieceOf[o] == p) id = localOf[o];
                     else {
                         if (stamp[o] != st) { stamp[o] = st; slot[o] = nHalo++; haloRow.push_back(P.cellRow[o]); }
                         id = n + slot[o];
                     }
-                    idx[e0 + (size_t)j * S + sl] = (uint16_t)id; face[e0 + (size_t)j * S + sl] = f;
+                    idx[e0 + (size_t)(j - j0) * S + sl] = (uint16_t)id; face[e0 + (size_t)(j - j0) * S + sl] = f;
                 }
             }
             for (size_t e = e0; e < idx.size(); e++) if (face[e] < 0) idx[e] = (uint16_t)(n + nHalo);
             ell.push_back((int32_t)idx.size()); halo.push_back((int32_t)haloRow.size());
+            stepStart.push_back(stepStart.back() + sc.nSteps);
             size_t need = sweepSmemBytes(n, S, nHalo, D);
             if (dir == 0) P.smemFwd = std::max(P.smemFwd, need); else P.smemBwd = std::max(P.smemBwd, need);
         }

@@ -80,14 +80,27 @@ struct SweepPlan {
     int stride[3] = {0, 0, 0};                      // detected stride-class centres (0 = absent)
     std::vector<int32_t> level, potJ, potK;         // per cell
     int32_t nLevels = 0;
+    // CHUNKED plans (some row has more than 3 lower or more than 3 upper neighbours: polyhedral cells).  Such a row is applied as a chain
+    // of CHUNKS of at most 3 consecutive sources, each chunk one (step, lane) entry that starts from the previous chunk's partial result --
+    // the arithmetic order inside the row is untouched, every entry has at most 3 sources (the register-resident fast path of the
+    // kernels), and a heavy row's early sources are consumed while the later ones are still being computed.  xlevel = the row's level in
+    // that expanded graph (== level when nothing is chunked); the bands are cut on xlevel.
+    bool chunked = false;
+    int indexBins = 0;                              // > 0: the stride-class potentials fragmented; potK = cell index / indexBins, potJ = 0
+    std::vector<int32_t> xlevel;
+    int32_t nXLevels = 0;
     std::vector<int32_t> rowCell, cellRow;          // device row <-> original cell
     int nTiles = 0, nTileLevels = 0;
     std::vector<int32_t> tileStart;                 // [nTiles+1] first row
     std::vector<int32_t> tileLevel;                 // [nTiles] longest-path level of the tile in the tile graph
-    // a tile is executed as STEPS of at most `lanes` rows of one level (one row per thread, a barrier after every step);
-    // step k of tile t owns the operand slots [k*lanes, (k+1)*lanes) of the tile's operand block (unused lanes are inert).
-    std::vector<int32_t> tileStepStart;             // [nTiles+1] CSR into stepRow / stepLen
-    std::vector<int32_t> stepRow, stepLen;          // first device row and number of rows of each step
+    // a tile is executed, per sweep direction, as STEPS of at most `lanes` entries (one per thread, a barrier after every step); step k
+    // of tile t owns the operand slots [k*lanes, (k+1)*lanes) of the tile's operand block (unused lanes are inert).  Unchunked plans:
+    // step = up to `lanes` rows of one level, the same steps in both directions (walked downwards by the backward sweep).
+    std::vector<int32_t> fwdStepStart, bwdStepStart;   // [nTiles+1] steps of the tiles before t (S = nSteps*lanes slots)
+    // own: per slot, the tile-local row the entry belongs to (SWEEP_OWN_NONE = inert lane) plus the flags
+    //   SWEEP_OWN_PARTIAL : not the row's last chunk (the result must not be published)
+    //   SWEEP_OWN_CARRY   : continues the chunk this lane computed in the previous step (start value = that result, still in a register)
+    std::vector<uint16_t> fwdOwn, bwdOwn;           // [fwdStepStart.back()*lanes], [bwdStepStart.back()*lanes]
     // per-tile ELL of the two sweeps in SLOT layout: column j of tile t = entries [ell[t] + j*S, +S), S = nSteps*lanes.
     // idx: source in the tile's value array (0..nRows-1 = row of this tile, nRows+h = halo entry h, nRows+nHalo = padding);
     // face: ORIGINAL face index of the coefficient (-1 = padding).  Forward columns are in ascending face order, backward
@@ -99,6 +112,7 @@ struct SweepPlan {
     std::vector<int32_t> fwdHaloRow, bwdHaloRow;    // device rows polled by the tile
     size_t smemFwd = 0, smemBwd = 0;                // largest per-tile shared-memory need (bytes)
 };
+constexpr uint16_t SWEEP_OWN_NONE = 0xffff, SWEEP_OWN_PARTIAL = 0x8000, SWEEP_OWN_CARRY = 0x4000, SWEEP_OWN_ROW = 0x1fff;
 // shared-memory bytes of one tile (the formula the kernels use): the value array (rows, start values overwritten in place by the
 // results; halo; padding; trash; +1 alignment shift) and the operand block: d coefficient columns and ceil(d/4) columns of
 // packed 16-bit offsets

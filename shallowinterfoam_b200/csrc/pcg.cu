@@ -74,8 +74,12 @@ static void launchCalcRD(DeviceMesh& m, PcgWorkspace& w, const double* diag, con
     fillSentinel(w.Dt, m.N);
     // forward operand blocks <- face products (fully parallel), so that the sweep stages them with one TMA copy per tile
     B200_LAUNCH(k_dic_coeffs, m.nTiles, sweepThreads(m), rt().stream, m.sweep(), (const double*)nullptr, upS, loS, cf, (double*)nullptr, gate);
-    B200_LAUNCH_SMEM(k_dic_fwd<1>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), diag, (const double*)nullptr, upS,
-                     (const double*)cf, w.Dt.p, rD, sweepCtl(w), gate, PcgFuse{});
+    if (m.plan.chunked)
+        B200_LAUNCH_SMEM((k_dic_fwd<1, true>), sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), diag, (const double*)nullptr, upS,
+                         (const double*)cf, w.Dt.p, rD, sweepCtl(w), gate, PcgFuse{});
+    else
+        B200_LAUNCH_SMEM((k_dic_fwd<1, false>), sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), diag, (const double*)nullptr, upS,
+                         (const double*)cf, w.Dt.p, rD, sweepCtl(w), gate, PcgFuse{});
 }
 // forward operand blocks <- rD[row]*srcF, backward <- rD[row]*srcB (DIC: both upper; DILU: lower/upper, transposed: upper/lower)
 static void launchCoeffs(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* srcF, const double* srcB, double* cf, double* cb,
@@ -100,13 +104,21 @@ static const PcgScalars* launchMatrixGate(DeviceMesh& m, PcgWorkspace& w, const 
 // pdl: the kernel may start (ticket, descriptor, operand-block staging) while its predecessor in the stream is still running
 static void launchFwd(DeviceMesh& m, PcgWorkspace& w, const double* rD, const double* rA, const PcgScalars* sc, PcgFuse fz = PcgFuse{}, bool pdl = false,
                       const double* cf = nullptr) {
-    B200_LAUNCH_PDL(pdl, k_dic_fwd<0>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), rD, rA, (const double*)nullptr,
-                    cf ? cf : (const double*)w.cf.p, w.y.p, (double*)nullptr, sweepCtl(w), sc, fz);
+    if (m.plan.chunked)
+        B200_LAUNCH_PDL(pdl, (k_dic_fwd<0, true>), sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), rD, rA, (const double*)nullptr,
+                        cf ? cf : (const double*)w.cf.p, w.y.p, (double*)nullptr, sweepCtl(w), sc, fz);
+    else
+        B200_LAUNCH_PDL(pdl, (k_dic_fwd<0, false>), sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), rD, rA, (const double*)nullptr,
+                        cf ? cf : (const double*)w.cf.p, w.y.p, (double*)nullptr, sweepCtl(w), sc, fz);
 }
 static void launchBwd(DeviceMesh& m, PcgWorkspace& w, const double* rA, PcgScalars* sc, double* part, unsigned* cnt, double* dotOut = nullptr, bool pdl = false,
                       const double* cb = nullptr, P2PFold fold = P2PFold{}, double* hist = nullptr) {
-    B200_LAUNCH_PDL(pdl, k_dic_bwd, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), cb ? cb : (const double*)w.cb.p, (const double*)rA, w.y.p, w.z.p,
-                    sweepCtl(w, true), sc, part, cnt, dotOut ? dotOut : (sc ? &sc->wArA : nullptr), fold, hist);
+    if (m.plan.chunked)
+        B200_LAUNCH_PDL(pdl, k_dic_bwd<true>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), cb ? cb : (const double*)w.cb.p, (const double*)rA, w.y.p, w.z.p,
+                        sweepCtl(w, true), sc, part, cnt, dotOut ? dotOut : (sc ? &sc->wArA : nullptr), fold, hist);
+    else
+        B200_LAUNCH_PDL(pdl, k_dic_bwd<false>, sweepGridOf(m, w), sweepThreads(m), m.sweepSmem, rt().stream, m.sweep(), cb ? cb : (const double*)w.cb.p, (const double*)rA, w.y.p, w.z.p,
+                        sweepCtl(w, true), sc, part, cnt, dotOut ? dotOut : (sc ? &sc->wArA : nullptr), fold, hist);
 }
 
 void amulDevice(DeviceMesh& m, const double* diag, const double* upS, const double* loS, const double* psi, double* Apsi,

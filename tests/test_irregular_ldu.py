@@ -1,5 +1,5 @@
 """BASELINE configs[3] in miniature: irregular (polyhedral-like) LDU addressing -- rows with 0..12+ lower / upper neighbours,
-long-range faces, no stride structure.  Exercises the generic (d > 3 / d = 0) paths of the DIC sweep tiles, the plan's
+long-range faces, no stride structure.  Exercises the chunked rows (more than 3 sources) and the isolated rows of the DIC sweep tiles, the plan's
 monotone potentials on an arbitrary DAG, and Amul / sumA / DIC / PCG parity (bitwise / 1e-8) against the oracle."""
 import numpy as np
 import pytest
@@ -51,10 +51,13 @@ def test_irregular_ldu_parity(lib, oracle, n, seed, max_deg, window):
     rowCell, level, nLevels = ldu.renumbering()
     bl, tr, ts = ldu.tiling()
     plan = mo.sweep_plan(lower, upper_addr, n, bl, tr)
-    assert np.array_equal(rowCell, plan["rowCell"]) and np.array_equal(ts, plan["tileStart"]) and np.array_equal(level, plan["level"])
-    for k in ("level", "potJ", "potK"):
-        assert np.all(plan[k][lower] <= plan[k][upper_addr])
-    inv = plan["cellRow"]
+    assert np.array_equal(level, plan["level"]) and np.all(level[lower] < level[upper_addr])
+    if not plan["chunked"]:   # (rows with more than 3 sources are applied as chains of chunks; that plan is checked by its properties)
+        assert np.array_equal(rowCell, plan["rowCell"]) and np.array_equal(ts, plan["tileStart"])
+        for k in ("potJ", "potK"):
+            assert np.all(plan[k][lower] <= plan[k][upper_addr])
+    assert sorted(rowCell.tolist()) == list(range(n)) and ts[0] == 0 and ts[-1] == n and np.all(np.diff(ts) > 0)
+    inv = np.empty(n, dtype=np.int64); inv[rowCell] = np.arange(n)
     tile_of_row = np.searchsorted(ts, np.arange(n), side="right") - 1
     assert np.all(tile_of_row[inv[lower]] <= tile_of_row[inv[upper_addr]])
     # arithmetic
