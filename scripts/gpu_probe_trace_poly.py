@@ -57,4 +57,11 @@ chain = chain[::-1]
 st = np.array([(tr[c, 3] - tr[c, 2]) for c in chain]) / 1e3
 hop = np.array([(tr[chain[i + 1], 2] - tr[chain[i], 3]) for i in range(len(chain) - 1)]) / 1e3
 print("critical chain: %d tiles, steps time total %.1f us (mean %.2f), hops total %.1f us (mean %.2f, max %.2f)" % (len(chain), st.sum(), st.mean(), hop.sum(), hop.mean() if len(hop) else 0, hop.max() if len(hop) else 0))
+dd = np.array([tr[chain[i], 3] for i in range(len(chain) - 1)])
+nx = np.array(chain[1:])
+print("chain tiles relative to their last dependency's steps-done (us): ticket %.2f (late for %d of %d), staged %.2f (late for %d), ready %.2f" % (
+    ((tr[nx, 0] - dd) / 1e3).mean(), ((tr[nx, 0] - dd) > 0).sum(), len(nx), ((tr[nx, 1] - dd) / 1e3).mean(), ((tr[nx, 1] - dd) > 0).sum(), ((tr[nx, 2] - dd) / 1e3).mean()))
+early = (tr[nx, 1] - dd) < 0
+print("hop of the chain tiles staged BEFORE their dependency finished: mean %.2f us (%d tiles); staged after: mean %.2f us (%d tiles)" % (
+    ((tr[nx[early], 2] - dd[early]) / 1e3).mean(), early.sum(), ((tr[nx[~early], 2] - dd[~early]) / 1e3).mean() if (~early).any() else 0.0, (~early).sum()))
 print("first tile of the chain became ready at %.1f us" % (tr[chain[0], 2] / 1e3))

@@ -697,7 +697,10 @@ void buildSweepPlan(int32_t N, const int32_t* lower, const int32_t* upper, int32
             bool tooBig = need > (size_t)smemBudget || n + std::max(hF, hB) + 2 > SWEEP_MAX_SLOTS || std::max(stepsF, stepsB) > SWEEP_MAX_STEPS;
             if (tooBig && n > 1) {
                 int32_t mid = pieces[p].b + n / 2;
-                if (lateralCuts) {
+                // lateral halves keep the piece's chain of steps; when the STEPS are what does not fit (operand slots, step count), cut by level
+                const bool byLevel = std::max(stepsF, stepsB) > SWEEP_MAX_STEPS ||
+                                     8 * (size_t)std::max(stepsF * (dF + 1), stepsB * (dB + 1)) * W > (size_t)smemBudget * 3 / 4;
+                if (lateralCuts && !byLevel) {
                     std::sort(order.begin() + pieces[p].b, order.begin() + pieces[p].e);
                     std::stable_sort(order.begin() + pieces[p].b, order.begin() + mid, [&](int32_t a, int32_t b) { return LV[a] < LV[b]; });
                     std::stable_sort(order.begin() + mid, order.begin() + pieces[p].e, [&](int32_t a, int32_t b) { return LV[a] < LV[b]; });
@@ -736,14 +739,19 @@ void buildSweepPlan(int32_t N, const int32_t* lower, const int32_t* upper, int32
     std::vector<int32_t> ticket(nT);
     std::iota(ticket.begin(), ticket.end(), 0);
     std::stable_sort(ticket.begin(), ticket.end(), [&](int32_t a, int32_t b) { return tl[a] < tl[b]; });
-    // ---- 8. rows: device row order = (tile in ticket order, level, original index)
+    // ---- 8. rows: device row order = (tile in ticket order, level, original index).  Chunked plans (whose entries name their row
+    //         explicitly) put the rows with the most faces first instead: the SELL-32 slices of the face arrays are as wide as their
+    //         widest row, and 24-face cells scattered among hexes would pad every slice to their width (3.5x the coefficient traffic of Amul)
     P.nTiles = nT; P.tileLevel.resize(nT);
+    std::vector<int32_t> storeOf(N, -1), store;
     int32_t row = 0;
     for (int t = 0; t < nT; t++) {
         const Piece& pc = pieces[ticket[t]];
         P.tileLevel[t] = tl[ticket[t]];
         P.nTileLevels = std::max(P.nTileLevels, tl[ticket[t]] + 1);
-        for (int32_t i = pc.b; i < pc.e; i++) { int32_t c = order[i]; P.rowCell[row] = c; P.cellRow[c] = row; row++; }
+        store.assign(order.begin() + pc.b, order.begin() + pc.e);
+        if (P.chunked) std::stable_sort(store.begin(), store.end(), [&](int32_t a, int32_t b) { return nSrc(a, 0) + nSrc(a, 1) > nSrc(b, 0) + nSrc(b, 1); });
+        for (size_t i = 0; i < store.size(); i++) { int32_t c = store[i]; P.rowCell[row] = c; P.cellRow[c] = row; storeOf[c] = (int32_t)i; row++; }
         P.tileStart.push_back(row);
     }
     // ---- 9. per-tile steps and ELL (slot layout) + halo lists of the two sweeps
@@ -778,12 +786,12 @@ void buildSweepPlan(int32_t N, const int32_t* lower, const int32_t* upper, int32
                 const Entry& e = sc.slot[sl];
                 if (e.row < 0) continue;
                 const int32_t c = order[pc.b + e.row];
-                own[o0 + sl] = (uint16_t)(e.row | (e.partial ? SWEEP_OWN_PARTIAL : 0) | (e.carry ? SWEEP_OWN_CARRY : 0));
+                own[o0 + sl] = (uint16_t)(storeOf[c] | (e.partial ? SWEEP_OWN_PARTIAL : 0) | (e.carry ? SWEEP_OWN_CARRY : 0));
                 const int j0 = P.chunked ? e.j0 : 0, j1 = P.chunked ? e.j1 : nSrc(c, dir);
                 for (int j = j0; j < j1; j++) {
                     const int32_t f = srcFace(c, dir, j), o = dir == 0 ? lower[f] : upper[f];
                     int32_t id;
-                    if (pieceOf[o] == p) id = localOf[o];
+                    if (pieceOf[o] == p) id = storeOf[o];
                     else {
                         if (stamp[o] != st) { stamp[o] = st; slot[o] = nHalo++; haloRow.push_back(P.cellRow[o]); }
                         id = n + slot[o];
