@@ -104,6 +104,41 @@ def decomposition(args, dims, world):
     return (world, 1, 1)
 
 
+def polyhedral_leg(lib, dims=(300, 180, 180), lengths=(30.0, 18.0, 18.0)):
+    """BASELINE configs[3] on one GPU: per-kernel CUDA-event times of Amul and the DIC precondition inside one PCG solve of a random SPD
+    system on the polyhedral box (what `solver b200PCG;` does on irregular lduAddressing).  Parity of this path: tests/test_polyhedral.py,
+    tests/test_irregular_ldu.py and tests/test_atsize_region.py (2.56 M cells, against the oracle)."""
+    from shallowinterfoam_b200 import capi
+    t0 = time.time()
+    box = lib.polymesh_box(*dims, *lengths, jitter=(0.25, 12345))
+    pm = box.agglomerate(capi.checkerboard_groups(*dims)); box.release()
+    N, F = pm.nCells, pm.nInternalFaces
+    ldu = pm.ldu()
+    build_s = time.time() - t0
+    rng = np.random.default_rng(1)
+    upper = -rng.uniform(0.5, 1.5, F)
+    diag = np.zeros(N); np.add.at(diag, pm.owner[:F], -upper); np.add.at(diag, pm.neighbour, -upper); diag += rng.uniform(0.01, 0.1, N)
+    b = rng.uniform(-1, 1, N)
+    ldu.pcg_solve(diag, upper, np.zeros(N), b, tol=1e-9, maxIter=5)          # warm-up (allocations)
+    lib.set_option("pcg_kernel_timers", 1); lib.timers_reset()
+    x, perf, hist = ldu.pcg_solve(diag, upper, np.zeros(N), b, tol=1e-9, maxIter=400)
+    tm = lib.timers()
+    lib.set_option("pcg_kernel_timers", 0)
+    it = max(1, perf.nIterations)
+    res = b - ldu.amul(diag, upper, x)                                        # true residual of the solution, by the product's own Amul
+    peak = measured_peak()[0]
+    out = {"workload": "polyhedral box from %dx%dx%d hexes (2/3 of the 2x2x2 blocks merged into 24-face cells, vertices jittered by 0.25 of the spacing): "
+                       "%d cells, %d internal faces (BASELINE configs[3])" % (dims + (N, F)),
+           "cells": N, "faces_per_cell": 2.0 * F / N, "wavefronts": int(ldu.renumbering()[2]), "sweep_tiles": int(len(ldu.tiling()[2]) - 1),
+           "setup_s": build_s, "pcg_iterations": int(perf.nIterations), "converged": bool(perf.converged), "pcg_solve_ms": tm["pcg_solve"][0],
+           "true_residual_L1_over_b_L1": float(np.abs(res).sum() / np.abs(b).sum())}
+    for k, t_ms, alg in (("amul", tm["amul"][0], 8 * (3 * N + F) + 8 * F), ("dic_precondition", tm["dic_fwd"][0] + tm["dic_bwd"][0], 48 * N + 32 * F)):
+        t = t_ms * 1e-3 / it
+        out[k] = {"us": 1e6 * t, "algorithmic_bytes": alg, "GBps": alg / t / 1e9, "frac_of_measured_peak": alg / t / 1e9 / peak}
+    ldu.release(); pm.release()
+    return out
+
+
 def workload(args, desc):
     return {"workload": desc, "deltaT": args.delta_t, "Co_target": "max Co ~0.2-0.35 (see `courant`)", "nCorrectors": 3, "nAlphaSubCycles": 2, "nAlphaCorr": 1,
             "pd_solver": "b200PCG+DIC tol 1e-7 relTol 0.05 (pdFinal relTol 0)", "momentumPredictor": "no", "turbulence": "laminar",
@@ -515,6 +550,12 @@ def run_ours(args):
                   "scaling": "strong", "decomposition": "simple %s" % (decomposition(sargs, sdims, world),) if world > 1 else "none"}
         sreg.release(); sdm.release(); spm.release()
 
+    # ---- polyhedral leg (default run, N = 1): BASELINE configs[3], a 4.05 M-cell polyhedral box (hexes + 24-face super-cells, jittered
+    #      vertices): the LDU kernels on irregular addressing -- Amul, DIC precondition (chunked sweep tiles), one PCG solve
+    poly = None
+    if world == 1 and args.scaling == "weak" and not args.no_poly_leg:
+        poly = polyhedral_leg(lib)
+
     if rank != 0:
         return
     its = sum(iters_value)
@@ -532,6 +573,8 @@ def run_ours(args):
     line["e2e_coupled"] = e2e_coupled
     if strong:
         line["strong_scaling_leg"] = strong
+    if poly is not None:
+        line["polyhedral_leg"] = poly
     if e2e_plugin:
         line["e2e_plugin"] = e2e_plugin
     if parity:
@@ -575,6 +618,7 @@ def main():
     ap.add_argument("--delta-t", dest="delta_t", type=float, default=DELTA_T)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-preflight", action="store_true")
+    ap.add_argument("--no-poly-leg", action="store_true", help="skip the configs[3] polyhedral leg of the default run")
     ap.add_argument("--no-strong-leg", action="store_true", help="skip the configs[2] strong-scaling leg of the default (weak) run")
     ap.add_argument("--cpu-procs", type=int, default=0, help="sub-domains (threads) of the CPU arm; default = host cores")
     ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of timed CPU work before the CPU arm stops early")

@@ -586,6 +586,20 @@ class Region3D:
 _LIB = None
 
 
+def checkerboard_groups(nx, ny, nz):
+    """group keys for PolyMesh.agglomerate: the complete 2x2x2 blocks with (I + J + K) % 3 != 0 of an nx x ny x nz hex box merge into
+    24-face super-cells, the other cells stay hexes -- the synthetic polyhedral mesh of BASELINE configs[3] (restated, and the resulting
+    mesh compared bit by bit, by oracle/mesh_oracle.py block_groups / agglomerate)"""
+    i = np.arange(nx, dtype=np.int64)[:, None, None]; j = np.arange(ny, dtype=np.int64)[None, :, None]; k = np.arange(nz, dtype=np.int64)[None, None, :]
+    I, J, K = i // 2, j // 2, k // 2
+    merged = (2 * I + 1 < nx) & (2 * J + 1 < ny) & (2 * K + 1 < nz) & ((I + J + K) % 3 != 0)
+    cell = i + nx * (j + ny * k)
+    key = np.where(merged, nx * ny * nz + (I + (nx // 2 + 1) * (J + (ny // 2 + 1) * K)), cell)
+    out = np.empty(nx * ny * nz, dtype=np.int64)
+    out[cell.ravel()] = key.ravel()
+    return out
+
+
 def load():
     """The product library (nvcc, sm_100a).  Raises when it is missing -- no fallback of any kind."""
     global _LIB

@@ -48,7 +48,7 @@ def one_step(lib, oracle, pm, L, deltaT, field_tol, **kw):
     assert ho.shape == hg.shape and np.allclose(ho, hg, rtol=1e-8, atol=1e-13)
     for k, d in diffs0.items():
         assert d <= field_tol, k
-    assert np.allclose(ro.alpha_stats(), rg.alpha_stats(), rtol=1e-12, atol=1e-25)
+    assert np.allclose(ro.alpha_stats(), rg.alpha_stats(), rtol=1e-10, atol=1e-25)     # (volume average: a sum of N addends in two orders)
     rg.release(); dm.release()
 
 

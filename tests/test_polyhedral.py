@@ -22,6 +22,7 @@ def test_polyhedral_mesh_bit_exact(dims):
     ref = mo.block_mesh_box(*dims, *L)
     ref = mo.jitter_points(ref, 0.25, L[0] / dims[0], L[1] / dims[1], L[2] / dims[2], 12345)
     ref = mo.agglomerate(ref, mo.block_groups(*dims))
+    assert np.array_equal(capi.checkerboard_groups(*dims), mo.block_groups(*dims))   # the product-side helper bench.py uses
     assert pm.nCells == ref["nCells"] < dims[0] * dims[1] * dims[2]
     assert np.array_equal(pm.points, ref["points"]) and np.array_equal(pm.faces, ref["faces"])
     assert np.array_equal(pm.owner, ref["owner"]) and np.array_equal(pm.neighbour, ref["neighbour"])
