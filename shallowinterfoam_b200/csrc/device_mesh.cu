@@ -155,6 +155,16 @@ void DeviceMesh::build(int32_t nCells, int32_t nFaces, const int32_t* lo, const 
                     const uint16_t o = own[d.slot0 + sl];
                     if (o != SWEEP_OWN_NONE) slotRow[d.slot0 + sl] = d.row0 + (o & SWEEP_OWN_ROW);
                 }
+                d.stepWarps[0] = d.stepWarps[1] = 0xffffffffu;
+                if (d.nSteps <= 16) {
+                    d.stepWarps[0] = d.stepWarps[1] = 0u;
+                    for (int k = 0; k < d.nSteps; k++) {
+                        int last = -1;
+                        for (int i = 0; i < W; i++) if (own[d.slot0 + (size_t)k * W + i] != SWEEP_OWN_NONE) last = i;
+                        const unsigned nw = (unsigned)std::min(15, (last + 32) / 32);   // (15 = every warp: 512+ lanes do not fit 4 bits)
+                        d.stepWarps[k >> 3] |= nw << (4 * (k & 7));
+                    }
+                }
                 if (!d.virt && d.nSteps == 16) {   // hybrid publish (dic_kernels.cuh bulkPlan): rows of an unchunked tile are contiguous in step order
                     int first4 = 0, first12 = 0;
                     for (size_t sl = 0; sl < S; sl++) if (own[d.slot0 + sl] != SWEEP_OWN_NONE) { if (sl < (size_t)4 * W) first4++; if (sl < (size_t)12 * W) first12++; }

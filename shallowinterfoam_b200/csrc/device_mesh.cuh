@@ -63,7 +63,8 @@ struct SweepTile {
     int halo, nHalo;       // halo list offset and length
     int virt;              // chunked plan (host_mesh.h): an entry may be one CHUNK of a row; its own-row offset carries OWN_PARTIAL / OWN_CARRY
     int bulkLo, bulkHi;    // hybrid publish: local rows of the first SWEEP_BULK_STEPS processing steps (bulkHi == 0: not eligible)
-    int pad;
+    unsigned stepWarps[2]; // 4 bits per step (tiles of <= 16 steps): warps that hold entries in that step; the others skip their operand loads
+    int pad[3];
 };
 // flag bits in an entry's own-row byte offset (rows are 8 bytes apart, so the low three bits are free)
 constexpr unsigned OWN_PARTIAL = 1u;   // not the last chunk of its row: the result stays in the tile

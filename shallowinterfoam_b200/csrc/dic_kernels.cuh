@@ -213,6 +213,23 @@ template <int DIR>
 __device__ __forceinline__ void loadRegOps(RegOps& o, const double* __restrict__ blk, const SweepTile& t) {
     const int W = blockDim.x, S = t.nSteps * W;
     const uint2* PK = (const uint2*)(blk + t.d * S);
+    if (DIR > 0) {
+        // forward sweep: warps without entries in a step (t.stepWarps) skip that step's loads -- their operands are the inert ones (zero
+        // coefficients, sources = the padding slot, own row = the trash slot); partly filled tiles otherwise stream mostly padding.
+        // (Forward only: the same code in the backward kernel makes ptxas lay its step loop out 7 us slower, profiles/r2_ncu_summary.md.)
+        const unsigned padOff = 8u * (unsigned)(t.nRows + t.nHalo), warp = threadIdx.x >> 5;
+        const uint2 inert = make_uint2(padOff | (padOff << 16), padOff | ((padOff + 8u) << 16));
+#pragma unroll
+        for (int it = 0; it < SWEEP_REG_STEPS; it++) {
+            const bool on = it < t.nSteps && warp < ((t.stepWarps[(it >> 3) & 1] >> (4 * (it & 7))) & 15u);
+            const int slot = (on ? it * W : 0) + (int)threadIdx.x;
+            o.c[it][0] = on ? ldgStream(blk + slot) : 0.0;
+            o.c[it][1] = (on && t.d > 1) ? ldgStream(blk + S + slot) : 0.0;
+            o.c[it][2] = (on && t.d > 2) ? ldgStream(blk + 2 * S + slot) : 0.0;
+            o.pk[it] = on ? ldgStream(PK + slot) : inert;
+        }
+        return;
+    }
 #pragma unroll
     for (int it = 0; it < SWEEP_REG_STEPS; it++) {
         const bool on = it < t.nSteps;
