@@ -47,6 +47,11 @@ struct Runtime {
 Runtime& rt();
 void requireDevice();  // throws B200_ERR_NO_DEVICE when no CUDA device is usable
 
+// bulk transfers between caller-owned (possibly pageable) host arrays and the device (host_copy.cu): chunked through pinned staging
+// buffers by a few worker threads; hostCopyIn returns when the source is consumed, hostCopyOut when the data has arrived
+void hostCopyIn(void* dev, const void* host, size_t bytes);
+void hostCopyOut(void* host, const void* dev, size_t bytes);
+
 // ---- kernel-class timers (CUDA events on the launching stream) -------------------------------------------
 enum TimerId { T_AMUL = 0, T_DIC_FWD, T_DIC_BWD, T_DIC_RD, T_PCG_VEC, T_PCG_SOLVE, T_MULES, T_FLUX, T_ASSEMBLY, T_UEQN, T_MISC, T_STEP, T_ALLREDUCE, T_HALO, T_COUNT };
 const char* timerName(int i);

@@ -276,30 +276,30 @@ MeshView DeviceMesh::view() const {
 // ------------------------------------------------------------------------------------ layout conversion
 void DeviceMesh::uploadCells(const double* host, double* dev) {
     double* st = stage(stageA, N);
-    B200_CHECK_CUDA(cudaMemcpyAsync(st, host, 8 * (size_t)N, cudaMemcpyHostToDevice, rt().stream));
+    hostCopyIn(st, host, 8 * (size_t)N);
     if (N) B200_LAUNCH(k_gather, gridFor(N), BLOCK, rt().stream, st, dRowCell.p, dev, N);
 }
 void DeviceMesh::downloadCells(const double* dev, double* host) {
     double* st = stage(stageA, N);
     if (N) B200_LAUNCH(k_gather, gridFor(N), BLOCK, rt().stream, dev, dCellRow.p, st, N);
-    B200_CHECK_CUDA(cudaMemcpyAsync(host, st, 8 * (size_t)N, cudaMemcpyDeviceToHost, rt().stream));
+    hostCopyOut(host, st, 8 * (size_t)N);
     syncStream();
 }
 void DeviceMesh::uploadCellVec(const double* hostXYZ, double* dx, double* dy, double* dz) {
     double* st = stage(stageA, 3 * (size_t)N);
-    B200_CHECK_CUDA(cudaMemcpyAsync(st, hostXYZ, 24 * (size_t)N, cudaMemcpyHostToDevice, rt().stream));
+    hostCopyIn(st, hostXYZ, 24 * (size_t)N);
     if (N) B200_LAUNCH(k_gather_vec, gridFor(N), BLOCK, rt().stream, st, dRowCell.p, dx, dy, dz, N);
 }
 void DeviceMesh::downloadCellVec(const double* dx, const double* dy, const double* dz, double* hostXYZ) {
     double* st = stage(stageA, 3 * (size_t)N);
     if (N) B200_LAUNCH(k_scatter_vec_to_aos, gridFor(N), BLOCK, rt().stream, dx, dy, dz, dCellRow.p, st, N);
-    B200_CHECK_CUDA(cudaMemcpyAsync(hostXYZ, st, 24 * (size_t)N, cudaMemcpyDeviceToHost, rt().stream));
+    hostCopyOut(hostXYZ, st, 24 * (size_t)N);
     syncStream();
 }
 void DeviceMesh::uploadFaces(const double* host, double* dev, bool withBoundary) {
     size_t n = (size_t)F + (withBoundary ? B : 0);
     double* st = stage(stageA, n);
-    B200_CHECK_CUDA(cudaMemcpyAsync(st, host, 8 * n, cudaMemcpyHostToDevice, rt().stream));
+    hostCopyIn(st, host, 8 * n);
     if (Fs) B200_LAUNCH(k_gather, gridFor(Fs), BLOCK, rt().stream, st, dSlotFace.p, dev, Fs);
     if (withBoundary && B)
         B200_CHECK_CUDA(cudaMemcpyAsync(dev + Fs, st + F, 8 * (size_t)B, cudaMemcpyDeviceToDevice, rt().stream));
@@ -310,21 +310,21 @@ void DeviceMesh::downloadFaces(const double* dev, double* host, bool withBoundar
     if (F) B200_LAUNCH(k_gather, gridFor(F), BLOCK, rt().stream, dev, dFacePos.p, st, F);
     if (withBoundary && B)
         B200_CHECK_CUDA(cudaMemcpyAsync(st + F, dev + Fs, 8 * (size_t)B, cudaMemcpyDeviceToDevice, rt().stream));
-    B200_CHECK_CUDA(cudaMemcpyAsync(host, st, 8 * n, cudaMemcpyDeviceToHost, rt().stream));
+    hostCopyOut(host, st, 8 * n);
     syncStream();
 }
 void DeviceMesh::uploadFaceVec(const double* hostXYZ, double* dx, double* dy, double* dz) {
     size_t n = (size_t)F + B;
     double* st = stage(stageA, 3 * n);
-    B200_CHECK_CUDA(cudaMemcpyAsync(st, hostXYZ, 24 * n, cudaMemcpyHostToDevice, rt().stream));
+    hostCopyIn(st, hostXYZ, 24 * n);
     if (Fs) B200_LAUNCH(k_gather_vec, gridFor(Fs), BLOCK, rt().stream, st, dSlotFace.p, dx, dy, dz, Fs);
     if (B) B200_LAUNCH(k_copy_vec_b, gridFor(B), BLOCK, rt().stream, st + 3 * (size_t)F, dx + Fs, dy + Fs, dz + Fs, B);
 }
 void DeviceMesh::uploadBoundary(const double* host, double* dev, int nc) {
-    if (B) B200_CHECK_CUDA(cudaMemcpyAsync(dev, host, 8 * (size_t)B * nc, cudaMemcpyHostToDevice, rt().stream));
+    if (B) hostCopyIn(dev, host, 8 * (size_t)B * nc);
 }
 void DeviceMesh::downloadBoundary(const double* dev, double* host, int nc) {
-    if (B) B200_CHECK_CUDA(cudaMemcpyAsync(host, dev, 8 * (size_t)B * nc, cudaMemcpyDeviceToHost, rt().stream));
+    if (B) hostCopyOut(host, dev, 8 * (size_t)B * nc);
     syncStream();
 }
 
