@@ -78,3 +78,29 @@ def test_irregular_addressing_1M_rows(oracle):
     k = min(len(hg), len(ho))
     assert np.allclose(hg[:30], ho[:30], rtol=1e-8, atol=1e-13 * ho[0]) and np.allclose(hg[:k], ho[:k], rtol=5e-2)
     ldu.release()
+
+
+def test_host_copy_pipeline_roundtrip(oracle):
+    """csrc/host_copy.cu: pageable host fields travel in 2 MB chunks through pinned buffers filled by worker threads; whatever the thread
+    count (1 = plain cudaMemcpyAsync; odd counts and more threads than chunks included), what comes back is what went in, bit by bit"""
+    from shallowinterfoam_b200 import capi
+    from cases import channel_case, default_controls
+    lib = get_gpu_lib()
+    L = (20.0, 5.0, 10.0)
+    pm = lib.polymesh_box(200, 50, 100, *L, weir=(0.45, 0.5, 0.3))
+    cs = channel_case(pm, *L)
+    dm = pm.device_mesh()
+    rg = dm.region3d(default_controls(capi.Region3dControls, 0.002), dm.bc(cs["tA"], 1, cs["rvA"]), dm.bc(cs["tU"], 3, cs["rvU"]), dm.bc(cs["tP"], 1),
+                     cs["alpha"], cs["U"], cs["pd"])
+    N, nF = pm.nCells, pm.nInternalFaces + pm.nBoundaryFaces
+    rng = np.random.default_rng(77)
+    try:
+        for thr in (1, 3, 4, 8, 16):
+            lib.set_option("host_copy_threads", thr)
+            a, U, pd, phi = rng.uniform(0, 1, N), rng.uniform(-1, 1, (N, 3)), rng.uniform(-1, 1, N), rng.uniform(-1, 1, nF)
+            rg.set_fields(alpha1=a, U=U, pd=pd, phi=phi)
+            f = rg.fields()
+            assert np.array_equal(f["alpha1"], a) and np.array_equal(f["U"], U) and np.array_equal(f["pd"], pd) and np.array_equal(f["phi"], phi), thr
+    finally:
+        lib.set_option("host_copy_threads", 4)
+    rg.release(); dm.release(); pm.release()
