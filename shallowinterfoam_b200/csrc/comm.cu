@@ -273,11 +273,11 @@ void peerHaloRelease(PeerHalo* h) {
     if (h->counter) cudaFree(h->counter);
     delete h;
 }
-void peerHaloPush(PeerHalo* h, const DeviceMesh& m, const double* cellField, bool pdl) {
+void peerHaloPush(PeerHalo* h, const DeviceMesh& m, const double* cellField, bool pdl, cudaStream_t stream) {
     h->epoch++;
     if (h->v.nNbr == 0) return;
     dim3 grid(std::max(1, gridFor(h->maxSize)), h->v.nNbr);
-    B200_LAUNCH_PDL(pdl, k_halo_push, grid, BLOCK, 0, rt().stream, m.view(), cellField, h->v, h->epoch, h->counter);
+    B200_LAUNCH_PDL(pdl && !stream, k_halo_push, grid, BLOCK, 0, stream ? stream : rt().stream, m.view(), cellField, h->v, h->epoch, h->counter);
 }
 const double* peerHaloRecv(const PeerHalo* h) { return h->own + 2 * PEER_MAX_RANKS + (size_t)(h->epoch & 1ull) * h->B; }
 PeerHaloWait peerHaloWait(const PeerHalo* h) {
@@ -333,7 +333,7 @@ P2PFold p2pFoldNext() { P2PFold f; memset(&f, 0, sizeof(f)); return f; }
 struct PeerHalo {};
 PeerHalo* peerHaloGet(DeviceMesh&) { return nullptr; }
 void peerHaloRelease(PeerHalo*) {}
-void peerHaloPush(PeerHalo*, const DeviceMesh&, const double*, bool) {}
+void peerHaloPush(PeerHalo*, const DeviceMesh&, const double*, bool, cudaStream_t) {}
 const double* peerHaloRecv(const PeerHalo*) { return nullptr; }
 PeerHaloWait peerHaloWait(const PeerHalo*) { PeerHaloWait w; memset(&w, 0, sizeof(w)); return w; }
 void haloExchange(const DeviceMesh& m, const double* send, double* recv) {
@@ -358,7 +358,7 @@ P2PFold p2pFoldNext() { P2PFold f; memset(&f, 0, sizeof(f)); return f; }
 struct PeerHalo {};
 PeerHalo* peerHaloGet(DeviceMesh&) { return nullptr; }
 void peerHaloRelease(PeerHalo*) {}
-void peerHaloPush(PeerHalo*, const DeviceMesh&, const double*, bool) {}
+void peerHaloPush(PeerHalo*, const DeviceMesh&, const double*, bool, cudaStream_t) {}
 const double* peerHaloRecv(const PeerHalo*) { return nullptr; }
 PeerHaloWait peerHaloWait(const PeerHalo*) { PeerHaloWait w; memset(&w, 0, sizeof(w)); return w; }
 #endif

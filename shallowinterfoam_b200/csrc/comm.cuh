@@ -78,7 +78,8 @@ struct PeerHalo;           // per mesh (comm.cu)
 PeerHalo* peerHaloGet(DeviceMesh& m);
 void peerHaloRelease(PeerHalo* h);
 // launches the push of cellField's processor-face values for a new epoch; afterwards peerHaloRecv / peerHaloWait describe that epoch
-void peerHaloPush(PeerHalo* h, const DeviceMesh& m, const double* cellField, bool pdl = false);
+// stream != null: launch there instead of the library stream (the caller orders it against the producer of cellField and against its reuse)
+void peerHaloPush(PeerHalo* h, const DeviceMesh& m, const double* cellField, bool pdl = false, cudaStream_t stream = nullptr);
 const double* peerHaloRecv(const PeerHalo* h);   // [B] receive buffer of the current epoch (read with ld.global.cg after the wait)
 PeerHaloWait peerHaloWait(const PeerHalo* h);
 __device__ __forceinline__ void peerHaloWaitDevice(const PeerHaloWait& w) {

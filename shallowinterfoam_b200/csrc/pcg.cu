@@ -12,6 +12,9 @@ PcgWorkspace::~PcgWorkspace() {
     peerHaloRelease(peer);
     if (hsc) cudaFreeHost(hsc);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (evP) cudaEventDestroy(evP);
+    if (evPush) cudaEventDestroy(evPush);
+    if (pushStream) cudaStreamDestroy(pushStream);
 }
 DeviceMesh::~DeviceMesh() { delete pcg; }
 
@@ -213,6 +216,15 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
     if (multi && !w.peerTried) { w.peerTried = true; w.peer = peerHaloGet(m); }   // collective: every rank reaches its first multi-rank solve
     PeerHalo* peer = halo ? w.peer : nullptr;
     bool firstIteration = true;
+    // peer-memory halo: k_halo_push (NVLink stores + system-scope fences, ~10 us) runs on a side stream BESIDE the local Amul instead of in
+    // front of it; the next p-update waits for it (it reads pA), which by then is long finished
+    const bool sidePush = peer && !kt && rt().opt("p2p_push_stream", 1) > 0;
+    if (sidePush && !w.pushStream) {
+        B200_CHECK_CUDA(cudaStreamCreateWithFlags(&w.pushStream, cudaStreamNonBlocking));
+        B200_CHECK_CUDA(cudaEventCreateWithFlags(&w.evP, cudaEventDisableTiming));
+        B200_CHECK_CUDA(cudaEventCreateWithFlags(&w.evPush, cudaEventDisableTiming));
+    }
+    bool pushPending = false;
     auto enqueueIteration = [&]() {
         // (an empty rank still runs the sweeps: they carry the iteration's residual sum / convergence test and the wArA sum)
         { KT(T_DIC_FWD);   // + the previous iteration's x / rA update, residual sum and convergence test (fused)
@@ -226,13 +238,22 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
         { KT(T_DIC_BWD); launchBwd(m, w, w.rA.p, sc, part, cnt, multi ? &sc->wArAnew : &sc->wArA, pdlSweeps, nullptr, fold1, hist); }
         if (multi && !fold1.on) { KT(T_ALLREDUCE);
           if (!allReduceSumThenPcgCheck(&sc->sumMagR, 2, sc, hist)) { allReduce(&sc->sumMagR, 2, RED_SUM); B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist); } }
+        if (pushPending) { B200_CHECK_CUDA(cudaStreamWaitEvent(st, w.evPush, 0)); pushPending = false; }
         { KT(T_PCG_VEC);
           B200_LAUNCH_PDL(pdl || (pdlSweeps && commUsesPeerMemory()), k_pcg_p_update, grid, BLOCK, 0, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc); }
         P2PFold fold2 = P2PFold{};
         if (halo) {
             // Amul of the local block with its dot product, then the interface update (+ dot correction) over the boundary rows only.
             // peer: the halo goes over NVLink peer memory -- push -> Amul (overlaps the transfer) -> wait inside k_iface_rows; else NCCL
-            { KT(T_HALO); if (peer) peerHaloPush(peer, m, w.pA, pdlSweeps); else haloPack(m, w.pA, w.sendBuf); }
+            { KT(T_HALO);
+              if (sidePush) {
+                  B200_CHECK_CUDA(cudaEventRecord(w.evP, st));
+                  B200_CHECK_CUDA(cudaStreamWaitEvent(w.pushStream, w.evP, 0));
+                  peerHaloPush(peer, m, w.pA, false, w.pushStream);
+                  B200_CHECK_CUDA(cudaEventRecord(w.evPush, w.pushStream));
+                  pushPending = true;
+              } else if (peer) peerHaloPush(peer, m, w.pA, pdlSweeps);
+              else haloPack(m, w.pA, w.sendBuf); }
             { KT(T_AMUL); B200_LAUNCH_AMUL(1, pdlSweeps && peer != nullptr, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt); }
             // ... and gSumProd(wA, pA) rides in the tail of the interface update (fold2)
             fold2 = !kt ? p2pFoldNext() : P2PFold{};
@@ -265,6 +286,7 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
         slot ^= 1; pendingSlots--;
     }
     // drain anything still queued (no-op iterations) and read the final scalars
+    if (pushPending) { B200_CHECK_CUDA(cudaStreamWaitEvent(st, w.evPush, 0)); pushPending = false; }   // the last side-stream push reads pA
     B200_CHECK_CUDA(cudaMemcpyAsync(&w.hsc[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
     syncStream();
     h = w.hsc[0];

@@ -27,6 +27,8 @@ struct PcgWorkspace {
     DevBuf<int> bRowOfSlot;
     PcgScalars* hsc = nullptr;                 // pinned mirror (2 slots)
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t pushStream = nullptr;         // side stream of the peer-memory halo push (runs beside the local Amul)
+    cudaEvent_t evP = nullptr, evPush = nullptr;
     int histCap = 0;
     int sweepGrid = 0;
     double rowsPerLevel = 1.0;
