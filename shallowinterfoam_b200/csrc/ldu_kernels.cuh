@@ -403,8 +403,12 @@ static __global__ void __launch_bounds__(BLOCK) k_iface_rows(MeshView mv, const 
                                                        double* __restrict__ Apsi, const double* __restrict__ psi, int nBRows,
                                                        const int* __restrict__ bRowOfSlot, PcgScalars* sc, double* partials,
                                                        unsigned* counter, PeerHaloWait hw, P2PFold fold) {
-    if (sc->stop) return;
+    // (programmatic dependent launch: the neighbours' flags do not depend on the local Amul, so the wait for them is the prologue; the next
+    //  forward sweep may start its own prologue as soon as every CTA is here)
     peerHaloWaitDevice(hw);
+    pdlWait();
+    pdlTrigger();
+    if (sc->stop) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double v[1] = {0.0};
     if (i < nBRows) {

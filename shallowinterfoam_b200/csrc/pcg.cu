@@ -259,8 +259,11 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
             fold2 = !kt ? p2pFoldNext() : P2PFold{};
             { KT(T_HALO);
               if (!peer) haloExchange(m, w.sendBuf, w.recvBuf);
-              B200_LAUNCH(k_iface_rows, std::max(1, gridFor(m.nBRows)), BLOCK, st, mv, bou, peer ? peerHaloRecv(peer) : (const double*)w.recvBuf.p, w.wA.p,
-                          (const double*)w.pA.p, m.nBRows, (const int*)w.bRowOfSlot.p, sc, part, cnt, peer ? peerHaloWait(peer) : PeerHaloWait{}, fold2); }
+              // (not itself launched early: measured at 2 GPUs, CTAs that spin on the neighbours' flags beside the Amul tail cost 10 us per iteration;
+              //  its pdlTrigger lets the next forward sweep's prologue overlap it)
+              B200_LAUNCH_PDL(false, k_iface_rows, std::max(1, gridFor(m.nBRows)), BLOCK, 0, st, mv, bou,
+                              peer ? peerHaloRecv(peer) : (const double*)w.recvBuf.p, w.wA.p, (const double*)w.pA.p, m.nBRows, (const int*)w.bRowOfSlot.p, sc, part, cnt,
+                              peer ? peerHaloWait(peer) : PeerHaloWait{}, fold2); }
         } else {
             KT(T_AMUL);
             B200_LAUNCH_AMUL(1, pdl, mv, diag, upS, upS, (const double*)w.pA.p, w.wA.p, sc, part, cnt);
