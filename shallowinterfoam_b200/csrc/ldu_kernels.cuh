@@ -433,17 +433,28 @@ static __global__ void __launch_bounds__(BLOCK) k_iface_rows(MeshView mv, const 
     }
 }
 // pA = z + beta*pA (first iteration: pA = z);  z <- sentinel (re-armed for the next sweep)
+// (two rows per thread through 16-byte accesses: the kernel is a 24 B/cell stream bound by requests in flight, not by arithmetic)
 static __global__ void __launch_bounds__(BLOCK) k_pcg_p_update(int N, double* __restrict__ z, double* __restrict__ pA,
                                                          const PcgScalars* sc) {
     pdlWait();
     pdlTrigger();
     if (sc->stop) return;
-    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (row >= N) return;
-    double zv = z[row];
-    if (sc->nIter == 0) pA[row] = zv;
-    else { double beta = sc->wArA / sc->wArAold; pA[row] = zv + beta * pA[row]; }
-    z[row] = sentinel();
+    const bool first = sc->nIter == 0;
+    const double beta = first ? 0.0 : sc->wArA / sc->wArAold;
+    if (row + 1 < N) {
+        const double2 zv = *reinterpret_cast<const double2*>(z + row);
+        double2 pv = *reinterpret_cast<const double2*>(pA + row);
+        pv.x = first ? zv.x : zv.x + beta * pv.x;
+        pv.y = first ? zv.y : zv.y + beta * pv.y;
+        *reinterpret_cast<double2*>(pA + row) = pv;
+        *reinterpret_cast<double2*>(z + row) = make_double2(sentinel(), sentinel());
+    } else {
+        const double zv = z[row];
+        pA[row] = first ? zv : zv + beta * pA[row];
+        z[row] = sentinel();
+    }
 }
 // (x += alpha*pA ; rA -= alpha*wA ; sum|rA| of upstream's loop tail are fused into the NEXT forward sweep: dic_kernels.cuh)
 

@@ -240,7 +240,7 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
           if (!allReduceSumThenPcgCheck(&sc->sumMagR, 2, sc, hist)) { allReduce(&sc->sumMagR, 2, RED_SUM); B200_LAUNCH(k_pcg_check, 1, 32, st, sc, hist); } }
         if (pushPending) { B200_CHECK_CUDA(cudaStreamWaitEvent(st, w.evPush, 0)); pushPending = false; }
         { KT(T_PCG_VEC);
-          B200_LAUNCH_PDL(pdl || (pdlSweeps && commUsesPeerMemory()), k_pcg_p_update, grid, BLOCK, 0, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc); }
+          B200_LAUNCH_PDL(pdl || (pdlSweeps && commUsesPeerMemory()), k_pcg_p_update, std::max(1, gridFor((N + 1) / 2)), BLOCK, 0, st, N, w.z.p, w.pA.p, (const PcgScalars*)sc); }
         P2PFold fold2 = P2PFold{};
         if (halo) {
             // Amul of the local block with its dot product, then the interface update (+ dot correction) over the boundary rows only.

@@ -29,6 +29,8 @@
 struct uint3 { unsigned x, y, z; };
 struct uint2 { unsigned x, y; };
 inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
+struct alignas(16) double2 { double x, y; };
+inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 
 namespace emu {
