@@ -220,7 +220,11 @@ b200_solver_perf pcgSolveDevice(DeviceMesh& m, const double* diag, const double*
     // front of it; the next p-update waits for it (it reads pA), which by then is long finished
     const bool sidePush = peer && !kt && rt().opt("p2p_push_stream", 1) > 0;
     if (sidePush && !w.pushStream) {
-        B200_CHECK_CUDA(cudaStreamCreateWithFlags(&w.pushStream, cudaStreamNonBlocking));
+        // (highest priority: its few small blocks are dispatched ahead of the pending CTAs of the big kernels whenever an SM has room --
+        //  the neighbours' interface updates wait for this rank's push)
+        int prLo = 0, prHi = 0;
+        B200_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+        B200_CHECK_CUDA(cudaStreamCreateWithPriority(&w.pushStream, cudaStreamNonBlocking, prHi));
         B200_CHECK_CUDA(cudaEventCreateWithFlags(&w.evP, cudaEventDisableTiming));
         B200_CHECK_CUDA(cudaEventCreateWithFlags(&w.evPush, cudaEventDisableTiming));
     }

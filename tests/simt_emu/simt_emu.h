@@ -152,6 +152,8 @@ inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) {
 inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return 0; }
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = nullptr; return 0; }
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = 0; return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 inline cudaError_t cudaDeviceSynchronize() { return 0; }
