@@ -82,3 +82,50 @@ def test_polyhedral_region_steps(lib, oracle):
     ho, hg = ro.res_hist(), rg.res_hist()
     assert ho.shape == hg.shape and np.allclose(ho, hg, rtol=1e-8, atol=1e-13)
     rg.release(); dm.release()
+
+
+@pytest.mark.parametrize("band,rows,smem,lanes", [(16, 4096, 225000, 256), (2, 64, 110 * 1024, 32), (32, 4096, 225000, 128), (16, 2048, 30000, 64),
+                                                  (8, 96, 110 * 1024, 64), (64, 8192, 225000, 256)])
+def test_polyhedral_tiling_variants_bitwise(oracle, band, rows, smem, lanes):
+    """(emulated build only: this is a test of the plan builder's branches; on the GPU the chunked kernels run in test_irregular_ldu.py,
+    the two tests above and tests/test_atsize_region.py)
+    chunked sweep plans (rows with up to 17 sources applied as chains of <= 3-source chunks) under different tilings: tiny tiles (almost
+    every source is a polled halo value), bands high enough for tiles of more than 16 steps (shared-memory operand path with chunk flags), a
+    tiny shared-memory budget (pieces halved laterally or by level), one tile per band.  DIC / DILU sweeps, calcReciprocalD and PCG stay
+    bitwise / 1e-8 against the oracle, and the plan keeps its invariants."""
+    from conftest import get_lib
+    lib = get_lib("emu")
+    lib.set_option("sweep_band_levels", band); lib.set_option("sweep_tile_rows", rows); lib.set_option("sweep_smem_bytes", smem)
+    lib.set_option("sweep_threads", lanes)
+    try:
+        pm = make(lib, (14, 10, 12))
+        m = oracle_mesh_of(pm)
+        ldu = pm.ldu()
+        F = pm.nInternalFaces
+        assert max(np.bincount(pm.owner[:F], minlength=m.N).max(), np.bincount(pm.neighbour, minlength=m.N).max()) > 3   # a chunked plan
+        rowCell, level, _ = ldu.renumbering()
+        bl, tr, ts = ldu.tiling()
+        assert sorted(rowCell.tolist()) == list(range(m.N)) and ts[0] == 0 and ts[-1] == m.N and np.all(np.diff(ts) > 0)
+        inv = np.empty(m.N, dtype=np.int64); inv[rowCell] = np.arange(m.N)
+        tile_of_row = np.searchsorted(ts, np.arange(m.N), side="right") - 1
+        assert np.all(tile_of_row[inv[pm.owner[:F]]] <= tile_of_row[inv[pm.neighbour]])        # ticket order is topological
+        diag, upper = random_spd(m, seed=31)
+        rng = np.random.default_rng(32)
+        rA = rng.uniform(-1, 1, m.N); b = rng.uniform(-1, 1, m.N)
+        rD = oracle.dic_calc_rd(m, diag, upper)
+        assert np.array_equal(rD, ldu.dic_calc_rd(diag, upper))
+        w = oracle.dic_precondition(m, rD, upper, rA)
+        for _ in range(2):
+            assert np.array_equal(w, ldu.dic_precondition(rD, upper, rA))
+        lower = -rng.uniform(0.5, 1.5, m.F)
+        rDl = oracle.dilu_calc_rd(m, diag, upper, lower)
+        assert np.array_equal(rDl, ldu.dilu_calc_rd(diag, upper, lower))
+        for tr_ in (False, True):
+            assert np.array_equal(oracle.dilu_precondition(m, rDl, upper, lower, rA, tr_), ldu.dilu_precondition(rDl, upper, lower, rA, tr_))
+        xo, po, ho = oracle.pcg_solve(m, diag, upper, np.zeros(m.N), b, tol=1e-10, maxIter=300)
+        xg, pg, hg = ldu.pcg_solve(diag, upper, np.zeros(m.N), b, tol=1e-10, maxIter=300)
+        assert pg.nIterations == po.nIterations and np.allclose(hg, ho, rtol=1e-8, atol=1e-13 * ho[0])
+        ldu.release()
+    finally:
+        for k, v in (("sweep_band_levels", 16), ("sweep_tile_rows", 4096), ("sweep_smem_bytes", 225000), ("sweep_threads", 256)):
+            lib.set_option(k, v)
